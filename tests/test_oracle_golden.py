@@ -1,0 +1,174 @@
+"""Pin the CPU oracle (oracle/vap_oracle.c) to the reference's own outputs (tests/golden/*.npz).
+
+Integer outputs and every stage that only uses IEEE +,-,*,/,sqrt,fma must be BIT-EXACT; the
+curvature / heading tables go through libm pow/atan2 and are pinned to <= 4 ulp (numpy's SIMD loops
+and scalar glibc already disagree by an ulp in a few percent of samples).
+Later stages are fed the golden tables so that their own arithmetic is checked bit-for-bit.
+"""
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN_DIR, bit_equal, case_names, load_case, ulp_diff
+
+CASES = case_names()
+
+
+def _assert_bits(a, b, what):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if not bit_equal(a, b):
+        u = ulp_diff(a, b)
+        raise AssertionError(f"{what}: {int((u > 0).sum())}/{u.size} differ, max {int(u.max())} ulp")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stagewise_bit_exact(oracle_mod, name):
+    o = oracle_mod
+    o.set_sq_mode(0)
+    g = load_case(name)
+    dt, dd = g["dt_dd"]
+    geo = o.Geometry(g["node_attr"], g["node_flags"])
+    # S0
+    _assert_bits(geo.seg, g["seg"], "segments")
+    assert geo.first_node.tolist() == g["spline_first_node"].tolist()
+    _assert_bits(geo.param_end, g["spline_param_end"], "param_end")
+    _assert_bits(geo.seglen, g["spline_seglen"], "segment_lengths")
+    _assert_bits(geo.params_concat, g["spline_params_concat"], "parameters")
+    # S1
+    ld, lt, total = geo.build_lut()
+    _assert_bits(ld, g["lut_d"], "lut distances")
+    _assert_bits(lt, g["lut_t"], "lut parameters")
+    _assert_bits(total, g["total_length"], "total_length")
+    # S2 (libm)
+    k, h = geo.build_props()
+    assert ulp_diff(k, g["prop_k"]).max() <= 4
+    assert ulp_diff(h, g["prop_h"]).max() <= 4
+    K, H = g["prop_k"], g["prop_h"]
+    # S3
+    ds = o.dist_sample(geo, g["ap_attr"], g["ap_flags"], g["constraints"], dd, ld, lt, total, K, H)
+    assert ds["D"] == len(g["t"])
+    _assert_bits(ds["t"], g["t"], "t_i")
+    _assert_bits(ds["kap"], g["kap"], "kappa_i")
+    _assert_bits(ds["th"], g["th"], "theta_i")
+    # the reference logs max_accels before appending the trailing entry (motion_profile_generator.py:169,176)
+    _assert_bits(ds["max_accels"][:-1], g["max_accels"], "max_accels")
+    assert ds["max_accels"][-1] == g["constraints"][1]
+    assert ds["bidx"].tolist() == g["boundary_idx"].tolist()
+    assert ds["bval"].tolist() == g["boundary_val"].tolist()
+    # S4 + S5
+    v = o.fwd_bwd(ds["kap"], ds["th"], ds["v0"], g["constraints"], dd, ds["max_accels"], ds["bidx"], ds["bval"])
+    _assert_bits(v, g["vel"], "velocities")
+    # S6
+    pr = o.profile(geo, g["ap_attr"], g["ap_flags"], g["constraints"], dt, dd, ld, lt, total, K, H, g["vel"])
+    assert pr["T"] == len(g["times"])
+    for a in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels"):
+        _assert_bits(pr[a], g[a], a)
+    _assert_bits(pr["x"], g["coords"][:, 0], "x")
+    _assert_bits(pr["y"], g["coords"][:, 1], "y")
+    assert pr["nodes_map"].tolist() == g["nodes_map"].tolist()
+    assert pr["actions_map"].tolist() == g["actions_map"].tolist()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_end_to_end_tolerance(oracle_mod, name):
+    """Whole path with the oracle's own libm tables: indices exact, values within north-star tolerances."""
+    o = oracle_mod
+    o.set_sq_mode(0)
+    g = load_case(name)
+    r = o.full(g["node_attr"], g["node_flags"], g["ap_attr"], g["ap_flags"], g["constraints"], *g["dt_dd"])
+    assert r["D"] == len(g["vel"]) and r["T"] == len(g["times"])
+    assert r["nodes_map"].tolist() == g["nodes_map"].tolist()
+    assert r["actions_map"].tolist() == g["actions_map"].tolist()
+    np.testing.assert_allclose(r["vel"], g["vel"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(r["x"], g["coords"][:, 0], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(r["y"], g["coords"][:, 1], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(r["times"], g["times"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(r["linear_vels"], g["linear_vels"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(r["angular_vels"], g["angular_vels"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(r["accelerations"], g["accelerations"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(r["headings"], g["headings"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_api_queries(oracle_mod, name):
+    o = oracle_mod
+    o.set_sq_mode(0)
+    g = load_case(name)
+    geo = o.Geometry(g["node_attr"], g["node_flags"])
+    for which, key in ((0, "api_point"), (1, "api_d1"), (2, "api_d2")):
+        got = np.array([geo.eval(which, t) for t in g["api_t"]])
+        _assert_bits(got, g[key], key)
+    hx = np.array([geo.exact_heading(t) for t in g["api_t"]])
+    kx = np.array([geo.exact_curvature(t) for t in g["api_t"]])
+    assert ulp_diff(hx, g["api_heading_exact"]).max() <= 2
+    np.testing.assert_allclose(kx, g["api_curv_exact"], rtol=1e-14, atol=1e-300)
+    hs = np.array([o.snap(g["prop_h"], g["n"], t) for t in g["api_t"]])
+    ks = np.array([o.snap(g["prop_k"], g["n"], t) for t in g["api_t"]])
+    _assert_bits(hs, g["api_heading_snap"], "snap heading")
+    _assert_bits(ks, g["api_curv_snap"], "snap curvature")
+    tt = np.array([o.distance_to_time(g["lut_d"], g["lut_t"], float(g["total_length"]), g["n"], d) for d in g["api_dist"]])
+    _assert_bits(tt, g["api_dist_t"], "distance_to_time")
+    # Gauss-Legendre arc length / inverse (API parity; quintic_hermite_spline.py:592-717)
+    pts, wts = np.polynomial.legendre.leggauss(20)
+    got = np.array([geo.gl_arclen(int(k), a, b, pts, wts) for k, a, b in zip(g["gl_spline"], g["gl_t0"], g["gl_t1"])])
+    _assert_bits(got, g["gl_len"], "GL arc length")
+    tot = np.array([geo.gl_arclen(k, 0.0, geo.param_end[k], pts, wts) for k in range(geo.S)])
+    _assert_bits(tot, g["gl_total"], "GL total")
+    inv = np.array([geo.gl_inverse(int(k), s, pts, wts) for k, s in zip(g["inv_spline"], g["inv_s"])])
+    _assert_bits(inv, g["inv_t"], "GL inverse")
+
+
+def test_misc_api(oracle_mod):
+    o = oracle_mod
+    o.set_sq_mode(0)
+    m = dict(np.load(f"{GOLDEN_DIR}/misc_api.npz"))
+    off = 0
+    for V, A, w, deg, rad, K in m["angle_meta"]:
+        K = int(K)
+        assert rad == deg * (np.pi / 180.0)
+        h, om = o.motion_profile_angle(rad, V, A, w)
+        assert len(h) == K
+        _assert_bits(h, m["angle_headings"][off:off + K], "turn headings")
+        _assert_bits(om, m["angle_omegas"][off:off + K], "turn omegas")
+        off += K
+    off = 0
+    for V, A, dist, K in m["trap_meta"]:
+        K = int(K)
+        v = o.trapezoid(V, A, dist)
+        assert len(v) == K
+        _assert_bits(v, m["trap_v"][off:off + K], "trapezoid")
+        off += K
+    got = np.array([o.lerp_uniform(x, 0.005, m["lerp_ys"]) for x in m["lerp_q"]])
+    _assert_bits(got, m["lerp_out"], "lerp")
+
+
+def test_error_conventions(oracle_mod):
+    """F7: turn/reverse at the last node -> IndexError; turn at node 0 -> IndexError in the profile."""
+    o = oracle_mod
+    g = load_case("cfg1_factory")
+    na, nf = g["node_attr"].copy(), g["node_flags"].copy()
+    nf2 = nf.copy(); nf2[-1] |= 1
+    with pytest.raises(o.OracleError) as e:
+        o.Geometry(na, nf2)
+    assert e.value.code == -2
+    na2 = na.copy(); na2[0, 2] = 30.0
+    with pytest.raises(o.OracleError) as e:
+        o.full(na2, nf, None, None, g["constraints"])
+    assert e.value.code == -2
+    with pytest.raises(o.OracleError) as e:
+        o.Geometry(na[:1], nf[:1])
+    assert e.value.code == -1
+
+
+def test_sq_mode_only_touches_last_bits(oracle_mod):
+    """x*x (engine) vs libm pow(x,2) (reference): same indices, values within a few ulp."""
+    o = oracle_mod
+    g = load_case("rand8_2")
+    o.set_sq_mode(1)
+    try:
+        r = o.full(g["node_attr"], g["node_flags"], g["ap_attr"], g["ap_flags"], g["constraints"], *g["dt_dd"])
+    finally:
+        o.set_sq_mode(0)
+    assert r["T"] == len(g["times"]) and r["nodes_map"].tolist() == g["nodes_map"].tolist()
+    np.testing.assert_allclose(r["vel"], g["vel"], rtol=1e-12)
