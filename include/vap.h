@@ -1,0 +1,164 @@
+/*
+ * vap.h -- C ABI of libvap.so, the B200 (sm_100a) batched spline -> motion-profile engine.
+ *
+ * The reference (RohitMovva/VexAutonomousPlanner) has no FFI layer: its boundary is the Python call
+ * surface of src/splines and src/motion_profiling_v2.  Each entry point below replaces one function
+ * of that surface (cited as file:line relative to the reference's src/) for a BATCH of independent
+ * paths.  The Python mirror of the reference classes (vexautonomousplanner_b200/*.py) binds these
+ * symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types.
+ *   - every pointer is a DEVICE pointer (caller-owned; e.g. torch.Tensor.data_ptr()) unless the
+ *     parameter name starts with h_ (host).  Arrays are C-contiguous, path-major.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - return value: 0 on success, <0 on a launch/argument error (text via vap_last_error()).
+ *     Per-path failures never abort the batch: they are reported in status[B]:
+ *        0 ok | -1 reference returns False | -2 reference raises IndexError
+ *        -3 reference raises ValueError    | -4 caller capacity (D_cap / T_cap) too small
+ *   - the library keeps no global mutable state and allocates nothing.
+ *
+ * Packed layouts
+ *   node_attr[B][N_max][12] f64 : x, y (feet), turn_deg, wait_time, max_velocity, max_acceleration,
+ *                                 tangent_x, tangent_y, incoming_magnitude, outgoing_magnitude,
+ *                                 rot_cos, rot_sin   (cos/sin of radians(turn)(+pi if reverse), evaluated
+ *                                 on the host with numpy exactly as spline_manager.py:105-113 does)
+ *   node_flags[B][N_max]   i32  : bit0 is_reverse_node, bit1 stop, bit2 tangent is not None
+ *   n_nodes[B]             i32
+ *   ap_attr[B][A_max][4]   f64  : t, wait_time, max_velocity, max_acceleration
+ *   ap_flags[B][A_max]     i32  : bit1 stop
+ *   n_ap[B]                i32
+ *   cons[B][6]             f64  : max_vel, max_acc, max_dec, friction_coef, max_jerk, track_width
+ *   seg[B][N_max-1][6][2]  f64  : rows p0, p1, d0, d1, dd0, dd1 of global segment g (node g -> g+1)
+ *   first_node[B][N_max+1] i32  : node index at which spline k starts; entry S = N-1
+ *   param_end[B][N_max]    f64  : spline.parameters[-1] per spline
+ */
+#ifndef VAP_H
+#define VAP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAP_NODE_ATTRS 12
+#define VAP_AP_ATTRS 4
+#define VAP_FLAG_REVERSE 1
+#define VAP_FLAG_STOP 2
+#define VAP_FLAG_TANGENT 4
+
+#define VAP_OK 0
+#define VAP_ERR_FALSE (-1)
+#define VAP_ERR_INDEX (-2)
+#define VAP_ERR_VALUE (-3)
+#define VAP_ERR_CAPACITY (-4)
+
+int vap_version(void);
+const char* vap_last_error(void);
+
+/* S0  QuinticHermiteSplineManager.build_path (spline_manager.py:42-172) + QuinticHermiteSpline.fit
+ *     (quintic_hermite_spline.py:30-219,719-736).  scratch: f64 [B][N_max][5].                        */
+int vap_build_path(int64_t B, int N_max, const double* node_attr, const int32_t* node_flags,
+                   const int32_t* n_nodes, double* seg, int32_t* first_node, double* param_end,
+                   double* seglen, int32_t* n_splines, int32_t* status, double* scratch, void* stream);
+
+/* S0' QuinticHermiteSpline.fit for stand-alone splines (quintic_hermite_spline.py:30-138): R runs of up to
+ *     n_max control points.  xy[R][n_max][2]; tan_has[R][n_max] (i32 bit0: incoming set, bit1: outgoing set);
+ *     tan_in/tan_out[R][n_max][2]; bnd_has[R] (bit0 starting_tangent, bit1 ending_tangent); bnd[R][2][2].
+ *     Outputs seg[R][n_max-1][12], seglen[R][n_max], params[R][n_max], status[R].                        */
+int vap_fit_splines(int64_t R, int n_max, const int32_t* n_pts, const double* xy, const int32_t* tan_has,
+                    const double* tan_in, const double* tan_out, const int32_t* bnd_has, const double* bnd,
+                    double* seg, double* seglen, double* params, int32_t* status, double* scratch,
+                    void* stream);
+
+/* Evaluation (get_point/derivative/second_derivative _at_parameter, spline_manager.py:204-275 ->
+ * quintic_hermite_spline.py:221-251,473-541).  which: 0 point, 1 first, 2 second derivative,
+ * 3 heading + curvature (Spline.get_heading/get_curvature, spline.py:48-80; out = {heading, curvature}).
+ * n queries: path[q] selects the path, t[q] the global parameter; out[q][2].                           */
+int vap_eval(int64_t n, const int32_t* path, const double* t, int which, int N_max, const double* seg,
+             const int32_t* first_node, const double* param_end, const int32_t* n_splines, double* out,
+             void* stream);
+
+/* S1  build_lookup_table (spline_manager.py:426-475): samples per spline (reference default 1000).
+ *     lut_d/lut_t[B][Q_cap] with Q_cap >= samples * max_b n_splines[b]; total_len[B].               */
+int vap_build_lut(int64_t B, int N_max, const double* seg, const int32_t* first_node, const double* param_end,
+                  const int32_t* n_splines, const int32_t* status, int samples, int64_t Q_cap, double* lut_d,
+                  double* lut_t, double* total_len, void* stream);
+
+/* S2  precompute_path_properties (spline_manager.py:477-548): spn samples per node (default 1000).
+ *     prop_k/prop_h[B][P_cap], P_cap >= spn * N_max.                                                   */
+int vap_build_props(int64_t B, int N_max, const int32_t* n_nodes, const double* seg, const int32_t* first_node,
+                    const double* param_end, const int32_t* n_splines, const int32_t* status, int spn,
+                    int64_t P_cap, double* prop_k, double* prop_h, void* stream);
+
+/* distance_to_time (spline_manager.py:291-318) and the snap gather _interpolate_property (:550-580) for
+ * n queries.  what: 0 distance->t, 1 heading(t), 2 curvature(t).                                      */
+int vap_query_tables(int64_t n, const int32_t* path, const double* x, int what, const int32_t* n_nodes,
+                     const int32_t* n_splines, int samples, int64_t Q_cap, const double* lut_d,
+                     const double* lut_t, const double* total_len, int spn, int64_t P_cap, const double* prop_k,
+                     const double* prop_h, double* out, void* stream);
+
+/* Accumulated distance grid d_0 = 0, d_{i+1} = fl(d_i + dd) (motion_profile_generator.py:91,122): identical
+ * for every path with the same dd, so it is built once (single serial chain) and reused.              */
+int vap_build_dgrid(int64_t n, double dd, double* dgrid, void* stream);
+
+/* S3  forward_backward_pass, sampling loop (motion_profile_generator.py:112-176) without the event logic:
+ *     n_samples[B] (= D), t/kap/th[B][D_cap].  status gets VAP_ERR_CAPACITY if D > D_cap.              */
+int vap_dist_sample(int64_t B, const int32_t* n_nodes, const int32_t* n_splines, int32_t* status, int64_t n_grid,
+                    const double* dgrid, int samples, int64_t Q_cap, const double* lut_d, const double* lut_t,
+                    const double* total_len, int spn, int64_t P_cap, const double* prop_k, const double* prop_h,
+                    int64_t D_cap, int32_t* n_samples, double* t, double* kap, double* th, void* stream);
+
+/* S3 events + S4 forward pass + S5 backward pass (motion_profile_generator.py:93-176,188-314).
+ *     vel[B][D_cap] out.  max_accels[B][E_cap], bidx/bval[B][E_cap], n_ev[B][2] (len(max_accels), len(map));
+ *     E_cap >= N_max + A_max + 2.  t_est[B]: estimate of the number of time samples (for sizing S6).
+ *     mode: 0 both passes, 1 forward only (for stage tests).                                           */
+int vap_fwd_bwd(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
+                const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
+                const double* cons, const int32_t* status, double dd, double dt, double start_vel, double end_vel,
+                int64_t D_cap, const int32_t* n_samples, const double* t, const double* kap, const double* th,
+                double* vel, int E_cap, double* max_accels, int32_t* bidx, int32_t* bval, int32_t* n_ev,
+                double* t_est, int mode, void* stream);
+
+/* S6  generate_motion_profile time loop + node-0 prologue + turn / wait inserts
+ *     (motion_profile_generator.py:414-628, one_dim_mp_generator.py:4-69) and S7 summary rows.
+ *     out[8][B][T_cap]: times, positions, linear_vels, accelerations, headings, angular_vels, x, y.
+ *     nodes_map[B][N_max+1] (with the caller's trailing len(times), gui/path.py:342), actions_map[B][A_max],
+ *     n_maps[B][2]; n_out[B]; summary[B][5] = {n_out, total_length, t_end, max|v|, status}.
+ *     If a path needs more than T_cap rows, n_out still holds the true count and status = -4.          */
+int vap_resample(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
+                 const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
+                 const double* cons, int32_t* status, double dt, double dd, const double* seg,
+                 const int32_t* first_node, const double* param_end, const int32_t* n_splines, int samples,
+                 int64_t Q_cap, const double* lut_d, const double* lut_t, const double* total_len, int spn,
+                 int64_t P_cap, const double* prop_k, const double* prop_h, int64_t D_cap,
+                 const int32_t* n_samples, const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
+                 int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary, void* stream);
+
+/* S1' QuinticHermiteSpline.get_arc_length (Gauss-Legendre, quintic_hermite_spline.py:592-644) and
+ *     get_parameter_by_arc_length (:661-717) for n queries on spline `spl[q]` of path `path[q]`.
+ *     gl_pts / gl_wts[npts] = np.polynomial.legendre.leggauss(npts) from the host (device copies).
+ *     mode 0: out[q] = arc length over [a[q], b[q]]; mode 1: out[q] = parameter at arc length a[q]
+ *     (b[q] = tolerance, max_iter iterations).  qstatus[q] = 0 or VAP_ERR_VALUE.                       */
+int vap_gl(int64_t n, const int32_t* path, const int32_t* spl, const double* a, const double* b, int mode,
+           int max_iter, int npts, const double* gl_pts, const double* gl_wts, int N_max, const double* seg,
+           const int32_t* first_node, const double* param_end, double* out, int32_t* qstatus, void* stream);
+
+/* motion_profile_angle (motion_profile_generator.py:319-346) / generate_trapezoidal_profile
+ * (one_dim_mp_generator.py:4-69) for n queries: q[n][5] = angle_rad (or total_distance when mode 1),
+ * max_vel, max_acc, track_width, dt.  mode 0: out_a = headings, out_b = angular velocities;
+ * mode 1: out_a = velocities.  Rows of K_cap; counts[n].                                               */
+int vap_turn_profile(int64_t n, const double* q, int mode, int64_t K_cap, double* out_a, double* out_b,
+                     int32_t* counts, void* stream);
+
+/* lerp (motion_profile_generator.py:349-386, cache=None) of n queries against one sorted table xs/ys[m],
+ * and get_wheel_trajectory (:631-646).                                                                  */
+int vap_lerp(int64_t n, const double* x, int64_t m, const double* xs, const double* ys, double* out, void* stream);
+int vap_wheel_trajectory(int64_t n, const double* lin, const double* ang, double track_width, double* left,
+                         double* right, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAP_H */

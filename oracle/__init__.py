@@ -43,6 +43,7 @@ def lib():
         build()
         L = C.CDLL(_SO)
         L.ora_set_sq_mode.argtypes = [C.c_int]
+        L.ora_set_threads.argtypes = [C.c_int]
         L.ora_get_sq_mode.restype = C.c_int
         L.ora_build_path.argtypes = [C.c_int, _dp, _ip, _dp, _ip, _dp, _dp, _dp]
         L.ora_build_path.restype = C.c_int
@@ -302,7 +303,7 @@ def full_batch(node_attr, node_flags, cons, n_ap=None, ap_attr=None, ap_flags=No
     nf = np.ascontiguousarray(node_flags, dtype=np.int32)
     cons = np.ascontiguousarray(cons, dtype=np.float64).reshape(B, 6)
     if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+        L.ora_set_threads(int(threads))
     summ = np.zeros((B, 5))
     if ap_attr is not None:
         apa = np.ascontiguousarray(ap_attr, dtype=np.float64)

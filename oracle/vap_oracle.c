@@ -29,6 +29,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define NA 12
 enum { A_X = 0, A_Y, A_TURN, A_WAIT, A_MAXVEL, A_MAXACC, A_TX, A_TY, A_INMAG, A_OUTMAG, A_RCOS, A_RSIN };
@@ -899,6 +902,16 @@ done:
     free(seg); free(fn); free(pe); free(sl); free(pc); free(lut_d); free(lut_t); free(kap); free(th);
     free(tq); free(kq); free(hq); free(ma); free(bidx); free(bval);
     return rc;
+}
+
+/* number of OpenMP threads ora_full_batch uses (0 = library default) */
+void ora_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 /* Batch driver for timing: B paths with identical node count, OpenMP over paths; only summaries are

@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle and the reference goldens.
+
+Stage-wise checks feed the oracle the engine's own upstream tables, so every stage that is pure IEEE
+arithmetic must agree BIT FOR BIT (the oracle runs with x**2 == x*x, the one place where the engine
+deliberately uses the correctly rounded product instead of libm pow).  End-to-end checks
+against the reference's golden outputs use the north-star tolerances (1e-9 relative for positions, 1e-6 for
+velocities and times) with exact integer outputs; coordinates and headings cross zero, so their relative
+tolerance is paired with atol = 1e-10 (1e-11 of the 12.1 ft field).
+"""
+import numpy as np
+import pytest
+
+from golden_util import bit_equal, case_names, load_case, ulp_diff
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from vexautonomousplanner_b200.engine import Engine
+    return Engine("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ora(oracle_mod):
+    oracle_mod.set_sq_mode(1)
+    yield oracle_mod
+    oracle_mod.set_sq_mode(0)
+
+
+def _bits(a, b, what):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if not bit_equal(a, b):
+        u = ulp_diff(a, b)
+        raise AssertionError(f"{what}: {int((u > 0).sum())}/{u.size} differ, max {int(u.max())} ulp")
+
+
+def golden_batch():
+    """All golden cases as ONE ragged batch (N from 2 to 16, 0..3 action points)."""
+    from vexautonomousplanner_b200.packing import PackedPaths
+    cases = [load_case(n) for n in case_names()]
+    B = len(cases)
+    N = max(c["n"] for c in cases)
+    A = max(max(len(c["ap_t"]) for c in cases), 1)
+    na = np.zeros((B, N, 12)); nf = np.zeros((B, N), dtype=np.int32); nn = np.zeros(B, dtype=np.int32)
+    apa = np.zeros((B, A, 4)); apf = np.zeros((B, A), dtype=np.int32); nap = np.zeros(B, dtype=np.int32)
+    cons = np.zeros((B, 6))
+    for b, c in enumerate(cases):
+        n, a = c["n"], len(c["ap_t"])
+        na[b, :n] = c["node_attr"]; nf[b, :n] = c["node_flags"]; nn[b] = n
+        apa[b, :a] = c["ap_attr"]; apf[b, :a] = c["ap_flags"]; nap[b] = a
+        cons[b] = c["constraints"]
+    return cases, PackedPaths(na, nf, nn, apa, apf, nap, cons)
+
+
+def stagewise_check(ora, packed, res, b, n_api=0):
+    """Oracle re-run of every stage on the engine's own upstream data; bit-exact comparisons."""
+    n = int(packed.n_nodes[b]); A = int(packed.n_ap[b])
+    na, nf = packed.node_attr[b, :n], packed.node_flags[b, :n]
+    apa, apf = packed.ap_attr[b, :A], packed.ap_flags[b, :A]
+    cons = packed.cons[b]
+    g, t, ex = res.geometry, res.tables, res.extra
+    geo = ora.Geometry(na, nf)
+    S = geo.S
+    assert int(g.n_splines[b]) == S
+    assert g.first_node[b, : S + 1].cpu().numpy().tolist() == geo.first_node.tolist()
+    _bits(g.seg[b, : n - 1].cpu().numpy(), geo.seg, "segments")
+    _bits(g.param_end[b, :S].cpu().numpy(), geo.param_end, "param_end")
+    _bits(g.seglen[b, : n - 1].cpu().numpy(), geo.seglen, "segment lengths")
+    ld, lt, total = geo.build_lut()
+    _bits(t.lut_d[b, : 1000 * S].cpu().numpy(), ld, "lut distances")
+    _bits(t.lut_t[b, : 1000 * S].cpu().numpy(), lt, "lut parameters")
+    _bits(t.total_len[b].cpu().numpy(), total, "total length")
+    K = np.ascontiguousarray(t.prop_k[b, : 1000 * n].cpu().numpy())
+    H = np.ascontiguousarray(t.prop_h[b, : 1000 * n].cpu().numpy())
+    ko, ho = geo.build_props()
+    assert ulp_diff(K, ko).max() <= 8, "curvature table"
+    assert ulp_diff(H, ho).max() <= 8, "heading table"
+    ds = ora.dist_sample(geo, apa, apf, cons, 0.005, ld, lt, total, K, H)
+    D = int(res.n_samples[b])
+    assert D == ds["D"]
+    _bits(ex["t"][b, :D].cpu().numpy(), ds["t"], "t_i")
+    _bits(ex["kap"][b, :D].cpu().numpy(), ds["kap"], "kappa_i")
+    _bits(ex["th"][b, :D].cpu().numpy(), ds["th"], "theta_i")
+    n_acc, n_b = (int(v) for v in ex["n_ev"][b])
+    _bits(ex["max_accels"][b, :n_acc].cpu().numpy(), ds["max_accels"], "max_accels")
+    assert ex["bidx"][b, :n_b].cpu().numpy().tolist() == ds["bidx"].tolist()
+    assert ex["bval"][b, :n_b].cpu().numpy().tolist() == ds["bval"].tolist()
+    v = ora.fwd_bwd(ds["kap"], ds["th"], ds["v0"], cons, 0.005, ds["max_accels"], ds["bidx"], ds["bval"])
+    vel = res.vel[b, :D].cpu().numpy()
+    _bits(vel, v, "velocities")
+    pr = ora.profile(geo, apa, apf, cons, 0.01, 0.005, ld, lt, total, K, H, v)
+    got = res.path(b)
+    assert got["status"] == 0
+    assert len(got["times"]) == pr["T"]
+    for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y"):
+        _bits(got[k], pr[k], k)
+    assert got["nodes_map"].tolist() == pr["nodes_map"].tolist()
+    assert got["actions_map"].tolist() == pr["actions_map"].tolist()
+    return got
+
+
+def test_golden_batch_stagewise_and_end_to_end(eng, ora):
+    cases, packed = golden_batch()
+    res = eng.profile(eng.upload(packed), keep=True)
+    torch.cuda.synchronize()
+    assert res.status.cpu().numpy().tolist() == [0] * len(cases)
+    for b, c in enumerate(cases):
+        got = stagewise_check(ora, packed, res, b)
+        # ---- against the reference's own outputs
+        n = c["n"]
+        seg = res.geometry.seg[b, : n - 1].cpu().numpy()
+        assert ulp_diff(seg, c["seg"]).max() <= 1               # rows 4,5: L*L vs libm pow(L,2)
+        _bits(seg[:, :4], c["seg"][:, :4], "segment rows 0-3 vs reference")
+        S = len(c["spline_param_end"])
+        np.testing.assert_allclose(res.tables.lut_d[b, : 1000 * S].cpu().numpy(), c["lut_d"], rtol=1e-13)
+        np.testing.assert_allclose(res.tables.lut_t[b, : 1000 * S].cpu().numpy(), c["lut_t"], rtol=0, atol=0)
+        assert ulp_diff(res.tables.prop_k[b, : 1000 * n].cpu().numpy(), c["prop_k"]).max() <= 8
+        assert ulp_diff(res.tables.prop_h[b, : 1000 * n].cpu().numpy(), c["prop_h"]).max() <= 8
+        D = len(c["vel"])
+        assert int(res.n_samples[b]) == D
+        np.testing.assert_allclose(res.extra["t"][b, :D].cpu().numpy(), c["t"], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(got["vel"], c["vel"], rtol=1e-6, atol=1e-12)
+        assert len(got["times"]) == len(c["times"])
+        assert got["nodes_map"].tolist() == c["nodes_map"].tolist()
+        assert got["actions_map"].tolist() == c["actions_map"].tolist()
+        np.testing.assert_allclose(got["x"], c["coords"][:, 0], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got["y"], c["coords"][:, 1], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got["positions"], c["positions"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(got["times"], c["times"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(got["linear_vels"], c["linear_vels"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got["angular_vels"], c["angular_vels"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got["accelerations"], c["accelerations"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(got["headings"], c["headings"], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("kind", ["cfg2", "cfg5"])
+def test_random_batch_vs_oracle(eng, ora, kind):
+    from vexautonomousplanner_b200 import synth
+    B = 192
+    packed = synth.random_paths(B, 8, seed=0) if kind == "cfg2" else synth.mixed_paths(B, 8, seed=3)
+    res = eng.profile(eng.upload(packed), keep=True)
+    torch.cuda.synchronize()
+    assert (res.status == 0).all()
+    for b in range(0, B, 7):
+        stagewise_check(ora, packed, res, b)
+    # every path end to end against the oracle with its own libm tables
+    summ = res.summary.cpu().numpy()
+    for b in range(B):
+        A = int(packed.n_ap[b])
+        ref = ora.full(packed.node_attr[b], packed.node_flags[b], packed.ap_attr[b, :A], packed.ap_flags[b, :A],
+                       packed.cons[b])
+        got = res.path(b)
+        assert len(got["times"]) == ref["T"], b
+        assert int(res.n_samples[b]) == ref["D"], b
+        assert got["nodes_map"].tolist() == ref["nodes_map"].tolist()
+        assert got["actions_map"].tolist() == ref["actions_map"].tolist()
+        np.testing.assert_allclose(got["vel"], ref["vel"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(got["x"], ref["x"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got["y"], ref["y"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got["times"], ref["times"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(got["linear_vels"], ref["linear_vels"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got["angular_vels"], ref["angular_vels"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got["headings"], ref["headings"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(summ[b, :4], ref["summary"][:4], rtol=1e-6)
+
+
+def test_cfg3_16_node_sample(eng, ora):
+    from vexautonomousplanner_b200 import synth
+    packed = synth.random_paths(24, 16, seed=1)
+    res = eng.profile(eng.upload(packed), keep=True)
+    torch.cuda.synchronize()
+    for b in range(0, 24, 5):
+        stagewise_check(ora, packed, res, b)
+
+
+def test_error_conventions(eng):
+    """F7: inputs that crash the reference come back as per-path status codes, the rest of the batch is fine."""
+    from vexautonomousplanner_b200 import synth
+    packed = synth.random_paths(6, 6, seed=11)
+    packed.node_flags[1, 5] |= 1                      # reverse at the last node -> IndexError
+    packed.node_attr[2, 0, 2] = 30.0                  # turn at node 0 -> IndexError in the profile
+    packed.node_attr[3, 5, 2] = 45.0                  # turn at the last node -> IndexError
+    packed.n_nodes[4] = 1                             # fewer than 2 points -> False
+    from vexautonomousplanner_b200.packing import rotation_table
+    packed.node_attr[:, :, 10], packed.node_attr[:, :, 11] = rotation_table(packed.node_attr[:, :, 2],
+                                                                             (packed.node_flags & 1) != 0)
+    res = eng.profile(eng.upload(packed))
+    torch.cuda.synchronize()
+    assert res.status.cpu().numpy().tolist() == [0, -2, -2, -2, -1, 0]
+    assert res.n_out.cpu().numpy()[[1, 2, 3, 4]].tolist() == [0, 0, 0, 0]
+    assert int(res.n_out[0]) > 100 and int(res.n_out[5]) > 100
+
+
+def test_cfg2_full_size_properties(eng, ora):
+    """4096 x 8-node batch (BASELINE configs[1]): size-independent properties, run-to-run determinism, and a
+    strided sample of paths against the oracle.
+
+    (Mirror symmetry is NOT a property of the reference: delta_theta in the velocity passes sees the atan2 branch
+    cut, motion_profile_generator.py:202,268, so a mirrored path gets a slightly different profile -- the golden
+    pair mixed8_0 / mixed8_0_mirror already differs in nodes_map.)"""
+    from vexautonomousplanner_b200 import synth
+    packed = synth.random_paths(4096, 8, seed=0)
+    db = eng.upload(packed)
+    res = eng.profile(db)
+    res2 = eng.profile(db, reuse_plan=True)
+    torch.cuda.synchronize()
+    assert (res.status == 0).all()
+    n = res.n_out.long()
+    T = res.T_cap
+    mask = torch.arange(T, device=n.device)[None, :] < n[:, None]
+    # determinism: same bits on a second run (different capacities are allowed, valid regions must agree)
+    assert torch.equal(res.n_out, res2.n_out)
+    Tm = min(T, res2.T_cap)
+    m2 = mask[:, :Tm]
+    for i in range(8):
+        assert torch.equal(res.out[i][:, :Tm][m2], res2.out[i][:, :Tm][m2])
+    # time advances by dt, velocity within the constraint, position is non-decreasing and ends just past L
+    tm = res.stream("times")
+    d = (tm[:, 1:] - tm[:, :-1])[mask[:, 1:]]
+    assert torch.allclose(d, torch.full_like(d, 0.01), rtol=0, atol=1e-9)
+    v = res.stream("linear_vels")[mask]
+    assert float(v.max()) <= 4.0 + 1e-12 and float(v.min()) >= 0.0
+    pos = res.stream("positions")
+    assert bool(((pos[:, 1:] - pos[:, :-1])[mask[:, 1:]] > 0).all())
+    last = pos.gather(1, (n - 1).clamp(min=0)[:, None])[:, 0]
+    assert torch.all(last >= res.summary[:, 1])
+    assert torch.all(last <= res.summary[:, 1] + 0.05)
+    summ = res.summary.cpu().numpy()
+    for b in range(0, 4096, 97):
+        ref = ora.full(packed.node_attr[b], packed.node_flags[b], None, None, packed.cons[b])
+        assert int(res.n_out[b]) == ref["T"] and int(res.n_samples[b]) == ref["D"]
+        np.testing.assert_allclose(summ[b, :4], ref["summary"][:4], rtol=1e-6)
+        got = res.path(b)
+        np.testing.assert_allclose(got["x"], ref["x"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got["linear_vels"], ref["linear_vels"], rtol=1e-6, atol=1e-9)

@@ -1,0 +1,312 @@
+"""Batched spline -> motion-profile engine: Python driver of libvap.so (include/vap.h).
+
+PyTorch is plumbing only: device memory, streams, a few reductions for sizing.  All arithmetic of the
+hot path happens in the hand-written sm_100a kernels of csrc/vap_kernels.cu; there is no CPU fallback.
+
+Stages: S0 build_path -> S1 distance LUT -> S2 curvature/heading tables -> S3 distance
+sampling -> S3 events + S4 forward + S5 backward -> S6 time-domain resampling (+ S7 summary rows).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from contextlib import contextmanager
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .packing import PackedPaths
+
+OUT_NAMES = ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")
+ST_OK, ST_FALSE, ST_INDEX, ST_VALUE, ST_CAPACITY = 0, -1, -2, -3, -4
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+@dataclass
+class DeviceBatch:
+    """PackedPaths resident on the device."""
+    node_attr: torch.Tensor
+    node_flags: torch.Tensor
+    n_nodes: torch.Tensor
+    ap_attr: torch.Tensor
+    ap_flags: torch.Tensor
+    n_ap: torch.Tensor
+    cons: torch.Tensor
+    max_splines: int
+
+    @property
+    def B(self):
+        return self.node_attr.shape[0]
+
+    @property
+    def N_max(self):
+        return self.node_attr.shape[1]
+
+    @property
+    def A_max(self):
+        return self.ap_attr.shape[1]
+
+    @staticmethod
+    def from_packed(p: PackedPaths, device, pinned: Optional[dict] = None, non_blocking: bool = True) -> "DeviceBatch":
+        def up(a):
+            t = torch.from_numpy(a)
+            return t.to(device, non_blocking=non_blocking)
+        return DeviceBatch(up(p.node_attr), up(p.node_flags), up(p.n_nodes), up(p.ap_attr), up(p.ap_flags), up(p.n_ap),
+                           up(p.cons), p.max_splines())
+
+
+@dataclass
+class Geometry:
+    seg: torch.Tensor          # [B, N_max-1, 6, 2]
+    first_node: torch.Tensor   # [B, N_max+1] i32
+    param_end: torch.Tensor    # [B, N_max]
+    seglen: torch.Tensor       # [B, N_max]
+    n_splines: torch.Tensor    # [B] i32
+    status: torch.Tensor       # [B] i32
+
+
+@dataclass
+class Tables:
+    samples: int
+    spn: int
+    Q_cap: int
+    P_cap: int
+    lut_d: torch.Tensor        # [B, Q_cap]
+    lut_t: torch.Tensor
+    total_len: torch.Tensor    # [B]
+    prop_k: Optional[torch.Tensor] = None   # [B, P_cap]
+    prop_h: Optional[torch.Tensor] = None
+
+
+@dataclass
+class ProfileResult:
+    """Device-resident result of one batch.  Row b of every [B, cap] array is valid up to its count."""
+    B: int
+    T_cap: int
+    out: torch.Tensor            # [8, B, T_cap]: times, positions, linear_vels, accelerations, headings, angular_vels, x, y
+    n_out: torch.Tensor          # [B] i32  number of time samples
+    nodes_map: torch.Tensor      # [B, N_max+1] i32
+    actions_map: torch.Tensor    # [B, A_max] i32
+    n_maps: torch.Tensor         # [B, 2] i32 (len(nodes_map), len(actions_map))
+    status: torch.Tensor         # [B] i32
+    summary: torch.Tensor        # [B, 5]: n_out, total_length, t_end, max|v|, status
+    vel: torch.Tensor            # [B, D_cap] velocities of forward_backward_pass
+    n_samples: torch.Tensor      # [B] i32 (= D)
+    geometry: Optional[Geometry] = None
+    tables: Optional[Tables] = None
+    extra: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+    def stream(self, name: str) -> torch.Tensor:
+        return self.out[OUT_NAMES.index(name)]
+
+    def path(self, b: int) -> Dict[str, np.ndarray]:
+        """Copy path b to the host as numpy arrays trimmed to their true lengths."""
+        T = int(self.n_out[b])
+        res = {nm: self.out[i, b, :T].cpu().numpy() for i, nm in enumerate(OUT_NAMES)}
+        nm_, am_ = (int(v) for v in self.n_maps[b])
+        res["nodes_map"] = self.nodes_map[b, :nm_].cpu().numpy()
+        res["actions_map"] = self.actions_map[b, :am_].cpu().numpy()
+        res["vel"] = self.vel[b, : int(self.n_samples[b])].cpu().numpy()
+        res["status"] = int(self.status[b])
+        return res
+
+
+class Engine:
+    """One engine per device/stream user.  Holds only the cached accumulated-distance grid and the last plan."""
+
+    def __init__(self, device="cuda:0", dt: float = 0.01, dd: float = 0.005, lut_samples: int = 1000,
+                 samples_per_node: int = 1000, start_vel: float = 0.01, end_vel: float = 0.01):
+        if not torch.cuda.is_available():
+            raise _lib.VapError("no CUDA device: vexautonomousplanner_b200 has no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        self.dt, self.dd = float(dt), float(dd)
+        self.samples, self.spn = int(lut_samples), int(samples_per_node)
+        self.start_vel, self.end_vel = float(start_vel), float(end_vel)
+        self._dgrid: Optional[torch.Tensor] = None
+        self._plan: Dict[tuple, tuple] = {}
+        self.launches = 0      # kernels launched by this engine (bench.py reports it)
+        self.stage_events = None   # set to a list to record (stage, start_event, end_event) per stage call
+
+    @contextmanager
+    def _stage(self, name: str):
+        if self.stage_events is None:
+            yield
+            return
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.stage_events.append((name, s, e))
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _empty(self, shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def upload(self, p: PackedPaths) -> DeviceBatch:
+        return DeviceBatch.from_packed(p, self.device)
+
+    def dgrid(self, n: int) -> torch.Tensor:
+        """Accumulated distance grid d_{i+1} = fl(d_i + dd), cached and grown geometrically."""
+        if self._dgrid is None or self._dgrid.numel() < n:
+            m = max(int(n * 1.5), 1 << 14)
+            g = self._empty((m,))
+            _lib.check(self.lib.vap_build_dgrid(C.c_int64(m), C.c_double(self.dd), _p(g), self._stream()), "vap_build_dgrid")
+            self.launches += 1
+            self._dgrid = g
+        return self._dgrid
+
+    # ------------------------------------------------------------------ stages
+    def build_geometry(self, db: DeviceBatch) -> Geometry:
+        B, N = db.B, db.N_max
+        g = Geometry(self._empty((B, max(N - 1, 1), 6, 2)), self._empty((B, N + 1), torch.int32), self._empty((B, N)),
+                     self._empty((B, N)), self._empty((B,), torch.int32), self._empty((B,), torch.int32))
+        scratch = self._empty((B, N, 9))
+        _lib.check(self.lib.vap_build_path(C.c_int64(B), C.c_int(N), _p(db.node_attr), _p(db.node_flags), _p(db.n_nodes),
+                                           _p(g.seg), _p(g.first_node), _p(g.param_end), _p(g.seglen), _p(g.n_splines),
+                                           _p(g.status), _p(scratch), self._stream()), "vap_build_path")
+        self.launches += 1
+        return g
+
+    def build_lut(self, db: DeviceBatch, g: Geometry, samples: Optional[int] = None) -> Tables:
+        samples = samples or self.samples
+        B = db.B
+        Q_cap = samples * max(db.max_splines, 1)
+        t = Tables(samples, self.spn, Q_cap, 0, self._empty((B, Q_cap)), self._empty((B, Q_cap)), self._empty((B,)))
+        _lib.check(self.lib.vap_build_lut(C.c_int64(B), C.c_int(db.N_max), _p(g.seg), _p(g.first_node), _p(g.param_end),
+                                          _p(g.n_splines), _p(g.status), C.c_int(samples), C.c_int64(Q_cap), _p(t.lut_d),
+                                          _p(t.lut_t), _p(t.total_len), self._stream()), "vap_build_lut")
+        self.launches += 1
+        return t
+
+    def build_props(self, db: DeviceBatch, g: Geometry, t: Tables, spn: Optional[int] = None) -> Tables:
+        spn = spn or self.spn
+        B = db.B
+        t.spn = spn
+        t.P_cap = spn * db.N_max
+        t.prop_k = self._empty((B, t.P_cap))
+        t.prop_h = self._empty((B, t.P_cap))
+        for lo in range(0, B, 65535):
+            hi = min(B, lo + 65535)
+            _lib.check(self.lib.vap_build_props(C.c_int64(hi - lo), C.c_int(db.N_max), _p(db.n_nodes[lo:hi]), _p(g.seg[lo:hi]),
+                                                _p(g.first_node[lo:hi]), _p(g.param_end[lo:hi]), _p(g.n_splines[lo:hi]),
+                                                _p(g.status[lo:hi]), C.c_int(spn), C.c_int64(t.P_cap), _p(t.prop_k[lo:hi]),
+                                                _p(t.prop_h[lo:hi]), self._stream()), "vap_build_props")
+            self.launches += 1
+        return t
+
+    def dist_sample(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int):
+        B = db.B
+        grid = self.dgrid(D_cap + 2)
+        n_samples = self._empty((B,), torch.int32)
+        tq, kap, th = self._empty((B, D_cap)), self._empty((B, D_cap)), self._empty((B, D_cap))
+        for lo in range(0, B, 65535):
+            hi = min(B, lo + 65535)
+            _lib.check(self.lib.vap_dist_sample(C.c_int64(hi - lo), _p(db.n_nodes[lo:hi]), _p(g.n_splines[lo:hi]),
+                                                _p(status[lo:hi]), C.c_int64(grid.numel()), _p(grid), C.c_int(t.samples),
+                                                C.c_int64(t.Q_cap), _p(t.lut_d[lo:hi]), _p(t.lut_t[lo:hi]),
+                                                _p(t.total_len[lo:hi]), C.c_int(t.spn), C.c_int64(t.P_cap),
+                                                _p(t.prop_k[lo:hi]), _p(t.prop_h[lo:hi]), C.c_int64(D_cap),
+                                                _p(n_samples[lo:hi]), _p(tq[lo:hi]), _p(kap[lo:hi]), _p(th[lo:hi]),
+                                                self._stream()), "vap_dist_sample")
+            self.launches += 2
+        return n_samples, tq, kap, th
+
+    def fwd_bwd(self, db: DeviceBatch, status, D_cap, n_samples, tq, kap, th, mode: int = 0):
+        B = db.B
+        E_cap = db.N_max + db.A_max + 2
+        vel = self._empty((B, D_cap))
+        ma = self._empty((B, E_cap))
+        bidx = self._empty((B, E_cap), torch.int32)
+        bval = self._empty((B, E_cap), torch.int32)
+        n_ev = self._empty((B, 2), torch.int32)
+        t_est = self._empty((B,))
+        _lib.check(self.lib.vap_fwd_bwd(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max), _p(db.node_attr),
+                                        _p(db.node_flags), _p(db.n_nodes), _p(db.ap_attr), _p(db.ap_flags), _p(db.n_ap),
+                                        _p(db.cons), _p(status), C.c_double(self.dd), C.c_double(self.dt),
+                                        C.c_double(self.start_vel), C.c_double(self.end_vel), C.c_int64(D_cap),
+                                        _p(n_samples), _p(tq), _p(kap), _p(th), _p(vel), C.c_int(E_cap), _p(ma), _p(bidx),
+                                        _p(bval), _p(n_ev), _p(t_est), C.c_int(mode), self._stream()), "vap_fwd_bwd")
+        self.launches += 1
+        return vel, ma, bidx, bval, n_ev, t_est
+
+    def resample(self, db: DeviceBatch, g: Geometry, t: Tables, status, D_cap, n_samples, vel, T_cap):
+        B = db.B
+        out = self._empty((8, B, T_cap))
+        nodes_map = self._empty((B, db.N_max + 1), torch.int32)
+        actions_map = self._empty((B, max(db.A_max, 1)), torch.int32)
+        n_maps = self._empty((B, 2), torch.int32)
+        n_out = self._empty((B,), torch.int32)
+        summary = self._empty((B, 5))
+        _lib.check(self.lib.vap_resample(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max), _p(db.node_attr),
+                                         _p(db.node_flags), _p(db.n_nodes), _p(db.ap_attr), _p(db.ap_flags), _p(db.n_ap),
+                                         _p(db.cons), _p(status), C.c_double(self.dt), C.c_double(self.dd), _p(g.seg),
+                                         _p(g.first_node), _p(g.param_end), _p(g.n_splines), C.c_int(t.samples),
+                                         C.c_int64(t.Q_cap), _p(t.lut_d), _p(t.lut_t), _p(t.total_len), C.c_int(t.spn),
+                                         C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h), C.c_int64(D_cap), _p(n_samples),
+                                         _p(vel), C.c_int64(T_cap), _p(out), _p(nodes_map), _p(actions_map), _p(n_maps),
+                                         _p(n_out), _p(summary), self._stream()), "vap_resample")
+        self.launches += 1
+        return out, nodes_map, actions_map, n_maps, n_out, summary
+
+    # ------------------------------------------------------------------ whole path
+    def profile(self, db: DeviceBatch, keep: bool = False, reuse_plan: bool = False) -> ProfileResult:
+        """build_path + generate_motion_profile for every path of the batch.
+
+        keep: also return geometry / tables / distance-domain intermediates.
+        reuse_plan: size D_cap / T_cap from the previous call with the same batch shape instead of synchronising
+        to read the maxima; capacity overflows are detected on the device and the call is redone exactly.
+        """
+        B = db.B
+        key = (B, db.N_max, db.A_max, db.max_splines)
+        with self._stage("S0_build_path"):
+            g = self.build_geometry(db)
+        with self._stage("S1_lut"):
+            t = self.build_lut(db, g)
+        with self._stage("S2_props"):
+            self.build_props(db, g, t)
+        plan = self._plan.get(key) if reuse_plan else None
+        if plan is None:
+            Lmax = float(t.total_len.max().item())
+            D_cap = int(Lmax / self.dd) + 8
+        else:
+            D_cap = plan[0]
+        status = g.status.clone()
+        with self._stage("S3_dist_sample"):
+            n_samples, tq, kap, th = self.dist_sample(db, g, t, status, D_cap)
+        with self._stage("S45_fwd_bwd"):
+            vel, ma, bidx, bval, n_ev, t_est = self.fwd_bwd(db, status, D_cap, n_samples, tq, kap, th)
+        if plan is None:
+            T_cap = int(float(t_est.max().item()) * 1.10) + 64
+        else:
+            T_cap = plan[1]
+        status_pre = status.clone()
+        with self._stage("S6_resample"):
+            out, nodes_map, actions_map, n_maps, n_out, summary = self.resample(db, g, t, status, D_cap, n_samples, vel,
+                                                                                T_cap)
+        if True:
+            # capacity check (one small read-back; also what a caller needs to trim the rows)
+            if bool((status == ST_CAPACITY).any().item()):
+                if bool((status_pre == ST_CAPACITY).any().item()):
+                    # distance capacity was too small: drop the plan and redo with exact sizing
+                    self._plan.pop(key, None)
+                    return self.profile(db, keep=keep, reuse_plan=False)
+                T_cap = int(n_out.max().item()) + 8
+                status = status_pre.clone()
+                out, nodes_map, actions_map, n_maps, n_out, summary = self.resample(db, g, t, status, D_cap, n_samples,
+                                                                                    vel, T_cap)
+        self._plan[key] = (D_cap, T_cap)
+        res = ProfileResult(B, T_cap, out, n_out, nodes_map, actions_map, n_maps, status, summary, vel, n_samples)
+        if keep:
+            res.geometry, res.tables = g, t
+            res.extra = dict(t=tq, kap=kap, th=th, max_accels=ma, bidx=bidx, bval=bval, n_ev=n_ev, t_est=t_est)
+        return res
