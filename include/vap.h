@@ -121,6 +121,33 @@ int vap_fwd_bwd(int64_t B, int N_max, int A_max, const double* node_attr, const 
                 double* vel, int E_cap, double* max_accels, int32_t* bidx, int32_t* bval, int32_t* n_ev,
                 double* t_est, int mode, void* stream);
 
+/* v2 of S3 + S4 + S5 (same results, bit for bit, as vap_dist_sample + vap_fwd_bwd; this is the fast path).
+ *   vap_dist_sample_events: distance sampling plus sample-parallel event detection and a per-path replay of the
+ *     sampling loop's event logic (motion_profile_generator.py:93-176).  Adds the initial-velocity regimes
+ *     vr_idx/vr_val[B][E_cap], the stop samples st_idx[B][E_cap] and n_vr[B][2].  ev_scratch: i32 scratch of
+ *     vap_event_scratch_ints(B, N_max, A_max) elements.  ins_est[B] f32: rows the time stage will insert for
+ *     waits / turn profiles (sizing only).
+ *   vap_fwd_bwd_chunked: pre-pass that hoists the state-independent terms of the recurrences into one 32-byte
+ *     record per sample (recF, recR: [B][D_cap][4] f64), then the forward and backward passes (:188-314) with
+ *     `chunks` (multiple of 32, <= 256) speculative chunks per path that are re-run until they merge bitwise with the serial evaluation.
+ *     vel_f[B][D_cap]: forward result; vel[B][D_cap]: final velocities; t_est[B] f32; rounds[B][2] fix-up sweeps. */
+int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
+                           const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
+                           const double* cons, const int32_t* n_splines, int32_t* status, int64_t n_grid,
+                           const double* dgrid, int samples, int64_t Q_cap, const double* lut_d, const double* lut_t,
+                           const double* total_len, int spn, int64_t P_cap, const double* prop_k, const double* prop_h,
+                           int64_t D_cap, int32_t* n_samples, double* t, double* kap, double* th, int E_cap,
+                           double* max_accels, int32_t* bidx, int32_t* bval, int32_t* n_ev, int32_t* vr_idx,
+                           double* vr_val, int32_t* st_idx, int32_t* n_vr, double dt, float* ins_est,
+                           int32_t* ev_scratch, void* stream);
+int64_t vap_event_scratch_ints(int64_t B, int N_max, int A_max);
+int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt, double start_vel,
+                        double end_vel, int64_t D_cap, const int32_t* n_samples, const double* kap, const double* th,
+                        int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
+                        const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
+                        const int32_t* n_vr, double* recF, double* recR, double* vel_f, double* vel, float* t_est,
+                        int32_t* rounds, int chunks, int mode, void* stream);
+
 /* S6  generate_motion_profile time loop + node-0 prologue + turn / wait inserts
  *     (motion_profile_generator.py:414-628, one_dim_mp_generator.py:4-69) and S7 summary rows.
  *     out[8][B][T_cap]: times, positions, linear_vels, accelerations, headings, angular_vels, x, y.

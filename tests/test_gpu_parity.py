@@ -16,10 +16,12 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["chunked", "serial"])
+def eng(request):
+    """Both implementations of the velocity passes go through every parity test: the chunk-speculative fast path
+    and the reference-shaped one-thread-per-path variant."""
     from vexautonomousplanner_b200.engine import Engine
-    return Engine("cuda:0")
+    return Engine("cuda:0", velocity_impl=request.param)
 
 
 @pytest.fixture(scope="module")
@@ -236,3 +238,32 @@ def test_cfg2_full_size_properties(eng, ora):
         got = res.path(b)
         np.testing.assert_allclose(got["x"], ref["x"], rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(got["linear_vels"], ref["linear_vels"], rtol=1e-6, atol=1e-9)
+
+
+def test_chunked_equals_serial_bitwise():
+    """The chunk-speculative velocity passes must reproduce the serial recurrences bit for bit, for every chunk count,
+    including ragged batches, node actions and a path long enough to need many fix-up sweeps."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    ser = Engine("cuda:0", velocity_impl="serial")
+    batches = [synth.random_paths(512, 8, seed=5), synth.mixed_paths(512, 8, seed=6), golden_batch()[1],
+               synth.random_paths(3, 120, seed=8)]
+    for packed in batches:
+        db = ser.upload(packed)
+        ref = ser.profile(db, keep=True)
+        for chunks in (32, 64, 256):
+            chk = Engine("cuda:0", velocity_impl="chunked", chunks=chunks)
+            got = chk.profile(db, keep=True)
+            torch.cuda.synchronize()
+            assert torch.equal(ref.n_samples, got.n_samples)
+            D = ref.n_samples.long()
+            m = torch.arange(ref.vel.shape[1], device=D.device)[None, :] < D[:, None]
+            assert torch.equal(ref.vel[m].view(torch.int64), got.vel[m].view(torch.int64)), f"chunks={chunks}"
+            assert torch.equal(ref.extra["n_ev"], got.extra["n_ev"])
+            assert torch.equal(ref.n_out, got.n_out)
+            n = ref.n_out.long()
+            Tm = min(ref.T_cap, got.T_cap)
+            mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+            for i in range(8):
+                assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64))
+            assert int(got.extra["rounds"].max()) < chunks

@@ -22,7 +22,8 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 SYMBOLS = [
     "vap_version", "vap_last_error", "vap_build_path", "vap_fit_splines", "vap_eval", "vap_build_lut",
     "vap_build_props", "vap_query_tables", "vap_build_dgrid", "vap_dist_sample", "vap_fwd_bwd", "vap_resample",
-    "vap_gl", "vap_turn_profile", "vap_lerp", "vap_wheel_trajectory",
+    "vap_gl", "vap_turn_profile", "vap_lerp", "vap_wheel_trajectory", "vap_dist_sample_events",
+    "vap_event_scratch_ints", "vap_fwd_bwd_chunked",
 ]
 
 _lib = None
@@ -60,6 +61,7 @@ def lib():
         L.vap_last_error.restype = C.c_char_p
         for name in SYMBOLS[2:]:
             getattr(L, name).restype = C.c_int
+        L.vap_event_scratch_ints.restype = C.c_int64
         _lib = L
     return _lib
 

@@ -12,6 +12,7 @@
 
 #include "../../include/vap.h"
 #include "vap_device.cuh"
+#include "vap_velocity.cuh"
 
 static thread_local char g_err[512] = "";
 static int set_err(const char* where, cudaError_t e)
@@ -1098,5 +1099,80 @@ extern "C" int vap_wheel_trajectory(int64_t n, const double* lin, const double* 
     if (n <= 0) return 0;
     k_wheel<<<blocks_for(n, 256), 256, 0, STREAM>>>(n, lin, ang, track_width, left, right);
     CHECK_LAUNCH("vap_wheel_trajectory");
+    return 0;
+}
+
+// ---- v2 velocity path ------------------------------------------------------------------------------------------
+extern "C" int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_attr,
+                                      const int32_t* node_flags, const int32_t* n_nodes, const double* ap_attr,
+                                      const int32_t* ap_flags, const int32_t* n_ap, const double* cons,
+                                      const int32_t* n_splines, int32_t* status, int64_t n_grid, const double* dgrid,
+                                      int samples, int64_t Q_cap, const double* lut_d, const double* lut_t,
+                                      const double* total_len, int spn, int64_t P_cap, const double* prop_k,
+                                      const double* prop_h, int64_t D_cap, int32_t* n_samples, double* t, double* kap,
+                                      double* th, int E_cap, double* max_accels, int32_t* bidx, int32_t* bval,
+                                      int32_t* n_ev, int32_t* vr_idx, double* vr_val, int32_t* st_idx, int32_t* n_vr,
+                                      double dt, float* ins_est, int32_t* ev_scratch, void* stream)
+{
+    if (B <= 0) return 0;
+    if (B > 65535) return arg_err("vap_dist_sample_events: B > 65535 per call (tile the batch)");
+    if (E_cap < N_max + A_max + 2) return arg_err("vap_dist_sample_events: E_cap < N_max + A_max + 2");
+    int Am = A_max > 0 ? A_max : 1;
+    // ev_scratch: wrap[B][N_max] | nwrap[B] | apc[B][Am][EV_AP_CAND] | napc[B][Am]
+    int32_t* ev_wrap = ev_scratch;
+    int32_t* ev_nwrap = ev_wrap + (size_t)B * N_max;
+    int32_t* ev_apc = ev_nwrap + B;
+    int32_t* ev_napc = ev_apc + (size_t)B * Am * EV_AP_CAND;
+    cudaError_t e = cudaMemsetAsync(ev_nwrap, 0, sizeof(int32_t) * (size_t)B, STREAM);
+    if (e != cudaSuccess) return set_err("vap_dist_sample_events/memset", e);
+    e = cudaMemsetAsync(ev_napc, 0, sizeof(int32_t) * (size_t)B * Am, STREAM);
+    if (e != cudaSuccess) return set_err("vap_dist_sample_events/memset", e);
+    k_count_samples<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, status, status, n_grid, dgrid, total_len, D_cap, n_samples);
+    CHECK_LAUNCH("vap_dist_sample_events/count");
+    dim3 grid(blocks_for(D_cap, 256), (unsigned)B);
+    k_dist_sample_ev<<<grid, 256, 0, STREAM>>>(N_max, Am, n_nodes, n_splines, status, ap_attr, n_ap, dgrid, samples, Q_cap,
+                                               lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h, D_cap, n_samples, t,
+                                               kap, th, ev_wrap, ev_nwrap, ev_apc, ev_napc);
+    CHECK_LAUNCH("vap_dist_sample_events/sample");
+    k_resolve_events<<<blocks_for(B, 64), 64, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, ap_flags,
+                                                          n_ap, cons, status, ev_wrap, ev_nwrap, ev_apc, ev_napc, E_cap,
+                                                          max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, dt, ins_est);
+    CHECK_LAUNCH("vap_dist_sample_events/resolve");
+    return 0;
+}
+
+extern "C" int64_t vap_event_scratch_ints(int64_t B, int N_max, int A_max)
+{
+    int Am = A_max > 0 ? A_max : 1;
+    return B * N_max + B + B * Am * EV_AP_CAND + B * Am;
+}
+
+extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
+                                   double start_vel, double end_vel, int64_t D_cap, const int32_t* n_samples,
+                                   const double* kap, const double* th, int E_cap, const double* max_accels,
+                                   const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
+                                   const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* recF,
+                                   double* recR, double* vel_f, double* vel, float* t_est, int32_t* rounds,
+                                   int chunks, int mode, void* stream)
+{
+    if (B <= 0) return 0;
+    if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
+    if (chunks < 32 || chunks > 256 || (chunks % 32) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be a multiple of 32 in [32, 256]");
+    dim3 grid(blocks_for(D_cap, 256), (unsigned)B);
+    size_t sm = (size_t)E_cap * (2 * sizeof(double) + 4 * sizeof(int));
+    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, end_vel, D_cap, n_samples, kap, th, E_cap, max_accels, bidx, bval,
+                                         n_ev, vr_idx, vr_val, st_idx, n_vr, reinterpret_cast<double4*>(recF),
+                                         reinterpret_cast<double4*>(recR));
+    CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
+    size_t ss = (size_t)chunks * 2 * sizeof(double);
+    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, D_cap, n_samples,
+                                                       reinterpret_cast<const double4*>(recF), E_cap, max_accels, bidx,
+                                                       bval, n_ev, vel_f, rounds);
+    CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
+    if (mode == 1) return 0;
+    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, D_cap, n_samples,
+                                                       reinterpret_cast<const double4*>(recR), E_cap, max_accels, bidx,
+                                                       bval, n_ev, vel_f, vel, t_est, rounds);
+    CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
     return 0;
 }

@@ -1,0 +1,529 @@
+// vap_velocity.cuh -- v2 of stages S3-events / S4 / S5: sample-parallel event detection, a pre-pass that hoists
+// every state-independent term of the forward / backward recurrences into one 32-byte record per sample, and
+// chunk-speculative kernels that run the exact serial recurrences on many chunks of one path at once.
+//
+// Exactness: the recurrences of motion_profile_generator.py:188-311 are NOT associative (the wheel-acceleration
+// term depends on v[i] and v[i-1]), so no scan is used.  A chunk starts from a guessed state, and
+// is re-run from its predecessor's true end state until two consecutive velocities are BITWISE equal to the ones
+// computed before; from there on the old results are the serial results.  The fix-up loop ends when no chunk
+// changed, at which point (by induction from chunk 0) every value equals the serial evaluation bit for bit.
+#pragma once
+#include "vap_device.cuh"
+
+#define EV_AP_CAND 4
+
+// ---- S3 (parallel): t, kappa, theta per distance sample + event candidates -----------------------------------
+// wrap candidates: samples with frac(t[i-1]) > frac(t[i]) and t[i] < N-1  (motion_profile_generator.py:124)
+// action candidates: samples with t[i-1] < ap.t <= t[i]                   (:142-146)
+__global__ void __launch_bounds__(256) k_dist_sample_ev(
+    int N_max, int A_max, const int* __restrict__ n_nodes, const int* __restrict__ n_splines,
+    const int* __restrict__ status, const double* __restrict__ ap_attr, const int* __restrict__ n_ap,
+    const double* __restrict__ dgrid, int samples, long long Q_cap, const double* __restrict__ lut_d,
+    const double* __restrict__ lut_t, const double* __restrict__ total_len, int spn, long long P_cap,
+    const double* __restrict__ prop_k, const double* __restrict__ prop_h, long long D_cap,
+    const int* __restrict__ n_samples, double* __restrict__ t_out, double* __restrict__ kap, double* __restrict__ th,
+    int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc)
+{
+    __shared__ double s_t[257];
+    long long b = blockIdx.y;
+    if (status[b] != ST_OK) return;
+    long long D = n_samples[b];
+    long long i0 = (long long)blockIdx.x * blockDim.x;
+    if (i0 >= D) return;
+    long long i = i0 + threadIdx.x;
+    int n = n_nodes[b];
+    const double* ld = lut_d + (size_t)b * Q_cap;
+    const double* lt = lut_t + (size_t)b * Q_cap;
+    long long Q = (long long)samples * n_splines[b];
+    double L = total_len[b];
+    double t = 0.0;
+    if (i < D) {
+        if (i == D - 1) t = (double)(n - 1);
+        else { long long hint = -1; t = distance_to_time(ld, lt, Q, L, n, dgrid[i], hint); }
+        long long P = (long long)spn * n;
+        double step = (double)(n - 1) / (double)(P - 1);
+        double k, h;
+        snap_gather2(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, P, n, step, 1.0 / step, k, h);
+        size_t o = (size_t)b * D_cap + i;
+        t_out[o] = t; kap[o] = k; th[o] = h;
+    }
+    s_t[threadIdx.x + 1] = t;
+    if (threadIdx.x == 0) {
+        double tp = 0.0;   // prev_t of sample 0 is 0
+        if (i0 > 0) { long long hint = -1; tp = distance_to_time(ld, lt, Q, L, n, dgrid[i0 - 1], hint); }
+        s_t[0] = tp;
+    }
+    __syncthreads();
+    if (i >= D - 1) return;            // the final appended sample takes no part in the event logic
+    double tp = s_t[threadIdx.x];
+    if (frac1(tp) > frac1(t) && t < (double)(n - 1)) {
+        int slot = atomicAdd(ev_nwrap + b, 1);
+        if (slot < N_max) ev_wrap[(size_t)b * N_max + slot] = (int)i;
+    }
+    int A = n_ap ? n_ap[b] : 0;
+    for (int k = 0; k < A; k++) {
+        double x = ap_attr[((size_t)b * A_max + k) * APA + P_T];
+        if (tp < x && t >= x) {
+            int slot = atomicAdd(ev_napc + (size_t)b * A_max + k, 1);
+            if (slot < EV_AP_CAND) ev_apc[((size_t)b * A_max + k) * EV_AP_CAND + slot] = (int)i;
+        }
+    }
+}
+
+// ---- S3 (per path): replay the sampling loop's event logic over the candidate samples only --------------------
+// Outputs the reference's max_accels / boundary_map plus the piecewise-constant initial-velocity regimes:
+//   vr_idx/vr_val: v0[i] = vr_val[j] for the last j with vr_idx[j] <= i      (max_velocity before sample i's events)
+//   st_idx       : samples whose initial velocity is overwritten with 0.01    (stop nodes / stop action points)
+__global__ void k_resolve_events(long long B, int N_max, int A_max, const double* __restrict__ node_attr,
+                                 const int* __restrict__ node_flags, const int* __restrict__ n_nodes,
+                                 const double* __restrict__ ap_attr, const int* __restrict__ ap_flags,
+                                 const int* __restrict__ n_ap, const double* __restrict__ cons,
+                                 int* __restrict__ status, int* __restrict__ ev_wrap, const int* __restrict__ ev_nwrap,
+                                 const int* __restrict__ ev_apc, const int* __restrict__ ev_napc, int E_cap,
+                                 double* __restrict__ max_accels, int* __restrict__ bidx, int* __restrict__ bval,
+                                 int* __restrict__ n_ev, int* __restrict__ vr_idx, double* __restrict__ vr_val,
+                                 int* __restrict__ st_idx, int* __restrict__ n_vr, double dt,
+                                 float* __restrict__ ins_est)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    n_ev[2 * b] = 0; n_ev[2 * b + 1] = 0; n_vr[2 * b] = 0; n_vr[2 * b + 1] = 0;
+    if (ins_est) ins_est[b] = 0.f;
+    if (status[b] != ST_OK) return;
+    const int n = n_nodes[b];
+    const int A = n_ap ? n_ap[b] : 0;
+    const double* na = node_attr + (size_t)b * N_max * NA;
+    const int* nf = node_flags + (size_t)b * N_max;
+    const double* apa = ap_attr + (size_t)b * A_max * APA;
+    const int* apf = ap_flags + (size_t)b * A_max;
+    const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1];
+    double* ma = max_accels + (size_t)b * E_cap;
+    int* bi = bidx + (size_t)b * E_cap;
+    int* bv = bval + (size_t)b * E_cap;
+    int* vi = vr_idx + (size_t)b * E_cap;
+    double* vv = vr_val + (size_t)b * E_cap;
+    int* si = st_idx + (size_t)b * E_cap;
+    int* wr = ev_wrap + (size_t)b * N_max;
+    int nw = ev_nwrap[b];
+    if (nw > N_max) { status[b] = ST_CAPACITY; return; }
+    for (int i = 1; i < nw; i++) {           // sort wrap samples ascending
+        int x = wr[i], j = i - 1;
+        while (j >= 0 && wr[j] > x) { wr[j + 1] = wr[j]; j--; }
+        wr[j + 1] = x;
+    }
+    int n_acc = 0, n_b = 0, nvr = 0, nst = 0;
+    double max_velocity = (na[A_MAXVEL] > 0) ? na[A_MAXVEL] : V;
+    ma[n_acc++] = (na[A_MAXACC] > 0) ? na[A_MAXACC] : A0;
+    bi[0] = 0; bv[0] = 0; n_b = 1;
+    vi[nvr] = 0; vv[nvr] = max_velocity; nvr++;
+    // action point k fires at its smallest candidate sample after the previous action point's sample
+    int node_num = 0, wptr = 0, action_idx = 0, last_fire = -1;
+    bool actions_dead = false;
+    while (true) {
+        // next action-point sample (if any)
+        int ai = 2147483647;
+        if (!actions_dead && action_idx < A) {
+            int nc = ev_napc[(size_t)b * A_max + action_idx];
+            if (nc > EV_AP_CAND) { status[b] = ST_CAPACITY; return; }
+            const int* c = ev_apc + ((size_t)b * A_max + action_idx) * EV_AP_CAND;
+            for (int k = 0; k < nc; k++) if (c[k] > last_fire && c[k] < ai) ai = c[k];
+            if (ai == 2147483647) actions_dead = true;      // this action point never fires -> none after it does
+        }
+        int wi = (wptr < nw) ? wr[wptr] : 2147483647;
+        if (wi == 2147483647 && ai == 2147483647) break;
+        int i = wi < ai ? wi : ai;
+        bool stop = false;
+        if (wi == i) {                       // node crossing first (:124-140)
+            wptr++;
+            node_num += 1;
+            const double* a = na + (size_t)node_num * NA;
+            if (nf[node_num] & F_STOP) stop = true;
+            max_velocity = (a[A_MAXVEL] > 0) ? a[A_MAXVEL] : V;
+            ma[n_acc++] = (a[A_MAXACC] > 0) ? a[A_MAXACC] : A0;
+            if (node_num < n - 1) {
+                if (bi[n_b - 1] == i) bv[n_b - 1] = n_acc - 1;
+                else { bi[n_b] = i; bv[n_b] = n_acc - 1; n_b++; }
+            }
+        }
+        if (ai == i) {                       // then the action point (:142-163)
+            const double* p = apa + (size_t)action_idx * APA;
+            max_velocity = (p[P_MAXVEL] > 0) ? p[P_MAXVEL] : V;
+            if (apf[action_idx] & F_STOP) stop = true;
+            ma[n_acc++] = (p[P_MAXACC] > 0) ? p[P_MAXACC] : A0;
+            if (bi[n_b - 1] == i) bv[n_b - 1] = n_acc - 1;
+            else { bi[n_b] = i; bv[n_b] = n_acc - 1; n_b++; }
+            action_idx += 1;
+            last_fire = i;
+        }
+        if (stop) si[nst++] = i;
+        if (vi[nvr - 1] == i + 1) vv[nvr - 1] = max_velocity;
+        else { vi[nvr] = i + 1; vv[nvr] = max_velocity; nvr++; }
+    }
+    ma[n_acc++] = A0;
+    n_ev[2 * b] = n_acc; n_ev[2 * b + 1] = n_b;
+    n_vr[2 * b] = nvr; n_vr[2 * b + 1] = nst;
+    if (ins_est) {
+        // rows the time-domain stage inserts for waits and turn profiles (upper bound: assume every one fires)
+        const double w = cons[b * 6 + 5];
+        double extra = 0.0;
+        for (int i = 0; i < n; i++) {
+            const double* a = na + (size_t)i * NA;
+            if (a[A_WAIT] > 0) extra += floor(a[A_WAIT] / dt);
+            if (a[A_TURN] != 0) {
+                double angle = a[A_TURN] * (VAP_PI / 180.0);
+                Trapezoid tz = trapezoid_setup(V, A0, fabs(angle) * w / 2, dt);
+                extra += (double)tz.K;
+            }
+        }
+        for (int i = 0; i < A; i++) if (apa[i * APA + P_WAIT] > 0) extra += floor(apa[i * APA + P_WAIT] / dt);
+        ins_est[b] = (float)extra;
+    }
+}
+
+// ---- pre-pass (parallel): one 32-byte record per sample and direction -----------------------------------------
+// forward  record F[i] = { |kappa_i|, 2|theta_{i+1}-theta_i| (NaN when straight), a_static_i, C_i }
+//    a_static = min(max_ang_acc/|k|, 2 acc/(w|k|+2), acc)  (acc when straight);  C_i = min(v0[i+1], vlim_i, cap_i)
+// backward record R[i] = { |kappa_i|, 2|theta_{i-1}-theta_i| (NaN when straight), d_static_i, G_i }
+//    d_static = min(max_ang_acc/|k|, 2 dec/(w|k|+2), dec);  G_i = min(vlim_i, cap_i)
+// A NaN denominator makes the wheel term NaN, which Python's min() ignores -- exactly the straight branch.
+__global__ void __launch_bounds__(256) k_prepass(
+    const int* __restrict__ status, const double* __restrict__ cons, double end_vel, long long D_cap,
+    const int* __restrict__ n_samples, const double* __restrict__ kap, const double* __restrict__ th, int E_cap,
+    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
+    const int* __restrict__ st_idx, const int* __restrict__ n_vr, double4* __restrict__ recF,
+    double4* __restrict__ recR)
+{
+    extern __shared__ unsigned char s_raw[];
+    long long b = blockIdx.y;
+    if (status[b] != ST_OK) return;
+    long long D = n_samples[b];
+    long long i0 = (long long)blockIdx.x * blockDim.x;
+    if (i0 >= D) return;
+    double* s_ma = reinterpret_cast<double*>(s_raw);
+    double* s_vv = s_ma + E_cap;
+    int* s_bi = reinterpret_cast<int*>(s_vv + E_cap);
+    int* s_bv = s_bi + E_cap;
+    int* s_vi = s_bv + E_cap;
+    int* s_si = s_vi + E_cap;
+    const int n_acc = n_ev[2 * b], n_b = n_ev[2 * b + 1], nvr = n_vr[2 * b], nst = n_vr[2 * b + 1];
+    for (int k = threadIdx.x; k < E_cap; k += blockDim.x) {
+        s_ma[k] = (k < n_acc) ? max_accels[(size_t)b * E_cap + k] : 0.0;
+        s_vv[k] = (k < nvr) ? vr_val[(size_t)b * E_cap + k] : 0.0;
+        s_bi[k] = (k < n_b) ? bidx[(size_t)b * E_cap + k] : 2147483647;
+        s_bv[k] = (k < n_b) ? bval[(size_t)b * E_cap + k] : 0;
+        s_vi[k] = (k < nvr) ? vr_idx[(size_t)b * E_cap + k] : 2147483647;
+        s_si[k] = (k < nst) ? st_idx[(size_t)b * E_cap + k] : -1;
+    }
+    __syncthreads();
+    long long i = i0 + threadIdx.x;
+    if (i >= D) return;
+    const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
+    const double max_angular_vel = 2 * V / w;
+    const double max_angular_accel = 2 * A0 / w;
+    const size_t row = (size_t)b * D_cap;
+    double k = kap[row + i], ak = fabs(k);
+    double th_i = th[row + i];
+    bool straight = ak < 1e-6;
+    double vlim, cap;
+    if (straight) vlim = V;
+    else {
+        double v_ang = max_angular_vel / ak;
+        double v_kin = 2 * V / (w * ak + 2);
+        double v_curve = max_speed_at_curvature(V, w, ak);
+        vlim = pymin(pymin(v_ang, v_kin), v_curve);
+    }
+    cap = fabs(V / (1 + (w * ak / 2)));
+    double G = pymin(vlim, cap);
+    // forward regime at step i: last boundary with bidx <= i
+    int jf = 0;
+    for (int j = 1; j < n_b; j++) if (s_bi[j] <= (int)i) jf = j;
+    double acc_f = s_ma[s_bv[jf]];
+    double dec_b = s_ma[s_bv[n_b - 1]];     // the backward pass keeps the forward pass's last max_dec
+    if (i < D - 1) {
+        double v0n;
+        if (i + 1 == D - 1) v0n = end_vel;
+        else {
+            int jv = 0;
+            for (int j = 1; j < nvr; j++) if (s_vi[j] <= (int)(i + 1)) jv = j;
+            v0n = s_vv[jv];
+            for (int j = 0; j < nst; j++) if (s_si[j] == (int)(i + 1)) v0n = 0.01;
+        }
+        double astat, h2;
+        if (straight) { astat = acc_f; h2 = __longlong_as_double(0x7ff8000000000000LL); }
+        else {
+            double a_ang = max_angular_accel / ak;
+            double a_kin = 2 * acc_f / (w * ak + 2);
+            astat = pymin(pymin(a_ang, a_kin), acc_f);
+            h2 = 2 * fabs(th[row + i + 1] - th_i);
+        }
+        recF[row + i] = make_double4(ak, h2, astat, pymin(v0n, G));
+    }
+    if (i >= 1) {
+        double dstat, h2;
+        if (straight) { dstat = dec_b; h2 = __longlong_as_double(0x7ff8000000000000LL); }
+        else {
+            double d_ang = max_angular_accel / ak;
+            double d_kin = 2 * dec_b / (w * ak + 2);
+            dstat = pymin(pymin(d_ang, d_kin), dec_b);
+            h2 = 2 * fabs(th[row + i - 1] - th_i);
+        }
+        recR[row + i] = make_double4(ak, h2, dstat, G);
+    }
+}
+
+// ---- chunk-speculative forward / backward kernels: one CTA per path, one chunk per thread ------------------------
+__device__ __forceinline__ bool same_bits(double a, double b)
+{
+    return __double_as_longlong(a) == __double_as_longlong(b);
+}
+
+// forward step i -> i+1 (motion_profile_generator.py:193-249 with the hoisted terms)
+__device__ __forceinline__ double fwd_step(const double4 r, double v, double& wp, double acc, double w, double dd)
+{
+    double ang_vel = v * r.x;
+    double accel_ang = (ang_vel * ang_vel - wp * wp) / r.y;
+    double a_wheel = wheel_accel(acc, fabs(accel_ang), w);
+    if (a_wheel < 0) a_wheel = 0;
+    double a = pymin(r.z, a_wheel);
+    double s = sqrt(v * v + 2 * a * dd);
+    wp = ang_vel;
+    return pymin(r.w, s);
+}
+// backward step i -> i-1 (:255-311)
+__device__ __forceinline__ double bwd_step(const double4 r, double v, double& wp, double acc, double w, double dd,
+                                           double vfwd_prev)
+{
+    double ang_vel = v * r.x;
+    double accel_ang = (ang_vel * ang_vel - wp * wp) / r.y;
+    double a_wheel = wheel_accel(acc, accel_ang, w);
+    if (a_wheel < 0) a_wheel = 0;
+    double dcl = pymin(r.z, a_wheel);
+    double pv = sqrt(v * v + 2 * dcl * dd);
+    wp = ang_vel;
+    return pymin(pymin(pv, vfwd_prev), r.w);
+}
+
+// Forward pass.  Steps i = 0 .. D-2; chunk c owns steps [c*Lc, min((c+1)*Lc, D-1)).  vel_f[i+1] is written.
+__global__ void __launch_bounds__(256) k_fwd_chunked(
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, long long D_cap,
+    const int* __restrict__ n_samples, const double4* __restrict__ recF, int E_cap,
+    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    const int* __restrict__ n_ev, double* __restrict__ vel_f, int* __restrict__ rounds_out)
+{
+    extern __shared__ double s_state[];           // [2][NT]: end state (v, wp) of every chunk
+    const int NT = blockDim.x, c = threadIdx.x;
+    long long b = blockIdx.x;
+    if (status[b] != ST_OK) return;
+    const long long D = n_samples[b];
+    const long long steps = D - 1;
+    const double w = cons[b * 6 + 5];
+    const size_t row = (size_t)b * D_cap;
+    const double4* F = recF + row;
+    double* vf = vel_f + row;
+    const double* ma = max_accels + (size_t)b * E_cap;
+    const int* bi = bidx + (size_t)b * E_cap;
+    const int* bv = bval + (size_t)b * E_cap;
+    const int n_b = n_ev[2 * b + 1];
+    if (c == 0) vf[0] = start_vel;
+    if (steps <= 0) return;
+    const long long Lc = (steps + NT - 1) / NT;
+    const int nch = (int)((steps + Lc - 1) / Lc);
+    const long long lo = (long long)c * Lc;
+    const long long hi = (lo + Lc < steps) ? lo + Lc : steps;
+    const bool active = c < nch;
+    double* s_v = s_state;
+    double* s_w = s_state + NT;
+
+    // regime at chunk start
+    int jn = 1;
+    double acc0 = ma[bv[0]];
+    if (active) {
+        while (jn < n_b && bi[jn] <= (int)lo) { acc0 = ma[bv[jn]]; jn++; }
+    }
+    const int jn0 = jn;
+    // start state: exact for chunk 0, guessed from the state-independent caps otherwise
+    double used_v = start_vel, used_w = 0.0;
+    if (active && c > 0) {
+        double vm1 = (lo >= 2) ? F[lo - 2].w : start_vel;      // guess of v[lo-1]
+        used_v = F[lo - 1].w;                                   // guess of v[lo]
+        used_w = vm1 * F[lo - 1].x;
+    }
+    double end_v = used_v, end_w = used_w;
+    if (active) {
+        double v = used_v, wp = used_w, acc = acc0;
+        int j = jn0;
+        int nb_next = (j < n_b) ? bi[j] : 2147483647;
+        double4 r = F[lo];
+        for (long long i = lo; i < hi; i++) {
+            double4 rn = (i + 1 < hi) ? F[i + 1] : r;          // software prefetch of the next record
+            if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
+            v = fwd_step(r, v, wp, acc, w, dd);
+            vf[i + 1] = v;
+            r = rn;
+        }
+        end_v = v; end_w = wp;
+    }
+    s_v[c] = end_v; s_w[c] = end_w;
+    __syncthreads();
+    int rounds = 0;
+    for (int round = 1; round < nch; round++) {
+        bool changed = false;
+        double in_v = 0.0, in_w = 0.0;
+        if (active && c >= round) { in_v = s_v[c - 1]; in_w = s_w[c - 1]; }
+        if (active && c >= round && !(same_bits(in_v, used_v) && same_bits(in_w, used_w))) {
+            changed = true;
+            bool prev_same = same_bits(in_v, used_v);
+            used_v = in_v; used_w = in_w;
+            double v = in_v, wp = in_w, acc = acc0;
+            int j = jn0;
+            int nb_next = (j < n_b) ? bi[j] : 2147483647;
+            bool merged = false;
+            double4 r = F[lo];
+            for (long long i = lo; i < hi; i++) {
+                double4 rn = (i + 1 < hi) ? F[i + 1] : r;
+                if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
+                v = fwd_step(r, v, wp, acc, w, dd);
+                double old = vf[i + 1];
+                bool same = same_bits(old, v);
+                if (same && prev_same) { merged = true; break; }   // state (v[i+1], v[i]*|k_i|) equals the old run's
+                vf[i + 1] = v;
+                prev_same = same;
+                r = rn;
+            }
+            if (!merged) { end_v = v; end_w = wp; }
+        }
+        int any = __syncthreads_or(changed ? 1 : 0);
+        if (!any) break;
+        rounds = round;
+        s_v[c] = end_v; s_w[c] = end_w;
+        __syncthreads();
+    }
+    if (c == 0 && rounds_out) rounds_out[2 * b] = rounds;
+}
+
+// Backward pass.  Steps i = D-1 .. 1 (step i writes vel[i-1]); chunk c owns the c-th block of steps counted from
+// the end.  Reads vel_f (forward result) and writes vel (final); vel[D-1] = end_vel.  Also accumulates the
+// travel-time estimate used to size the time-domain outputs.
+__global__ void __launch_bounds__(256) k_bwd_chunked(
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel,
+    long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recR, int E_cap,
+    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    const int* __restrict__ n_ev, const double* __restrict__ vel_f, double* __restrict__ vel,
+    float* __restrict__ t_est, int* __restrict__ rounds_out)
+{
+    extern __shared__ double s_state[];
+    const int NT = blockDim.x, c = threadIdx.x;
+    long long b = blockIdx.x;
+    if (status[b] != ST_OK) return;
+    const long long D = n_samples[b];
+    const long long steps = D - 1;
+    const double w = cons[b * 6 + 5];
+    const size_t row = (size_t)b * D_cap;
+    const double4* R = recR + row;
+    const double* vf = vel_f + row;
+    double* vo = vel + row;
+    const double* ma = max_accels + (size_t)b * E_cap;
+    const int* bi = bidx + (size_t)b * E_cap;
+    const int* bv = bval + (size_t)b * E_cap;
+    const int n_b = n_ev[2 * b + 1];
+    if (c == 0) vo[D - 1] = end_vel;
+    if (steps <= 0) { if (c == 0 && t_est) t_est[b] = 0.f; return; }
+    const long long Lc = (steps + NT - 1) / NT;
+    const int nch = (int)((steps + Lc - 1) / Lc);
+    // chunk c: steps i = hi, hi-1, ..., lo+1 with hi = D-1 - c*Lc, lo = max(hi - Lc, 0)
+    const long long hi = (D - 1) - (long long)c * Lc;
+    const long long lo = (hi - Lc > 0) ? hi - Lc : 0;
+    const bool active = c < nch;
+    double* s_v = s_state;
+    double* s_w = s_state + NT;
+
+    // regime at chunk start (walking down from D-1): the smallest boundary index > hi was the last one applied
+    double acc_fwd_last = ma[bv[n_b - 1]];
+    double acc0 = acc_fwd_last;
+    int jb = n_b - 1;                        // next boundary entry to test while walking down (bidx[jb] <= i)
+    if (active) {
+        while (jb >= 0 && bi[jb] > (int)hi) { acc0 = ma[bv[jb] + 1]; jb--; }
+    }
+    const int jb0 = jb;
+    double used_v = end_vel, used_w = 0.0;
+    if (active && c > 0) {
+        // v[hi] was produced by step hi+1: min(pv, vel_f[hi], G[hi+1]); guess = the state-independent part
+        used_v = pymin(vf[hi], R[hi + 1].w);
+        double vp1 = (hi + 2 <= D - 1) ? pymin(vf[hi + 1], R[hi + 2].w) : end_vel;
+        used_w = vp1 * R[hi + 1].x;
+    }
+    double end_v = used_v, end_w = used_w;
+    if (active) {
+        double v = used_v, wp = used_w, acc = acc0;
+        int j = jb0;
+        int nb_next = (j >= 0) ? bi[j] : -1;
+        double4 r = R[hi];
+        double vfp = vf[hi - 1];
+        for (long long i = hi; i > lo; i--) {
+            double4 rn = (i - 1 > lo) ? R[i - 1] : r;
+            double vfn = (i - 1 > lo) ? vf[i - 2] : 0.0;
+            if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
+            v = bwd_step(r, v, wp, acc, w, dd, vfp);
+            vo[i - 1] = v;
+            r = rn; vfp = vfn;
+        }
+        end_v = v; end_w = wp;
+    }
+    s_v[c] = end_v; s_w[c] = end_w;
+    __syncthreads();
+    int rounds = 0;
+    for (int round = 1; round < nch; round++) {
+        bool changed = false;
+        double in_v = 0.0, in_w = 0.0;
+        if (active && c >= round) { in_v = s_v[c - 1]; in_w = s_w[c - 1]; }
+        if (active && c >= round && !(same_bits(in_v, used_v) && same_bits(in_w, used_w))) {
+            changed = true;
+            bool prev_same = same_bits(in_v, used_v);
+            used_v = in_v; used_w = in_w;
+            double v = in_v, wp = in_w, acc = acc0;
+            int j = jb0;
+            int nb_next = (j >= 0) ? bi[j] : -1;
+            bool merged = false;
+            double4 r = R[hi];
+            double vfp = vf[hi - 1];
+            for (long long i = hi; i > lo; i--) {
+                double4 rn = (i - 1 > lo) ? R[i - 1] : r;
+                double vfn = (i - 1 > lo) ? vf[i - 2] : 0.0;
+                if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
+                v = bwd_step(r, v, wp, acc, w, dd, vfp);
+                double old = vo[i - 1];
+                bool same = same_bits(old, v);
+                if (same && prev_same) { merged = true; break; }
+                vo[i - 1] = v;
+                prev_same = same;
+                r = rn; vfp = vfn;
+            }
+            if (!merged) { end_v = v; end_w = wp; }
+        }
+        int any = __syncthreads_or(changed ? 1 : 0);
+        if (!any) break;
+        rounds = round;
+        s_v[c] = end_v; s_w[c] = end_w;
+        __syncthreads();
+    }
+    if (c == 0 && rounds_out) rounds_out[2 * b + 1] = rounds;
+    // travel-time estimate (single precision is plenty: it only sizes buffers)
+    __syncthreads();
+    float est = 0.f;
+    if (active) {
+        for (long long i = hi; i > lo; i--) {
+            float vm = 0.5f * ((float)vo[i] + (float)vo[i - 1]);
+            est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
+        }
+    }
+    __syncthreads();
+    float* s_f = reinterpret_cast<float*>(s_state);
+    s_f[c] = est;
+    __syncthreads();
+    if (c == 0 && t_est) {
+        float tot = 0.f;
+        for (int k = 0; k < NT; k++) tot += s_f[k];
+        t_est[b] = tot;
+    }
+}

@@ -120,7 +120,8 @@ class Engine:
     """One engine per device/stream user.  Holds only the cached accumulated-distance grid and the last plan."""
 
     def __init__(self, device="cuda:0", dt: float = 0.01, dd: float = 0.005, lut_samples: int = 1000,
-                 samples_per_node: int = 1000, start_vel: float = 0.01, end_vel: float = 0.01):
+                 samples_per_node: int = 1000, start_vel: float = 0.01, end_vel: float = 0.01,
+                 velocity_impl: str = "chunked", chunks: int = 32):
         if not torch.cuda.is_available():
             raise _lib.VapError("no CUDA device: vexautonomousplanner_b200 has no CPU fallback")
         self.lib = _lib.lib()
@@ -128,6 +129,9 @@ class Engine:
         self.dt, self.dd = float(dt), float(dd)
         self.samples, self.spn = int(lut_samples), int(samples_per_node)
         self.start_vel, self.end_vel = float(start_vel), float(end_vel)
+        if velocity_impl not in ("chunked", "serial"):
+            raise ValueError("velocity_impl must be 'chunked' or 'serial'")
+        self.velocity_impl, self.chunks = velocity_impl, int(chunks)
         self._dgrid: Optional[torch.Tensor] = None
         self._plan: Dict[tuple, tuple] = {}
         self.launches = 0      # kernels launched by this engine (bench.py reports it)
@@ -239,6 +243,57 @@ class Engine:
         self.launches += 1
         return vel, ma, bidx, bval, n_ev, t_est
 
+    def velocity_chunked(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0):
+        """S3 + events + S4 + S5, fast path: sample-parallel events, hoisted pre-pass, chunk-speculative passes."""
+        B = db.B
+        if B > 65535:
+            raise _lib.VapError("tile the batch: at most 65535 paths per profile() call")
+        E_cap = db.N_max + db.A_max + 2
+        grid = self.dgrid(D_cap + 2)
+        n_samples = self._empty((B,), torch.int32)
+        tq, kap, th = self._empty((B, D_cap)), self._empty((B, D_cap)), self._empty((B, D_cap))
+        ma = self._empty((B, E_cap)); bidx = self._empty((B, E_cap), torch.int32); bval = self._empty((B, E_cap), torch.int32)
+        n_ev = self._empty((B, 2), torch.int32)
+        vr_idx = self._empty((B, E_cap), torch.int32); vr_val = self._empty((B, E_cap))
+        st_idx = self._empty((B, E_cap), torch.int32); n_vr = self._empty((B, 2), torch.int32)
+        ins_est = self._empty((B,), torch.float32)
+        nscr = int(self.lib.vap_event_scratch_ints(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max)))
+        scr = self._empty((nscr,), torch.int32)
+        with self._stage("S3_dist_sample"):
+            _lib.check(self.lib.vap_dist_sample_events(
+                C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max), _p(db.node_attr), _p(db.node_flags), _p(db.n_nodes),
+                _p(db.ap_attr), _p(db.ap_flags), _p(db.n_ap), _p(db.cons), _p(g.n_splines), _p(status),
+                C.c_int64(grid.numel()), _p(grid), C.c_int(t.samples), C.c_int64(t.Q_cap), _p(t.lut_d), _p(t.lut_t),
+                _p(t.total_len), C.c_int(t.spn), C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h), C.c_int64(D_cap),
+                _p(n_samples), _p(tq), _p(kap), _p(th), C.c_int(E_cap), _p(ma), _p(bidx), _p(bval), _p(n_ev), _p(vr_idx),
+                _p(vr_val), _p(st_idx), _p(n_vr), C.c_double(self.dt), _p(ins_est), _p(scr), self._stream()),
+                "vap_dist_sample_events")
+            self.launches += 3
+        recF = self._empty((B, D_cap, 4)); recR = self._empty((B, D_cap, 4))
+        vel_f = self._empty((B, D_cap)); vel = self._empty((B, D_cap))
+        t_est = self._empty((B,), torch.float32)
+        rounds = torch.zeros((B, 2), dtype=torch.int32, device=self.device)
+        chunks = self.chunks if D_cap <= 65536 else 256
+        with self._stage("S45_fwd_bwd"):
+            _lib.check(self.lib.vap_fwd_bwd_chunked(
+                C.c_int64(B), _p(db.cons), _p(status), C.c_double(self.dd), C.c_double(self.dt), C.c_double(self.start_vel),
+                C.c_double(self.end_vel), C.c_int64(D_cap), _p(n_samples), _p(kap), _p(th), C.c_int(E_cap), _p(ma),
+                _p(bidx), _p(bval), _p(n_ev), _p(vr_idx), _p(vr_val), _p(st_idx), _p(n_vr), _p(recF), _p(recR), _p(vel_f),
+                _p(vel), _p(t_est), _p(rounds), C.c_int(chunks), C.c_int(mode), self._stream()), "vap_fwd_bwd_chunked")
+            self.launches += 3 if mode == 0 else 2
+        extra = dict(t=tq, kap=kap, th=th, max_accels=ma, bidx=bidx, bval=bval, n_ev=n_ev, vel_f=vel_f, rounds=rounds,
+                     vr_idx=vr_idx, vr_val=vr_val, st_idx=st_idx, n_vr=n_vr)
+        return n_samples, (vel if mode == 0 else vel_f), t_est + ins_est, extra
+
+    def velocity_serial(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0):
+        """S3 + events + S4 + S5, reference-shaped variant: one thread walks each path (kept as a cross-check)."""
+        with self._stage("S3_dist_sample"):
+            n_samples, tq, kap, th = self.dist_sample(db, g, t, status, D_cap)
+        with self._stage("S45_fwd_bwd"):
+            vel, ma, bidx, bval, n_ev, t_est = self.fwd_bwd(db, status, D_cap, n_samples, tq, kap, th, mode)
+        extra = dict(t=tq, kap=kap, th=th, max_accels=ma, bidx=bidx, bval=bval, n_ev=n_ev)
+        return n_samples, vel, t_est, extra
+
     def resample(self, db: DeviceBatch, g: Geometry, t: Tables, status, D_cap, n_samples, vel, T_cap):
         B = db.B
         out = self._empty((8, B, T_cap))
@@ -281,10 +336,8 @@ class Engine:
         else:
             D_cap = plan[0]
         status = g.status.clone()
-        with self._stage("S3_dist_sample"):
-            n_samples, tq, kap, th = self.dist_sample(db, g, t, status, D_cap)
-        with self._stage("S45_fwd_bwd"):
-            vel, ma, bidx, bval, n_ev, t_est = self.fwd_bwd(db, status, D_cap, n_samples, tq, kap, th)
+        vfun = self.velocity_chunked if self.velocity_impl == "chunked" else self.velocity_serial
+        n_samples, vel, t_est, extra = vfun(db, g, t, status, D_cap)
         if plan is None:
             T_cap = int(float(t_est.max().item()) * 1.10) + 64
         else:
@@ -308,5 +361,5 @@ class Engine:
         res = ProfileResult(B, T_cap, out, n_out, nodes_map, actions_map, n_maps, status, summary, vel, n_samples)
         if keep:
             res.geometry, res.tables = g, t
-            res.extra = dict(t=tq, kap=kap, th=th, max_accels=ma, bidx=bidx, bval=bval, n_ev=n_ev, t_est=t_est)
+            res.extra = dict(extra, t_est=t_est)
         return res
