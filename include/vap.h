@@ -163,6 +163,22 @@ int vap_resample(int64_t B, int N_max, int A_max, const double* node_attr, const
                  const int32_t* n_samples, const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
                  int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary, void* stream);
 
+/* v2 of S6 + S7 (same results, bit for bit, as vap_resample; this is the fast path).  The loop-carried state of
+ *     the reference's time loop is only (current_pos, current_vel), so the stage runs as: the exact state recurrence
+ *     (one thread per path), sample-parallel lookups + event candidates, a per-path replay of the event logic with the
+ *     `current_time += dt` chain and the inserted rows, and a sample-parallel scatter to the final rows.
+ *     n_main[B] i32: number of main-loop iterations (valid even on overflow); stage: f64 scratch [8][B][T_cap+1];
+ *     seg_tab: i32 scratch [3*B*E_cap + B]; ev_scratch: i32 scratch of vap_event_scratch_ints elements.          */
+int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
+                     const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
+                     const double* cons, int32_t* status, double dt, double dd, const double* seg,
+                     const int32_t* first_node, const double* param_end, const int32_t* n_splines, int samples,
+                     int64_t Q_cap, const double* lut_d, const double* lut_t, const double* total_len, int spn,
+                     int64_t P_cap, const double* prop_k, const double* prop_h, int64_t D_cap,
+                     const int32_t* n_samples, const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
+                     int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary, int32_t* n_main,
+                     double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch, void* stream);
+
 /* S1' QuinticHermiteSpline.get_arc_length (Gauss-Legendre, quintic_hermite_spline.py:592-644) and
  *     get_parameter_by_arc_length (:661-717) for n queries on spline `spl[q]` of path `path[q]`.
  *     gl_pts / gl_wts[npts] = np.polynomial.legendre.leggauss(npts) from the host (device copies).

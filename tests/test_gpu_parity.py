@@ -16,12 +16,14 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["chunked", "serial"])
+@pytest.fixture(scope="module", params=["fast", "serial"])
 def eng(request):
-    """Both implementations of the velocity passes go through every parity test: the chunk-speculative fast path
-    and the reference-shaped one-thread-per-path variant."""
+    """Both implementations go through every parity test: the fast path (chunk-speculative velocity passes, split
+    time loop) and the reference-shaped one-thread-per-path kernels."""
     from vexautonomousplanner_b200.engine import Engine
-    return Engine("cuda:0", velocity_impl=request.param)
+    if request.param == "fast":
+        return Engine("cuda:0", velocity_impl="chunked", time_impl="split")
+    return Engine("cuda:0", velocity_impl="serial", time_impl="serial")
 
 
 @pytest.fixture(scope="module")
@@ -245,14 +247,14 @@ def test_chunked_equals_serial_bitwise():
     including ragged batches, node actions and a path long enough to need many fix-up sweeps."""
     from vexautonomousplanner_b200 import synth
     from vexautonomousplanner_b200.engine import Engine
-    ser = Engine("cuda:0", velocity_impl="serial")
+    ser = Engine("cuda:0", velocity_impl="serial", time_impl="serial")
     batches = [synth.random_paths(512, 8, seed=5), synth.mixed_paths(512, 8, seed=6), golden_batch()[1],
                synth.random_paths(3, 120, seed=8)]
     for packed in batches:
         db = ser.upload(packed)
         ref = ser.profile(db, keep=True)
         for chunks in (32, 64, 256):
-            chk = Engine("cuda:0", velocity_impl="chunked", chunks=chunks)
+            chk = Engine("cuda:0", velocity_impl="chunked", chunks=chunks, time_impl="split")
             got = chk.profile(db, keep=True)
             torch.cuda.synchronize()
             assert torch.equal(ref.n_samples, got.n_samples)
@@ -267,3 +269,28 @@ def test_chunked_equals_serial_bitwise():
             for i in range(8):
                 assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64))
             assert int(got.extra["rounds"].max()) < chunks
+            assert torch.equal(ref.n_maps, got.n_maps)
+            nmm = torch.arange(ref.nodes_map.shape[1], device=D.device)[None, :] < ref.n_maps[:, 0:1]
+            assert torch.equal(ref.nodes_map[nmm], got.nodes_map[nmm])
+            am = torch.arange(ref.actions_map.shape[1], device=D.device)[None, :] < ref.n_maps[:, 1:2]
+            assert torch.equal(ref.actions_map[am], got.actions_map[am])
+            assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64))
+
+
+def test_capacity_retry():
+    """A deliberately undersized plan must be detected on the device and redone exactly."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    packed = synth.mixed_paths(64, 8, seed=9)
+    e1 = Engine("cuda:0")
+    db = e1.upload(packed)
+    ref = e1.profile(db)
+    e2 = Engine("cuda:0")
+    key = (db.B, db.N_max, db.A_max, db.max_splines)
+    e2._plan[key] = (int(ref.n_samples.max()) + 8, 300)          # T_cap far too small
+    got = e2.profile(db, reuse_plan=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ref.n_out, got.n_out) and (got.status == 0).all()
+    e2._plan[key] = (1000, ref.T_cap)                             # D_cap far too small
+    got = e2.profile(db, reuse_plan=True)
+    assert torch.equal(ref.n_out, got.n_out) and (got.status == 0).all()

@@ -138,6 +138,17 @@ __device__ __forceinline__ int map_spline(const PathGeo& g, double t)
     }
     return k;
 }
+__device__ __forceinline__ PathGeo path_geo(long long b, int N_max, const double* seg, const int* first_node,
+                                            const double* param_end, const int* n_splines)
+{
+    PathGeo g;
+    g.seg = seg + (size_t)b * (N_max - 1) * 12;
+    g.first = first_node + (size_t)b * (N_max + 1);
+    g.pend = param_end + (size_t)b * N_max;
+    g.S = n_splines[b];
+    return g;
+}
+
 template <int WHICH>
 __device__ __forceinline__ void eval_path(const PathGeo& g, double t, double& ox, double& oy)
 {

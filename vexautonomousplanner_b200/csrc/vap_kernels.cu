@@ -13,6 +13,7 @@
 #include "../../include/vap.h"
 #include "vap_device.cuh"
 #include "vap_velocity.cuh"
+#include "vap_timeloop.cuh"
 
 static thread_local char g_err[512] = "";
 static int set_err(const char* where, cudaError_t e)
@@ -246,17 +247,6 @@ __global__ void k_fit_splines(long long Rn, int n_max, const int* __restrict__ n
     fit_run(n, R, (bh & 1) != 0, bd[0], bd[1], (bh & 2) != 0, bd[2], bd[3], seg + (size_t)r * (n_max - 1) * 12,
             seglen + (size_t)r * n_max, params + (size_t)r * n_max, &pe, scratch + (size_t)r * n_max * 5);
     status[r] = ST_OK;
-}
-
-__device__ __forceinline__ PathGeo path_geo(long long b, int N_max, const double* seg, const int* first_node,
-                                            const double* param_end, const int* n_splines)
-{
-    PathGeo g;
-    g.seg = seg + (size_t)b * (N_max - 1) * 12;
-    g.first = first_node + (size_t)b * (N_max + 1);
-    g.pend = param_end + (size_t)b * N_max;
-    g.S = n_splines[b];
-    return g;
 }
 
 // evaluation queries
@@ -1174,5 +1164,56 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
                                                        reinterpret_cast<const double4*>(recR), E_cap, max_accels, bidx,
                                                        bval, n_ev, vel_f, vel, t_est, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
+    return 0;
+}
+
+// ---- v2 time-domain stage ----------------------------------------------------------------------------------------
+extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
+                                const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags,
+                                const int32_t* n_ap, const double* cons, int32_t* status, double dt, double dd,
+                                const double* seg, const int32_t* first_node, const double* param_end,
+                                const int32_t* n_splines, int samples, int64_t Q_cap, const double* lut_d,
+                                const double* lut_t, const double* total_len, int spn, int64_t P_cap,
+                                const double* prop_k, const double* prop_h, int64_t D_cap, const int32_t* n_samples,
+                                const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
+                                int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary,
+                                int32_t* n_main, double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch,
+                                void* stream)
+{
+    (void)ap_flags;
+    if (B <= 0) return 0;
+    if (B > 65535) return arg_err("vap_time_profile: B > 65535 per call (tile the batch)");
+    if (E_cap < N_max + A_max + 2) return arg_err("vap_time_profile: E_cap < N_max + A_max + 2");
+    int Am = A_max > 0 ? A_max : 1;
+    const int64_t M_cap = T_cap;
+    int32_t* ev_wrap = ev_scratch;
+    int32_t* ev_nwrap = ev_wrap + (size_t)B * N_max;
+    int32_t* ev_apc = ev_nwrap + B;
+    int32_t* ev_napc = ev_apc + (size_t)B * Am * EV_AP_CAND;
+    int32_t* seg_k = seg_tab;
+    int32_t* seg_off = seg_k + (size_t)B * E_cap;
+    int32_t* seg_rev = seg_off + (size_t)B * E_cap;
+    int32_t* n_seg = seg_rev + (size_t)B * E_cap;
+    cudaError_t e = cudaMemsetAsync(ev_nwrap, 0, sizeof(int32_t) * (size_t)B, STREAM);
+    if (e != cudaSuccess) return set_err("vap_time_profile/memset", e);
+    e = cudaMemsetAsync(ev_napc, 0, sizeof(int32_t) * (size_t)B * Am, STREAM);
+    if (e != cudaSuccess) return set_err("vap_time_profile/memset", e);
+    k_time_state<<<blocks_for(B, 32), 32, 0, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples, vel, M_cap,
+                                                      stage, n_main);
+    CHECK_LAUNCH("vap_time_profile/state");
+    dim3 grid(blocks_for(M_cap, 256), (unsigned)B);
+    k_time_sample<<<grid, 256, 0, STREAM>>>(B, N_max, Am, n_nodes, status, ap_attr, n_ap, seg, first_node, param_end,
+                                            n_splines, samples, Q_cap, lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h,
+                                            M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc, ev_napc);
+    CHECK_LAUNCH("vap_time_profile/sample");
+    k_time_events<<<blocks_for(B, 32), 32, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, n_ap, cons,
+                                                       status, dt, seg, first_node, param_end, n_splines, spn, P_cap,
+                                                       prop_h, total_len, M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc,
+                                                       ev_napc, E_cap, seg_k, seg_off, seg_rev, n_seg, T_cap, out,
+                                                       nodes_map, actions_map, n_maps, n_out, summary);
+    CHECK_LAUNCH("vap_time_profile/events");
+    k_time_finalize<<<grid, 256, 0, STREAM>>>(B, status, M_cap, n_main, stage, E_cap, seg_k, seg_off, seg_rev, n_seg,
+                                              T_cap, out, summary);
+    CHECK_LAUNCH("vap_time_profile/finalize");
     return 0;
 }

@@ -1,0 +1,391 @@
+// vap_timeloop.cuh -- v2 of stage S6 (generate_motion_profile's time loop, motion_profile_generator.py:414-628).
+//
+// The reference's loop carries only (current_pos, current_vel) from one iteration to the next; everything else
+// it appends (parameter, heading, curvature, coordinates, angular velocity) is a pure function of the position
+// before the step, and the node / action-point events only insert rows and flip signs.  So the stage is split:
+//   A  k_time_state     one thread per path: the exact (pos, vel) recurrence alone (3 divisions per step)
+//   B1 k_time_sample    one thread per (path, step): t = distance_to_time(pos), snap gathers, point evaluation,
+//                       omega, and the event candidates (frac wrap of t, action-point crossings)
+//   C  k_time_events    one thread per path: replay of the event logic over the candidates only (turn / wait
+//                       inserts, reverse toggles, nodes_map / actions_map), the sequential `current_time += dt`
+//                       chain, and the inserted rows
+//   B2 k_time_finalize  one thread per (path, step): signs, heading normalisation, scatter to the final rows
+// Every floating-point operation is the reference's, in the reference's order; only the schedule changed.
+#pragma once
+#include "vap_device.cuh"
+#include "vap_velocity.cuh"
+
+#define TS_POS 0     // pos[k]: position before main step k (pos[k+1] = position appended by step k)
+#define TS_VEL 1     // current_vel after step k
+#define TS_ACC 2     // accel of step k
+#define TS_TV 3      // target_vel of step k
+#define TS_TH 4      // snapped heading table value at t_k (before the reverse / normalisation logic)
+#define TS_OM 5      // angular_vel of step k
+#define TS_X 6
+#define TS_Y 7
+#define TS_PLANES 8
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// A: the state recurrence (motion_profile_generator.py:523,567-583)
+__global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
+                                                   const int* __restrict__ status, double dt, double dd,
+                                                   const double* __restrict__ total_len, long long D_cap,
+                                                   const int* __restrict__ n_samples, const double* __restrict__ vel,
+                                                   long long M_cap, double* __restrict__ stage, int* __restrict__ n_main)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (status[b] != ST_OK) { n_main[b] = 0; return; }
+    const double L = total_len[b];
+    const double max_acc = cons[b * 6 + 1], max_dec = cons[b * 6 + 2];
+    const long long D = n_samples[b];
+    const double* vv = vel + (size_t)b * D_cap;
+    const double inv_dd = 1.0 / dd;
+    const size_t plane = (size_t)B * (M_cap + 1);
+    double* P = stage + TS_POS * plane + (size_t)b * (M_cap + 1);
+    double* Vo = stage + TS_VEL * plane + (size_t)b * (M_cap + 1);
+    double* Ao = stage + TS_ACC * plane + (size_t)b * (M_cap + 1);
+    double* To = stage + TS_TV * plane + (size_t)b * (M_cap + 1);
+    double pos = 0.0, v = vv[0];
+    long long k = 0;
+    const double hdt = 0.1 * dt;
+    while (pos < L) {
+        if (k < M_cap) P[k] = pos;
+        // lerp(pos) and lerp(pos + dd) on xs[i] = fl(i * dd)
+        long long i1 = uniform_index(pos, dd, inv_dd, D);
+        double x2 = pos + dd;
+        long long i2 = uniform_index(x2, dd, inv_dd, D);
+        double tv1, tv2;
+        if (i1 < 0) tv1 = vv[0];
+        else if (i1 >= D - 1) tv1 = vv[D - 1];
+        else {
+            double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, y0 = vv[i1], y1 = vv[i1 + 1];
+            tv1 = y0 + (pos - x0) * (y1 - y0) / (x1 - x0);
+        }
+        if (i2 < 0) tv2 = vv[0];
+        else if (i2 >= D - 1) tv2 = vv[D - 1];
+        else {
+            double x0 = (double)i2 * dd, x1 = (double)(i2 + 1) * dd, y0 = vv[i2], y1 = vv[i2 + 1];
+            tv2 = y0 + (x2 - x0) * (y1 - y0) / (x1 - x0);
+        }
+        if (i2 + 24 < D) prefetch_l1(vv + i2 + 24);
+        double tv = pymax((tv1 + tv2) / 2, 0.001);
+        double accel = (tv - v) / dt;
+        accel = fmin(fmax(accel, -max_dec), max_acc);          // np.clip
+        v = fmin(fmax(v + accel * dt, 0.0), tv);
+        double dpos = v * dt + 0.5 * accel * dt * dt;
+        if (v <= 0.1) dpos = hdt + 0.5 * accel * dt * dt;
+        pos += dpos;
+        if (k < M_cap) { Vo[k] = v; Ao[k] = accel; To[k] = tv; }
+        k++;
+    }
+    if (k <= M_cap) P[k] = pos;
+    n_main[b] = (int)(k > 2147483647LL ? 2147483647LL : k);
+}
+
+// B1: per-step lookups + event candidates
+__global__ void __launch_bounds__(256) k_time_sample(
+    long long B, int N_max, int A_max, const int* __restrict__ n_nodes, const int* __restrict__ status,
+    const double* __restrict__ ap_attr, const int* __restrict__ n_ap, const double* __restrict__ seg,
+    const int* __restrict__ first_node, const double* __restrict__ param_end, const int* __restrict__ n_splines,
+    int samples, long long Q_cap, const double* __restrict__ lut_d, const double* __restrict__ lut_t,
+    const double* __restrict__ total_len, int spn, long long P_cap, const double* __restrict__ prop_k,
+    const double* __restrict__ prop_h, long long M_cap, const int* __restrict__ n_main, double* __restrict__ stage,
+    int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc)
+{
+    __shared__ double s_t[257];
+    long long b = blockIdx.y;
+    if (status[b] != ST_OK) return;
+    long long M = n_main[b];
+    if (M > M_cap) return;                     // capacity overflow: the caller re-runs with a larger M_cap
+    long long k0 = (long long)blockIdx.x * blockDim.x;
+    if (k0 >= M) return;
+    long long k = k0 + threadIdx.x;
+    const int n = n_nodes[b];
+    const double* ld = lut_d + (size_t)b * Q_cap;
+    const double* lt = lut_t + (size_t)b * Q_cap;
+    PathGeo g = path_geo(b, N_max, seg, first_node, param_end, n_splines);
+    const long long Q = (long long)samples * g.S;
+    const double L = total_len[b];
+    const size_t plane = (size_t)B * (M_cap + 1);
+    const size_t row = (size_t)b * (M_cap + 1);
+    double t = 0.0;
+    if (k < M) {
+        long long hint = -1;
+        double pos = stage[TS_POS * plane + row + k];
+        t = distance_to_time(ld, lt, Q, L, n, pos, hint);
+        const long long P = (long long)spn * n;
+        const double pstep = (double)(n - 1) / (double)(P - 1);
+        double curvature, heading, cx, cy;
+        snap_gather2(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, P, n, pstep, 1.0 / pstep, curvature, heading);
+        eval_path<0>(g, t, cx, cy);
+        double tv = stage[TS_TV * plane + row + k];
+        stage[TS_TH * plane + row + k] = heading;
+        stage[TS_OM * plane + row + k] = tv * curvature * -1;
+        stage[TS_X * plane + row + k] = cx;
+        stage[TS_Y * plane + row + k] = cy;
+    }
+    s_t[threadIdx.x + 1] = t;
+    if (threadIdx.x == 0) {
+        double tp = 0.0;                       // prev_t starts at 0 (:479)
+        if (k0 > 0) { long long hint = -1; tp = distance_to_time(ld, lt, Q, L, n, stage[TS_POS * plane + row + k0 - 1], hint); }
+        s_t[0] = tp;
+    }
+    __syncthreads();
+    if (k >= M) return;
+    double tp = s_t[threadIdx.x];
+    if (frac1(t) < frac1(tp) && t < (double)(n - 1)) {      // :527
+        int slot = atomicAdd(ev_nwrap + b, 1);
+        if (slot < N_max) ev_wrap[(size_t)b * N_max + slot] = (int)k;
+    }
+    int A = n_ap ? n_ap[b] : 0;
+    for (int j = 0; j < A; j++) {
+        double x = ap_attr[((size_t)b * A_max + j) * APA + P_T];
+        if (tp < x && x < t) {                               // :549 (strict on both sides)
+            int slot = atomicAdd(ev_napc + (size_t)b * A_max + j, 1);
+            if (slot < EV_AP_CAND) ev_apc[((size_t)b * A_max + j) * EV_AP_CAND + slot] = (int)k;
+        }
+    }
+}
+
+__device__ __forceinline__ double final_heading(double th_raw, bool rev)
+{   // :559-563
+    double h = th_raw - (rev ? VAP_PI : 0.0);
+    h = pymod_pos(h + VAP_PI, 2 * VAP_PI) - VAP_PI;
+    return h * -1;
+}
+
+// C: events, inserted rows, the current_time chain, maps.  seg_k/seg_off/seg_rev[B][E_cap]: for main steps
+// k >= seg_k[j] the output row is k + seg_off[j] and the reverse state is seg_rev[j].
+__global__ void __launch_bounds__(32) k_time_events(
+    long long B, int N_max, int A_max, const double* __restrict__ node_attr, const int* __restrict__ node_flags,
+    const int* __restrict__ n_nodes, const double* __restrict__ ap_attr, const int* __restrict__ n_ap,
+    const double* __restrict__ cons, int* __restrict__ status, double dt, const double* __restrict__ seg,
+    const int* __restrict__ first_node, const double* __restrict__ param_end, const int* __restrict__ n_splines,
+    int spn, long long P_cap, const double* __restrict__ prop_h, const double* __restrict__ total_len,
+    long long M_cap, const int* __restrict__ n_main, const double* __restrict__ stage, int* __restrict__ ev_wrap,
+    const int* __restrict__ ev_nwrap, const int* __restrict__ ev_apc, const int* __restrict__ ev_napc, int E_cap,
+    int* __restrict__ seg_k, int* __restrict__ seg_off, int* __restrict__ seg_rev, int* __restrict__ n_seg,
+    long long T_cap, double* __restrict__ out, int* __restrict__ nodes_map, int* __restrict__ actions_map,
+    int* __restrict__ n_maps, int* __restrict__ n_out, double* __restrict__ summary)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int st = status[b];
+    int* nmap = nodes_map + (size_t)b * (N_max + 1);
+    int* amap = actions_map + (size_t)b * (A_max > 0 ? A_max : 1);
+    int nm = 0, am = 0;
+    double* sr = summary + (size_t)b * 5;
+    const double L = total_len[b];
+    n_seg[b] = 0;
+    long long T = 0;
+    double last_time = 0.0;
+    if (st == ST_OK) {
+        const long long M = n_main[b];
+        const int n = n_nodes[b];
+        const int A = n_ap ? n_ap[b] : 0;
+        const double* na = node_attr + (size_t)b * N_max * NA;
+        const int* nf = node_flags + (size_t)b * N_max;
+        const double* apa = ap_attr + (size_t)b * A_max * APA;
+        const double V = cons[b * 6 + 0], max_acc = cons[b * 6 + 1], w = cons[b * 6 + 5];
+        const size_t oplane = (size_t)B * T_cap;
+        double* o_tm = out + (size_t)b * T_cap;
+        double* o_pos = o_tm + oplane; double* o_lin = o_pos + oplane; double* o_acc = o_lin + oplane;
+        double* o_head = o_acc + oplane; double* o_ang = o_head + oplane; double* o_x = o_ang + oplane;
+        double* o_y = o_x + oplane;
+        const size_t plane = (size_t)B * (M_cap + 1);
+        const size_t row = (size_t)b * (M_cap + 1);
+        const double* s_pos = stage + TS_POS * plane + row;
+        const double* s_th = stage + TS_TH * plane + row;
+        const double* s_x = stage + TS_X * plane + row;
+        const double* s_y = stage + TS_Y * plane + row;
+        int* sk = seg_k + (size_t)b * E_cap;
+        int* so = seg_off + (size_t)b * E_cap;
+        int* sv = seg_rev + (size_t)b * E_cap;
+        int ns = 0;
+        if (M > M_cap) st = ST_CAPACITY;
+        bool rev = (nf[0] & F_REVERSE) != 0;
+        nmap[nm++] = 0;
+        if (st == ST_OK && na[A_TURN] != 0) st = ST_INDEX;          // headings[-1] on an empty list (:440)
+        long long off = 0;                 // rows inserted so far
+        double time = 0.0;
+        double last_pos = 0.0, last_head = 0.0, last_x = 0.0, last_y = 0.0;
+#define PUSH(tm_, p_, h_, w_, x_, y_)                                                                           \
+        do { long long r_ = T; if (r_ < T_cap) { o_tm[r_] = (tm_); o_pos[r_] = (p_); o_lin[r_] = 0.0; o_acc[r_] = 0.0; \
+             o_head[r_] = (h_); o_ang[r_] = (w_); o_x[r_] = (x_); o_y[r_] = (y_); } T++; } while (0)
+        if (st == ST_OK && na[A_WAIT] > 0) {                          // :459-476
+            long long steps = (long long)(na[A_WAIT] / dt);
+            const long long P = (long long)spn * n;
+            const double pstep = (double)(n - 1) / (double)(P - 1);
+            double h = -1 * snap_gather(prop_h + (size_t)b * P_cap, 0.0, P, n, pstep, 1.0 / pstep);
+            if (rev) h -= VAP_PI;
+            if (h > VAP_PI) h -= 2 * VAP_PI;
+            if (h < -VAP_PI) h += 2 * VAP_PI;
+            PathGeo g = path_geo(b, N_max, seg, first_node, param_end, n_splines);
+            double px, py;
+            eval_path<0>(g, 0.0, px, py);
+            for (long long i = 0; i < steps; i++) PUSH(time + (double)i * dt, 0.0, h, 0.0, px, py);
+            time += (double)steps * dt;
+            off += steps;
+            last_head = h; last_x = px; last_y = py;
+        }
+        if (st == ST_OK) {
+            sk[ns] = 0; so[ns] = (int)off; sv[ns] = rev ? 1 : 0; ns++;
+            // events in step order: node crossing first, then the action point of the same step
+            int* wr = ev_wrap + (size_t)b * N_max;
+            int nw = ev_nwrap[b];
+            if (nw > N_max) st = ST_CAPACITY;
+            for (int i = 1; i < nw && st == ST_OK; i++) {
+                int x = wr[i], j = i - 1;
+                while (j >= 0 && wr[j] > x) { wr[j + 1] = wr[j]; j--; }
+                wr[j + 1] = x;
+            }
+            int node_idx = 0, wptr = 0, action_idx = 0, last_fire = -1;
+            bool actions_dead = false;
+            long long kdone = 0;            // main steps whose time stamp has been written
+            while (st == ST_OK) {
+                int ai = 2147483647;
+                if (!actions_dead && action_idx < A) {
+                    int nc = ev_napc[(size_t)b * A_max + action_idx];
+                    if (nc > EV_AP_CAND) { st = ST_CAPACITY; break; }
+                    const int* c = ev_apc + ((size_t)b * A_max + action_idx) * EV_AP_CAND;
+                    for (int q = 0; q < nc; q++) if (c[q] > last_fire && c[q] < ai) ai = c[q];
+                    if (ai == 2147483647) actions_dead = true;
+                }
+                int wi = (wptr < nw) ? wr[wptr] : 2147483647;
+                long long ke = (wi < ai) ? wi : ai;
+                bool have_event = ke != 2147483647;
+                long long kstop = have_event ? ke : M;
+                // time stamps of main steps kdone .. kstop-1 (times.append(current_time); current_time += dt)
+                for (long long k = kdone; k < kstop; k++) {
+                    long long r = k + off;
+                    if (r < T_cap) o_tm[r] = time;
+                    last_time = time;
+                    time += dt;
+                }
+                if (kstop > kdone) {
+                    // [-1] entries of the result lists = outputs of main step kstop-1
+                    long long kl = kstop - 1;
+                    last_pos = s_pos[kl + 1];
+                    last_head = final_heading(s_th[kl], rev);
+                    last_x = s_x[kl]; last_y = s_y[kl];
+                }
+                kdone = kstop;
+                T = kstop + off;
+                if (!have_event) break;
+                if (wi == ke) {
+                    wptr++;
+                    nmap[nm++] = (int)T;
+                    node_idx += 1;
+                    const double* a = na + (size_t)node_idx * NA;
+                    if (a[A_TURN] != 0) {                        // handle_turn (:487-507)
+                        double angle = a[A_TURN] * (VAP_PI / 180.0);
+                        Trapezoid tz = trapezoid_setup(V, max_acc, fabs(angle) * w / 2, dt);
+                        double sgn = angle > 0 ? -1.0 : 1.0;
+                        double accum = 0.0, hprev = 0.0;
+                        double start_heading = last_head;
+                        for (long long i = 0; i < tz.K; i++) {
+                            double v = trapezoid_vel(tz, i, dt);
+                            double hraw = (accum / (w / 2)) * sgn;
+                            accum += v * dt;
+                            double om = (i == 0) ? 0.0 : (hraw - hprev) / dt;
+                            hprev = hraw;
+                            double hh = hraw;
+                            while (hh + start_heading > VAP_PI) hh -= 2 * VAP_PI;
+                            while (hh + start_heading < -VAP_PI) hh += 2 * VAP_PI;
+                            last_head = start_heading + hh;
+                            PUSH(time + (double)i * dt, last_pos, last_head, om, last_x, last_y);
+                        }
+                        time = time + (double)tz.K * dt;
+                        off += tz.K;
+                    }
+                    if (nf[node_idx] & F_REVERSE) rev = !rev;
+                    if (a[A_WAIT] > 0) {                         // handle_wait (:509-518)
+                        long long steps = (long long)(a[A_WAIT] / dt);
+                        for (long long i = 0; i < steps; i++) PUSH(time + (double)i * dt, 0.0, last_head, 0.0, last_x, last_y);
+                        if (steps > 0) last_pos = 0.0;
+                        time = time + (double)steps * dt;
+                        off += steps;
+                    }
+                }
+                if (ai == ke) {
+                    const double* p = apa + (size_t)action_idx * APA;
+                    amap[am++] = (int)T;
+                    if (p[P_WAIT] > 0) {
+                        long long steps = (long long)(p[P_WAIT] / dt);
+                        for (long long i = 0; i < steps; i++) PUSH(time + (double)i * dt, 0.0, last_head, 0.0, last_x, last_y);
+                        if (steps > 0) last_pos = 0.0;
+                        time = time + (double)steps * dt;
+                        off += steps;
+                    }
+                    action_idx += 1;
+                    last_fire = (int)ke;
+                }
+                if (ns < E_cap) { sk[ns] = (int)ke; so[ns] = (int)off; sv[ns] = rev ? 1 : 0; ns++; }
+                else st = ST_CAPACITY;
+            }
+            if (st == ST_OK) nmap[nm++] = (int)T;                 // gui/path.py:342
+            if (st == ST_OK && T > T_cap) st = ST_CAPACITY;
+        }
+#undef PUSH
+        n_seg[b] = (st == ST_OK) ? ns : 0;
+        if (!(st == ST_OK || st == ST_CAPACITY)) T = 0;
+        if (st == ST_CAPACITY && M > M_cap) T = M;              // lower bound of the true row count
+    }
+    n_out[b] = (int)T;
+    n_maps[2 * b] = nm; n_maps[2 * b + 1] = am;
+    status[b] = st;
+    sr[0] = (double)T; sr[1] = L; sr[2] = last_time; sr[3] = 0.0; sr[4] = (double)st;
+}
+
+// B2: scatter the main-loop rows (times were written by C)
+__global__ void __launch_bounds__(256) k_time_finalize(long long B, const int* __restrict__ status, long long M_cap,
+                                                       const int* __restrict__ n_main, const double* __restrict__ stage,
+                                                       int E_cap, const int* __restrict__ seg_k,
+                                                       const int* __restrict__ seg_off, const int* __restrict__ seg_rev,
+                                                       const int* __restrict__ n_seg, long long T_cap,
+                                                       double* __restrict__ out, double* __restrict__ summary)
+{
+    __shared__ double s_max[8];
+    long long b = blockIdx.y;
+    if (status[b] != ST_OK) return;
+    long long M = n_main[b];
+    long long k0 = (long long)blockIdx.x * blockDim.x;
+    if (k0 >= M) return;
+    long long k = k0 + threadIdx.x;
+    const int ns = n_seg[b];
+    const int* sk = seg_k + (size_t)b * E_cap;
+    double vabs = 0.0;
+    if (k < M) {
+        int j = 0;
+        for (int q = 1; q < ns; q++) if (sk[q] <= (int)k) j = q;
+        long long r = k + seg_off[(size_t)b * E_cap + j];
+        bool rev = seg_rev[(size_t)b * E_cap + j] != 0;
+        const size_t plane = (size_t)B * (M_cap + 1);
+        const size_t row = (size_t)b * (M_cap + 1);
+        double v = stage[TS_VEL * plane + row + k];
+        vabs = v;
+        if (r < T_cap) {
+            const size_t oplane = (size_t)B * T_cap;
+            double* o = out + (size_t)b * T_cap + r;
+            double sgn = rev ? -1.0 : 1.0;
+            o[1 * oplane] = stage[TS_POS * plane + row + k + 1];
+            o[2 * oplane] = v * sgn;
+            o[3 * oplane] = stage[TS_ACC * plane + row + k] * sgn;
+            o[4 * oplane] = final_heading(stage[TS_TH * plane + row + k], rev);
+            o[5 * oplane] = stage[TS_OM * plane + row + k];
+            o[6 * oplane] = stage[TS_X * plane + row + k];
+            o[7 * oplane] = stage[TS_Y * plane + row + k];
+        }
+    }
+    // max |v| for the summary row (velocities are >= 0 before the sign; atomicMax on the bit pattern is exact)
+    for (int o = 16; o > 0; o >>= 1) vabs = fmax(vabs, __shfl_xor_sync(0xffffffffu, vabs, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = vabs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) m = fmax(m, s_max[q]);
+        atomicMax(reinterpret_cast<unsigned long long*>(summary + (size_t)b * 5 + 3), (unsigned long long)__double_as_longlong(m));
+    }
+}

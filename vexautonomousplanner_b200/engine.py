@@ -121,7 +121,7 @@ class Engine:
 
     def __init__(self, device="cuda:0", dt: float = 0.01, dd: float = 0.005, lut_samples: int = 1000,
                  samples_per_node: int = 1000, start_vel: float = 0.01, end_vel: float = 0.01,
-                 velocity_impl: str = "chunked", chunks: int = 32):
+                 velocity_impl: str = "chunked", chunks: int = 32, time_impl: str = "split"):
         if not torch.cuda.is_available():
             raise _lib.VapError("no CUDA device: vexautonomousplanner_b200 has no CPU fallback")
         self.lib = _lib.lib()
@@ -132,6 +132,9 @@ class Engine:
         if velocity_impl not in ("chunked", "serial"):
             raise ValueError("velocity_impl must be 'chunked' or 'serial'")
         self.velocity_impl, self.chunks = velocity_impl, int(chunks)
+        if time_impl not in ("split", "serial"):
+            raise ValueError("time_impl must be 'split' or 'serial'")
+        self.time_impl = time_impl
         self._dgrid: Optional[torch.Tensor] = None
         self._plan: Dict[tuple, tuple] = {}
         self.launches = 0      # kernels launched by this engine (bench.py reports it)
@@ -313,6 +316,45 @@ class Engine:
         self.launches += 1
         return out, nodes_map, actions_map, n_maps, n_out, summary
 
+    def _insert_bound(self, db: DeviceBatch) -> int:
+        """Upper bound of the rows one path can insert for waits and turn profiles (sizing only)."""
+        na = db.node_attr
+        waits = (na[:, :, 3] / self.dt).floor().clamp(min=0).sum(dim=1) + (db.ap_attr[:, :, 1] / self.dt).floor().clamp(min=0).sum(dim=1)
+        V, A, w = db.cons[:, 0:1], db.cons[:, 1:2], db.cons[:, 5:6]
+        arc = (na[:, :, 2].abs() * (3.141592653589793 / 180.0)) * w / 2
+        # trapezoid / triangle duration: never longer than 2 V/A + arc / V, plus two samples of slack per turn
+        turn_rows = torch.where(na[:, :, 2] != 0, ((2 * V / A + arc / V) / self.dt).ceil() + 3, torch.zeros_like(arc)).sum(dim=1)
+        return int((waits + turn_rows).max().item())
+
+    def time_profile(self, db: DeviceBatch, g: Geometry, t: Tables, status, D_cap, n_samples, vel, T_cap):
+        """S6 + S7, fast path (vap_time_profile): state recurrence / parallel lookups / event replay / scatter."""
+        B = db.B
+        if B > 65535:
+            raise _lib.VapError("tile the batch: at most 65535 paths per profile() call")
+        E_cap = db.N_max + db.A_max + 2
+        out = self._empty((8, B, T_cap))
+        nodes_map = self._empty((B, db.N_max + 1), torch.int32)
+        actions_map = self._empty((B, max(db.A_max, 1)), torch.int32)
+        n_maps = self._empty((B, 2), torch.int32)
+        n_out = self._empty((B,), torch.int32)
+        summary = self._empty((B, 5))
+        n_main = self._empty((B,), torch.int32)
+        stage = self._empty((8, B, T_cap + 1))
+        seg_tab = self._empty((3 * B * E_cap + B,), torch.int32)
+        nscr = int(self.lib.vap_event_scratch_ints(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max)))
+        scr = self._empty((nscr,), torch.int32)
+        _lib.check(self.lib.vap_time_profile(
+            C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max), _p(db.node_attr), _p(db.node_flags), _p(db.n_nodes),
+            _p(db.ap_attr), _p(db.ap_flags), _p(db.n_ap), _p(db.cons), _p(status), C.c_double(self.dt), C.c_double(self.dd),
+            _p(g.seg), _p(g.first_node), _p(g.param_end), _p(g.n_splines), C.c_int(t.samples), C.c_int64(t.Q_cap),
+            _p(t.lut_d), _p(t.lut_t), _p(t.total_len), C.c_int(t.spn), C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h),
+            C.c_int64(D_cap), _p(n_samples), _p(vel), C.c_int64(T_cap), _p(out), _p(nodes_map), _p(actions_map), _p(n_maps),
+            _p(n_out), _p(summary), _p(n_main), _p(stage), C.c_int(E_cap), _p(seg_tab), _p(scr), self._stream()),
+            "vap_time_profile")
+        self.launches += 4
+        self._n_main = n_main
+        return out, nodes_map, actions_map, n_maps, n_out, summary
+
     # ------------------------------------------------------------------ whole path
     def profile(self, db: DeviceBatch, keep: bool = False, reuse_plan: bool = False) -> ProfileResult:
         """build_path + generate_motion_profile for every path of the batch.
@@ -343,9 +385,9 @@ class Engine:
         else:
             T_cap = plan[1]
         status_pre = status.clone()
+        tfun = self.time_profile if self.time_impl == "split" else self.resample
         with self._stage("S6_resample"):
-            out, nodes_map, actions_map, n_maps, n_out, summary = self.resample(db, g, t, status, D_cap, n_samples, vel,
-                                                                                T_cap)
+            out, nodes_map, actions_map, n_maps, n_out, summary = tfun(db, g, t, status, D_cap, n_samples, vel, T_cap)
         if True:
             # capacity check (one small read-back; also what a caller needs to trim the rows)
             if bool((status == ST_CAPACITY).any().item()):
@@ -353,10 +395,13 @@ class Engine:
                     # distance capacity was too small: drop the plan and redo with exact sizing
                     self._plan.pop(key, None)
                     return self.profile(db, keep=keep, reuse_plan=False)
-                T_cap = int(n_out.max().item()) + 8
+                if self.time_impl == "split":
+                    # n_main is exact even on overflow; inserted rows are bounded by the insert estimate
+                    T_cap = int(self._n_main.max().item()) + int(self._insert_bound(db)) + 8
+                else:
+                    T_cap = int(n_out.max().item()) + 8
                 status = status_pre.clone()
-                out, nodes_map, actions_map, n_maps, n_out, summary = self.resample(db, g, t, status, D_cap, n_samples,
-                                                                                    vel, T_cap)
+                out, nodes_map, actions_map, n_maps, n_out, summary = tfun(db, g, t, status, D_cap, n_samples, vel, T_cap)
         self._plan[key] = (D_cap, T_cap)
         res = ProfileResult(B, T_cap, out, n_out, nodes_map, actions_map, n_maps, status, summary, vel, n_samples)
         if keep:
