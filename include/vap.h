@@ -167,6 +167,7 @@ int vap_resample(int64_t B, int N_max, int A_max, const double* node_attr, const
  *     the reference's time loop is only (current_pos, current_vel), so the stage runs as: the exact state recurrence
  *     (one thread per path), sample-parallel lookups + event candidates, a per-path replay of the event logic with the
  *     `current_time += dt` chain and the inserted rows, and a sample-parallel scatter to the final rows.
+ *     D_cap must be a multiple of 128 (velocity rows are staged in 128-sample blocks through shared memory).
  *     n_main[B] i32: number of main-loop iterations (valid even on overflow); stage: f64 scratch [8][B][T_cap+1];
  *     seg_tab: i32 scratch [3*B*E_cap + B]; ev_scratch: i32 scratch of vap_event_scratch_ints elements.          */
 int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
@@ -200,6 +201,10 @@ int vap_turn_profile(int64_t n, const double* q, int mode, int64_t K_cap, double
 int vap_lerp(int64_t n, const double* x, int64_t m, const double* xs, const double* ys, double* out, void* stream);
 int vap_wheel_trajectory(int64_t n, const double* lin, const double* ang, double track_width, double* left,
                          double* right, void* stream);
+
+/* Test hook: counts (into the device word *bad) the pseudo-random numerators a, out of n, for which the hoisted-
+ * reciprocal division used inside the time loop differs from the IEEE quotient a / b.  Must stay 0.            */
+int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* bad, void* stream);
 
 #ifdef __cplusplus
 }

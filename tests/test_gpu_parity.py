@@ -294,3 +294,16 @@ def test_capacity_retry():
     e2._plan[key] = (1000, ref.T_cap)                             # D_cap far too small
     got = e2.profile(db, reuse_plan=True)
     assert torch.equal(ref.n_out, got.n_out) and (got.status == 0).all()
+
+
+def test_const_division_is_ieee():
+    """The hoisted-reciprocal division by dt inside the time loop must equal the IEEE quotient for every numerator."""
+    import ctypes as C
+    from vexautonomousplanner_b200 import _lib
+    L = _lib.lib()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for seed, b in ((1, 0.01), (2, 0.01), (3, 0.005), (4, 0.025), (5, 0.02), (6, 1.0 / 3.0)):
+        _lib.check(L.vap_test_div_const(C.c_int64(1 << 26), C.c_uint64(seed), C.c_double(b), C.c_void_p(bad.data_ptr()), st))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0

@@ -1198,15 +1198,27 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     if (e != cudaSuccess) return set_err("vap_time_profile/memset", e);
     e = cudaMemsetAsync(ev_napc, 0, sizeof(int32_t) * (size_t)B * Am, STREAM);
     if (e != cudaSuccess) return set_err("vap_time_profile/memset", e);
-    k_time_state<<<blocks_for(B, 32), 32, 0, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples, vel, M_cap,
-                                                      stage, n_main);
+    if (D_cap % TS_BLK != 0) return arg_err("vap_time_profile: D_cap must be a multiple of 128 (rows are staged in 128-sample blocks)");
+    const size_t ring_bytes = (size_t)32 * TS_STRIDE * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+        if (ea != cudaSuccess) return set_err("vap_time_profile/attr", ea);
+        attr_set = true;
+    }
+    // Serial per-path chains: spread the paths over every warp scheduler (148 SMs x 4) before filling warps, so that
+    // data-dependent branches of one path stall as few other paths as possible.
+    int lanes = (int)((B + 591) / 592);
+    lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
+    k_time_state<<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
+                                                                     vel, M_cap, stage, n_main);
     CHECK_LAUNCH("vap_time_profile/state");
     dim3 grid(blocks_for(M_cap, 256), (unsigned)B);
     k_time_sample<<<grid, 256, 0, STREAM>>>(B, N_max, Am, n_nodes, status, ap_attr, n_ap, seg, first_node, param_end,
                                             n_splines, samples, Q_cap, lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h,
                                             M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc, ev_napc);
     CHECK_LAUNCH("vap_time_profile/sample");
-    k_time_events<<<blocks_for(B, 32), 32, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, n_ap, cons,
+    k_time_events<<<blocks_for(B, lanes), lanes, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, n_ap, cons,
                                                        status, dt, seg, first_node, param_end, n_splines, spn, P_cap,
                                                        prop_h, total_len, M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc,
                                                        ev_napc, E_cap, seg_k, seg_off, seg_rev, n_seg, T_cap, out,
@@ -1215,5 +1227,14 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     k_time_finalize<<<grid, 256, 0, STREAM>>>(B, status, M_cap, n_main, stage, E_cap, seg_k, seg_off, seg_rev, n_seg,
                                               T_cap, out, summary);
     CHECK_LAUNCH("vap_time_profile/finalize");
+    return 0;
+}
+
+// test hook: number of numerators (out of n pseudo-random ones) for which div_const(a, b, 1/b) != a / b
+extern "C" int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* bad, void* stream)
+{
+    if (n <= 0) return 0;
+    k_test_div_const<<<blocks_for(n, 256), 256, 0, STREAM>>>(n, seed, b, reinterpret_cast<unsigned long long*>(bad));
+    CHECK_LAUNCH("vap_test_div_const");
     return 0;
 }

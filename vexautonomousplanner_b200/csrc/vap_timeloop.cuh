@@ -27,61 +27,174 @@
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// A: the state recurrence (motion_profile_generator.py:523,567-583)
+// ---- exact IEEE division helpers ------------------------------------------------------------------------------
+// a / b for b > 0 when a == 0: the quotient is a itself (sign kept); skips the slow path of the division sequence.
+// The division is fed a harmless numerator in that case: nvcc evaluates both arms of a select, and a zero numerator
+// sends the whole warp through the ~90-instruction slow path of the inlined division.
+__device__ __forceinline__ double div_pos(double a, double b)
+{
+    bool z = (a == 0.0);
+    double n = z ? 1.0 : a;
+    asm volatile("" : "+d"(n));          // keep nvcc from folding the select back into the division's numerator
+    double q = n / b;
+    return z ? a : q;
+}
+// a / b with r = RN(1/b) hoisted out of the loop: q0 = a*r, two fused residual corrections.  After the first
+// correction the quotient is faithful, and (Markstein) one more correction with the correctly rounded reciprocal
+// gives the correctly rounded quotient, i.e. exactly what '/' returns.  Tiny / huge / non-finite numerators take
+// the ordinary division.  tests/test_gpu_parity.py::test_const_division_is_ieee checks 2^28 random numerators.
+__device__ __forceinline__ double div_const(double a, double b, double r)
+{
+    double aa = fabs(a);
+    if (!(aa > 1e-280 && aa < 1e280)) return div_pos(a, b);
+    double q = a * r;
+    q = fma(fma(-b, q, a), r, q);
+    q = fma(fma(-b, q, a), r, q);
+    return q;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#define TS_BLK 128                 // samples per staged block of the velocity row
+#define TS_RING (2 * TS_BLK)       // two blocks resident per thread
+#define TS_STRIDE (TS_RING + 2)    // per-thread ring stride in doubles (16-byte aligned, spreads banks)
+
+// index of np.searchsorted(xs, x, side='right') - 1 on xs[i] = fl(i*dd), 32-bit arithmetic
+__device__ __forceinline__ int uniform_index32(double x, double dd, double inv_dd, int D)
+{
+    double e = x * inv_dd;
+    int k = (e > 0.0) ? ((e < (double)(D - 1)) ? __double2int_rd(e) : D - 1) : 0;
+    while (k + 1 < D && (double)(k + 1) * dd <= x) k++;
+    while (k >= 0 && (double)k * dd > x) k--;
+    return k;
+}
+
+// A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row is
+// staged through a per-thread shared-memory ring with cp.async two blocks ahead, so the loop never waits on HBM.
 __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
                                                    const int* __restrict__ status, double dt, double dd,
                                                    const double* __restrict__ total_len, long long D_cap,
                                                    const int* __restrict__ n_samples, const double* __restrict__ vel,
                                                    long long M_cap, double* __restrict__ stage, int* __restrict__ n_main)
 {
+    extern __shared__ __align__(16) double s_ring[];
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     if (status[b] != ST_OK) { n_main[b] = 0; return; }
     const double L = total_len[b];
     const double max_acc = cons[b * 6 + 1], max_dec = cons[b * 6 + 2];
-    const long long D = n_samples[b];
+    const int D = n_samples[b];
     const double* vv = vel + (size_t)b * D_cap;
-    const double inv_dd = 1.0 / dd;
+    const double inv_dd = 1.0 / dd, inv_dt = 1.0 / dt;
     const size_t plane = (size_t)B * (M_cap + 1);
     double* P = stage + TS_POS * plane + (size_t)b * (M_cap + 1);
     double* Vo = stage + TS_VEL * plane + (size_t)b * (M_cap + 1);
     double* Ao = stage + TS_ACC * plane + (size_t)b * (M_cap + 1);
     double* To = stage + TS_TV * plane + (size_t)b * (M_cap + 1);
+    double* ring = s_ring + (size_t)threadIdx.x * TS_STRIDE;
+    const int nblk = (int)((D_cap + TS_BLK - 1) / TS_BLK);
+    auto stage_block = [&](int blk) {          // rows are padded to a multiple of TS_BLK samples by the host
+        if (blk < nblk) {
+            const double* src = vv + (size_t)blk * TS_BLK;
+            double* dst = ring + (blk & 1) * TS_BLK;
+#pragma unroll 8
+            for (int j = 0; j < TS_BLK; j += 2) cp_async16(dst + j, src + j);
+        }
+        cp_async_commit();
+    };
+    int blk_lo = 0;                             // blocks blk_lo and blk_lo+1 are resident
+    bool pending = false;
+    stage_block(0);
+    stage_block(1);
+    cp_async_wait<0>();
     double pos = 0.0, v = vv[0];
+    const double vlast = vv[D - 1];
     long long k = 0;
     const double hdt = 0.1 * dt;
     while (pos < L) {
-        if (k < M_cap) P[k] = pos;
-        // lerp(pos) and lerp(pos + dd) on xs[i] = fl(i * dd)
-        long long i1 = uniform_index(pos, dd, inv_dd, D);
+        const bool room = k < M_cap;
+        if (room) *P = pos;
+        int i1 = uniform_index32(pos, dd, inv_dd, D);
         double x2 = pos + dd;
-        long long i2 = uniform_index(x2, dd, inv_dd, D);
         double tv1, tv2;
-        if (i1 < 0) tv1 = vv[0];
-        else if (i1 >= D - 1) tv1 = vv[D - 1];
-        else {
-            double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, y0 = vv[i1], y1 = vv[i1 + 1];
-            tv1 = y0 + (pos - x0) * (y1 - y0) / (x1 - x0);
+        if (i1 >= 0 && i1 + 3 < D && i1 >= blk_lo * TS_BLK) {
+            // fast path: y[i1 .. i1+2] from the ring; lerp(pos + dd) lands on i1 or one of the next two samples.
+            // Invariant: block blk_lo is complete; block blk_lo+1 is complete unless `pending`.
+            if (i1 >= (blk_lo + 1) * TS_BLK) {
+                if (pending) { cp_async_wait<0>(); pending = false; }
+                int adv = 0;
+                while (i1 >= (blk_lo + 1) * TS_BLK) { blk_lo++; stage_block(blk_lo + 1); adv++; }
+                if (adv == 1) pending = true;          // the block after the current one streams in behind us
+                else cp_async_wait<0>();
+            }
+            if (pending && i1 + 2 >= (blk_lo + 1) * TS_BLK) { cp_async_wait<0>(); pending = false; }
+            double y0 = ring[i1 & (TS_RING - 1)], y1 = ring[(i1 + 1) & (TS_RING - 1)], y2 = ring[(i1 + 2) & (TS_RING - 1)];
+            double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, xx2 = (double)(i1 + 2) * dd;
+            tv1 = y0 + div_pos((pos - x0) * (y1 - y0), x1 - x0);
+            if (x1 <= x2 && x2 < xx2) {
+                tv2 = y1 + div_pos((x2 - x1) * (y2 - y1), xx2 - x1);
+            } else {
+                int i2 = uniform_index32(x2, dd, inv_dd, D);
+                if (i2 < 0) tv2 = vv[0];
+                else if (i2 >= D - 1) tv2 = vlast;
+                else {
+                    double a0 = (double)i2 * dd, a1 = (double)(i2 + 1) * dd, b0 = vv[i2], b1 = vv[i2 + 1];
+                    tv2 = b0 + div_pos((x2 - a0) * (b1 - b0), a1 - a0);
+                }
+            }
+        } else {
+            // generic path (path start / end, or a position that moved backwards)
+            int i2 = uniform_index32(x2, dd, inv_dd, D);
+            if (i1 < 0) tv1 = vv[0];
+            else if (i1 >= D - 1) tv1 = vlast;
+            else {
+                double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, y0 = vv[i1], y1 = vv[i1 + 1];
+                tv1 = y0 + div_pos((pos - x0) * (y1 - y0), x1 - x0);
+            }
+            if (i2 < 0) tv2 = vv[0];
+            else if (i2 >= D - 1) tv2 = vlast;
+            else {
+                double x0 = (double)i2 * dd, x1 = (double)(i2 + 1) * dd, y0 = vv[i2], y1 = vv[i2 + 1];
+                tv2 = y0 + div_pos((x2 - x0) * (y1 - y0), x1 - x0);
+            }
         }
-        if (i2 < 0) tv2 = vv[0];
-        else if (i2 >= D - 1) tv2 = vv[D - 1];
-        else {
-            double x0 = (double)i2 * dd, x1 = (double)(i2 + 1) * dd, y0 = vv[i2], y1 = vv[i2 + 1];
-            tv2 = y0 + (x2 - x0) * (y1 - y0) / (x1 - x0);
-        }
-        if (i2 + 24 < D) prefetch_l1(vv + i2 + 24);
         double tv = pymax((tv1 + tv2) / 2, 0.001);
-        double accel = (tv - v) / dt;
+        double accel = div_const(tv - v, dt, inv_dt);
         accel = fmin(fmax(accel, -max_dec), max_acc);          // np.clip
         v = fmin(fmax(v + accel * dt, 0.0), tv);
         double dpos = v * dt + 0.5 * accel * dt * dt;
         if (v <= 0.1) dpos = hdt + 0.5 * accel * dt * dt;
         pos += dpos;
-        if (k < M_cap) { Vo[k] = v; Ao[k] = accel; To[k] = tv; }
+        if (room) { *Vo = v; *Ao = accel; *To = tv; P++; Vo++; Ao++; To++; }
         k++;
     }
-    if (k <= M_cap) P[k] = pos;
+    cp_async_wait<0>();
+    if (k <= M_cap) *P = pos;
     n_main[b] = (int)(k > 2147483647LL ? 2147483647LL : k);
+}
+
+// exactness check of div_const against the IEEE division (test hook)
+__global__ void k_test_div_const(long long n, unsigned long long seed, double b, unsigned long long* __restrict__ bad)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // splitmix64 -> random double with a random exponent in [-40, 40) and a random sign
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z ^= z >> 31;
+    unsigned long long mant = z & 0x000FFFFFFFFFFFFFULL;
+    int ex = (int)((z >> 52) % 80) - 40 + 1023;
+    unsigned long long bits = ((z >> 63) << 63) | ((unsigned long long)ex << 52) | mant;
+    double a = __longlong_as_double((long long)bits);
+    double r = 1.0 / b;
+    double q1 = div_const(a, b, r), q2 = a / b;
+    if (__double_as_longlong(q1) != __double_as_longlong(q2)) atomicAdd(bad, 1ULL);
 }
 
 // B1: per-step lookups + event candidates

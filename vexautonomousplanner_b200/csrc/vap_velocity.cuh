@@ -278,11 +278,25 @@ __device__ __forceinline__ bool same_bits(double a, double b)
     return __double_as_longlong(a) == __double_as_longlong(b);
 }
 
+// (w_i^2 - w_{i-1}^2) / (2|dtheta|) with IEEE results for every special case, but without sending the warp through the
+// slow path of the inlined division when the numerator is 0 (cruise), or the denominator is 0 (two samples snapped
+// to the same table entry) or NaN (the "straight" marker of the pre-pass).
+__device__ __forceinline__ double accel_ang_div(double num, double h2)
+{
+    bool special = !(h2 > 0.0) || num == 0.0 || !(fabs(num) < 1e300);
+    double n = special ? 1.0 : num, d = special ? 1.0 : h2;
+    asm volatile("" : "+d"(n), "+d"(d));   // keep nvcc from folding the selects back into the division's operands
+    double q = n / d;
+    if (!special) return q;
+    if (h2 > 0.0 && num == 0.0) return num;            // +-0 / positive
+    return num / h2;                                     // rare: NaN / inf / zero denominators, exact IEEE semantics
+}
+
 // forward step i -> i+1 (motion_profile_generator.py:193-249 with the hoisted terms)
 __device__ __forceinline__ double fwd_step(const double4 r, double v, double& wp, double acc, double w, double dd)
 {
     double ang_vel = v * r.x;
-    double accel_ang = (ang_vel * ang_vel - wp * wp) / r.y;
+    double accel_ang = accel_ang_div(ang_vel * ang_vel - wp * wp, r.y);
     double a_wheel = wheel_accel(acc, fabs(accel_ang), w);
     if (a_wheel < 0) a_wheel = 0;
     double a = pymin(r.z, a_wheel);
@@ -295,7 +309,7 @@ __device__ __forceinline__ double bwd_step(const double4 r, double v, double& wp
                                            double vfwd_prev)
 {
     double ang_vel = v * r.x;
-    double accel_ang = (ang_vel * ang_vel - wp * wp) / r.y;
+    double accel_ang = accel_ang_div(ang_vel * ang_vel - wp * wp, r.y);
     double a_wheel = wheel_accel(acc, accel_ang, w);
     if (a_wheel < 0) a_wheel = 0;
     double dcl = pymin(r.z, a_wheel);

@@ -374,9 +374,10 @@ class Engine:
         plan = self._plan.get(key) if reuse_plan else None
         if plan is None:
             Lmax = float(t.total_len.max().item())
-            D_cap = int(Lmax / self.dd) + 8
+            D_cap = (int(Lmax / self.dd) + 8 + 127) // 128 * 128      # rows padded to whole 128-sample blocks
         else:
             D_cap = plan[0]
+        D_cap = (D_cap + 127) // 128 * 128
         status = g.status.clone()
         vfun = self.velocity_chunked if self.velocity_impl == "chunked" else self.velocity_serial
         n_samples, vel, t_est, extra = vfun(db, g, t, status, D_cap)
