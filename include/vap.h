@@ -58,19 +58,26 @@ int vap_version(void);
 const char* vap_last_error(void);
 
 /* S0  QuinticHermiteSplineManager.build_path (spline_manager.py:42-172) + QuinticHermiteSpline.fit
- *     (quintic_hermite_spline.py:30-219,719-736).  scratch: f64 [B][N_max][5].                        */
+ *     (quintic_hermite_spline.py:30-219,719-736).  scratch: f64 [B][N_max][9].  Optional (may be NULL):
+ *     params[B][2*N_max]: every spline's `parameters` array, concatenated (N - 1 + S values);
+ *     derivs[B][2*N_max][4]: first_derivatives / second_derivatives of every spline's control points.    */
 int vap_build_path(int64_t B, int N_max, const double* node_attr, const int32_t* node_flags,
                    const int32_t* n_nodes, double* seg, int32_t* first_node, double* param_end,
-                   double* seglen, int32_t* n_splines, int32_t* status, double* scratch, void* stream);
+                   double* seglen, int32_t* n_splines, int32_t* status, double* scratch, double* params,
+                   double* derivs, void* stream);
 
 /* S0' QuinticHermiteSpline.fit for stand-alone splines (quintic_hermite_spline.py:30-138): R runs of up to
  *     n_max control points.  xy[R][n_max][2]; tan_has[R][n_max] (i32 bit0: incoming set, bit1: outgoing set);
- *     tan_in/tan_out[R][n_max][2]; bnd_has[R] (bit0 starting_tangent, bit1 ending_tangent); bnd[R][2][2].
- *     Outputs seg[R][n_max-1][12], seglen[R][n_max], params[R][n_max], status[R].                        */
+ *     tan_in/tan_out[R][n_max][2]; bnd[R][2][2] = starting / ending tangent; bnd_has[R]: bit0 / bit1 apply the
+ *     starting / ending tangent to the segment table (a valid ndarray(2), :543-590), bit2 / bit3 the attribute
+ *     "is not None" (what _compute_derivatives tests, :170,:181), bit4 use the caller's derivatives
+ *     deriv_in[R][n_max][4] = (first.x, first.y, second.x, second.y) instead of computing them.
+ *     Outputs seg[R][n_max-1][12], seglen[R][n_max], params[R][n_max], status[R], deriv_out[R][n_max][4] (or NULL).
+ *     scratch: f64 [R][n_max][5].                                                                          */
 int vap_fit_splines(int64_t R, int n_max, const int32_t* n_pts, const double* xy, const int32_t* tan_has,
                     const double* tan_in, const double* tan_out, const int32_t* bnd_has, const double* bnd,
                     double* seg, double* seglen, double* params, int32_t* status, double* scratch,
-                    void* stream);
+                    const double* deriv_in, double* deriv_out, void* stream);
 
 /* Evaluation (get_point/derivative/second_derivative _at_parameter, spline_manager.py:204-275 ->
  * quintic_hermite_spline.py:221-251,473-541).  which: 0 point, 1 first, 2 second derivative,

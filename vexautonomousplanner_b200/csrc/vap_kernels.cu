@@ -49,8 +49,12 @@ struct RunView {
 __device__ void fit_run(int n, const RunView& R, bool have_start, double stx, double sty, bool have_end,
                         double etx, double ety, double* __restrict__ seg, double* __restrict__ seglen,
                         double* __restrict__ params_out, double* __restrict__ param_end,
-                        double* __restrict__ scratch)
+                        double* __restrict__ scratch, bool start_attr, bool end_attr,
+                        const double* __restrict__ deriv_in = nullptr, double* __restrict__ deriv_out = nullptr)
 {
+    // have_start / have_end: a valid boundary tangent is applied to the segment table (:129-132, :543-590);
+    // start_attr / end_attr: the attribute "is not None", which is what _compute_derivatives tests (:170,:181);
+    // deriv_in: caller-provided first/second derivatives [n][4] (fit(..., first_derivatives, second_derivatives)).
     double* dist = scratch;
     double* fd = scratch + n;
     double* sd = scratch + 3 * n;
@@ -79,11 +83,11 @@ __device__ void fit_run(int n, const RunView& R, bool have_start, double stx, do
         double fx, fy;
         if (i == 0) {
             double cx = PX(1) - PX(0), cy = PY(1) - PY(0);
-            if (n == 2 && have_end) { fx = cx; fy = cy; }
+            if (n == 2 && end_attr) { fx = cx; fy = cy; }
             else { fx = cx / dist[0]; fy = cy / dist[0]; }
         } else if (i == n - 1) {
             double cx = PX(n - 1) - PX(n - 2), cy = PY(n - 1) - PY(n - 2);
-            if (n == 2 && have_start) { fx = cx; fy = cy; }
+            if (n == 2 && start_attr) { fx = cx; fy = cy; }
             else { fx = cx / dist[n - 2]; fy = cy / dist[n - 2]; }
         } else {
             double ax = (PX(i) - PX(i - 1)) / dist[i - 1], ay = (PY(i) - PY(i - 1)) / dist[i - 1];
@@ -101,6 +105,12 @@ __device__ void fit_run(int n, const RunView& R, bool have_start, double stx, do
             sy = (fd[2 * (i + 1) + 1] - fd[2 * (i - 1) + 1]) / den;
         }
         sd[2 * i] = sx; sd[2 * i + 1] = sy;
+    }
+    if (deriv_in) {
+        for (int i = 0; i < n; i++) {
+            fd[2 * i] = deriv_in[4 * i]; fd[2 * i + 1] = deriv_in[4 * i + 1];
+            sd[2 * i] = deriv_in[4 * i + 2]; sd[2 * i + 1] = deriv_in[4 * i + 3];
+        }
     }
     // segment tables
     for (int i = 0; i < n - 1; i++) {
@@ -128,8 +138,14 @@ __device__ void fit_run(int n, const RunView& R, bool have_start, double stx, do
     }
     // starting tangent lands on the LAST segment's row 2 (quintic_hermite_spline.py:561), ending on row 3
     double* last = seg + (size_t)(n - 2) * 12;
-    if (have_start) { last[4] = stx; last[5] = sty; }
-    if (have_end) { last[6] = etx; last[7] = ety; }
+    if (have_start) { last[4] = stx; last[5] = sty; fd[0] = stx; fd[1] = sty; }
+    if (have_end) { last[6] = etx; last[7] = ety; fd[2 * (n - 1)] = etx; fd[2 * (n - 1) + 1] = ety; }
+    if (deriv_out) {
+        for (int i = 0; i < n; i++) {
+            deriv_out[4 * i] = fd[2 * i]; deriv_out[4 * i + 1] = fd[2 * i + 1];
+            deriv_out[4 * i + 2] = sd[2 * i]; deriv_out[4 * i + 3] = sd[2 * i + 1];
+        }
+    }
 #undef PX
 #undef PY
 }
@@ -139,11 +155,14 @@ __global__ void k_build_path(long long B, int N_max, const double* __restrict__ 
                              const int* __restrict__ node_flags, const int* __restrict__ n_nodes,
                              double* __restrict__ seg, int* __restrict__ first_node, double* __restrict__ param_end,
                              double* __restrict__ seglen, int* __restrict__ n_splines, int* __restrict__ status,
-                             double* __restrict__ scratch)
+                             double* __restrict__ scratch, double* __restrict__ params, double* __restrict__ derivs)
 {
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int n = n_nodes[b];
+    double* pr = params ? params + (size_t)b * 2 * N_max : nullptr;     // concatenated spline.parameters
+    double* dv = derivs ? derivs + (size_t)b * 2 * N_max * 4 : nullptr; // concatenated first/second derivatives
+    int pc = 0;
     const double* na = node_attr + (size_t)b * N_max * NA;
     const int* nf = node_flags + (size_t)b * N_max;
     double* sg = seg + (size_t)b * (N_max - 1) * 12;
@@ -217,7 +236,9 @@ __global__ void k_build_path(long long B, int N_max, const double* __restrict__ 
         R.px = na + (size_t)cur * NA + A_X; R.py = na + (size_t)cur * NA + A_Y; R.stride = NA;
         R.has = nf + cur; R.has_stride = 1; R.in_mask = F_TANGENT; R.out_mask = F_TANGENT;
         R.tin = tin + 2 * cur; R.tout = tout + 2 * cur;
-        fit_run(m, R, use_start, usx, usy, have_end, etx, ety, sg + (size_t)cur * 12, sl + cur, nullptr, pe + S, scr);
+        fit_run(m, R, use_start, usx, usy, have_end, etx, ety, sg + (size_t)cur * 12, sl + cur, pr ? pr + pc : nullptr,
+                pe + S, scr, use_start, have_end, nullptr, dv ? dv + (size_t)pc * 4 : nullptr);
+        pc += m;
         S++;
         fn[S] = i;
         if ((rev || turn) && i < n - 1) cur = i;
@@ -231,7 +252,8 @@ __global__ void k_fit_splines(long long Rn, int n_max, const int* __restrict__ n
                               const int* __restrict__ tan_has, const double* __restrict__ tan_in,
                               const double* __restrict__ tan_out, const int* __restrict__ bnd_has,
                               const double* __restrict__ bnd, double* __restrict__ seg, double* __restrict__ seglen,
-                              double* __restrict__ params, int* __restrict__ status, double* __restrict__ scratch)
+                              double* __restrict__ params, int* __restrict__ status, double* __restrict__ scratch,
+                              const double* __restrict__ deriv_in, double* __restrict__ deriv_out)
 {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= Rn) return;
@@ -245,7 +267,9 @@ __global__ void k_fit_splines(long long Rn, int n_max, const int* __restrict__ n
     const double* bd = bnd + (size_t)r * 4;
     double pe;
     fit_run(n, R, (bh & 1) != 0, bd[0], bd[1], (bh & 2) != 0, bd[2], bd[3], seg + (size_t)r * (n_max - 1) * 12,
-            seglen + (size_t)r * n_max, params + (size_t)r * n_max, &pe, scratch + (size_t)r * n_max * 5);
+            seglen + (size_t)r * n_max, params + (size_t)r * n_max, &pe, scratch + (size_t)r * n_max * 5,
+            (bh & 4) != 0, (bh & 8) != 0, (bh & 16) ? deriv_in + (size_t)r * n_max * 4 : nullptr,
+            deriv_out ? deriv_out + (size_t)r * n_max * 4 : nullptr);
     status[r] = ST_OK;
 }
 
@@ -918,12 +942,13 @@ static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + 
 
 extern "C" int vap_build_path(int64_t B, int N_max, const double* node_attr, const int32_t* node_flags,
                               const int32_t* n_nodes, double* seg, int32_t* first_node, double* param_end,
-                              double* seglen, int32_t* n_splines, int32_t* status, double* scratch, void* stream)
+                              double* seglen, int32_t* n_splines, int32_t* status, double* scratch, double* params,
+                              double* derivs, void* stream)
 {
     if (B <= 0) return 0;
     if (N_max < 2) return arg_err("vap_build_path: N_max < 2");
     k_build_path<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, N_max, node_attr, node_flags, n_nodes, seg, first_node,
-                                                        param_end, seglen, n_splines, status, scratch);
+                                                        param_end, seglen, n_splines, status, scratch, params, derivs);
     CHECK_LAUNCH("vap_build_path");
     return 0;
 }
@@ -931,12 +956,12 @@ extern "C" int vap_build_path(int64_t B, int N_max, const double* node_attr, con
 extern "C" int vap_fit_splines(int64_t R, int n_max, const int32_t* n_pts, const double* xy, const int32_t* tan_has,
                                const double* tan_in, const double* tan_out, const int32_t* bnd_has, const double* bnd,
                                double* seg, double* seglen, double* params, int32_t* status, double* scratch,
-                               void* stream)
+                               const double* deriv_in, double* deriv_out, void* stream)
 {
     if (R <= 0) return 0;
     if (n_max < 2) return arg_err("vap_fit_splines: n_max < 2");
     k_fit_splines<<<blocks_for(R, 128), 128, 0, STREAM>>>(R, n_max, n_pts, xy, tan_has, tan_in, tan_out, bnd_has, bnd,
-                                                         seg, seglen, params, status, scratch);
+                                                         seg, seglen, params, status, scratch, deriv_in, deriv_out);
     CHECK_LAUNCH("vap_fit_splines");
     return 0;
 }

@@ -68,6 +68,8 @@ class Geometry:
     seglen: torch.Tensor       # [B, N_max]
     n_splines: torch.Tensor    # [B] i32
     status: torch.Tensor       # [B] i32
+    params: Optional[torch.Tensor] = None   # [B, 2*N_max] concatenated spline.parameters (only when requested)
+    derivs: Optional[torch.Tensor] = None   # [B, 2*N_max, 4] first / second derivatives of the control points
 
 
 @dataclass
@@ -173,14 +175,18 @@ class Engine:
         return self._dgrid
 
     # ------------------------------------------------------------------ stages
-    def build_geometry(self, db: DeviceBatch) -> Geometry:
+    def build_geometry(self, db: DeviceBatch, with_params: bool = False) -> Geometry:
         B, N = db.B, db.N_max
         g = Geometry(self._empty((B, max(N - 1, 1), 6, 2)), self._empty((B, N + 1), torch.int32), self._empty((B, N)),
                      self._empty((B, N)), self._empty((B,), torch.int32), self._empty((B,), torch.int32))
         scratch = self._empty((B, N, 9))
+        if with_params:
+            g.params = torch.zeros((B, 2 * N), dtype=torch.float64, device=self.device)
+            g.derivs = torch.zeros((B, 2 * N, 4), dtype=torch.float64, device=self.device)
         _lib.check(self.lib.vap_build_path(C.c_int64(B), C.c_int(N), _p(db.node_attr), _p(db.node_flags), _p(db.n_nodes),
                                            _p(g.seg), _p(g.first_node), _p(g.param_end), _p(g.seglen), _p(g.n_splines),
-                                           _p(g.status), _p(scratch), self._stream()), "vap_build_path")
+                                           _p(g.status), _p(scratch), _p(g.params), _p(g.derivs), self._stream()),
+                   "vap_build_path")
         self.launches += 1
         return g
 
