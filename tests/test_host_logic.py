@@ -1,0 +1,176 @@
+"""CPU-side tests (no GPU): the C ABI exports, host packing, synthetic workloads, sharding + gloo gather."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """libvap.so must load without a GPU and export exactly the functions include/vap.h declares."""
+    import vexautonomousplanner_b200 as vap
+    from vexautonomousplanner_b200 import _lib
+    so = vap.build()
+    header = open(os.path.join(ROOT, "include", "vap.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(vap_\w+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    lib = ctypes.CDLL(so)
+    for name in declared:
+        assert hasattr(lib, name), name
+    L = vap.lib()
+    assert L.vap_version() == 100
+    assert L.vap_last_error() is not None
+    nm = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (vap_\w+)", nm))
+    assert declared <= exported
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vexautonomousplanner_b200 import VapError
+    from vexautonomousplanner_b200.engine import Engine
+    with pytest.raises(VapError):
+        Engine("cuda:0")
+
+
+def test_sass_is_sm100a_without_fma_contraction():
+    """The shared library carries sm_100a code, and the index-critical kernels contain explicit DFMA only where
+    fma() is written (build_path's norm / rotation), i.e. -fmad=false is in effect."""
+    import vexautonomousplanner_b200 as vap
+    so = vap.build()
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    full = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    lines, keep = [], False
+    for ln in full.splitlines():
+        if "Function :" in ln:
+            keep = "k_build_lut" in ln
+        if keep:
+            lines.append(ln)
+    sass = "\n".join(lines)
+    assert "DMUL" in sass and "DADD" in sass
+    # the only DFMA in the LUT kernel belong to the inlined sqrt / division sequences, never to a*b+c of the basis sums:
+    # there must be at least as many DMUL+DADD as basis terms (6 polynomials x 3 terms + 12 accumulations)
+    assert sass.count("DMUL") >= 20 and sass.count("DADD") >= 20
+
+
+class _Node:
+    def __init__(self, **kw):
+        self.is_reverse_node = False; self.turn = 0; self.wait_time = 0; self.stop = False; self.tangent = None
+        self.incoming_magnitude = None; self.outgoing_magnitude = None; self.max_velocity = 0; self.max_acceleration = 0
+        self.__dict__.update(kw)
+
+
+class _AP:
+    def __init__(self, t, **kw):
+        self.t = t; self.stop = False; self.wait_time = 0; self.max_velocity = 0; self.max_acceleration = 0
+        self.__dict__.update(kw)
+
+
+def test_pack_paths_layout_and_rotation_table():
+    from vexautonomousplanner_b200 import pack_arrays, pack_paths, px_to_ft
+    from vexautonomousplanner_b200.packing import F_REVERSE, F_STOP, F_TANGENT
+    pts = px_to_ft([[300, 300], [700, 500], [1000, 1200], [1400, 900]])
+    assert pts[0, 0] == (300 / 2000 - 0.5) * 12.1090395251
+    nodes = [_Node(), _Node(turn=45, is_reverse_node=True, stop=True), _Node(tangent=np.array([0.6, 0.8]),
+             incoming_magnitude=1.5, outgoing_magnitude=2.0, wait_time=0.2, max_velocity=2.5), _Node(max_acceleration=5.0)]
+    aps = [_AP(1.5, stop=True, wait_time=0.1, max_velocity=2.0)]
+    p = pack_paths([(pts, nodes, aps), (pts[:3], nodes[:3], [])], [4.0, 8.0, 8.0, 0.8, 16.0, 1.0])
+    assert p.node_attr.shape == (2, 4, 12) and p.n_nodes.tolist() == [4, 3] and p.n_ap.tolist() == [1, 0]
+    assert p.node_flags[0].tolist() == [0, F_REVERSE | F_STOP, F_TANGENT, 0]
+    ang = np.radians(45) + np.pi
+    assert p.node_attr[0, 1, 10] == np.cos(ang) and p.node_attr[0, 1, 11] == np.sin(ang)
+    assert p.node_attr[0, 0, 10] == 1.0 and p.node_attr[0, 0, 11] == 0.0
+    assert p.node_attr[0, 2, 6:10].tolist() == [0.6, 0.8, 1.5, 2.0]
+    assert p.ap_attr[0, 0].tolist() == [1.5, 0.1, 2.0, 0.0] and p.ap_flags[0, 0] == F_STOP
+    assert p.max_splines() == 2
+    q = pack_arrays(pts[None], [4.0, 8.0, 8.0, 0.8, 16.0, 1.0], reverse=[[0, 1, 0, 0]], stop=[[0, 1, 0, 0]],
+                    turn=[[0, 45, 0, 0]], wait=[[0, 0, 0.2, 0]], max_velocity=[[0, 0, 2.5, 0]],
+                    max_acceleration=[[0, 0, 0, 5.0]], tangent=[[[np.nan, np.nan]] * 2 + [[0.6, 0.8]] + [[np.nan, np.nan]]],
+                    in_mag=[[0, 0, 1.5, 0]], out_mag=[[0, 0, 2.0, 0]], ap_t=[[1.5]], ap_stop=[[True]], ap_wait=[[0.1]],
+                    ap_max_velocity=[[2.0]])
+    assert np.array_equal(q.node_attr[0], p.node_attr[0]) and np.array_equal(q.node_flags[0], p.node_flags[0])
+    assert np.array_equal(q.ap_attr[0], p.ap_attr[0]) and np.array_equal(q.ap_flags[0], p.ap_flags[0])
+    m = q.mirrored()
+    assert np.array_equal(m.node_attr[:, :, 0], -q.node_attr[:, :, 0]) and m.node_attr[0, 1, 2] == -45.0
+
+
+def test_synthetic_workloads_follow_the_spec():
+    from vexautonomousplanner_b200 import synth
+    p = synth.random_paths(64, 8, seed=0)
+    px = (p.node_attr[:, :, 0:2] / 12.1090395251 + 0.5) * 2000
+    assert px.min() >= 15 - 1e-9 and px.max() <= 1985 + 1e-9
+    assert np.linalg.norm(np.diff(px, axis=1), axis=2).min() >= 30 - 1e-9
+    assert np.array_equal(p.cons[0], np.array(synth.FACTORY))
+    m = synth.mixed_paths(64, 8, seed=3)
+    assert (m.node_attr[:, 0, 2] == 0).all() and (m.node_attr[:, -1, 2] == 0).all()       # no turn at first / last node
+    assert ((m.node_flags[:, -1] & 1) == 0).all()                                            # no reverse at the last node
+    # second half = mirror in PIXEL space (x_px -> 2000 - x_px, gui/path.py:596-600), so feet agree to rounding only
+    assert np.allclose(m.node_attr[32:, :, 0], -m.node_attr[:32, :, 0], rtol=0, atol=1e-12)
+    assert np.array_equal(m.node_attr[32:, :, 2], -m.node_attr[:32, :, 2])
+    assert (m.node_attr[:, :, 2] != 0).any() and (m.node_attr[:, :, 3] > 0).any() and (m.n_ap > 0).any()
+    assert synth.cfg1().node_attr.shape == (1, 6, 12)
+
+
+def test_shard_bounds_cover_and_balance():
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.sharding import chord_weights, local_shard, shard_bounds
+    for B, W in ((10, 3), (4096, 8), (5, 8), (1, 2)):
+        b = shard_bounds(B, W)
+        assert b[0][0] == 0 and b[-1][1] == B and all(b[i][1] == b[i + 1][0] for i in range(W - 1))
+    p = synth.random_paths(512, 8, seed=4)
+    w = chord_weights(p)
+    b = shard_bounds(512, 4, w)
+    assert b[0][0] == 0 and b[-1][1] == 512
+    loads = [w[lo:hi].sum() for lo, hi in b]
+    assert max(loads) / min(loads) < 1.05
+    sub, (lo, hi) = local_shard(p, 1, 4)
+    assert sub.B == hi - lo and np.array_equal(sub.node_attr, p.node_attr[lo:hi])
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from vexautonomousplanner_b200 import synth
+from vexautonomousplanner_b200.sharding import gather_summaries, local_shard
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+packed = synth.random_paths(37, 6, seed=2)
+sub, (lo, hi) = local_shard(packed, rank, world)
+# stand-in for the per-path summary rows a rank would produce (n_out, L, t_end, max|v|, status)
+rows = torch.tensor(np.stack([np.arange(lo, hi), sub.node_attr[:, 0, 0], sub.node_attr[:, 1, 1],
+                              sub.node_attr[:, 2, 0], np.zeros(hi - lo)], axis=1))
+allrows = gather_summaries(rows)
+assert allrows.shape == (37, 5), allrows.shape
+assert torch.equal(allrows[:, 0], torch.arange(37, dtype=torch.float64))
+assert torch.equal(allrows[:, 1], torch.tensor(packed.node_attr[:, 0, 0]))
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_shard_and_gather(tmp_path):
+    """The N > 1 path on CPU: two processes shard one batch and all_gather the summary rows over gloo."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT, "port": port})
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
