@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/vap.h"
 #include "vap_device.cuh"
@@ -1224,17 +1225,19 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     e = cudaMemsetAsync(ev_napc, 0, sizeof(int32_t) * (size_t)B * Am, STREAM);
     if (e != cudaSuccess) return set_err("vap_time_profile/memset", e);
     if (D_cap % TS_BLK != 0) return arg_err("vap_time_profile: D_cap must be a multiple of 128 (rows are staged in 128-sample blocks)");
-    const size_t ring_bytes = (size_t)32 * TS_STRIDE * sizeof(double);
+    // Serial per-path chains are latency-bound (about 4.6 cycles per dependent instruction, measured): spread the paths
+    // over the warp schedulers (148 SMs x 4) with few paths per warp, so that one path's data-dependent branches stall
+    // few other paths and the schedulers still have another warp to issue from.  VAP_STATE_LANES overrides (tuning).
+    int lanes = (int)((B + 591) / 592);
+    if (const char* ev = getenv("VAP_STATE_LANES")) lanes = atoi(ev);
+    lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
+    const size_t ring_bytes = (size_t)lanes * TS_STRIDE * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+        cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * TS_STRIDE * sizeof(double)));
         if (ea != cudaSuccess) return set_err("vap_time_profile/attr", ea);
         attr_set = true;
     }
-    // Serial per-path chains: spread the paths over every warp scheduler (148 SMs x 4) before filling warps, so that
-    // data-dependent branches of one path stall as few other paths as possible.
-    int lanes = (int)((B + 591) / 592);
-    lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
     k_time_state<<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
                                                                      vel, M_cap, stage, n_main);
     CHECK_LAUNCH("vap_time_profile/state");

@@ -12,6 +12,9 @@
 
 #define EV_AP_CAND 4
 
+__device__ __forceinline__ void prefetch_l1v(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#define PF_DIST 12      // records ahead of the serial walk (3 cache lines of 32-byte records)
+
 // ---- S3 (parallel): t, kappa, theta per distance sample + event candidates -----------------------------------
 // wrap candidates: samples with frac(t[i-1]) > frac(t[i]) and t[i] < N-1  (motion_profile_generator.py:124)
 // action candidates: samples with t[i-1] < ap.t <= t[i]                   (:142-146)
@@ -283,13 +286,25 @@ __device__ __forceinline__ bool same_bits(double a, double b)
 // to the same table entry) or NaN (the "straight" marker of the pre-pass).
 __device__ __forceinline__ double accel_ang_div(double num, double h2)
 {
+    // ~44 % of consecutive distance samples snap to the same table entry (h2 == 0), so the special cases are the
+    // common ones and must not touch the division at all.
     bool special = !(h2 > 0.0) || num == 0.0 || !(fabs(num) < 1e300);
     double n = special ? 1.0 : num, d = special ? 1.0 : h2;
     asm volatile("" : "+d"(n), "+d"(d));   // keep nvcc from folding the selects back into the division's operands
     double q = n / d;
     if (!special) return q;
-    if (h2 > 0.0 && num == 0.0) return num;            // +-0 / positive
-    return num / h2;                                     // rare: NaN / inf / zero denominators, exact IEEE semantics
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (h2 > 0.0) {
+        if (num == 0.0) return num;                      // +-0 / positive
+        return (num != num) ? qnan : copysign(inf, num); // |num| >= 1e300 or inf: overflow / inf / NaN, as IEEE '/' gives
+    }
+    if (h2 == 0.0) {                                     // x / +0
+        if (num > 0.0) return inf;
+        if (num < 0.0) return -inf;
+        return qnan;                                     // 0/0 or NaN/0
+    }
+    return qnan;                                         // NaN denominator (the pre-pass's "straight" marker)
 }
 
 // forward step i -> i+1 (motion_profile_generator.py:193-249 with the hoisted terms)
@@ -370,7 +385,8 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
         int nb_next = (j < n_b) ? bi[j] : 2147483647;
         double4 r = F[lo];
         for (long long i = lo; i < hi; i++) {
-            double4 rn = (i + 1 < hi) ? F[i + 1] : r;          // software prefetch of the next record
+            double4 rn = (i + 1 < hi) ? F[i + 1] : r;          // next record into registers
+            if (i + PF_DIST < hi) prefetch_l1v(F + i + PF_DIST);   // and the line three ahead into L1
             if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
             v = fwd_step(r, v, wp, acc, w, dd);
             vf[i + 1] = v;
@@ -396,6 +412,7 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
             double4 r = F[lo];
             for (long long i = lo; i < hi; i++) {
                 double4 rn = (i + 1 < hi) ? F[i + 1] : r;
+                if (i + PF_DIST < hi) { prefetch_l1v(F + i + PF_DIST); prefetch_l1v(vf + i + 2 * PF_DIST); }
                 if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
                 v = fwd_step(r, v, wp, acc, w, dd);
                 double old = vf[i + 1];
@@ -477,6 +494,7 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
         for (long long i = hi; i > lo; i--) {
             double4 rn = (i - 1 > lo) ? R[i - 1] : r;
             double vfn = (i - 1 > lo) ? vf[i - 2] : 0.0;
+            if (i - 2 * PF_DIST > lo) { prefetch_l1v(R + i - PF_DIST); prefetch_l1v(vf + i - 2 * PF_DIST); }
             if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
             v = bwd_step(r, v, wp, acc, w, dd, vfp);
             vo[i - 1] = v;
@@ -504,6 +522,7 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
             for (long long i = hi; i > lo; i--) {
                 double4 rn = (i - 1 > lo) ? R[i - 1] : r;
                 double vfn = (i - 1 > lo) ? vf[i - 2] : 0.0;
+                if (i - 2 * PF_DIST > lo) { prefetch_l1v(R + i - PF_DIST); prefetch_l1v(vf + i - 2 * PF_DIST); prefetch_l1v(vo + i - 2 * PF_DIST); }
                 if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
                 v = bwd_step(r, v, wp, acc, w, dd, vfp);
                 double old = vo[i - 1];
