@@ -150,8 +150,10 @@ def run_b200(args):
     db = eng.upload(packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    graphed = eng.capture(db, tiles=args.tiles) if args.graph else None
+
     def step():
-        res = eng.profile(db, reuse_plan=True)
+        res = graphed.run() if graphed else eng.profile(db, reuse_plan=True, tiles=args.tiles)
         if world > 1:
             gather_summaries(res.summary, counts=[B] * world)
         return res
@@ -236,7 +238,7 @@ def run_b200(args):
             dist.barrier()
         t0 = time.perf_counter()
         dbi = DeviceBatch(*[t.to(dev, non_blocking=True) for t in host_in], msp)
-        r = eng.profile(dbi, reuse_plan=True)
+        r = eng.profile(dbi, reuse_plan=True, tiles=args.tiles)
         if host_out is None or host_out[0].shape != r.out.shape:
             host_out = [torch.empty(r.out.shape, dtype=r.out.dtype).pin_memory(),
                         torch.empty(r.n_out.shape, dtype=r.n_out.dtype).pin_memory(),
@@ -273,6 +275,7 @@ def run_b200(args):
             "config": {"workload": f"{B} random {N}-node paths per GPU, factory constraints, dt=0.01 dd=0.005 "
                                    "(BASELINE.json configs[1])",
                        "paths_per_gpu": B, "nodes": N, "l2": "flushed between timed steps (256 MB write)",
+                       "tiles": args.tiles, "cuda_graph": bool(args.graph),
                        "mean_D": Dsum / B, "mean_T": Tsum / B, "wall_s": wall},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -292,6 +295,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-sample", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tiles", type=int, default=4, help="row tiles of the batch, one CUDA stream each")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

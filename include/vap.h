@@ -176,7 +176,9 @@ int vap_resample(int64_t B, int N_max, int A_max, const double* node_attr, const
  *     `current_time += dt` chain and the inserted rows, and a sample-parallel scatter to the final rows.
  *     D_cap must be a multiple of 128 (velocity rows are staged in 128-sample blocks through shared memory).
  *     n_main[B] i32: number of main-loop iterations (valid even on overflow); stage: f64 scratch [8][B][T_cap+1];
- *     seg_tab: i32 scratch [3*B*E_cap + B]; ev_scratch: i32 scratch of vap_event_scratch_ints elements.          */
+ *     seg_tab: i32 scratch [3*B*E_cap + B]; ev_scratch: i32 scratch of vap_event_scratch_ints elements.
+ *     out_plane_stride: elements between the eight planes of `out` (0 = B*T_cap); lets a tile of a larger batch
+ *     write straight into its rows of the batch-wide output.                                                   */
 int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
                      const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
                      const double* cons, int32_t* status, double dt, double dd, const double* seg,
@@ -185,7 +187,8 @@ int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, c
                      int64_t P_cap, const double* prop_k, const double* prop_h, int64_t D_cap,
                      const int32_t* n_samples, const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
                      int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary, int32_t* n_main,
-                     double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch, void* stream);
+                     double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch, int64_t out_plane_stride,
+                     void* stream);
 
 /* S1' QuinticHermiteSpline.get_arc_length (Gauss-Legendre, quintic_hermite_spline.py:592-644) and
  *     get_parameter_by_arc_length (:661-717) for n queries on spline `spl[q]` of path `path[q]`.

@@ -307,3 +307,46 @@ def test_const_division_is_ieee():
         _lib.check(L.vap_test_div_const(C.c_int64(1 << 26), C.c_uint64(seed), C.c_double(b), C.c_void_p(bad.data_ptr()), st))
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+def test_tiled_multistream_equals_untiled():
+    """Row tiles on separate CUDA streams must give the same bits as one pass over the batch."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    for packed in (synth.random_paths(700, 8, seed=21), synth.mixed_paths(300, 8, seed=22)):
+        db = eng.upload(packed)
+        ref = eng.profile(db)
+        for tiles in (2, 4, 7):
+            got = eng.profile(db, reuse_plan=True, tiles=tiles)
+            torch.cuda.synchronize()
+            assert torch.equal(ref.n_out, got.n_out) and torch.equal(ref.status, got.status)
+            assert torch.equal(ref.n_samples, got.n_samples)
+            n = ref.n_out.long()
+            Tm = min(ref.T_cap, got.T_cap)
+            mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+            for i in range(8):
+                assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64))
+            assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64))
+            nmm = torch.arange(ref.nodes_map.shape[1], device=n.device)[None, :] < ref.n_maps[:, 0:1]
+            assert torch.equal(ref.nodes_map[nmm], got.nodes_map[nmm])
+
+
+def test_cuda_graph_replay_equals_eager():
+    """The captured step (tiles forked over streams inside one CUDA graph) reproduces the eager results bit for bit,
+    also after new inputs are copied into the static buffers."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    a, b = synth.mixed_paths(512, 8, seed=31), synth.mixed_paths(512, 8, seed=32)
+    ref_a, ref_b = eng.profile(eng.upload(a)), eng.profile(eng.upload(b))
+    g = eng.capture(eng.upload(a), tiles=4)
+    for ref, new in ((ref_a, None), (ref_b, eng.upload(b)), (ref_a, eng.upload(a))):
+        got = g.run(new)
+        torch.cuda.synchronize()
+        assert torch.equal(ref.n_out, got.n_out) and torch.equal(ref.status, got.status)
+        n = ref.n_out.long()
+        Tm = min(ref.T_cap, got.T_cap)
+        mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+        for i in range(8):
+            assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64))

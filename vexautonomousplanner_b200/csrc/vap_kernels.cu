@@ -1204,9 +1204,10 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
                                 const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
                                 int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary,
                                 int32_t* n_main, double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch,
-                                void* stream)
+                                int64_t out_plane_stride, void* stream)
 {
     (void)ap_flags;
+    const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_time_profile: B > 65535 per call (tile the batch)");
     if (E_cap < N_max + A_max + 2) return arg_err("vap_time_profile: E_cap < N_max + A_max + 2");
@@ -1249,11 +1250,11 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     k_time_events<<<blocks_for(B, lanes), lanes, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, n_ap, cons,
                                                        status, dt, seg, first_node, param_end, n_splines, spn, P_cap,
                                                        prop_h, total_len, M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc,
-                                                       ev_napc, E_cap, seg_k, seg_off, seg_rev, n_seg, T_cap, out,
-                                                       nodes_map, actions_map, n_maps, n_out, summary);
+                                                       ev_napc, E_cap, seg_k, seg_off, seg_rev, n_seg, T_cap, oplane,
+                                                       out, nodes_map, actions_map, n_maps, n_out, summary);
     CHECK_LAUNCH("vap_time_profile/events");
     k_time_finalize<<<grid, 256, 0, STREAM>>>(B, status, M_cap, n_main, stage, E_cap, seg_k, seg_off, seg_rev, n_seg,
-                                              T_cap, out, summary);
+                                              T_cap, oplane, out, summary);
     CHECK_LAUNCH("vap_time_profile/finalize");
     return 0;
 }

@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(32) k_time_events(
     long long M_cap, const int* __restrict__ n_main, const double* __restrict__ stage, int* __restrict__ ev_wrap,
     const int* __restrict__ ev_nwrap, const int* __restrict__ ev_apc, const int* __restrict__ ev_napc, int E_cap,
     int* __restrict__ seg_k, int* __restrict__ seg_off, int* __restrict__ seg_rev, int* __restrict__ n_seg,
-    long long T_cap, double* __restrict__ out, int* __restrict__ nodes_map, int* __restrict__ actions_map,
-    int* __restrict__ n_maps, int* __restrict__ n_out, double* __restrict__ summary)
+    long long T_cap, long long oplane, double* __restrict__ out, int* __restrict__ nodes_map,
+    int* __restrict__ actions_map, int* __restrict__ n_maps, int* __restrict__ n_out, double* __restrict__ summary)
 {
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -302,7 +302,6 @@ __global__ void __launch_bounds__(32) k_time_events(
         const int* nf = node_flags + (size_t)b * N_max;
         const double* apa = ap_attr + (size_t)b * A_max * APA;
         const double V = cons[b * 6 + 0], max_acc = cons[b * 6 + 1], w = cons[b * 6 + 5];
-        const size_t oplane = (size_t)B * T_cap;
         double* o_tm = out + (size_t)b * T_cap;
         double* o_pos = o_tm + oplane; double* o_lin = o_pos + oplane; double* o_acc = o_lin + oplane;
         double* o_head = o_acc + oplane; double* o_ang = o_head + oplane; double* o_x = o_ang + oplane;
@@ -458,7 +457,8 @@ __global__ void __launch_bounds__(256) k_time_finalize(long long B, const int* _
                                                        int E_cap, const int* __restrict__ seg_k,
                                                        const int* __restrict__ seg_off, const int* __restrict__ seg_rev,
                                                        const int* __restrict__ n_seg, long long T_cap,
-                                                       double* __restrict__ out, double* __restrict__ summary)
+                                                       long long oplane, double* __restrict__ out,
+                                                       double* __restrict__ summary)
 {
     __shared__ double s_max[8];
     long long b = blockIdx.y;
@@ -480,7 +480,6 @@ __global__ void __launch_bounds__(256) k_time_finalize(long long B, const int* _
         double v = stage[TS_VEL * plane + row + k];
         vabs = v;
         if (r < T_cap) {
-            const size_t oplane = (size_t)B * T_cap;
             double* o = out + (size_t)b * T_cap + r;
             double sgn = rev ? -1.0 : 1.0;
             o[1 * oplane] = stage[TS_POS * plane + row + k + 1];

@@ -384,13 +384,13 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
         int j = jn0;
         int nb_next = (j < n_b) ? bi[j] : 2147483647;
         double4 r = F[lo];
+        double4 r1 = (lo + 1 < hi) ? F[lo + 1] : r;
         for (long long i = lo; i < hi; i++) {
-            double4 rn = (i + 1 < hi) ? F[i + 1] : r;          // next record into registers
-            if (i + PF_DIST < hi) prefetch_l1v(F + i + PF_DIST);   // and the line three ahead into L1
+            double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;          // records run two steps ahead of their use
             if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
             v = fwd_step(r, v, wp, acc, w, dd);
             vf[i + 1] = v;
-            r = rn;
+            r = r1; r1 = r2;
         }
         end_v = v; end_w = wp;
     }
@@ -410,17 +410,19 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
             int nb_next = (j < n_b) ? bi[j] : 2147483647;
             bool merged = false;
             double4 r = F[lo];
+            double4 r1 = (lo + 1 < hi) ? F[lo + 1] : r;
+            double old = vf[lo + 1];
+            double old1 = (lo + 1 < hi) ? vf[lo + 2] : 0.0;
             for (long long i = lo; i < hi; i++) {
-                double4 rn = (i + 1 < hi) ? F[i + 1] : r;
-                if (i + PF_DIST < hi) { prefetch_l1v(F + i + PF_DIST); prefetch_l1v(vf + i + 2 * PF_DIST); }
+                double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;            // loads run two steps ahead of their use
+                double old2 = (i + 2 < hi) ? vf[i + 3] : 0.0;
                 if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
                 v = fwd_step(r, v, wp, acc, w, dd);
-                double old = vf[i + 1];
                 bool same = same_bits(old, v);
                 if (same && prev_same) { merged = true; break; }   // state (v[i+1], v[i]*|k_i|) equals the old run's
                 vf[i + 1] = v;
                 prev_same = same;
-                r = rn;
+                r = r1; r1 = r2; old = old1; old1 = old2;
             }
             if (!merged) { end_v = v; end_w = wp; }
         }
@@ -491,14 +493,15 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
         int nb_next = (j >= 0) ? bi[j] : -1;
         double4 r = R[hi];
         double vfp = vf[hi - 1];
+        double4 r1 = (hi - 1 > lo) ? R[hi - 1] : r;
+        double vf1 = (hi - 1 > lo) ? vf[hi - 2] : 0.0;
         for (long long i = hi; i > lo; i--) {
-            double4 rn = (i - 1 > lo) ? R[i - 1] : r;
-            double vfn = (i - 1 > lo) ? vf[i - 2] : 0.0;
-            if (i - 2 * PF_DIST > lo) { prefetch_l1v(R + i - PF_DIST); prefetch_l1v(vf + i - 2 * PF_DIST); }
+            double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;          // loads run two steps ahead of their use
+            double vf2 = (i - 2 > lo) ? vf[i - 3] : 0.0;
             if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
             v = bwd_step(r, v, wp, acc, w, dd, vfp);
             vo[i - 1] = v;
-            r = rn; vfp = vfn;
+            r = r1; vfp = vf1; r1 = r2; vf1 = vf2;
         }
         end_v = v; end_w = wp;
     }
@@ -519,18 +522,21 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
             bool merged = false;
             double4 r = R[hi];
             double vfp = vf[hi - 1];
+            double old = vo[hi - 1];
+            double4 r1 = (hi - 1 > lo) ? R[hi - 1] : r;
+            double vf1 = (hi - 1 > lo) ? vf[hi - 2] : 0.0;
+            double old1 = (hi - 1 > lo) ? vo[hi - 2] : 0.0;
             for (long long i = hi; i > lo; i--) {
-                double4 rn = (i - 1 > lo) ? R[i - 1] : r;
-                double vfn = (i - 1 > lo) ? vf[i - 2] : 0.0;
-                if (i - 2 * PF_DIST > lo) { prefetch_l1v(R + i - PF_DIST); prefetch_l1v(vf + i - 2 * PF_DIST); prefetch_l1v(vo + i - 2 * PF_DIST); }
+                double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;            // loads run two steps ahead of their use
+                double vf2 = (i - 2 > lo) ? vf[i - 3] : 0.0;
+                double old2 = (i - 2 > lo) ? vo[i - 3] : 0.0;
                 if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
                 v = bwd_step(r, v, wp, acc, w, dd, vfp);
-                double old = vo[i - 1];
                 bool same = same_bits(old, v);
                 if (same && prev_same) { merged = true; break; }
                 vo[i - 1] = v;
                 prev_same = same;
-                r = rn; vfp = vfn;
+                r = r1; vfp = vf1; old = old1; r1 = r2; vf1 = vf2; old1 = old2;
             }
             if (!merged) { end_v = v; end_w = wp; }
         }

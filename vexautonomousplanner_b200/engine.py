@@ -139,6 +139,7 @@ class Engine:
         self.time_impl = time_impl
         self._dgrid: Optional[torch.Tensor] = None
         self._plan: Dict[tuple, tuple] = {}
+        self._streams: list = []
         self.launches = 0      # kernels launched by this engine (bench.py reports it)
         self.stage_events = None   # set to a list to record (stage, start_event, end_event) per stage call
 
@@ -252,14 +253,15 @@ class Engine:
         self.launches += 1
         return vel, ma, bidx, bval, n_ev, t_est
 
-    def velocity_chunked(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0):
+    def velocity_chunked(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0,
+                         outs: Optional[dict] = None):
         """S3 + events + S4 + S5, fast path: sample-parallel events, hoisted pre-pass, chunk-speculative passes."""
         B = db.B
         if B > 65535:
             raise _lib.VapError("tile the batch: at most 65535 paths per profile() call")
         E_cap = db.N_max + db.A_max + 2
         grid = self.dgrid(D_cap + 2)
-        n_samples = self._empty((B,), torch.int32)
+        n_samples = outs["n_samples"] if outs else self._empty((B,), torch.int32)
         tq, kap, th = self._empty((B, D_cap)), self._empty((B, D_cap)), self._empty((B, D_cap))
         ma = self._empty((B, E_cap)); bidx = self._empty((B, E_cap), torch.int32); bval = self._empty((B, E_cap), torch.int32)
         n_ev = self._empty((B, 2), torch.int32)
@@ -278,11 +280,11 @@ class Engine:
                 _p(vr_val), _p(st_idx), _p(n_vr), C.c_double(self.dt), _p(ins_est), _p(scr), self._stream()),
                 "vap_dist_sample_events")
             self.launches += 3
+        chunks = self.chunks if D_cap <= 65536 else 256
         recF = self._empty((B, D_cap, 4)); recR = self._empty((B, D_cap, 4))
-        vel_f = self._empty((B, D_cap)); vel = self._empty((B, D_cap))
+        vel_f = self._empty((B, D_cap)); vel = outs["vel"] if outs else self._empty((B, D_cap))
         t_est = self._empty((B,), torch.float32)
         rounds = torch.zeros((B, 2), dtype=torch.int32, device=self.device)
-        chunks = self.chunks if D_cap <= 65536 else 256
         with self._stage("S45_fwd_bwd"):
             _lib.check(self.lib.vap_fwd_bwd_chunked(
                 C.c_int64(B), _p(db.cons), _p(status), C.c_double(self.dd), C.c_double(self.dt), C.c_double(self.start_vel),
@@ -332,19 +334,26 @@ class Engine:
         turn_rows = torch.where(na[:, :, 2] != 0, ((2 * V / A + arc / V) / self.dt).ceil() + 3, torch.zeros_like(arc)).sum(dim=1)
         return int((waits + turn_rows).max().item())
 
-    def time_profile(self, db: DeviceBatch, g: Geometry, t: Tables, status, D_cap, n_samples, vel, T_cap):
+    def time_profile(self, db: DeviceBatch, g: Geometry, t: Tables, status, D_cap, n_samples, vel, T_cap,
+                     outs: Optional[dict] = None):
         """S6 + S7, fast path (vap_time_profile): state recurrence / parallel lookups / event replay / scatter."""
         B = db.B
         if B > 65535:
             raise _lib.VapError("tile the batch: at most 65535 paths per profile() call")
         E_cap = db.N_max + db.A_max + 2
-        out = self._empty((8, B, T_cap))
-        nodes_map = self._empty((B, db.N_max + 1), torch.int32)
-        actions_map = self._empty((B, max(db.A_max, 1)), torch.int32)
-        n_maps = self._empty((B, 2), torch.int32)
-        n_out = self._empty((B,), torch.int32)
-        summary = self._empty((B, 5))
-        n_main = self._empty((B,), torch.int32)
+        plane_stride = 0
+        if outs:
+            out, nodes_map, actions_map = outs["out"], outs["nodes_map"], outs["actions_map"]
+            n_maps, n_out, summary, n_main = outs["n_maps"], outs["n_out"], outs["summary"], outs["n_main"]
+            plane_stride = outs["plane_stride"]
+        else:
+            out = self._empty((8, B, T_cap))
+            nodes_map = self._empty((B, db.N_max + 1), torch.int32)
+            actions_map = self._empty((B, max(db.A_max, 1)), torch.int32)
+            n_maps = self._empty((B, 2), torch.int32)
+            n_out = self._empty((B,), torch.int32)
+            summary = self._empty((B, 5))
+            n_main = self._empty((B,), torch.int32)
         stage = self._empty((8, B, T_cap + 1))
         seg_tab = self._empty((3 * B * E_cap + B,), torch.int32)
         nscr = int(self.lib.vap_event_scratch_ints(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max)))
@@ -355,14 +364,65 @@ class Engine:
             _p(g.seg), _p(g.first_node), _p(g.param_end), _p(g.n_splines), C.c_int(t.samples), C.c_int64(t.Q_cap),
             _p(t.lut_d), _p(t.lut_t), _p(t.total_len), C.c_int(t.spn), C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h),
             C.c_int64(D_cap), _p(n_samples), _p(vel), C.c_int64(T_cap), _p(out), _p(nodes_map), _p(actions_map), _p(n_maps),
-            _p(n_out), _p(summary), _p(n_main), _p(stage), C.c_int(E_cap), _p(seg_tab), _p(scr), self._stream()),
-            "vap_time_profile")
+            _p(n_out), _p(summary), _p(n_main), _p(stage), C.c_int(E_cap), _p(seg_tab), _p(scr), C.c_int64(plane_stride),
+            self._stream()), "vap_time_profile")
         self.launches += 4
         self._n_main = n_main
         return out, nodes_map, actions_map, n_maps, n_out, summary
 
+    # ------------------------------------------------------------------ tiled, multi-stream execution
+    def _profile_tiled(self, db: DeviceBatch, D_cap: int, T_cap: int, tiles: int) -> ProfileResult:
+        """The fast path over `tiles` row slices of the batch, each on its own CUDA stream.
+
+        The serial chains (time loop, chunked velocity passes) are latency-bound and leave most issue slots idle,
+        while the table / sampling / pre-pass kernels are throughput-bound; running tiles on separate streams lets the
+        block scheduler co-schedule one tile's chains with another tile's sample-parallel kernels.  Tiles write straight
+        into their rows of the batch-wide outputs (out_plane_stride).  Capacities come from the cached plan.
+        """
+        B = db.B
+        main = torch.cuda.current_stream(self.device)
+        out = self._empty((8, B, T_cap))
+        whole = dict(nodes_map=self._empty((B, db.N_max + 1), torch.int32),
+                     actions_map=self._empty((B, max(db.A_max, 1)), torch.int32), n_maps=self._empty((B, 2), torch.int32),
+                     n_out=self._empty((B,), torch.int32), summary=self._empty((B, 5)), n_main=self._empty((B,), torch.int32),
+                     n_samples=self._empty((B,), torch.int32), vel=self._empty((B, D_cap)),
+                     status=self._empty((B,), torch.int32), status_pre=self._empty((B,), torch.int32))
+        self.dgrid(D_cap + 2)                      # make sure the shared grid exists before the side streams read it
+        while len(self._streams) < tiles:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        bounds = [(B * k // tiles, B * (k + 1) // tiles) for k in range(tiles)]
+        for k, (lo, hi) in enumerate(bounds):
+            if hi <= lo:
+                continue
+            s = self._streams[k]
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                sub = DeviceBatch(db.node_attr[lo:hi], db.node_flags[lo:hi], db.n_nodes[lo:hi], db.ap_attr[lo:hi],
+                                  db.ap_flags[lo:hi], db.n_ap[lo:hi], db.cons[lo:hi], db.max_splines)
+                outs = {key: val[lo:hi] for key, val in whole.items()}
+                outs["out"] = out[:, lo:hi]          # only its data_ptr() is used: rows lo.. of plane 0
+                outs["plane_stride"] = B * T_cap
+                g = self.build_geometry(sub)
+                t = self.build_lut(sub, g)
+                self.build_props(sub, g, t)
+                outs["status"].copy_(g.status)
+                n_samples, vel, _, _ = self.velocity_chunked(sub, g, t, outs["status"], D_cap, outs=outs)
+                outs["status_pre"].copy_(outs["status"])
+                self.time_profile(sub, g, t, outs["status"], D_cap, n_samples, vel, T_cap, outs=outs)
+        for k in range(tiles):
+            main.wait_stream(self._streams[k])
+        self._n_main = whole["n_main"]
+        res = ProfileResult(B, T_cap, out, whole["n_out"], whole["nodes_map"], whole["actions_map"], whole["n_maps"],
+                            whole["status"], whole["summary"], whole["vel"], whole["n_samples"])
+        res.extra = dict(status_pre=whole["status_pre"])
+        return res
+
+    def capture(self, db: DeviceBatch, tiles: int = 4) -> "GraphedProfile":
+        """Capture the tiled fast path for this batch shape into a CUDA graph (one launch per step afterwards)."""
+        return GraphedProfile(self, db, tiles)
+
     # ------------------------------------------------------------------ whole path
-    def profile(self, db: DeviceBatch, keep: bool = False, reuse_plan: bool = False) -> ProfileResult:
+    def profile(self, db: DeviceBatch, keep: bool = False, reuse_plan: bool = False, tiles: int = 1) -> ProfileResult:
         """build_path + generate_motion_profile for every path of the batch.
 
         keep: also return geometry / tables / distance-domain intermediates.
@@ -371,6 +431,14 @@ class Engine:
         """
         B = db.B
         key = (B, db.N_max, db.A_max, db.max_splines)
+        if (tiles > 1 and reuse_plan and not keep and key in self._plan and self.stage_events is None
+                and self.velocity_impl == "chunked" and self.time_impl == "split"):
+            D_cap, T_cap = self._plan[key]
+            res = self._profile_tiled(db, D_cap, T_cap, min(tiles, B))
+            if bool((res.status == ST_CAPACITY).any().item()):     # undersized plan: redo exactly, untiled
+                self._plan.pop(key, None)
+                return self.profile(db, keep=keep, reuse_plan=False)
+            return res
         with self._stage("S0_build_path"):
             g = self.build_geometry(db)
         with self._stage("S1_lut"):
@@ -415,3 +483,38 @@ class Engine:
             res.geometry, res.tables = g, t
             res.extra = dict(extra, t_est=t_est)
         return res
+
+
+class GraphedProfile:
+    """The whole hot path for one batch shape as a CUDA graph: every kernel of every tile, forked over the engine's
+    streams and joined again, replayed with a single launch.  The serial chains are latency-bound, so what limits a
+    small batch is how quickly independent tiles can be put in flight; a graph removes the per-launch host cost.
+
+    Inputs live in static device tensors (`self.db`); `run(new_batch)` copies a new batch of the same shape into them.
+    An undersized plan is detected after the replay and the step is redone exactly through Engine.profile.
+    """
+
+    def __init__(self, eng: Engine, db: DeviceBatch, tiles: int = 4):
+        if eng.velocity_impl != "chunked" or eng.time_impl != "split":
+            raise ValueError("graph capture needs the fast path (velocity_impl='chunked', time_impl='split')")
+        self.eng, self.db, self.tiles = eng, db, max(1, min(tiles, db.B))
+        key = (db.B, db.N_max, db.A_max, db.max_splines)
+        warm = eng.profile(db, reuse_plan=True)                # sizes the plan, builds the distance grid
+        self.D_cap, self.T_cap = eng._plan[key]
+        eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles)   # warm the per-stream allocator pools
+        torch.cuda.synchronize(eng.device)
+        del warm
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.res = eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles)
+        self.launches_per_run = 13 * self.tiles
+
+    def run(self, new_db: Optional[DeviceBatch] = None, check: bool = True) -> ProfileResult:
+        if new_db is not None:
+            for name in ("node_attr", "node_flags", "n_nodes", "ap_attr", "ap_flags", "n_ap", "cons"):
+                getattr(self.db, name).copy_(getattr(new_db, name), non_blocking=True)
+        self.graph.replay()
+        self.eng.launches += self.launches_per_run
+        if check and bool((self.res.status == ST_CAPACITY).any().item()):
+            return self.eng.profile(self.db, reuse_plan=False)
+        return self.res
