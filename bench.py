@@ -221,44 +221,40 @@ def run_b200(args):
                                "frac": total_bytes / 1e9 / (ms_per_step * 1e-3) / peak},
                 "stages": stages}
 
-    # ---------------- end to end through the public API with HOST buffers (h2d + d2h inside the timed region)
-    host_in = [torch.from_numpy(a).pin_memory() for a in
-               (packed.node_attr, packed.node_flags, packed.n_nodes, packed.ap_attr, packed.ap_flags, packed.n_ap,
-                packed.cons)]
-    from vexautonomousplanner_b200.engine import DeviceBatch
-    msp = packed.max_splines()
-    host_out = None
+    # ---------------- end to end through the public API with HOST buffers (h2d + d2h inside the timed region):
+    # numpy node tables on the host -> Engine -> every output stream of every path back in (pinned) host memory
+    g2h = eng.capture(eng.upload(packed), tiles=args.e2e_tiles, to_host=True) if args.e2e_mode == "graph" else None
+    hstate = None
     e2e_ms = []
-    h2d = sum(t.numel() * t.element_size() for t in host_in)
-    d2h = 0
     for it in range(3 + args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        dbi = DeviceBatch(*[t.to(dev, non_blocking=True) for t in host_in], msp)
-        r = eng.profile(dbi, reuse_plan=True, tiles=args.tiles)
-        if host_out is None or host_out[0].shape != r.out.shape:
-            host_out = [torch.empty(r.out.shape, dtype=r.out.dtype).pin_memory(),
-                        torch.empty(r.n_out.shape, dtype=r.n_out.dtype).pin_memory(),
-                        torch.empty(r.summary.shape, dtype=r.summary.dtype).pin_memory(),
-                        torch.empty(r.nodes_map.shape, dtype=r.nodes_map.dtype).pin_memory()]
-        host_out[0].copy_(r.out, non_blocking=True)
-        host_out[1].copy_(r.n_out, non_blocking=True)
-        host_out[2].copy_(r.summary, non_blocking=True)
-        host_out[3].copy_(r.nodes_map, non_blocking=True)
-        torch.cuda.synchronize()
+        if g2h is not None:
+            hres = g2h.run_host(packed)
+        else:
+            hres = eng.profile_to_host(packed, tiles=args.e2e_tiles, state=hstate)
+            hstate = hres.state
         el = (time.perf_counter() - t0) * 1e3
         if it >= 3:
             e2e_ms.append(el)
-        d2h = sum(t.numel() * t.element_size() for t in host_out)
+    assert int(hres.n_out.sum()) == int(res.n_out.sum().item())
+    b0 = hres.path(B - 1)
+    assert np.array_equal(b0["x"], res.path(B - 1)["x"])
     tt = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_step_ms = float(tt.item())
+    h2d = sum(a.nbytes for a in (packed.node_attr, packed.node_flags, packed.n_nodes, packed.ap_attr, packed.ap_flags,
+                                 packed.n_ap, packed.cons))
     e2e = {"value": world * B / (e2e_step_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_step_ms}
+           "d2h_bytes_per_step": hres.bytes_per_step(), "ms_per_step": e2e_step_ms,
+           "how": (f"host numpy node tables -> pinned -> device, {args.e2e_tiles} tiles on separate streams, dense result "
+                   "rows " + ("written to pinned host memory by the pack kernels inside one CUDA graph"
+                              if g2h is not None else "packed on the device and moved by the copy engine tile by tile")
+                   + ", wall clock incl. the final sync")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -295,7 +291,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-sample", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--tiles", type=int, default=4, help="row tiles of the batch, one CUDA stream each")
+    ap.add_argument("--tiles", type=int, default=1, help="row tiles of the batch, one CUDA stream each")
+    ap.add_argument("--e2e-mode", default="copy", choices=["copy", "graph"])
+    ap.add_argument("--e2e-tiles", type=int, default=4, help="tiles of the end-to-end (host in / host out) run")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -212,6 +212,13 @@ int vap_lerp(int64_t n, const double* x, int64_t m, const double* xs, const doub
 int vap_wheel_trajectory(int64_t n, const double* lin, const double* ang, double track_width, double* left,
                          double* right, void* stream);
 
+/* Dense packing of the result rows: offsets[B+1] (i64) = exclusive prefix sum of min(n_out, T_cap) over the ok paths,
+ * dst[8*offsets[b] + s*n_b + k] = out[s][b][k] for the eight planes s.  `dst` may be pinned (mapped) HOST memory: the
+ * kernel then streams exactly the valid rows over PCIe, which is how the Python layer returns results to the host
+ * (the reference hands back Python lists, motion_profile_generator.py:618-628).                                  */
+int vap_pack_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const double* out, const int32_t* n_out,
+                  const int32_t* status, int64_t* offsets, double* dst, void* stream);
+
 /* Test hook: counts (into the device word *bad) the pseudo-random numerators a, out of n, for which the hoisted-
  * reciprocal division used inside the time loop differs from the IEEE quotient a / b.  Must stay 0.            */
 int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* bad, void* stream);

@@ -350,3 +350,30 @@ def test_cuda_graph_replay_equals_eager():
         mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
         for i in range(8):
             assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64))
+
+
+def test_host_in_host_out_packing():
+    """run_host: numpy in, pinned host buffers out (dense rows written by the pack kernels) == device results."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    packed = synth.mixed_paths(400, 8, seed=41)
+    packed.node_attr[7, 0, 2] = 30.0            # one failing path (turn at node 0): packs to zero rows
+    ref = eng.profile(eng.upload(packed))
+    g = eng.capture(eng.upload(packed), tiles=3, to_host=True)
+    state = None
+    for it in range(4):
+        if it < 2:
+            h = g.run_host(packed)                              # pack kernels write pinned host memory (CUDA graph)
+        else:
+            h = eng.profile_to_host(packed, tiles=5, state=state)   # dense device rows + copy engine
+            state = h.state
+        assert h.status.tolist() == ref.status.cpu().tolist()
+        assert h.n_out.tolist() == ref.n_out.cpu().tolist()
+        for b in (0, 7, 133, 134, 266, 399):
+            got, want = h.path(b), ref.path(b)
+            for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y"):
+                assert np.array_equal(got[k], want[k]), (b, k)
+            assert got["nodes_map"].tolist() == want["nodes_map"].tolist()
+        assert np.array_equal(h.summary.numpy(), ref.summary.cpu().numpy())
+        assert h.bytes_per_step() < 8 * 8 * 400 * g.T_cap

@@ -1267,3 +1267,20 @@ extern "C" int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* 
     CHECK_LAUNCH("vap_test_div_const");
     return 0;
 }
+
+// dense per-path packing of the output planes (optionally straight into pinned host memory)
+extern "C" int vap_pack_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const double* out, const int32_t* n_out,
+                             const int32_t* status, int64_t* offsets, double* dst, void* stream)
+{
+    if (B <= 0) return 0;
+    if (B > 65535) return arg_err("vap_pack_rows: B > 65535 per call (tile the batch)");
+    const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
+    k_row_offsets<<<1, 1024, 0, STREAM>>>(B, n_out, status, T_cap, reinterpret_cast<long long*>(offsets));
+    CHECK_LAUNCH("vap_pack_rows/offsets");
+    int ctas = 16;
+    if (const char* ev = getenv("VAP_PACK_CTAS")) ctas = atoi(ev);
+    if (ctas < 1) ctas = 1;
+    k_pack_rows<<<ctas, 256, 0, STREAM>>>(B, n_out, status, T_cap, oplane, out, reinterpret_cast<const long long*>(offsets), dst);
+    CHECK_LAUNCH("vap_pack_rows");
+    return 0;
+}

@@ -501,3 +501,61 @@ __global__ void __launch_bounds__(256) k_time_finalize(long long B, const int* _
         atomicMax(reinterpret_cast<unsigned long long*>(summary + (size_t)b * 5 + 3), (unsigned long long)__double_as_longlong(m));
     }
 }
+
+
+// ---- output packing -----------------------------------------------------------------------------------------------
+// Exclusive prefix sum of the row counts (one CTA): offsets[b] = sum_{b' < b} n_out[b'], offsets[B] = total.
+__global__ void __launch_bounds__(1024) k_row_offsets(long long B, const int* __restrict__ n_out,
+                                                      const int* __restrict__ status, long long T_cap,
+                                                      long long* __restrict__ offsets)
+{
+    __shared__ long long s_part[1024];
+    const int t = threadIdx.x, NT = blockDim.x;
+    const long long per = (B + NT - 1) / NT;
+    const long long lo = (long long)t * per, hi = (lo + per < B) ? lo + per : B;
+    long long sum = 0;
+    for (long long b = lo; b < hi; b++) {
+        long long n = (status[b] == ST_OK) ? n_out[b] : 0;
+        sum += (n < T_cap) ? n : T_cap;
+    }
+    s_part[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        long long acc = 0;
+        for (int k = 0; k < NT; k++) { long long v = s_part[k]; s_part[k] = acc; acc += v; }
+        offsets[B] = acc;
+    }
+    __syncthreads();
+    long long acc = s_part[t];
+    for (long long b = lo; b < hi; b++) {
+        offsets[b] = acc;
+        long long n = (status[b] == ST_OK) ? n_out[b] : 0;
+        acc += (n < T_cap) ? n : T_cap;
+    }
+}
+
+// Gather the valid part of every row of the eight output planes into one dense block per path:
+// dst[8 * offsets[b] + s * n_b + k] = out[s][b][k].  dst may be pinned host memory (the kernel then streams the
+// result over PCIe itself, with no padding and no size known to the host in advance).
+__global__ void __launch_bounds__(256) k_pack_rows(long long B, const int* __restrict__ n_out,
+                                                   const int* __restrict__ status, long long T_cap, long long oplane,
+                                                   const double* __restrict__ out,
+                                                   const long long* __restrict__ offsets, double* __restrict__ dst)
+{
+    // Persistent, deliberately small grid: a handful of CTAs saturates PCIe, and the other tiles' kernels keep the SMs.
+    // Work item = (path, 256-row block); items are dealt round-robin to the CTAs.
+    const long long blocks_per_row = (T_cap + blockDim.x - 1) / blockDim.x;
+    const long long items = B * blocks_per_row;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        long long b = it / blocks_per_row;
+        if (status[b] != ST_OK) continue;
+        long long n = n_out[b];
+        if (n > T_cap) n = T_cap;
+        long long k = (it - b * blocks_per_row) * blockDim.x + threadIdx.x;
+        if (k >= n) continue;
+        const double* src = out + (size_t)b * T_cap + k;
+        double* d = dst + 8 * offsets[b] + k;
+#pragma unroll
+        for (int s = 0; s < 8; s++) d[(size_t)s * n] = src[(size_t)s * oplane];
+    }
+}

@@ -254,7 +254,7 @@ class Engine:
         return vel, ma, bidx, bval, n_ev, t_est
 
     def velocity_chunked(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0,
-                         outs: Optional[dict] = None):
+                         outs: Optional[dict] = None, after_sample=None):
         """S3 + events + S4 + S5, fast path: sample-parallel events, hoisted pre-pass, chunk-speculative passes."""
         B = db.B
         if B > 65535:
@@ -371,7 +371,9 @@ class Engine:
         return out, nodes_map, actions_map, n_maps, n_out, summary
 
     # ------------------------------------------------------------------ tiled, multi-stream execution
-    def _profile_tiled(self, db: DeviceBatch, D_cap: int, T_cap: int, tiles: int) -> ProfileResult:
+    def _profile_tiled(self, db: DeviceBatch, D_cap: int, T_cap: int, tiles: int, host: "Optional[HostResult]" = None,
+                       dense: Optional[torch.Tensor] = None, events: Optional[list] = None,
+                       stagger: bool = False) -> ProfileResult:
         """The fast path over `tiles` row slices of the batch, each on its own CUDA stream.
 
         The serial chains (time loop, chunked velocity passes) are latency-bound and leave most issue slots idle,
@@ -389,13 +391,22 @@ class Engine:
                      status=self._empty((B,), torch.int32), status_pre=self._empty((B,), torch.int32))
         self.dgrid(D_cap + 2)                      # make sure the shared grid exists before the side streams read it
         while len(self._streams) < tiles:
-            self._streams.append(torch.cuda.Stream(device=self.device))
+            # earlier tiles get higher stream priority, so that they finish (and start streaming their rows to the host)
+            # while later tiles still compute, instead of all tiles finishing together
+            k = len(self._streams)
+            self._streams.append(torch.cuda.Stream(device=self.device, priority=max(-5, -(5 - min(k, 5)))))
         bounds = [(B * k // tiles, B * (k + 1) // tiles) for k in range(tiles)]
+        sampled = None          # event: the previous tile's sample-parallel front (S0-S3) has been issued and finished
         for k, (lo, hi) in enumerate(bounds):
             if hi <= lo:
                 continue
             s = self._streams[k]
             s.wait_stream(main)
+            if sampled is not None and stagger:
+                # software pipeline: the throughput-bound front of tile k runs while the latency-bound chains of the
+                # earlier tiles are in flight; early tiles finish (and stream their rows to the host) first
+                s.wait_event(sampled)
+            sampled = torch.cuda.Event()
             with torch.cuda.stream(s):
                 sub = DeviceBatch(db.node_attr[lo:hi], db.node_flags[lo:hi], db.n_nodes[lo:hi], db.ap_attr[lo:hi],
                                   db.ap_flags[lo:hi], db.n_ap[lo:hi], db.cons[lo:hi], db.max_splines)
@@ -406,9 +417,28 @@ class Engine:
                 t = self.build_lut(sub, g)
                 self.build_props(sub, g, t)
                 outs["status"].copy_(g.status)
-                n_samples, vel, _, _ = self.velocity_chunked(sub, g, t, outs["status"], D_cap, outs=outs)
+                ev = sampled
+                n_samples, vel, _, _ = self.velocity_chunked(sub, g, t, outs["status"], D_cap, outs=outs,
+                                                             after_sample=lambda: ev.record(s))
                 outs["status_pre"].copy_(outs["status"])
                 self.time_profile(sub, g, t, outs["status"], D_cap, n_samples, vel, T_cap, outs=outs)
+                if host is not None:
+                    # dense rows straight into pinned host memory (the kernel streams them over PCIe), then the small
+                    # per-path arrays with ordinary async copies; all of it overlaps the other tiles' kernels
+                    offs = host.dev_offsets[lo + k: hi + k + 1]
+                    # dst: pinned host memory (the kernel streams over PCIe itself) or a dense device buffer that the
+                    # copy engine moves afterwards, once the host knows the tile's row count
+                    base = host.packed if dense is None else dense
+                    dst = C.c_void_p(base.data_ptr() + 8 * 8 * lo * T_cap)
+                    _lib.check(self.lib.vap_pack_rows(C.c_int64(hi - lo), C.c_int64(T_cap), C.c_int64(B * T_cap),
+                                                      _p(outs["out"]), _p(outs["n_out"]), _p(outs["status"]), _p(offs), dst,
+                                                      self._stream()), "vap_pack_rows")
+                    self.launches += 2
+                    host.offsets[lo + k: hi + k + 1].copy_(offs, non_blocking=True)
+                    for name in ("n_out", "status", "nodes_map", "actions_map", "n_maps", "summary"):
+                        getattr(host, name)[lo:hi].copy_(outs[name], non_blocking=True)
+                    if events is not None:
+                        events[k].record(s)
         for k in range(tiles):
             main.wait_stream(self._streams[k])
         self._n_main = whole["n_main"]
@@ -417,9 +447,54 @@ class Engine:
         res.extra = dict(status_pre=whole["status_pre"])
         return res
 
-    def capture(self, db: DeviceBatch, tiles: int = 4) -> "GraphedProfile":
-        """Capture the tiled fast path for this batch shape into a CUDA graph (one launch per step afterwards)."""
-        return GraphedProfile(self, db, tiles)
+    def profile_to_host(self, packed: PackedPaths, tiles: int = 8, state: Optional[dict] = None) -> "HostResult":
+        """Host buffers in, host buffers out, copy-engine variant: every tile packs its valid rows densely on the device;
+        as soon as a tile's row count has reached the host, the copy engine moves exactly those bytes into pinned memory
+        while later tiles are still computing.  `state` (returned in HostResult.state) carries the reusable buffers."""
+        B = packed.B
+        st = state or {}
+        key = (B, packed.N_max, packed.A_max, packed.max_splines())
+        if st.get("key") != key:
+            db = self.upload(packed)
+            self.profile(db, reuse_plan=True)                       # plan (D_cap, T_cap) for this shape
+            D_cap, T_cap = self._plan[(B, db.N_max, db.A_max, db.max_splines)]
+            tiles = max(1, min(tiles, B))
+            st = dict(key=key, db=db, D_cap=D_cap, T_cap=T_cap, tiles=tiles,
+                      host=HostResult(self, B, db.N_max, db.A_max, T_cap, tiles),
+                      dense=self._empty((8 * B * T_cap,)), events=[torch.cuda.Event() for _ in range(tiles)],
+                      copy_stream=torch.cuda.Stream(device=self.device),
+                      pin=[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
+                           (db.node_attr, db.node_flags, db.n_nodes, db.ap_attr, db.ap_flags, db.n_ap, db.cons)])
+        db, host, T_cap = st["db"], st["host"], st["T_cap"]
+        srcs = (packed.node_attr, packed.node_flags, packed.n_nodes, packed.ap_attr, packed.ap_flags, packed.n_ap, packed.cons)
+        dsts = (db.node_attr, db.node_flags, db.n_nodes, db.ap_attr, db.ap_flags, db.n_ap, db.cons)
+        for pin, src, dst in zip(st["pin"], srcs, dsts):
+            pin.copy_(torch.from_numpy(src))
+            dst.copy_(pin, non_blocking=True)
+        self._profile_tiled(db, st["D_cap"], T_cap, st["tiles"], host=host, dense=st["dense"], events=st["events"],
+                            stagger=True)
+        cs = st["copy_stream"]
+        for k, (lo, hi) in enumerate(host.bounds):
+            if hi <= lo:
+                continue
+            st["events"][k].synchronize()                          # tile k packed; its counts are in pinned memory
+            total = int(host.offsets[hi + k])
+            a = 8 * lo * T_cap
+            with torch.cuda.stream(cs):
+                host.packed[a: a + 8 * total].copy_(st["dense"][a: a + 8 * total], non_blocking=True)
+        cs.synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
+        if bool((host.status == ST_CAPACITY).any()):
+            self._plan.pop((B, db.N_max, db.A_max, db.max_splines), None)
+            st["key"] = None
+            return self.profile_to_host(packed, tiles, st)
+        host.state = st
+        return host
+
+    def capture(self, db: DeviceBatch, tiles: int = 4, to_host: bool = False) -> "GraphedProfile":
+        """Capture the tiled fast path for this batch shape into a CUDA graph (one launch per step afterwards).
+        to_host=True adds the pack kernels that stream the dense result rows into pinned host memory."""
+        return GraphedProfile(self, db, tiles, to_host=to_host)
 
     # ------------------------------------------------------------------ whole path
     def profile(self, db: DeviceBatch, keep: bool = False, reuse_plan: bool = False, tiles: int = 1) -> ProfileResult:
@@ -485,6 +560,48 @@ class Engine:
         return res
 
 
+class HostResult:
+    """Pinned host buffers for one batch shape: results packed densely per path (no padding crosses PCIe).
+
+    packed: for tile k (paths lo..hi) the block starts at element 8*lo*T_cap; inside it path b's eight streams are stored
+    back to back at 8*offsets[b] .. 8*(offsets[b] + n_out[b]) in the order of engine.OUT_NAMES.
+    """
+
+    def __init__(self, eng: "Engine", B: int, N_max: int, A_max: int, T_cap: int, tiles: int):
+        self.B, self.T_cap, self.tiles = B, T_cap, tiles
+        self.bounds = [(B * k // tiles, B * (k + 1) // tiles) for k in range(tiles)]
+        pin = dict(pin_memory=True)
+        self.packed = torch.empty(8 * B * T_cap, dtype=torch.float64, **pin)
+        self.offsets = torch.zeros(B + tiles, dtype=torch.int64, **pin)         # tile k owns offsets[lo+k : hi+k+1]
+        self.dev_offsets = torch.zeros(B + tiles, dtype=torch.int64, device=eng.device)
+        self.n_out = torch.zeros(B, dtype=torch.int32, **pin)
+        self.status = torch.zeros(B, dtype=torch.int32, **pin)
+        self.nodes_map = torch.zeros((B, N_max + 1), dtype=torch.int32, **pin)
+        self.actions_map = torch.zeros((B, max(A_max, 1)), dtype=torch.int32, **pin)
+        self.n_maps = torch.zeros((B, 2), dtype=torch.int32, **pin)
+        self.summary = torch.zeros((B, 5), dtype=torch.float64, **pin)
+
+    def bytes_per_step(self) -> int:
+        """Bytes that crossed PCIe towards the host for the last batch."""
+        rows = int(sum(int(self.offsets[hi + k]) for k, (lo, hi) in enumerate(self.bounds)))
+        small = sum(t.numel() * t.element_size() for t in (self.offsets, self.n_out, self.status, self.nodes_map,
+                                                          self.actions_map, self.n_maps, self.summary))
+        return rows * 8 * 8 + small
+
+    def path(self, b: int) -> Dict[str, np.ndarray]:
+        k = next(i for i, (lo, hi) in enumerate(self.bounds) if lo <= b < hi)
+        lo, _ = self.bounds[k]
+        n = int(self.n_out[b])
+        off = 8 * lo * self.T_cap + 8 * int(self.offsets[b + k])
+        blk = self.packed[off: off + 8 * n].numpy().reshape(8, n)
+        res = {nm: blk[i] for i, nm in enumerate(OUT_NAMES)}
+        nm_, am_ = (int(v) for v in self.n_maps[b])
+        res["nodes_map"] = self.nodes_map[b, :nm_].numpy()
+        res["actions_map"] = self.actions_map[b, :am_].numpy()
+        res["status"] = int(self.status[b])
+        return res
+
+
 class GraphedProfile:
     """The whole hot path for one batch shape as a CUDA graph: every kernel of every tile, forked over the engine's
     streams and joined again, replayed with a single launch.  The serial chains are latency-bound, so what limits a
@@ -494,20 +611,25 @@ class GraphedProfile:
     An undersized plan is detected after the replay and the step is redone exactly through Engine.profile.
     """
 
-    def __init__(self, eng: Engine, db: DeviceBatch, tiles: int = 4):
+    def __init__(self, eng: Engine, db: DeviceBatch, tiles: int = 4, to_host: bool = False):
         if eng.velocity_impl != "chunked" or eng.time_impl != "split":
             raise ValueError("graph capture needs the fast path (velocity_impl='chunked', time_impl='split')")
         self.eng, self.db, self.tiles = eng, db, max(1, min(tiles, db.B))
+        self.host: Optional[HostResult] = None
         key = (db.B, db.N_max, db.A_max, db.max_splines)
         warm = eng.profile(db, reuse_plan=True)                # sizes the plan, builds the distance grid
         self.D_cap, self.T_cap = eng._plan[key]
-        eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles)   # warm the per-stream allocator pools
+        if to_host:
+            self.host = HostResult(eng, db.B, db.N_max, db.A_max, self.T_cap, self.tiles)
+            self.host_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
+                            (db.node_attr, db.node_flags, db.n_nodes, db.ap_attr, db.ap_flags, db.n_ap, db.cons)]
+        eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles, host=self.host)   # warm the per-stream allocator pools
         torch.cuda.synchronize(eng.device)
         del warm
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.res = eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles)
-        self.launches_per_run = 13 * self.tiles
+            self.res = eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles, host=self.host)
+        self.launches_per_run = (13 + (2 if to_host else 0)) * self.tiles
 
     def run(self, new_db: Optional[DeviceBatch] = None, check: bool = True) -> ProfileResult:
         if new_db is not None:
@@ -518,3 +640,24 @@ class GraphedProfile:
         if check and bool((self.res.status == ST_CAPACITY).any().item()):
             return self.eng.profile(self.db, reuse_plan=False)
         return self.res
+
+    def run_host(self, packed: PackedPaths) -> HostResult:
+        """Host buffers in, host buffers out: copy the packed inputs to the device, replay the graph (whose pack kernels
+        stream the dense rows into pinned host memory while other tiles still compute), wait, return the host view."""
+        if self.host is None:
+            raise ValueError("capture(..., to_host=True) first")
+        srcs = (packed.node_attr, packed.node_flags, packed.n_nodes, packed.ap_attr, packed.ap_flags, packed.n_ap, packed.cons)
+        dsts = (self.db.node_attr, self.db.node_flags, self.db.n_nodes, self.db.ap_attr, self.db.ap_flags, self.db.n_ap,
+                self.db.cons)
+        for pin, src, dst in zip(self.host_in, srcs, dsts):
+            pin.copy_(torch.from_numpy(src))
+            dst.copy_(pin, non_blocking=True)
+        self.graph.replay()
+        self.eng.launches += self.launches_per_run
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        if bool((self.host.status == ST_CAPACITY).any()):
+            raise _lib.VapError("capacity plan too small for this batch: re-capture (Engine.capture) with the new batch")
+        return self.host
+
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.host_in)
