@@ -90,11 +90,13 @@ def cpu_port_rate(packed, seconds: float, threads: int):
     oracle.full_batch(packed.node_attr[:n0], packed.node_flags[:n0], packed.cons[:n0], threads=threads)
     r0 = n0 / (time.perf_counter() - t)
     n = int(min(packed.B, max(n0, r0 * seconds)))
+    reps = max(1, int(round(r0 * seconds / n)))          # bounded sample: about `seconds` of CPU work
     t = time.perf_counter()
-    s = oracle.full_batch(packed.node_attr[:n], packed.node_flags[:n], packed.cons[:n], threads=threads)
+    for _ in range(reps):
+        s = oracle.full_batch(packed.node_attr[:n], packed.node_flags[:n], packed.cons[:n], threads=threads)
     el = time.perf_counter() - t
     assert (s[:, 4] == 0).all()
-    return n / el, n, el
+    return n * reps / el, f"{reps} x the first {n}", el
 
 
 def run_reference(args):
@@ -119,8 +121,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.paths} random {args.nodes}-node paths, factory constraints, dt=0.01 dd=0.005",
-                   "sample": f"first {sample} paths per step"},
+        "config": {"workload": f"{args.paths} random {args.nodes}-node paths per GPU, factory constraints, dt=0.01 dd=0.005 "
+                               "(BASELINE.json configs[1])",
+                   "paths_per_gpu": args.paths, "nodes": args.nodes, "sample": f"first {sample} paths per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} paths x {args.steps} steps, C restatement of the reference (oracle/), OpenMP"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -261,7 +264,7 @@ def run_b200(args):
         threads = os.cpu_count() or 1
         rate, n, el = cpu_port_rate(packed, args.cpu_seconds, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {n} of the {B} paths, {el:.1f} s, C restatement of the reference (oracle/) with OpenMP; "
+               "sample": f"{n} of the {B} paths, {el:.1f} s, C restatement of the reference (oracle/) with OpenMP; "
                          "the Python reference itself measured 0.37 paths/s/core on this workload (BASELINE.md)"}
     if rank == 0:
         line = {

@@ -377,3 +377,36 @@ def test_host_in_host_out_packing():
             assert got["nodes_map"].tolist() == want["nodes_map"].tolist()
         assert np.array_equal(h.summary.numpy(), ref.summary.cpu().numpy())
         assert h.bytes_per_step() < 8 * 8 * 400 * g.T_cap
+
+
+def test_cfg4_single_long_path(ora):
+    """BASELINE configs[3]: one very long path (N = 801 nodes, about 10^6 distance samples) -- the case that needs the
+    intra-path chunked passes (256 chunks).  Every stage bit-exact against the oracle fed with the engine's tables."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    packed = synth.long_path(801, seed=2)
+    res = eng.profile(eng.upload(packed), keep=True)
+    torch.cuda.synchronize()
+    assert int(res.status[0]) == 0
+    assert int(res.n_samples[0]) > 900_000
+    got = stagewise_check(ora, packed, res, 0)
+    assert len(got["times"]) > 100_000
+    assert int(res.extra["rounds"].max()) < 256
+
+
+def test_cfg3_tiled_job_summaries(ora):
+    """BASELINE configs[2] in miniature: a job bigger than one call is tiled by profile_many; summaries match the oracle."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    packed = synth.random_paths(700, 16, seed=1)
+    seen = []
+    summ = eng.profile_many(packed, tile_paths=256, sink=lambda lo, hi, r: seen.append((lo, hi, int(r.n_out.sum())))).cpu().numpy()
+    assert [s[:2] for s in seen] == [(0, 256), (256, 512), (512, 700)]
+    assert summ.shape == (700, 5) and (summ[:, 4] == 0).all()
+    assert sum(s[2] for s in seen) == int(summ[:, 0].sum())
+    for b in range(0, 700, 41):
+        ref = ora.full(packed.node_attr[b], packed.node_flags[b], None, None, packed.cons[b])
+        assert int(summ[b, 0]) == ref["T"]
+        np.testing.assert_allclose(summ[b, :4], ref["summary"][:4], rtol=1e-6)

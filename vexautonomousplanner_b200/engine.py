@@ -447,6 +447,20 @@ class Engine:
         res.extra = dict(status_pre=whole["status_pre"])
         return res
 
+    def profile_many(self, packed: PackedPaths, tile_paths: int = 16384, sink=None) -> torch.Tensor:
+        """Jobs larger than one call (e.g. 2**20 16-node paths: 190 GB of trajectories): profile `tile_paths` paths at a
+        time, hand every tile's device-resident ProfileResult to `sink(lo, hi, result)` (export, reduction, D2H ...) and
+        return the [B, 5] summary rows of the whole job.  Capacities are planned once per tile shape and reused."""
+        B = packed.B
+        rows = []
+        for lo in range(0, B, tile_paths):
+            hi = min(B, lo + tile_paths)
+            res = self.profile(self.upload(packed.slice(lo, hi)), reuse_plan=True)
+            if sink is not None:
+                sink(lo, hi, res)
+            rows.append(res.summary)
+        return torch.cat(rows, dim=0) if rows else self._empty((0, 5))
+
     def profile_to_host(self, packed: PackedPaths, tiles: int = 8, state: Optional[dict] = None) -> "HostResult":
         """Host buffers in, host buffers out, copy-engine variant: every tile packs its valid rows densely on the device;
         as soon as a tile's row count has reached the host, the copy engine moves exactly those bytes into pinned memory
