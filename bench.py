@@ -218,8 +218,18 @@ def run_b200(args):
     dom = max(stage_ms, key=stage_ms.get)
     achieved = stage_bytes[dom] / 1e9 / (stage_ms[dom] * 1e-3)
     total_bytes = sum(stage_bytes.values())
+    # measured DRAM traffic of the dominant stage from the committed ncu capture (profiles/, same workload), if present
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_kernel_table.json")) as f:
+            prof = json.load(f)
+        if (B, N) == (4096, 8):
+            traffic = prof["stages"][dom]["dram_bytes_per_step"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": "profiles/r01_kernel_table.json (ncu dram__bytes_read+write, sum over the stage's kernels)",
                 "whole_step": {"alg_GB": total_bytes / 1e9, "GBps": total_bytes / 1e9 / (ms_per_step * 1e-3),
                                "frac": total_bytes / 1e9 / (ms_per_step * 1e-3) / peak},
                 "stages": stages}

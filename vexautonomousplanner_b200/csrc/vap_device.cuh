@@ -249,6 +249,57 @@ __device__ __forceinline__ double distance_to_time(const double* __restrict__ ld
     return t0 + (t1 - t0) * (d - d0) / (d1 - d0);
 }
 
+// ---- 32-bit index variants for the sample-parallel kernels (tables have < 2^31 entries) ---------------------------
+struct PropGrid {            // per-path constants of the analytic parameter grid np.linspace(0, n-1, P)
+    int P, n;
+    double step, inv_step;
+};
+__device__ __forceinline__ PropGrid prop_grid(int spn, int n)
+{
+    PropGrid g;
+    g.P = spn * n; g.n = n;
+    g.step = (double)(n - 1) / (double)(g.P - 1);
+    g.inv_step = 1.0 / g.step;
+    return g;
+}
+__device__ __forceinline__ double prop_param32(int j, const PropGrid& g)
+{
+    return (j == g.P - 1) ? (double)(g.n - 1) : (double)j * g.step;
+}
+__device__ __forceinline__ void snap_gather2_32(const double* __restrict__ ka, const double* __restrict__ ha, double t,
+                                                const PropGrid& g, double& k, double& h)
+{
+    double e = t * g.inv_step;
+    int j = (e > 0.0) ? (e < (double)g.P ? __double2int_rz(e) : g.P) : 0;
+    while (j > 0 && prop_param32(j - 1, g) >= t) j--;
+    while (j < g.P && prop_param32(j, g) < t) j++;
+    if (j == 0) { k = ka[0]; h = ha[0]; return; }
+    if (j >= g.P) { k = ka[g.P - 1]; h = ha[g.P - 1]; return; }
+    double t0 = prop_param32(j - 1, g), t1 = prop_param32(j, g);
+    if (frac1(t0) != frac1(t1)) {
+        int q = (frac1(t) > 0.5) ? j - 1 : j;
+        k = ka[q]; h = ha[q];
+        return;
+    }
+    double w = (t - t0);
+    k = ka[j - 1] + (ka[j] - ka[j - 1]) * w / (t1 - t0);
+    h = ha[j - 1] + (ha[j] - ha[j - 1]) * w / (t1 - t0);
+}
+__device__ __forceinline__ double distance_to_time32(const double* __restrict__ ld, const double* __restrict__ lt, int Q,
+                                                     double total, int n, double d)
+{
+    if (d <= 0) return 0.0;
+    if (d >= total) return (double)(n - 1);
+    int lo = 0, hi = Q;      // np.searchsorted side='left'
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(ld + mid) < d) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return lt[0];
+    double d0 = ld[lo - 1], d1 = ld[lo], t0 = lt[lo - 1], t1 = lt[lo];
+    return t0 + (t1 - t0) * (d - d0) / (d1 - d0);
+}
+
 // lerp on xs[i] = fl(i*dd) (motion_profile_generator.py:349-386,:484): index of searchsorted(side='right') - 1
 __device__ __forceinline__ long long uniform_index(double x, double dd, double inv_dd, long long D)
 {

@@ -219,19 +219,17 @@ __global__ void __launch_bounds__(256) k_time_sample(
     const double* ld = lut_d + (size_t)b * Q_cap;
     const double* lt = lut_t + (size_t)b * Q_cap;
     PathGeo g = path_geo(b, N_max, seg, first_node, param_end, n_splines);
-    const long long Q = (long long)samples * g.S;
+    const int Q = samples * g.S;
     const double L = total_len[b];
     const size_t plane = (size_t)B * (M_cap + 1);
     const size_t row = (size_t)b * (M_cap + 1);
+    const PropGrid pg = prop_grid(spn, n);
     double t = 0.0;
     if (k < M) {
-        long long hint = -1;
         double pos = stage[TS_POS * plane + row + k];
-        t = distance_to_time(ld, lt, Q, L, n, pos, hint);
-        const long long P = (long long)spn * n;
-        const double pstep = (double)(n - 1) / (double)(P - 1);
+        t = distance_to_time32(ld, lt, Q, L, n, pos);
         double curvature, heading, cx, cy;
-        snap_gather2(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, P, n, pstep, 1.0 / pstep, curvature, heading);
+        snap_gather2_32(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, pg, curvature, heading);
         eval_path<0>(g, t, cx, cy);
         double tv = stage[TS_TV * plane + row + k];
         stage[TS_TH * plane + row + k] = heading;
@@ -240,11 +238,7 @@ __global__ void __launch_bounds__(256) k_time_sample(
         stage[TS_Y * plane + row + k] = cy;
     }
     s_t[threadIdx.x + 1] = t;
-    if (threadIdx.x == 0) {
-        double tp = 0.0;                       // prev_t starts at 0 (:479)
-        if (k0 > 0) { long long hint = -1; tp = distance_to_time(ld, lt, Q, L, n, stage[TS_POS * plane + row + k0 - 1], hint); }
-        s_t[0] = tp;
-    }
+    if (threadIdx.x == 0) s_t[0] = (k0 > 0) ? distance_to_time32(ld, lt, Q, L, n, stage[TS_POS * plane + row + k0 - 1]) : 0.0;
     __syncthreads();
     if (k >= M) return;
     double tp = s_t[threadIdx.x];

@@ -30,32 +30,26 @@ __global__ void __launch_bounds__(256) k_dist_sample_ev(
     __shared__ double s_t[257];
     long long b = blockIdx.y;
     if (status[b] != ST_OK) return;
-    long long D = n_samples[b];
-    long long i0 = (long long)blockIdx.x * blockDim.x;
+    const int D = n_samples[b];
+    const int i0 = blockIdx.x * blockDim.x;
     if (i0 >= D) return;
-    long long i = i0 + threadIdx.x;
-    int n = n_nodes[b];
+    const int i = i0 + threadIdx.x;
+    const int n = n_nodes[b];
     const double* ld = lut_d + (size_t)b * Q_cap;
     const double* lt = lut_t + (size_t)b * Q_cap;
-    long long Q = (long long)samples * n_splines[b];
-    double L = total_len[b];
+    const int Q = samples * n_splines[b];
+    const double L = total_len[b];
+    const PropGrid pg = prop_grid(spn, n);
     double t = 0.0;
     if (i < D) {
-        if (i == D - 1) t = (double)(n - 1);
-        else { long long hint = -1; t = distance_to_time(ld, lt, Q, L, n, dgrid[i], hint); }
-        long long P = (long long)spn * n;
-        double step = (double)(n - 1) / (double)(P - 1);
+        t = (i == D - 1) ? (double)(n - 1) : distance_to_time32(ld, lt, Q, L, n, dgrid[i]);
         double k, h;
-        snap_gather2(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, P, n, step, 1.0 / step, k, h);
+        snap_gather2_32(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, pg, k, h);
         size_t o = (size_t)b * D_cap + i;
         t_out[o] = t; kap[o] = k; th[o] = h;
     }
     s_t[threadIdx.x + 1] = t;
-    if (threadIdx.x == 0) {
-        double tp = 0.0;   // prev_t of sample 0 is 0
-        if (i0 > 0) { long long hint = -1; tp = distance_to_time(ld, lt, Q, L, n, dgrid[i0 - 1], hint); }
-        s_t[0] = tp;
-    }
+    if (threadIdx.x == 0) s_t[0] = (i0 > 0) ? distance_to_time32(ld, lt, Q, L, n, dgrid[i0 - 1]) : 0.0;   // prev_t of sample 0 is 0
     __syncthreads();
     if (i >= D - 1) return;            // the final appended sample takes no part in the event logic
     double tp = s_t[threadIdx.x];
@@ -218,12 +212,24 @@ __global__ void __launch_bounds__(256) k_prepass(
         s_vi[k] = (k < nvr) ? vr_idx[(size_t)b * E_cap + k] : 2147483647;
         s_si[k] = (k < nst) ? st_idx[(size_t)b * E_cap + k] : -1;
     }
+    // per-path constants and the block's starting positions in the (sorted) event tables: once per CTA
+    __shared__ double s_c[4];
+    __shared__ int s_j0[2];
+    if (threadIdx.x == 0) {
+        const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
+        s_c[0] = 2 * V_ / w_;                 // max_angular_vel   (:81)
+        s_c[1] = 2 * A0_ / w_;                // max_angular_accel (:82)
+        int jf = 0, jv = 0;
+        for (int j = 1; j < n_b; j++) if (s_bi[j] <= (int)i0) jf = j;
+        for (int j = 1; j < nvr; j++) if (s_vi[j] <= (int)i0 + 1) jv = j;
+        s_j0[0] = jf; s_j0[1] = jv;
+    }
     __syncthreads();
     long long i = i0 + threadIdx.x;
     if (i >= D) return;
-    const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
-    const double max_angular_vel = 2 * V / w;
-    const double max_angular_accel = 2 * A0 / w;
+    const double V = cons[b * 6 + 0], w = cons[b * 6 + 5];
+    const double max_angular_vel = s_c[0];
+    const double max_angular_accel = s_c[1];
     const size_t row = (size_t)b * D_cap;
     double k = kap[row + i], ak = fabs(k);
     double th_i = th[row + i];
@@ -233,22 +239,24 @@ __global__ void __launch_bounds__(256) k_prepass(
     else {
         double v_ang = max_angular_vel / ak;
         double v_kin = 2 * V / (w * ak + 2);
-        double v_curve = max_speed_at_curvature(V, w, ak);
+        // Constraints.max_speed_at_curvature (:23-33) with 2*V/w already evaluated
+        double m = (max_angular_vel * V) / (ak * V + max_angular_vel);
+        double v_curve = pymin(m, V);
         vlim = pymin(pymin(v_ang, v_kin), v_curve);
     }
     cap = fabs(V / (1 + (w * ak / 2)));
     double G = pymin(vlim, cap);
     // forward regime at step i: last boundary with bidx <= i
-    int jf = 0;
-    for (int j = 1; j < n_b; j++) if (s_bi[j] <= (int)i) jf = j;
+    int jf = s_j0[0];
+    while (jf + 1 < n_b && s_bi[jf + 1] <= (int)i) jf++;
     double acc_f = s_ma[s_bv[jf]];
     double dec_b = s_ma[s_bv[n_b - 1]];     // the backward pass keeps the forward pass's last max_dec
     if (i < D - 1) {
         double v0n;
         if (i + 1 == D - 1) v0n = end_vel;
         else {
-            int jv = 0;
-            for (int j = 1; j < nvr; j++) if (s_vi[j] <= (int)(i + 1)) jv = j;
+            int jv = s_j0[1];
+            while (jv + 1 < nvr && s_vi[jv + 1] <= (int)(i + 1)) jv++;
             v0n = s_vv[jv];
             for (int j = 0; j < nst; j++) if (s_si[j] == (int)(i + 1)) v0n = 0.01;
         }
