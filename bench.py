@@ -149,7 +149,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B, N = args.paths, args.nodes
     packed = synth.random_paths(B, N, seed=rank)      # weak scaling: every rank its own cfg2 batch
-    eng = Engine(dev)
+    eng = Engine(dev, chunks=args.chunks)
     db = eng.upload(packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-sample", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunks", type=int, default=32, help="speculative chunks per path in the velocity passes")
     ap.add_argument("--tiles", type=int, default=1, help="row tiles of the batch, one CUDA stream each")
     ap.add_argument("--e2e-mode", default="copy", choices=["copy", "graph"])
     ap.add_argument("--e2e-tiles", type=int, default=4, help="tiles of the end-to-end (host in / host out) run")

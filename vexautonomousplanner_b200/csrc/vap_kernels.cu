@@ -1180,15 +1180,24 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
                                          n_ev, vr_idx, vr_val, st_idx, n_vr, reinterpret_cast<double4*>(recF),
                                          reinterpret_cast<double4*>(recR));
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
-    size_t ss = (size_t)chunks * 2 * sizeof(double);
-    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, D_cap, n_samples,
-                                                       reinterpret_cast<const double4*>(recF), E_cap, max_accels, bidx,
-                                                       bval, n_ev, vel_f, rounds);
+    // CTA = PB paths x `chunks` chunk threads; the fix-up re-runs of all PB paths share the CTA's first warps.
+    // Measured on 4096 x 8-node paths: PB = 1 is fastest (3.14 ms vs 3.39 ms at PB = 4): the passes are bound by the
+    // dependent-instruction latency of the longest path, and CTA-wide barriers over several paths only add waiting.
+    int PB = 1;
+    if (const char* ev = getenv("VAP_CHUNK_PB")) PB = atoi(ev);
+    if (PB < 1) PB = 1;
+    if (PB * chunks > 256) PB = 256 / chunks;
+    const int nth = PB * chunks;
+    size_t ss = (size_t)PB * sizeof(ChunkCtx) + (size_t)nth * (4 * sizeof(double) + sizeof(int));
+    const unsigned nblk = (unsigned)((B + PB - 1) / PB);
+    k_fwd_chunked<<<nblk, nth, ss, STREAM>>>(B, chunks, status, cons, dd, start_vel, D_cap, n_samples,
+                                             reinterpret_cast<const double4*>(recF), E_cap, max_accels, bidx, bval, n_ev,
+                                             vel_f, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
     if (mode == 1) return 0;
-    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, D_cap, n_samples,
-                                                       reinterpret_cast<const double4*>(recR), E_cap, max_accels, bidx,
-                                                       bval, n_ev, vel_f, vel, t_est, rounds);
+    k_bwd_chunked<<<nblk, nth, ss, STREAM>>>(B, chunks, status, cons, dd, dt, end_vel, D_cap, n_samples,
+                                             reinterpret_cast<const double4*>(recR), E_cap, max_accels, bidx, bval, n_ev,
+                                             vel_f, vel, t_est, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
     return 0;
 }

@@ -118,14 +118,21 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     const double vlast = vv[D - 1];
     long long k = 0;
     const double hdt = 0.1 * dt;
+    const double dlim = (double)(D - 3);
+    const double ndec = -max_dec;
     while (pos < L) {
         const bool room = k < M_cap;
         if (room) *P = pos;
-        int i1 = uniform_index32(pos, dd, inv_dd, D);
-        double x2 = pos + dd;
         double tv1, tv2;
-        if (i1 >= 0 && i1 + 3 < D && i1 >= blk_lo * TS_BLK) {
-            // fast path: y[i1 .. i1+2] from the ring; lerp(pos + dd) lands on i1 or one of the next two samples.
+        const double x2 = pos + dd;
+        // Fast path: the interval index is guessed as trunc(pos / dd) and VERIFIED against xs[i] = fl(i*dd) (that is the
+        // definition of np.searchsorted(side='right') - 1), and lerp(pos + dd) is verified to fall in the next interval;
+        // anything else (first / last samples, a guess off by one, a position that moved backwards) takes the generic path.
+        const double e = pos * inv_dd;
+        const int i1 = (e < dlim) ? __double2int_rz(e) : 0;
+        const double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, xx2 = (double)(i1 + 2) * dd;
+        const bool fast = (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) & (i1 >= blk_lo * TS_BLK);
+        if (fast) {
             // Invariant: block blk_lo is complete; block blk_lo+1 is complete unless `pending`.
             if (i1 >= (blk_lo + 1) * TS_BLK) {
                 if (pending) { cp_async_wait<0>(); pending = false; }
@@ -135,42 +142,35 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 else cp_async_wait<0>();
             }
             if (pending && i1 + 2 >= (blk_lo + 1) * TS_BLK) { cp_async_wait<0>(); pending = false; }
-            double y0 = ring[i1 & (TS_RING - 1)], y1 = ring[(i1 + 1) & (TS_RING - 1)], y2 = ring[(i1 + 2) & (TS_RING - 1)];
-            double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, xx2 = (double)(i1 + 2) * dd;
+            const double y0 = ring[i1 & (TS_RING - 1)], y1 = ring[(i1 + 1) & (TS_RING - 1)], y2 = ring[(i1 + 2) & (TS_RING - 1)];
             tv1 = y0 + div_pos((pos - x0) * (y1 - y0), x1 - x0);
-            if (x1 <= x2 && x2 < xx2) {
-                tv2 = y1 + div_pos((x2 - x1) * (y2 - y1), xx2 - x1);
-            } else {
-                int i2 = uniform_index32(x2, dd, inv_dd, D);
-                if (i2 < 0) tv2 = vv[0];
-                else if (i2 >= D - 1) tv2 = vlast;
-                else {
-                    double a0 = (double)i2 * dd, a1 = (double)(i2 + 1) * dd, b0 = vv[i2], b1 = vv[i2 + 1];
-                    tv2 = b0 + div_pos((x2 - a0) * (b1 - b0), a1 - a0);
-                }
-            }
+            tv2 = y1 + div_pos((x2 - x1) * (y2 - y1), xx2 - x1);
         } else {
-            // generic path (path start / end, or a position that moved backwards)
-            int i2 = uniform_index32(x2, dd, inv_dd, D);
-            if (i1 < 0) tv1 = vv[0];
-            else if (i1 >= D - 1) tv1 = vlast;
+            const int j1 = uniform_index32(pos, dd, inv_dd, D);
+            const int j2 = uniform_index32(x2, dd, inv_dd, D);
+            if (j1 < 0) tv1 = vv[0];
+            else if (j1 >= D - 1) tv1 = vlast;
             else {
-                double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, y0 = vv[i1], y1 = vv[i1 + 1];
-                tv1 = y0 + div_pos((pos - x0) * (y1 - y0), x1 - x0);
+                double a0 = (double)j1 * dd, a1 = (double)(j1 + 1) * dd, b0 = vv[j1], b1 = vv[j1 + 1];
+                tv1 = b0 + div_pos((pos - a0) * (b1 - b0), a1 - a0);
             }
-            if (i2 < 0) tv2 = vv[0];
-            else if (i2 >= D - 1) tv2 = vlast;
+            if (j2 < 0) tv2 = vv[0];
+            else if (j2 >= D - 1) tv2 = vlast;
             else {
-                double x0 = (double)i2 * dd, x1 = (double)(i2 + 1) * dd, y0 = vv[i2], y1 = vv[i2 + 1];
-                tv2 = y0 + div_pos((x2 - x0) * (y1 - y0), x1 - x0);
+                double a0 = (double)j2 * dd, a1 = (double)(j2 + 1) * dd, b0 = vv[j2], b1 = vv[j2 + 1];
+                tv2 = b0 + div_pos((x2 - a0) * (b1 - b0), a1 - a0);
             }
         }
-        double tv = pymax((tv1 + tv2) / 2, 0.001);
+        const double tvm = (tv1 + tv2) / 2;
+        const double tv = (0.001 > tvm) ? 0.001 : tvm;                 // max(tvm, 0.001)
         double accel = div_const(tv - v, dt, inv_dt);
-        accel = fmin(fmax(accel, -max_dec), max_acc);          // np.clip
-        v = fmin(fmax(v + accel * dt, 0.0), tv);
-        double dpos = v * dt + 0.5 * accel * dt * dt;
-        if (v <= 0.1) dpos = hdt + 0.5 * accel * dt * dt;
+        accel = (accel > ndec) ? accel : ndec;                         // np.clip(accel, -max_dec, max_acc)
+        accel = (accel < max_acc) ? accel : max_acc;
+        double vn = v + accel * dt;
+        vn = (vn > 0.0) ? vn : 0.0;                                    // np.clip(v, 0, tv)
+        v = (vn < tv) ? vn : tv;
+        const double half = 0.5 * accel * dt * dt;
+        const double dpos = ((v <= 0.1) ? hdt : v * dt) + half;
         pos += dpos;
         if (room) { *Vo = v; *Ao = accel; *To = tv; P++; Vo++; Ao++; To++; }
         k++;

@@ -341,236 +341,323 @@ __device__ __forceinline__ double bwd_step(const double4 r, double v, double& wp
     return pymin(pymin(pv, vfwd_prev), r.w);
 }
 
-// Forward pass.  Steps i = 0 .. D-2; chunk c owns steps [c*Lc, min((c+1)*Lc, D-1)).  vel_f[i+1] is written.
+// ------------------------------------------------------------------------------------------------------------------
+// Chunk-speculative passes, CTA = PB paths x NT chunks (thread (p, c) = path p of the CTA, chunk c).
+//
+// Sweep 1: every thread runs its own chunk from the guessed state (lockstep, all lanes busy).
+// Fix-up rounds: only a few chunks per path have to be re-run (their predecessor's end state differs bitwise from the
+// state they started from).  Those (path, chunk) items are pushed into a shared-memory queue and re-run by the FIRST
+// threads of the CTA, so that the re-runs of all PB paths share a few dense warps instead of every path keeping a
+// mostly idle warp spinning.  A re-run stops as soon as two consecutive velocities equal the stored ones bitwise.
+// Rounds end when the queue stays empty; then, by induction from the first chunk, every value is the serial value.
+// ------------------------------------------------------------------------------------------------------------------
+struct ChunkCtx {                 // per path of the CTA, in shared memory
+    long long D, Lc;
+    int nch, n_b, ok;
+    double w;
+    const double4* rec;
+    const double* vin;            // backward: forward velocities
+    double* vout;
+    const double* ma;
+    const int* bi;
+    const int* bv;
+};
+
+// Forward pass.  Steps i = 0 .. D-2; chunk c owns steps [c*Lc, min((c+1)*Lc, D-1)); step i writes vel_f[i+1].
 __global__ void __launch_bounds__(256) k_fwd_chunked(
-    const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, long long D_cap,
-    const int* __restrict__ n_samples, const double4* __restrict__ recF, int E_cap,
+    long long B, int NT, const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel,
+    long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recF, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, double* __restrict__ vel_f, int* __restrict__ rounds_out)
 {
-    extern __shared__ double s_state[];           // [2][NT]: end state (v, wp) of every chunk
-    const int NT = blockDim.x, c = threadIdx.x;
-    long long b = blockIdx.x;
-    if (status[b] != ST_OK) return;
-    const long long D = n_samples[b];
-    const long long steps = D - 1;
-    const double w = cons[b * 6 + 5];
-    const size_t row = (size_t)b * D_cap;
-    const double4* F = recF + row;
-    double* vf = vel_f + row;
-    const double* ma = max_accels + (size_t)b * E_cap;
-    const int* bi = bidx + (size_t)b * E_cap;
-    const int* bv = bval + (size_t)b * E_cap;
-    const int n_b = n_ev[2 * b + 1];
-    if (c == 0) vf[0] = start_vel;
-    if (steps <= 0) return;
-    const long long Lc = (steps + NT - 1) / NT;
-    const int nch = (int)((steps + Lc - 1) / Lc);
-    const long long lo = (long long)c * Lc;
-    const long long hi = (lo + Lc < steps) ? lo + Lc : steps;
-    const bool active = c < nch;
-    double* s_v = s_state;
-    double* s_w = s_state + NT;
+    extern __shared__ __align__(16) unsigned char s_mem[];
+    const int NTH = blockDim.x, PB = NTH / NT;
+    const int tid = threadIdx.x, p = tid / NT, c = tid - p * NT;
+    ChunkCtx* ctx = reinterpret_cast<ChunkCtx*>(s_mem);
+    double* s_endv = reinterpret_cast<double*>(ctx + PB);        // [NTH] end state of every chunk
+    double* s_endw = s_endv + NTH;
+    double* s_usev = s_endw + NTH;                                // [NTH] start state every chunk last used
+    double* s_usew = s_usev + NTH;
+    int* s_queue = reinterpret_cast<int*>(s_usew + NTH);          // [NTH]
+    __shared__ int s_qn;
+    const long long b = (long long)blockIdx.x * PB + p;
+    if (c == 0) {
+        ChunkCtx x;
+        x.ok = (b < B) && status[b] == ST_OK;
+        x.D = x.ok ? n_samples[b] : 1;
+        long long steps = x.D - 1;
+        x.Lc = steps > 0 ? (steps + NT - 1) / NT : 1;
+        x.nch = steps > 0 ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
+        if (x.ok) {
+            x.n_b = n_ev[2 * b + 1];
+            x.w = cons[b * 6 + 5];
+            x.rec = recF + (size_t)b * D_cap;
+            x.vin = nullptr;
+            x.vout = vel_f + (size_t)b * D_cap;
+            x.ma = max_accels + (size_t)b * E_cap;
+            x.bi = bidx + (size_t)b * E_cap;
+            x.bv = bval + (size_t)b * E_cap;
+            x.vout[0] = start_vel;
+        } else { x.n_b = 0; x.w = 1.0; x.rec = nullptr; x.vin = nullptr; x.vout = nullptr; x.ma = nullptr; x.bi = nullptr; x.bv = nullptr; x.nch = 0; }
+        ctx[p] = x;
+    }
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
 
-    // regime at chunk start
-    int jn = 1;
-    double acc0 = ma[bv[0]];
-    if (active) {
-        while (jn < n_b && bi[jn] <= (int)lo) { acc0 = ma[bv[jn]]; jn++; }
-    }
-    const int jn0 = jn;
-    // start state: exact for chunk 0, guessed from the state-independent caps otherwise
-    double used_v = start_vel, used_w = 0.0;
-    if (active && c > 0) {
-        double vm1 = (lo >= 2) ? F[lo - 2].w : start_vel;      // guess of v[lo-1]
-        used_v = F[lo - 1].w;                                   // guess of v[lo]
-        used_w = vm1 * F[lo - 1].x;
-    }
-    double end_v = used_v, end_w = used_w;
-    if (active) {
-        double v = used_v, wp = used_w, acc = acc0;
-        int j = jn0;
-        int nb_next = (j < n_b) ? bi[j] : 2147483647;
+    // runs chunk cc of path context x from state (v, wp); mode 0: first sweep (plain stores), mode 1: re-run with
+    // bitwise merge detection against the stored velocities.  Returns true when the re-run merged (end state unchanged).
+    auto run_chunk = [&](const ChunkCtx& x, int cc, double& v, double& wp, bool rerun, bool prev_same) -> bool {
+        const long long steps = x.D - 1;
+        const long long lo = (long long)cc * x.Lc;
+        const long long hi = (lo + x.Lc < steps) ? lo + x.Lc : steps;
+        const double4* F = x.rec;
+        double* vf = x.vout;
+        int j = 1;
+        double acc = x.ma[x.bv[0]];
+        while (j < x.n_b && x.bi[j] <= (int)lo) { acc = x.ma[x.bv[j]]; j++; }
+        int nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
         double4 r = F[lo];
         double4 r1 = (lo + 1 < hi) ? F[lo + 1] : r;
-        for (long long i = lo; i < hi; i++) {
-            double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;          // records run two steps ahead of their use
-            if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
-            v = fwd_step(r, v, wp, acc, w, dd);
-            vf[i + 1] = v;
-            r = r1; r1 = r2;
-        }
-        end_v = v; end_w = wp;
-    }
-    s_v[c] = end_v; s_w[c] = end_w;
-    __syncthreads();
-    int rounds = 0;
-    for (int round = 1; round < nch; round++) {
-        bool changed = false;
-        double in_v = 0.0, in_w = 0.0;
-        if (active && c >= round) { in_v = s_v[c - 1]; in_w = s_w[c - 1]; }
-        if (active && c >= round && !(same_bits(in_v, used_v) && same_bits(in_w, used_w))) {
-            changed = true;
-            bool prev_same = same_bits(in_v, used_v);
-            used_v = in_v; used_w = in_w;
-            double v = in_v, wp = in_w, acc = acc0;
-            int j = jn0;
-            int nb_next = (j < n_b) ? bi[j] : 2147483647;
-            bool merged = false;
-            double4 r = F[lo];
-            double4 r1 = (lo + 1 < hi) ? F[lo + 1] : r;
-            double old = vf[lo + 1];
-            double old1 = (lo + 1 < hi) ? vf[lo + 2] : 0.0;
+        if (!rerun) {
             for (long long i = lo; i < hi; i++) {
-                double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;            // loads run two steps ahead of their use
-                double old2 = (i + 2 < hi) ? vf[i + 3] : 0.0;
-                if ((int)i == nb_next) { acc = ma[bv[j]]; j++; nb_next = (j < n_b) ? bi[j] : 2147483647; }
-                v = fwd_step(r, v, wp, acc, w, dd);
-                bool same = same_bits(old, v);
-                if (same && prev_same) { merged = true; break; }   // state (v[i+1], v[i]*|k_i|) equals the old run's
+                double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;          // records run two steps ahead of their use
+                if ((int)i == nb_next) { acc = x.ma[x.bv[j]]; j++; nb_next = (j < x.n_b) ? x.bi[j] : 2147483647; }
+                v = fwd_step(r, v, wp, acc, x.w, dd);
                 vf[i + 1] = v;
-                prev_same = same;
-                r = r1; r1 = r2; old = old1; old1 = old2;
+                r = r1; r1 = r2;
             }
-            if (!merged) { end_v = v; end_w = wp; }
+            return false;
         }
-        int any = __syncthreads_or(changed ? 1 : 0);
-        if (!any) break;
+        double old = vf[lo + 1];
+        double old1 = (lo + 1 < hi) ? vf[lo + 2] : 0.0;
+        for (long long i = lo; i < hi; i++) {
+            double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;
+            double old2 = (i + 2 < hi) ? vf[i + 3] : 0.0;
+            if ((int)i == nb_next) { acc = x.ma[x.bv[j]]; j++; nb_next = (j < x.n_b) ? x.bi[j] : 2147483647; }
+            v = fwd_step(r, v, wp, acc, x.w, dd);
+            bool same = same_bits(old, v);
+            if (same && prev_same) return true;        // state (v[i+1], v[i]*|k_i|) equals the old run's: rest is unchanged
+            vf[i + 1] = v;
+            prev_same = same;
+            r = r1; r1 = r2; old = old1; old1 = old2;
+        }
+        return false;
+    };
+
+    // ---- sweep 1
+    {
+        const ChunkCtx x = ctx[p];
+        const bool active = x.ok && c < x.nch;
+        double v = start_vel, wp = 0.0;
+        if (active) {
+            const long long lo = (long long)c * x.Lc;
+            if (c > 0) {            // guess: the state-independent caps bind on the two samples before the chunk
+                double vm1 = (lo >= 2) ? x.rec[lo - 2].w : start_vel;
+                double4 fm1 = x.rec[lo - 1];
+                v = fm1.w;
+                wp = vm1 * fm1.x;
+            }
+            s_usev[tid] = v; s_usew[tid] = wp;
+            run_chunk(x, c, v, wp, false, false);
+        }
+        s_endv[tid] = v; s_endw[tid] = wp;
+    }
+    __syncthreads();
+
+    // ---- fix-up rounds
+    int rounds = 0;
+    for (int round = 1; round < NT; round++) {
+        {
+            const ChunkCtx& x = ctx[p];
+            if (x.ok && c < x.nch && c >= round) {
+                if (!(same_bits(s_endv[tid - 1], s_usev[tid]) && same_bits(s_endw[tid - 1], s_usew[tid])))
+                    s_queue[atomicAdd(&s_qn, 1)] = tid;
+            }
+        }
+        __syncthreads();
+        const int n = s_qn;
+        if (n == 0) break;
         rounds = round;
-        s_v[c] = end_v; s_w[c] = end_w;
+        // read the inputs of this round before anybody publishes new end states
+        int item = -1;
+        double in_v = 0.0, in_w = 0.0, old_usev = 0.0;
+        if (tid < n) { item = s_queue[tid]; in_v = s_endv[item - 1]; in_w = s_endw[item - 1]; old_usev = s_usev[item]; }
+        __syncthreads();
+        if (tid == 0) s_qn = 0;
+        if (item >= 0) {
+            const int pp = item / NT, cc = item - pp * NT;
+            const ChunkCtx x = ctx[pp];
+            double v = in_v, wp = in_w;
+            bool merged = run_chunk(x, cc, v, wp, true, same_bits(in_v, old_usev));
+            s_usev[item] = in_v; s_usew[item] = in_w;
+            if (!merged) { s_endv[item] = v; s_endw[item] = wp; }
+        }
         __syncthreads();
     }
-    if (c == 0 && rounds_out) rounds_out[2 * b] = rounds;
+    if (c == 0 && rounds_out && ctx[p].ok) rounds_out[2 * b] = rounds;
 }
 
-// Backward pass.  Steps i = D-1 .. 1 (step i writes vel[i-1]); chunk c owns the c-th block of steps counted from
-// the end.  Reads vel_f (forward result) and writes vel (final); vel[D-1] = end_vel.  Also accumulates the
-// travel-time estimate used to size the time-domain outputs.
+// Backward pass.  Steps i = D-1 .. 1 (step i writes vel[i-1]); chunk c owns the c-th block of steps counted from the
+// end.  Reads vel_f (forward result) and writes vel (final); vel[D-1] = end_vel.  Also accumulates the travel-time
+// estimate used to size the time-domain outputs.
 __global__ void __launch_bounds__(256) k_bwd_chunked(
-    const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel,
-    long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recR, int E_cap,
+    long long B, int NT, const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt,
+    double end_vel, long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recR, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const double* __restrict__ vel_f, double* __restrict__ vel,
     float* __restrict__ t_est, int* __restrict__ rounds_out)
 {
-    extern __shared__ double s_state[];
-    const int NT = blockDim.x, c = threadIdx.x;
-    long long b = blockIdx.x;
-    if (status[b] != ST_OK) return;
-    const long long D = n_samples[b];
-    const long long steps = D - 1;
-    const double w = cons[b * 6 + 5];
-    const size_t row = (size_t)b * D_cap;
-    const double4* R = recR + row;
-    const double* vf = vel_f + row;
-    double* vo = vel + row;
-    const double* ma = max_accels + (size_t)b * E_cap;
-    const int* bi = bidx + (size_t)b * E_cap;
-    const int* bv = bval + (size_t)b * E_cap;
-    const int n_b = n_ev[2 * b + 1];
-    if (c == 0) vo[D - 1] = end_vel;
-    if (steps <= 0) { if (c == 0 && t_est) t_est[b] = 0.f; return; }
-    const long long Lc = (steps + NT - 1) / NT;
-    const int nch = (int)((steps + Lc - 1) / Lc);
-    // chunk c: steps i = hi, hi-1, ..., lo+1 with hi = D-1 - c*Lc, lo = max(hi - Lc, 0)
-    const long long hi = (D - 1) - (long long)c * Lc;
-    const long long lo = (hi - Lc > 0) ? hi - Lc : 0;
-    const bool active = c < nch;
-    double* s_v = s_state;
-    double* s_w = s_state + NT;
+    extern __shared__ __align__(16) unsigned char s_mem[];
+    const int NTH = blockDim.x, PB = NTH / NT;
+    const int tid = threadIdx.x, p = tid / NT, c = tid - p * NT;
+    ChunkCtx* ctx = reinterpret_cast<ChunkCtx*>(s_mem);
+    double* s_endv = reinterpret_cast<double*>(ctx + PB);
+    double* s_endw = s_endv + NTH;
+    double* s_usev = s_endw + NTH;
+    double* s_usew = s_usev + NTH;
+    int* s_queue = reinterpret_cast<int*>(s_usew + NTH);
+    __shared__ int s_qn;
+    const long long b = (long long)blockIdx.x * PB + p;
+    if (c == 0) {
+        ChunkCtx x;
+        x.ok = (b < B) && status[b] == ST_OK;
+        x.D = x.ok ? n_samples[b] : 1;
+        long long steps = x.D - 1;
+        x.Lc = steps > 0 ? (steps + NT - 1) / NT : 1;
+        x.nch = steps > 0 ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
+        if (x.ok) {
+            x.n_b = n_ev[2 * b + 1];
+            x.w = cons[b * 6 + 5];
+            x.rec = recR + (size_t)b * D_cap;
+            x.vin = vel_f + (size_t)b * D_cap;
+            x.vout = vel + (size_t)b * D_cap;
+            x.ma = max_accels + (size_t)b * E_cap;
+            x.bi = bidx + (size_t)b * E_cap;
+            x.bv = bval + (size_t)b * E_cap;
+            x.vout[x.D - 1] = end_vel;
+        } else { x.n_b = 0; x.w = 1.0; x.rec = nullptr; x.vin = nullptr; x.vout = nullptr; x.ma = nullptr; x.bi = nullptr; x.bv = nullptr; x.nch = 0; }
+        ctx[p] = x;
+    }
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
 
-    // regime at chunk start (walking down from D-1): the smallest boundary index > hi was the last one applied
-    double acc_fwd_last = ma[bv[n_b - 1]];
-    double acc0 = acc_fwd_last;
-    int jb = n_b - 1;                        // next boundary entry to test while walking down (bidx[jb] <= i)
-    if (active) {
-        while (jb >= 0 && bi[jb] > (int)hi) { acc0 = ma[bv[jb] + 1]; jb--; }
-    }
-    const int jb0 = jb;
-    double used_v = end_vel, used_w = 0.0;
-    if (active && c > 0) {
-        // v[hi] was produced by step hi+1: min(pv, vel_f[hi], G[hi+1]); guess = the state-independent part
-        used_v = pymin(vf[hi], R[hi + 1].w);
-        double vp1 = (hi + 2 <= D - 1) ? pymin(vf[hi + 1], R[hi + 2].w) : end_vel;
-        used_w = vp1 * R[hi + 1].x;
-    }
-    double end_v = used_v, end_w = used_w;
-    if (active) {
-        double v = used_v, wp = used_w, acc = acc0;
-        int j = jb0;
-        int nb_next = (j >= 0) ? bi[j] : -1;
+    // chunk cc: steps i = hi, hi-1, ..., lo+1 with hi = D-1 - cc*Lc, lo = max(hi - Lc, 0)
+    auto run_chunk = [&](const ChunkCtx& x, int cc, double& v, double& wp, bool rerun, bool prev_same) -> bool {
+        const long long hi = (x.D - 1) - (long long)cc * x.Lc;
+        const long long lo = (hi - x.Lc > 0) ? hi - x.Lc : 0;
+        const double4* R = x.rec;
+        const double* vf = x.vin;
+        double* vo = x.vout;
+        // regime at chunk start (walking down from D-1): the smallest boundary index > hi was the last one applied
+        double acc = x.ma[x.bv[x.n_b - 1]];
+        int j = x.n_b - 1;
+        while (j >= 0 && x.bi[j] > (int)hi) { acc = x.ma[x.bv[j] + 1]; j--; }
+        int nb_next = (j >= 0) ? x.bi[j] : -1;
         double4 r = R[hi];
         double vfp = vf[hi - 1];
         double4 r1 = (hi - 1 > lo) ? R[hi - 1] : r;
         double vf1 = (hi - 1 > lo) ? vf[hi - 2] : 0.0;
-        for (long long i = hi; i > lo; i--) {
-            double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;          // loads run two steps ahead of their use
-            double vf2 = (i - 2 > lo) ? vf[i - 3] : 0.0;
-            if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
-            v = bwd_step(r, v, wp, acc, w, dd, vfp);
-            vo[i - 1] = v;
-            r = r1; vfp = vf1; r1 = r2; vf1 = vf2;
-        }
-        end_v = v; end_w = wp;
-    }
-    s_v[c] = end_v; s_w[c] = end_w;
-    __syncthreads();
-    int rounds = 0;
-    for (int round = 1; round < nch; round++) {
-        bool changed = false;
-        double in_v = 0.0, in_w = 0.0;
-        if (active && c >= round) { in_v = s_v[c - 1]; in_w = s_w[c - 1]; }
-        if (active && c >= round && !(same_bits(in_v, used_v) && same_bits(in_w, used_w))) {
-            changed = true;
-            bool prev_same = same_bits(in_v, used_v);
-            used_v = in_v; used_w = in_w;
-            double v = in_v, wp = in_w, acc = acc0;
-            int j = jb0;
-            int nb_next = (j >= 0) ? bi[j] : -1;
-            bool merged = false;
-            double4 r = R[hi];
-            double vfp = vf[hi - 1];
-            double old = vo[hi - 1];
-            double4 r1 = (hi - 1 > lo) ? R[hi - 1] : r;
-            double vf1 = (hi - 1 > lo) ? vf[hi - 2] : 0.0;
-            double old1 = (hi - 1 > lo) ? vo[hi - 2] : 0.0;
+        if (!rerun) {
             for (long long i = hi; i > lo; i--) {
-                double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;            // loads run two steps ahead of their use
+                double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;          // loads run two steps ahead of their use
                 double vf2 = (i - 2 > lo) ? vf[i - 3] : 0.0;
-                double old2 = (i - 2 > lo) ? vo[i - 3] : 0.0;
-                if ((int)i == nb_next) { acc = ma[bv[j] + 1]; j--; nb_next = (j >= 0) ? bi[j] : -1; }
-                v = bwd_step(r, v, wp, acc, w, dd, vfp);
-                bool same = same_bits(old, v);
-                if (same && prev_same) { merged = true; break; }
+                if ((int)i == nb_next) { acc = x.ma[x.bv[j] + 1]; j--; nb_next = (j >= 0) ? x.bi[j] : -1; }
+                v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
                 vo[i - 1] = v;
-                prev_same = same;
-                r = r1; vfp = vf1; old = old1; r1 = r2; vf1 = vf2; old1 = old2;
+                r = r1; vfp = vf1; r1 = r2; vf1 = vf2;
             }
-            if (!merged) { end_v = v; end_w = wp; }
+            return false;
         }
-        int any = __syncthreads_or(changed ? 1 : 0);
-        if (!any) break;
+        double old = vo[hi - 1];
+        double old1 = (hi - 1 > lo) ? vo[hi - 2] : 0.0;
+        for (long long i = hi; i > lo; i--) {
+            double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;
+            double vf2 = (i - 2 > lo) ? vf[i - 3] : 0.0;
+            double old2 = (i - 2 > lo) ? vo[i - 3] : 0.0;
+            if ((int)i == nb_next) { acc = x.ma[x.bv[j] + 1]; j--; nb_next = (j >= 0) ? x.bi[j] : -1; }
+            v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
+            bool same = same_bits(old, v);
+            if (same && prev_same) return true;
+            vo[i - 1] = v;
+            prev_same = same;
+            r = r1; vfp = vf1; old = old1; r1 = r2; vf1 = vf2; old1 = old2;
+        }
+        return false;
+    };
+
+    // ---- sweep 1
+    {
+        const ChunkCtx x = ctx[p];
+        const bool active = x.ok && c < x.nch;
+        double v = end_vel, wp = 0.0;
+        if (active) {
+            const long long hi = (x.D - 1) - (long long)c * x.Lc;
+            if (c > 0) {
+                // v[hi] was produced by step hi+1: min(pv, vel_f[hi], G[hi+1]); guess = the state-independent part
+                double4 r1 = x.rec[hi + 1];
+                v = pymin(x.vin[hi], r1.w);
+                double vp1 = (hi + 2 <= x.D - 1) ? pymin(x.vin[hi + 1], x.rec[hi + 2].w) : end_vel;
+                wp = vp1 * r1.x;
+            }
+            s_usev[tid] = v; s_usew[tid] = wp;
+            run_chunk(x, c, v, wp, false, false);
+        }
+        s_endv[tid] = v; s_endw[tid] = wp;
+    }
+    __syncthreads();
+
+    // ---- fix-up rounds (states flow from chunk c-1 to chunk c, as in the forward kernel)
+    int rounds = 0;
+    for (int round = 1; round < NT; round++) {
+        {
+            const ChunkCtx& x = ctx[p];
+            if (x.ok && c < x.nch && c >= round) {
+                if (!(same_bits(s_endv[tid - 1], s_usev[tid]) && same_bits(s_endw[tid - 1], s_usew[tid])))
+                    s_queue[atomicAdd(&s_qn, 1)] = tid;
+            }
+        }
+        __syncthreads();
+        const int n = s_qn;
+        if (n == 0) break;
         rounds = round;
-        s_v[c] = end_v; s_w[c] = end_w;
+        int item = -1;
+        double in_v = 0.0, in_w = 0.0, old_usev = 0.0;
+        if (tid < n) { item = s_queue[tid]; in_v = s_endv[item - 1]; in_w = s_endw[item - 1]; old_usev = s_usev[item]; }
+        __syncthreads();
+        if (tid == 0) s_qn = 0;
+        if (item >= 0) {
+            const int pp = item / NT, cc = item - pp * NT;
+            const ChunkCtx x = ctx[pp];
+            double v = in_v, wp = in_w;
+            bool merged = run_chunk(x, cc, v, wp, true, same_bits(in_v, old_usev));
+            s_usev[item] = in_v; s_usew[item] = in_w;
+            if (!merged) { s_endv[item] = v; s_endw[item] = wp; }
+        }
         __syncthreads();
     }
-    if (c == 0 && rounds_out) rounds_out[2 * b + 1] = rounds;
-    // travel-time estimate (single precision is plenty: it only sizes buffers)
+    if (c == 0 && rounds_out && ctx[p].ok) rounds_out[2 * b + 1] = rounds;
+
+    // ---- travel-time estimate (single precision is plenty: it only sizes buffers)
     __syncthreads();
     float est = 0.f;
-    if (active) {
-        for (long long i = hi; i > lo; i--) {
-            float vm = 0.5f * ((float)vo[i] + (float)vo[i - 1]);
-            est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
+    {
+        const ChunkCtx x = ctx[p];
+        if (x.ok && c < x.nch) {
+            const long long hi = (x.D - 1) - (long long)c * x.Lc;
+            const long long lo = (hi - x.Lc > 0) ? hi - x.Lc : 0;
+            for (long long i = hi; i > lo; i--) {
+                float vm = 0.5f * ((float)x.vout[i] + (float)x.vout[i - 1]);
+                est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
+            }
         }
     }
+    float* s_f = reinterpret_cast<float*>(s_endv);      // end states are no longer needed
     __syncthreads();
-    float* s_f = reinterpret_cast<float*>(s_state);
-    s_f[c] = est;
+    s_f[tid] = est;
     __syncthreads();
-    if (c == 0 && t_est) {
+    if (c == 0 && t_est && b < B) {
         float tot = 0.f;
-        for (int k = 0; k < NT; k++) tot += s_f[k];
+        if (ctx[p].ok) for (int k = 0; k < NT; k++) tot += s_f[p * NT + k];
         t_est[b] = tot;
     }
 }
