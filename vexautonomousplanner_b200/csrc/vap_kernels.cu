@@ -1188,16 +1188,19 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     if (PB < 1) PB = 1;
     if (PB * chunks > 256) PB = 256 / chunks;
     const int nth = PB * chunks;
-    size_t ss = (size_t)PB * sizeof(ChunkCtx) + (size_t)nth * (4 * sizeof(double) + sizeof(int));
+    int warm = 0;                     // warm-up steps a speculative chunk runs before its own range (tuning: VAP_CHUNK_WARM)
+    if (const char* ev = getenv("VAP_CHUNK_WARM")) warm = atoi(ev);
+    if (warm < 0) warm = 0;
+    size_t ss = (size_t)nth * (4 * sizeof(double) + sizeof(int));
     const unsigned nblk = (unsigned)((B + PB - 1) / PB);
     k_fwd_chunked<<<nblk, nth, ss, STREAM>>>(B, chunks, status, cons, dd, start_vel, D_cap, n_samples,
                                              reinterpret_cast<const double4*>(recF), E_cap, max_accels, bidx, bval, n_ev,
-                                             vel_f, rounds);
+                                             vel_f, rounds, warm);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
     if (mode == 1) return 0;
     k_bwd_chunked<<<nblk, nth, ss, STREAM>>>(B, chunks, status, cons, dd, dt, end_vel, D_cap, n_samples,
                                              reinterpret_cast<const double4*>(recR), E_cap, max_accels, bidx, bval, n_ev,
-                                             vel_f, vel, t_est, rounds);
+                                             vel_f, vel, t_est, rounds, warm);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
     return 0;
 }

@@ -12,6 +12,13 @@
 
 #define EV_AP_CAND 4
 
+// read-only (ld.global.nc) load of a 32-byte record
+__device__ __forceinline__ double4 ldg_d4(const double4* p)
+{
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ void prefetch_l1v(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #define PF_DIST 12      // records ahead of the serial walk (3 cache lines of 32-byte records)
 
@@ -351,7 +358,7 @@ __device__ __forceinline__ double bwd_step(const double4 r, double v, double& wp
 // mostly idle warp spinning.  A re-run stops as soon as two consecutive velocities equal the stored ones bitwise.
 // Rounds end when the queue stays empty; then, by induction from the first chunk, every value is the serial value.
 // ------------------------------------------------------------------------------------------------------------------
-struct ChunkCtx {                 // per path of the CTA, in shared memory
+struct ChunkCtx {                 // per path; built in registers from the kernel parameters
     long long D, Lc;
     int nch, n_b, ok;
     double w;
@@ -368,39 +375,40 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
     long long B, int NT, const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel,
     long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recF, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, double* __restrict__ vel_f, int* __restrict__ rounds_out)
+    const int* __restrict__ n_ev, double* __restrict__ vel_f, int* __restrict__ rounds_out, int warm)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
     const int NTH = blockDim.x, PB = NTH / NT;
     const int tid = threadIdx.x, p = tid / NT, c = tid - p * NT;
-    ChunkCtx* ctx = reinterpret_cast<ChunkCtx*>(s_mem);
-    double* s_endv = reinterpret_cast<double*>(ctx + PB);        // [NTH] end state of every chunk
+    double* s_endv = reinterpret_cast<double*>(s_mem);           // [NTH] end state of every chunk
     double* s_endw = s_endv + NTH;
     double* s_usev = s_endw + NTH;                                // [NTH] start state every chunk last used
     double* s_usew = s_usev + NTH;
     int* s_queue = reinterpret_cast<int*>(s_usew + NTH);          // [NTH]
     __shared__ int s_qn;
-    const long long b = (long long)blockIdx.x * PB + p;
-    if (c == 0) {
+    // path context from the kernel parameters (pointers stay provably global: ld.global.nc, no generic loads)
+    auto make_ctx = [&](int pp) -> ChunkCtx {
         ChunkCtx x;
-        x.ok = (b < B) && status[b] == ST_OK;
-        x.D = x.ok ? n_samples[b] : 1;
+        const long long bb = (long long)blockIdx.x * PB + pp;
+        x.ok = (bb < B) && status[bb] == ST_OK;
+        x.D = x.ok ? n_samples[bb] : 1;
         long long steps = x.D - 1;
         x.Lc = steps > 0 ? (steps + NT - 1) / NT : 1;
-        x.nch = steps > 0 ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
-        if (x.ok) {
-            x.n_b = n_ev[2 * b + 1];
-            x.w = cons[b * 6 + 5];
-            x.rec = recF + (size_t)b * D_cap;
-            x.vin = nullptr;
-            x.vout = vel_f + (size_t)b * D_cap;
-            x.ma = max_accels + (size_t)b * E_cap;
-            x.bi = bidx + (size_t)b * E_cap;
-            x.bv = bval + (size_t)b * E_cap;
-            x.vout[0] = start_vel;
-        } else { x.n_b = 0; x.w = 1.0; x.rec = nullptr; x.vin = nullptr; x.vout = nullptr; x.ma = nullptr; x.bi = nullptr; x.bv = nullptr; x.nch = 0; }
-        ctx[p] = x;
-    }
+        x.nch = (x.ok && steps > 0) ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
+        const long long bs = x.ok ? bb : 0;
+        x.n_b = x.ok ? n_ev[2 * bs + 1] : 0;
+        x.w = cons[bs * 6 + 5];
+        x.rec = recF + (size_t)bs * D_cap;
+        x.vin = nullptr;
+        x.vout = vel_f + (size_t)bs * D_cap;
+        x.ma = max_accels + (size_t)bs * E_cap;
+        x.bi = bidx + (size_t)bs * E_cap;
+        x.bv = bval + (size_t)bs * E_cap;
+        return x;
+    };
+    const long long b = (long long)blockIdx.x * PB + p;
+    const ChunkCtx mine = make_ctx(p);
+    if (c == 0 && mine.ok) mine.vout[0] = start_vel;
     if (tid == 0) s_qn = 0;
     __syncthreads();
 
@@ -413,15 +421,20 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
         const double4* F = x.rec;
         double* vf = x.vout;
         int j = 1;
-        double acc = x.ma[x.bv[0]];
-        while (j < x.n_b && x.bi[j] <= (int)lo) { acc = x.ma[x.bv[j]]; j++; }
+        double acc = __ldg(x.ma + x.bv[0]);
+        while (j < x.n_b && x.bi[j] <= (int)lo) { acc = __ldg(x.ma + x.bv[j]); j++; }
         int nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
-        double4 r = F[lo];
-        double4 r1 = (lo + 1 < hi) ? F[lo + 1] : r;
+        double acc_next = (j < x.n_b) ? __ldg(x.ma + x.bv[j]) : acc;   // fetched one regime ahead: no load on the per-step path
+        double4 r = ldg_d4(F + lo);
+        double4 r1 = (lo + 1 < hi) ? ldg_d4(F + lo + 1) : r;
         if (!rerun) {
             for (long long i = lo; i < hi; i++) {
-                double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;          // records run two steps ahead of their use
-                if ((int)i == nb_next) { acc = x.ma[x.bv[j]]; j++; nb_next = (j < x.n_b) ? x.bi[j] : 2147483647; }
+                double4 r2 = (i + 2 < hi) ? ldg_d4(F + i + 2) : r1;          // records run two steps ahead of their use
+                if ((int)i == nb_next) {
+                    acc = acc_next; j++;
+                    nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
+                    acc_next = (j < x.n_b) ? __ldg(x.ma + x.bv[j]) : acc;
+                }
                 v = fwd_step(r, v, wp, acc, x.w, dd);
                 vf[i + 1] = v;
                 r = r1; r1 = r2;
@@ -431,9 +444,13 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
         double old = vf[lo + 1];
         double old1 = (lo + 1 < hi) ? vf[lo + 2] : 0.0;
         for (long long i = lo; i < hi; i++) {
-            double4 r2 = (i + 2 < hi) ? F[i + 2] : r1;
+            double4 r2 = (i + 2 < hi) ? ldg_d4(F + i + 2) : r1;
             double old2 = (i + 2 < hi) ? vf[i + 3] : 0.0;
-            if ((int)i == nb_next) { acc = x.ma[x.bv[j]]; j++; nb_next = (j < x.n_b) ? x.bi[j] : 2147483647; }
+            if ((int)i == nb_next) {
+                acc = acc_next; j++;
+                nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
+                acc_next = (j < x.n_b) ? __ldg(x.ma + x.bv[j]) : acc;
+            }
             v = fwd_step(r, v, wp, acc, x.w, dd);
             bool same = same_bits(old, v);
             if (same && prev_same) return true;        // state (v[i+1], v[i]*|k_i|) equals the old run's: rest is unchanged
@@ -444,18 +461,37 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
         return false;
     };
 
-    // ---- sweep 1
+    // ---- sweep 1.  Chunk c > 0 starts `warm` steps BEFORE its own range from the guess "the state-independent caps bind
+    // on the two samples before that point" and only computes (no stores) until it reaches its range: a wrong guess
+    // survives for at most one acceleration ramp, so after the warm-up the state is usually already the true one and the
+    // fix-up round has nothing to re-run.  (Exactness never depends on the guess: the rounds below verify bitwise.)
     {
-        const ChunkCtx x = ctx[p];
+        const ChunkCtx& x = mine;
         const bool active = x.ok && c < x.nch;
         double v = start_vel, wp = 0.0;
         if (active) {
             const long long lo = (long long)c * x.Lc;
-            if (c > 0) {            // guess: the state-independent caps bind on the two samples before the chunk
-                double vm1 = (lo >= 2) ? x.rec[lo - 2].w : start_vel;
-                double4 fm1 = x.rec[lo - 1];
+            if (c > 0) {
+                const long long wl = (warm < lo - 2) ? warm : ((lo - 2 > 0) ? lo - 2 : 0);
+                const long long s0 = lo - wl;                       // first warm-up step (>= 2 unless lo < 2)
+                double vm1 = (s0 >= 2) ? x.rec[s0 - 2].w : start_vel;
+                double4 fm1 = x.rec[s0 - 1];
                 v = fm1.w;
                 wp = vm1 * fm1.x;
+                if (wl > 0) {
+                    int j = 1;
+                    double acc = x.ma[x.bv[0]];
+                    while (j < x.n_b && x.bi[j] <= (int)s0) { acc = x.ma[x.bv[j]]; j++; }
+                    int nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
+                    double4 r = x.rec[s0];
+                    double4 r1 = (s0 + 1 < lo) ? x.rec[s0 + 1] : r;
+                    for (long long i = s0; i < lo; i++) {
+                        double4 r2 = (i + 2 < lo) ? x.rec[i + 2] : r1;
+                        if ((int)i == nb_next) { acc = x.ma[x.bv[j]]; j++; nb_next = (j < x.n_b) ? x.bi[j] : 2147483647; }
+                        v = fwd_step(r, v, wp, acc, x.w, dd);
+                        r = r1; r1 = r2;
+                    }
+                }
             }
             s_usev[tid] = v; s_usew[tid] = wp;
             run_chunk(x, c, v, wp, false, false);
@@ -468,7 +504,7 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
     int rounds = 0;
     for (int round = 1; round < NT; round++) {
         {
-            const ChunkCtx& x = ctx[p];
+            const ChunkCtx& x = mine;
             if (x.ok && c < x.nch && c >= round) {
                 if (!(same_bits(s_endv[tid - 1], s_usev[tid]) && same_bits(s_endw[tid - 1], s_usew[tid])))
                     s_queue[atomicAdd(&s_qn, 1)] = tid;
@@ -486,7 +522,7 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
         if (tid == 0) s_qn = 0;
         if (item >= 0) {
             const int pp = item / NT, cc = item - pp * NT;
-            const ChunkCtx x = ctx[pp];
+            const ChunkCtx x = (pp == p) ? mine : make_ctx(pp);
             double v = in_v, wp = in_w;
             bool merged = run_chunk(x, cc, v, wp, true, same_bits(in_v, old_usev));
             s_usev[item] = in_v; s_usew[item] = in_w;
@@ -494,7 +530,7 @@ __global__ void __launch_bounds__(256) k_fwd_chunked(
         }
         __syncthreads();
     }
-    if (c == 0 && rounds_out && ctx[p].ok) rounds_out[2 * b] = rounds;
+    if (c == 0 && rounds_out && mine.ok) rounds_out[2 * b] = rounds;
 }
 
 // Backward pass.  Steps i = D-1 .. 1 (step i writes vel[i-1]); chunk c owns the c-th block of steps counted from the
@@ -505,39 +541,39 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
     double end_vel, long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recR, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const double* __restrict__ vel_f, double* __restrict__ vel,
-    float* __restrict__ t_est, int* __restrict__ rounds_out)
+    float* __restrict__ t_est, int* __restrict__ rounds_out, int warm)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
     const int NTH = blockDim.x, PB = NTH / NT;
     const int tid = threadIdx.x, p = tid / NT, c = tid - p * NT;
-    ChunkCtx* ctx = reinterpret_cast<ChunkCtx*>(s_mem);
-    double* s_endv = reinterpret_cast<double*>(ctx + PB);
+    double* s_endv = reinterpret_cast<double*>(s_mem);
     double* s_endw = s_endv + NTH;
     double* s_usev = s_endw + NTH;
     double* s_usew = s_usev + NTH;
     int* s_queue = reinterpret_cast<int*>(s_usew + NTH);
     __shared__ int s_qn;
-    const long long b = (long long)blockIdx.x * PB + p;
-    if (c == 0) {
+    auto make_ctx = [&](int pp) -> ChunkCtx {
         ChunkCtx x;
-        x.ok = (b < B) && status[b] == ST_OK;
-        x.D = x.ok ? n_samples[b] : 1;
+        const long long bb = (long long)blockIdx.x * PB + pp;
+        x.ok = (bb < B) && status[bb] == ST_OK;
+        x.D = x.ok ? n_samples[bb] : 1;
         long long steps = x.D - 1;
         x.Lc = steps > 0 ? (steps + NT - 1) / NT : 1;
-        x.nch = steps > 0 ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
-        if (x.ok) {
-            x.n_b = n_ev[2 * b + 1];
-            x.w = cons[b * 6 + 5];
-            x.rec = recR + (size_t)b * D_cap;
-            x.vin = vel_f + (size_t)b * D_cap;
-            x.vout = vel + (size_t)b * D_cap;
-            x.ma = max_accels + (size_t)b * E_cap;
-            x.bi = bidx + (size_t)b * E_cap;
-            x.bv = bval + (size_t)b * E_cap;
-            x.vout[x.D - 1] = end_vel;
-        } else { x.n_b = 0; x.w = 1.0; x.rec = nullptr; x.vin = nullptr; x.vout = nullptr; x.ma = nullptr; x.bi = nullptr; x.bv = nullptr; x.nch = 0; }
-        ctx[p] = x;
-    }
+        x.nch = (x.ok && steps > 0) ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
+        const long long bs = x.ok ? bb : 0;
+        x.n_b = x.ok ? n_ev[2 * bs + 1] : 0;
+        x.w = cons[bs * 6 + 5];
+        x.rec = recR + (size_t)bs * D_cap;
+        x.vin = vel_f + (size_t)bs * D_cap;
+        x.vout = vel + (size_t)bs * D_cap;
+        x.ma = max_accels + (size_t)bs * E_cap;
+        x.bi = bidx + (size_t)bs * E_cap;
+        x.bv = bval + (size_t)bs * E_cap;
+        return x;
+    };
+    const long long b = (long long)blockIdx.x * PB + p;
+    const ChunkCtx mine = make_ctx(p);
+    if (c == 0 && mine.ok) mine.vout[mine.D - 1] = end_vel;
     if (tid == 0) s_qn = 0;
     __syncthreads();
 
@@ -549,19 +585,24 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
         const double* vf = x.vin;
         double* vo = x.vout;
         // regime at chunk start (walking down from D-1): the smallest boundary index > hi was the last one applied
-        double acc = x.ma[x.bv[x.n_b - 1]];
+        double acc = __ldg(x.ma + x.bv[x.n_b - 1]);
         int j = x.n_b - 1;
-        while (j >= 0 && x.bi[j] > (int)hi) { acc = x.ma[x.bv[j] + 1]; j--; }
+        while (j >= 0 && x.bi[j] > (int)hi) { acc = __ldg(x.ma + x.bv[j] + 1); j--; }
         int nb_next = (j >= 0) ? x.bi[j] : -1;
-        double4 r = R[hi];
-        double vfp = vf[hi - 1];
-        double4 r1 = (hi - 1 > lo) ? R[hi - 1] : r;
-        double vf1 = (hi - 1 > lo) ? vf[hi - 2] : 0.0;
+        double acc_next = (j >= 0) ? __ldg(x.ma + x.bv[j] + 1) : acc;   // fetched one regime ahead
+        double4 r = ldg_d4(R + hi);
+        double vfp = __ldg(vf + hi - 1);
+        double4 r1 = (hi - 1 > lo) ? ldg_d4(R + hi - 1) : r;
+        double vf1 = (hi - 1 > lo) ? __ldg(vf + hi - 2) : 0.0;
         if (!rerun) {
             for (long long i = hi; i > lo; i--) {
-                double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;          // loads run two steps ahead of their use
-                double vf2 = (i - 2 > lo) ? vf[i - 3] : 0.0;
-                if ((int)i == nb_next) { acc = x.ma[x.bv[j] + 1]; j--; nb_next = (j >= 0) ? x.bi[j] : -1; }
+                double4 r2 = (i - 2 > lo) ? ldg_d4(R + i - 2) : r1;          // loads run two steps ahead of their use
+                double vf2 = (i - 2 > lo) ? __ldg(vf + i - 3) : 0.0;
+                if ((int)i == nb_next) {
+                    acc = acc_next; j--;
+                    nb_next = (j >= 0) ? x.bi[j] : -1;
+                    acc_next = (j >= 0) ? __ldg(x.ma + x.bv[j] + 1) : acc;
+                }
                 v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
                 vo[i - 1] = v;
                 r = r1; vfp = vf1; r1 = r2; vf1 = vf2;
@@ -571,10 +612,14 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
         double old = vo[hi - 1];
         double old1 = (hi - 1 > lo) ? vo[hi - 2] : 0.0;
         for (long long i = hi; i > lo; i--) {
-            double4 r2 = (i - 2 > lo) ? R[i - 2] : r1;
-            double vf2 = (i - 2 > lo) ? vf[i - 3] : 0.0;
+            double4 r2 = (i - 2 > lo) ? ldg_d4(R + i - 2) : r1;
+            double vf2 = (i - 2 > lo) ? __ldg(vf + i - 3) : 0.0;
             double old2 = (i - 2 > lo) ? vo[i - 3] : 0.0;
-            if ((int)i == nb_next) { acc = x.ma[x.bv[j] + 1]; j--; nb_next = (j >= 0) ? x.bi[j] : -1; }
+            if ((int)i == nb_next) {
+                acc = acc_next; j--;
+                nb_next = (j >= 0) ? x.bi[j] : -1;
+                acc_next = (j >= 0) ? __ldg(x.ma + x.bv[j] + 1) : acc;
+            }
             v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
             bool same = same_bits(old, v);
             if (same && prev_same) return true;
@@ -587,17 +632,38 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
 
     // ---- sweep 1
     {
-        const ChunkCtx x = ctx[p];
+        const ChunkCtx& x = mine;
         const bool active = x.ok && c < x.nch;
         double v = end_vel, wp = 0.0;
         if (active) {
             const long long hi = (x.D - 1) - (long long)c * x.Lc;
             if (c > 0) {
-                // v[hi] was produced by step hi+1: min(pv, vel_f[hi], G[hi+1]); guess = the state-independent part
-                double4 r1 = x.rec[hi + 1];
-                v = pymin(x.vin[hi], r1.w);
-                double vp1 = (hi + 2 <= x.D - 1) ? pymin(x.vin[hi + 1], x.rec[hi + 2].w) : end_vel;
+                // warm-up (see the forward kernel): start `warm` steps above the chunk from the guess
+                // v[s0] = min(vel_f[s0], G[s0+1]) (the state-independent part of what step s0+1 produces)
+                const long long room = (x.D - 1) - hi - 2;
+                const long long wl = (warm < room) ? warm : (room > 0 ? room : 0);
+                const long long s0 = hi + wl;
+                double4 r1 = x.rec[s0 + 1];
+                v = pymin(x.vin[s0], r1.w);
+                double vp1 = (s0 + 2 <= x.D - 1) ? pymin(x.vin[s0 + 1], x.rec[s0 + 2].w) : end_vel;
                 wp = vp1 * r1.x;
+                if (wl > 0) {
+                    double acc = x.ma[x.bv[x.n_b - 1]];
+                    int j = x.n_b - 1;
+                    while (j >= 0 && x.bi[j] > (int)s0) { acc = x.ma[x.bv[j] + 1]; j--; }
+                    int nb_next = (j >= 0) ? x.bi[j] : -1;
+                    double4 r = x.rec[s0];
+                    double vfp = x.vin[s0 - 1];
+                    double4 ra = (s0 - 1 > hi) ? x.rec[s0 - 1] : r;
+                    double vfa = (s0 - 1 > hi) ? x.vin[s0 - 2] : 0.0;
+                    for (long long i = s0; i > hi; i--) {
+                        double4 rb = (i - 2 > hi) ? x.rec[i - 2] : ra;
+                        double vfb = (i - 2 > hi) ? x.vin[i - 3] : 0.0;
+                        if ((int)i == nb_next) { acc = x.ma[x.bv[j] + 1]; j--; nb_next = (j >= 0) ? x.bi[j] : -1; }
+                        v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
+                        r = ra; vfp = vfa; ra = rb; vfa = vfb;
+                    }
+                }
             }
             s_usev[tid] = v; s_usew[tid] = wp;
             run_chunk(x, c, v, wp, false, false);
@@ -610,7 +676,7 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
     int rounds = 0;
     for (int round = 1; round < NT; round++) {
         {
-            const ChunkCtx& x = ctx[p];
+            const ChunkCtx& x = mine;
             if (x.ok && c < x.nch && c >= round) {
                 if (!(same_bits(s_endv[tid - 1], s_usev[tid]) && same_bits(s_endw[tid - 1], s_usew[tid])))
                     s_queue[atomicAdd(&s_qn, 1)] = tid;
@@ -627,7 +693,7 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
         if (tid == 0) s_qn = 0;
         if (item >= 0) {
             const int pp = item / NT, cc = item - pp * NT;
-            const ChunkCtx x = ctx[pp];
+            const ChunkCtx x = (pp == p) ? mine : make_ctx(pp);
             double v = in_v, wp = in_w;
             bool merged = run_chunk(x, cc, v, wp, true, same_bits(in_v, old_usev));
             s_usev[item] = in_v; s_usew[item] = in_w;
@@ -635,13 +701,13 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
         }
         __syncthreads();
     }
-    if (c == 0 && rounds_out && ctx[p].ok) rounds_out[2 * b + 1] = rounds;
+    if (c == 0 && rounds_out && mine.ok) rounds_out[2 * b + 1] = rounds;
 
     // ---- travel-time estimate (single precision is plenty: it only sizes buffers)
     __syncthreads();
     float est = 0.f;
     {
-        const ChunkCtx x = ctx[p];
+        const ChunkCtx& x = mine;
         if (x.ok && c < x.nch) {
             const long long hi = (x.D - 1) - (long long)c * x.Lc;
             const long long lo = (hi - x.Lc > 0) ? hi - x.Lc : 0;
@@ -657,7 +723,7 @@ __global__ void __launch_bounds__(256) k_bwd_chunked(
     __syncthreads();
     if (c == 0 && t_est && b < B) {
         float tot = 0.f;
-        if (ctx[p].ok) for (int k = 0; k < NT; k++) tot += s_f[p * NT + k];
+        if (mine.ok) for (int k = 0; k < NT; k++) tot += s_f[p * NT + k];
         t_est[b] = tot;
     }
 }
