@@ -24,6 +24,16 @@ enum { P_T = 0, P_WAIT, P_MAXVEL, P_MAXACC };
 
 #define VAP_PI 3.141592653589793
 
+// cp.async (LDGSTS): 16-byte asynchronous global -> shared copies, tracked per thread in commit groups
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Python builtin min / max on floats: the first argument survives unless a later one is strictly smaller / larger.
 __device__ __forceinline__ double pymin(double a, double b) { return (b < a) ? b : a; }
 __device__ __forceinline__ double pymax(double a, double b) { return (b > a) ? b : a; }

@@ -53,15 +53,6 @@ __device__ __forceinline__ double div_const(double a, double b, double r)
     return q;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
-{
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 #define TS_BLK 128                 // samples per staged block of the velocity row
 #define TS_RING (2 * TS_BLK)       // two blocks resident per thread
 #define TS_STRIDE (TS_RING + 2)    // per-thread ring stride in doubles (16-byte aligned, spreads banks)

@@ -19,8 +19,6 @@ __device__ __forceinline__ double4 ldg_d4(const double4* p)
     double2 a = __ldg(q), b = __ldg(q + 1);
     return make_double4(a.x, a.y, b.x, b.y);
 }
-__device__ __forceinline__ void prefetch_l1v(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#define PF_DIST 12      // records ahead of the serial walk (3 cache lines of 32-byte records)
 
 // ---- S3 (parallel): t, kappa, theta per distance sample + event candidates -----------------------------------
 // wrap candidates: samples with frac(t[i-1]) > frac(t[i]) and t[i] < N-1  (motion_profile_generator.py:124)
