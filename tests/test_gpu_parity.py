@@ -410,3 +410,21 @@ def test_cfg3_tiled_job_summaries(ora):
         ref = ora.full(packed.node_attr[b], packed.node_flags[b], None, None, packed.cons[b])
         assert int(summ[b, 0]) == ref["T"]
         np.testing.assert_allclose(summ[b, :4], ref["summary"][:4], rtol=1e-6)
+
+
+def test_stream_to_host_pipeline():
+    """Bulk streaming API: results of a pipelined stream equal the one-batch-at-a-time results, in order."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    batches = [synth.mixed_paths(256, 8, seed=50 + i) for i in range(5)]
+    refs = [eng.profile(eng.upload(p)) for p in batches]
+    n = 0
+    for h, ref in zip(eng.stream_to_host(batches, tiles=3), refs):
+        assert h.n_out.tolist() == ref.n_out.cpu().tolist()
+        for b in (0, 100, 255):
+            got, want = h.path(b), ref.path(b)
+            for k in ("times", "x", "linear_vels", "headings"):
+                assert np.array_equal(got[k], want[k])
+        n += 1
+    assert n == 5

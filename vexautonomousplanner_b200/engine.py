@@ -140,6 +140,7 @@ class Engine:
         self._dgrid: Optional[torch.Tensor] = None
         self._plan: Dict[tuple, tuple] = {}
         self._streams: list = []
+        self._host_slots: Dict[int, list] = {}
         self.launches = 0      # kernels launched by this engine (bench.py reports it)
         self.stage_events = None   # set to a list to record (stage, start_event, end_event) per stage call
 
@@ -461,33 +462,39 @@ class Engine:
             rows.append(res.summary)
         return torch.cat(rows, dim=0) if rows else self._empty((0, 5))
 
-    def profile_to_host(self, packed: PackedPaths, tiles: int = 8, state: Optional[dict] = None) -> "HostResult":
-        """Host buffers in, host buffers out, copy-engine variant: every tile packs its valid rows densely on the device;
-        as soon as a tile's row count has reached the host, the copy engine moves exactly those bytes into pinned memory
-        while later tiles are still computing.  `state` (returned in HostResult.state) carries the reusable buffers."""
+    def _host_state(self, packed: PackedPaths, tiles: int, state: Optional[dict]) -> dict:
+        """Reusable buffers of the host-in / host-out path for one batch shape (device inputs, dense device rows, pinned
+        inputs and results, per-tile events, a copy stream)."""
         B = packed.B
-        st = state or {}
         key = (B, packed.N_max, packed.A_max, packed.max_splines())
-        if st.get("key") != key:
-            db = self.upload(packed)
-            self.profile(db, reuse_plan=True)                       # plan (D_cap, T_cap) for this shape
-            D_cap, T_cap = self._plan[(B, db.N_max, db.A_max, db.max_splines)]
-            tiles = max(1, min(tiles, B))
-            st = dict(key=key, db=db, D_cap=D_cap, T_cap=T_cap, tiles=tiles,
-                      host=HostResult(self, B, db.N_max, db.A_max, T_cap, tiles),
-                      dense=self._empty((8 * B * T_cap,)), events=[torch.cuda.Event() for _ in range(tiles)],
-                      copy_stream=torch.cuda.Stream(device=self.device),
-                      pin=[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
-                           (db.node_attr, db.node_flags, db.n_nodes, db.ap_attr, db.ap_flags, db.n_ap, db.cons)])
-        db, host, T_cap = st["db"], st["host"], st["T_cap"]
+        st = state or {}
+        if st.get("key") == key:
+            return st
+        db = self.upload(packed)
+        self.profile(db, reuse_plan=True)                       # plan (D_cap, T_cap) for this shape
+        D_cap, T_cap = self._plan[(B, db.N_max, db.A_max, db.max_splines)]
+        tiles = max(1, min(tiles, B))
+        return dict(key=key, db=db, D_cap=D_cap, T_cap=T_cap, tiles=tiles,
+                    host=HostResult(self, B, db.N_max, db.A_max, T_cap, tiles),
+                    dense=self._empty((8 * B * T_cap,)), events=[torch.cuda.Event() for _ in range(tiles)],
+                    copy_stream=torch.cuda.Stream(device=self.device),
+                    pin=[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
+                         (db.node_attr, db.node_flags, db.n_nodes, db.ap_attr, db.ap_flags, db.n_ap, db.cons)])
+
+    def _host_submit(self, packed: PackedPaths, st: dict) -> None:
+        """Enqueue one batch: inputs host -> device, every tile's kernels, dense packing, small result arrays."""
+        db = st["db"]
         srcs = (packed.node_attr, packed.node_flags, packed.n_nodes, packed.ap_attr, packed.ap_flags, packed.n_ap, packed.cons)
         dsts = (db.node_attr, db.node_flags, db.n_nodes, db.ap_attr, db.ap_flags, db.n_ap, db.cons)
         for pin, src, dst in zip(st["pin"], srcs, dsts):
             pin.copy_(torch.from_numpy(src))
             dst.copy_(pin, non_blocking=True)
-        self._profile_tiled(db, st["D_cap"], T_cap, st["tiles"], host=host, dense=st["dense"], events=st["events"],
-                            stagger=True)
-        cs = st["copy_stream"]
+        self._profile_tiled(db, st["D_cap"], st["T_cap"], st["tiles"], host=st["host"], dense=st["dense"],
+                            events=st["events"], stagger=True)
+
+    def _host_collect(self, st: dict) -> "HostResult":
+        """As each tile's row count reaches the host, let the copy engine move exactly those bytes; wait for all."""
+        host, T_cap, cs = st["host"], st["T_cap"], st["copy_stream"]
         for k, (lo, hi) in enumerate(host.bounds):
             if hi <= lo:
                 continue
@@ -497,12 +504,47 @@ class Engine:
             with torch.cuda.stream(cs):
                 host.packed[a: a + 8 * total].copy_(st["dense"][a: a + 8 * total], non_blocking=True)
         cs.synchronize()
+        host.state = st
+        return host
+
+    def profile_to_host(self, packed: PackedPaths, tiles: int = 8, state: Optional[dict] = None) -> "HostResult":
+        """Host buffers in, host buffers out: every tile packs its valid rows densely on the device; as soon as a tile's
+        row count has reached the host, the copy engine moves exactly those bytes into pinned memory while later tiles
+        are still computing.  `state` (returned in HostResult.state) carries the reusable buffers."""
+        st = self._host_state(packed, tiles, state)
+        self._host_submit(packed, st)
+        host = self._host_collect(st)
         torch.cuda.current_stream(self.device).synchronize()
         if bool((host.status == ST_CAPACITY).any()):
-            self._plan.pop((B, db.N_max, db.A_max, db.max_splines), None)
+            self._plan.pop((packed.B, st["db"].N_max, st["db"].A_max, st["db"].max_splines), None)
             st["key"] = None
             return self.profile_to_host(packed, tiles, st)
-        host.state = st
+        return host
+
+    def stream_to_host(self, batches, tiles: int = 4, depth: int = 2):
+        """Bulk jobs: a generator over HostResults for an iterable of same-shape PackedPaths batches, software-pipelined
+        `depth` deep -- batch n+1's kernels are already in flight while batch n's rows cross PCIe.  A yielded HostResult
+        stays valid until `depth` more batches have been submitted."""
+        slots = self._host_slots.setdefault(depth, [None] * depth)   # pinned buffers are expensive: kept across calls
+        inflight = []                                            # (slot index, batch) in submission order
+        n = 0
+        for packed in batches:
+            k = n % depth
+            if len(inflight) == depth:                           # the slot is still owned by an older batch: finish it
+                ks, pk = inflight.pop(0)
+                yield self._finish_streamed(slots, ks, pk, tiles)
+            slots[k] = self._host_state(packed, tiles, slots[k])
+            self._host_submit(packed, slots[k])
+            inflight.append((k, packed))
+            n += 1
+        while inflight:
+            ks, pk = inflight.pop(0)
+            yield self._finish_streamed(slots, ks, pk, tiles)
+
+    def _finish_streamed(self, slots, k, packed, tiles):
+        host = self._host_collect(slots[k])
+        if bool((host.status == ST_CAPACITY).any()):             # rare: plan too small -> exact, unpipelined redo
+            host = self.profile_to_host(packed, tiles, None)
         return host
 
     def capture(self, db: DeviceBatch, tiles: int = 4, to_host: bool = False) -> "GraphedProfile":
