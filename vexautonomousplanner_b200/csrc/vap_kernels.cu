@@ -1296,3 +1296,18 @@ extern "C" int vap_pack_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride,
     CHECK_LAUNCH("vap_pack_rows");
     return 0;
 }
+
+// numeric rows of the trajectory export, dense per path
+extern "C" int vap_export_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const double* out, const int32_t* n_out,
+                               const int32_t* status, int64_t* offsets, double* dst, void* stream)
+{
+    if (B <= 0) return 0;
+    if (B > 65535) return arg_err("vap_export_rows: B > 65535 per call (tile the batch)");
+    const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
+    k_row_offsets<<<1, 1024, 0, STREAM>>>(B, n_out, status, T_cap, reinterpret_cast<long long*>(offsets));
+    CHECK_LAUNCH("vap_export_rows/offsets");
+    dim3 grid(blocks_for(T_cap, 256), (unsigned)B);
+    k_export_rows<<<grid, 256, 0, STREAM>>>(B, n_out, status, T_cap, oplane, out, reinterpret_cast<const long long*>(offsets), dst);
+    CHECK_LAUNCH("vap_export_rows");
+    return 0;
+}

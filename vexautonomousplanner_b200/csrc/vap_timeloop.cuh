@@ -544,3 +544,28 @@ __global__ void __launch_bounds__(256) k_pack_rows(long long B, const int* __res
         for (int s = 0; s < 8; s++) d[(size_t)s * n] = src[(size_t)s * oplane];
     }
 }
+
+
+// ---- "next" row f1: numeric rows of the trajectory export (gui_manager.py:284-295) --------------------------------
+// For every time sample the reference writes [0, t, x*12, y*-12, heading, v*12, omega]; dst[7*(offsets[b] + k) + c].
+__global__ void __launch_bounds__(256) k_export_rows(long long B, const int* __restrict__ n_out,
+                                                     const int* __restrict__ status, long long T_cap, long long oplane,
+                                                     const double* __restrict__ out,
+                                                     const long long* __restrict__ offsets, double* __restrict__ dst)
+{
+    long long b = blockIdx.y;
+    if (status[b] != ST_OK) return;
+    long long n = n_out[b];
+    if (n > T_cap) n = T_cap;
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* src = out + (size_t)b * T_cap + k;
+    double* d = dst + 7 * (offsets[b] + k);
+    d[0] = 0.0;
+    d[1] = src[0];                          // times
+    d[2] = src[(size_t)6 * oplane] * 12;    // coords[i][0] * 12
+    d[3] = src[(size_t)7 * oplane] * -12;   // coords[i][1] * -12
+    d[4] = src[(size_t)4 * oplane];         // headings
+    d[5] = src[(size_t)2 * oplane] * 12;    // velocities * 12
+    d[6] = src[(size_t)5 * oplane];         // angular velocities
+}

@@ -1,0 +1,146 @@
+"""'Next' rows f1 + f2 of SURVEY.md section 8: what runs right after / right before the profiled path.
+
+f1  trajectory export (gui_manager.py:220-230, 284-316): rows [0, t, x*12, -y*12, heading, v*12, omega] per time sample
+    (built on the device, vap_export_rows), action rows [1, *action_values] spliced at nodes_map[i] + i and
+    actions_map[i] + i, text written as f"{v} " per value -- the same formatting expression as the reference, so the
+    text is identical for identical numbers.
+f2  node JSON codec (gui_manager.py:388-427, gui/path.py:590-644): [[x_in, y_in, start, end, reverse, stop, turn, wait,
+    tangent, in_mag, out_mag, *actions], ...], [[x_in, y_in, t, stop, wait, *actions], ...] with the inch <-> pixel <->
+    foot conversions of the GUI (145.308474301 in, 12.1090395251 ft per 2000 px).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine, ProfileResult, _p
+from .packing import PX_TO_FT
+
+PX_TO_IN = 145.308474301          # gui/node.py:39-40
+
+
+def export_rows(eng: Engine, res: ProfileResult):
+    """Device-built numeric export rows for every path: returns (rows[sum_T, 7] tensor, offsets[B+1] tensor)."""
+    B, T_cap = res.B, res.T_cap
+    offsets = torch.zeros(B + 1, dtype=torch.int64, device=eng.device)
+    total_cap = int(res.n_out.clamp(min=0).sum().item())
+    rows = torch.empty((max(total_cap, 1), 7), dtype=torch.float64, device=eng.device)
+    _lib.check(eng.lib.vap_export_rows(C.c_int64(B), C.c_int64(T_cap), C.c_int64(res.out.shape[1] * T_cap), _p(res.out),
+                                       _p(res.n_out), _p(res.status), _p(offsets), _p(rows), eng._stream()),
+               "vap_export_rows")
+    eng.launches += 2
+    return rows[:total_cap], offsets
+
+
+def splice_action_rows(traj_rows: Sequence[Sequence[float]], nodes_map: Sequence[int], node_actions: Sequence[Sequence],
+                       actions_map: Sequence[int] = (), action_rows: Sequence[Sequence] = ()) -> List[list]:
+    """gui_manager.py:284-310: trajectory rows with the node / action-point rows inserted at map[i] + i."""
+    data = [[0] + [v for v in r[1:]] for r in traj_rows]
+    for i in range(len(nodes_map)):
+        data.insert(int(nodes_map[i] / 1) + i, [1] + list(node_actions[i]))
+    for i in range(len(actions_map)):
+        data.insert(int(actions_map[i] / 1) + i, [1] + list(action_rows[i]))
+    return data
+
+
+def format_rows(nodes_data: Sequence[Sequence]) -> str:
+    """fill_txt_file (gui_manager.py:220-230): every value followed by a blank, one row per line."""
+    res = ""
+    for data in nodes_data:
+        for v in data:
+            res += f"{v} "
+        res += "\n"
+    return res
+
+
+def trajectory_text(eng: Engine, res: ProfileResult, b: int, node_actions: Sequence[Sequence],
+                    action_rows: Sequence[Sequence] = ()) -> str:
+    """The .txt body the reference writes for path b (nodes_map includes the trailing len(times), gui/path.py:342)."""
+    rows, offsets = export_rows(eng, res)
+    lo, hi = int(offsets[b]), int(offsets[b + 1])
+    r = rows[lo:hi].cpu().numpy()
+    nm = res.nodes_map[b, : int(res.n_maps[b, 0])].cpu().numpy()
+    am = res.actions_map[b, : int(res.n_maps[b, 1])].cpu().numpy()
+    traj = [[0] + [np.float64(v) for v in row[1:]] for row in r]
+    return format_rows(splice_action_rows(traj, nm, node_actions, am, action_rows))
+
+
+# ---------------------------------------------------------------------------------------------------- f2: JSON codec
+def px_to_in(px: float) -> float:
+    return ((px / 2000) - 0.5) * PX_TO_IN          # Node.get_abs_x (gui/node.py:53-55)
+
+
+def in_to_px(v: float) -> float:
+    return (v / PX_TO_IN + 0.5) * 2000             # PathWidget.convert_point (gui/path.py:590-594)
+
+
+def nodes_to_json(points_px, nodes, action_points=(), action_points_px=(), as_list: bool = False):
+    """convert_nodes (gui_manager.py:388-427).  Node objects are duck-typed (attributes of gui/node.py)."""
+    nodes_data = []
+    for (x, y), nd in zip(points_px, nodes):
+        tan = getattr(nd, "tangent", None)
+        nodes_data.append([px_to_in(x), px_to_in(y), int(getattr(nd, "is_start_node", False)),
+                           int(getattr(nd, "is_end_node", False)), int(nd.is_reverse_node), int(nd.stop), nd.turn,
+                           nd.wait_time, None if tan is None else [float(tan[0]), float(tan[1])],
+                           nd.incoming_magnitude, nd.outgoing_magnitude] + list(getattr(nd, "action_values", [])))
+    action_data = []
+    for (x, y), ap in zip(action_points_px, action_points):
+        action_data.append([px_to_in(x), px_to_in(y), ap.t, int(ap.stop), ap.wait_time]
+                           + list(getattr(ap, "action_values", [])))
+    if as_list:
+        return [nodes_data, action_data]
+    return json.dumps([nodes_data, action_data], separators=(",", ":"))
+
+
+class RouteNode:
+    """Plain stand-in for gui.node.Node with the attributes the hot path reads."""
+
+    def __init__(self):
+        self.is_start_node = False; self.is_end_node = False; self.is_reverse_node = False; self.stop = False
+        self.turn = 0; self.wait_time = 0; self.tangent = None; self.incoming_magnitude = None
+        self.outgoing_magnitude = None; self.max_velocity = 0; self.max_acceleration = 0; self.action_values = []
+
+
+class RouteActionPoint:
+    def __init__(self, t):
+        self.t = t; self.stop = False; self.wait_time = 0; self.max_velocity = 0; self.max_acceleration = 0
+        self.action_values = []
+
+
+def load_nodes(node_str: str):
+    """load_nodes (gui/path.py:602-644) without Qt: returns (points_px[N,2], nodes, action_points, action_px[A,2]).
+    Like the GUI, the start node is moved to the front and the end node to the back of the point list
+    (PathWidget._execute_update_path, gui/path.py:407-413)."""
+    data = json.loads(node_str)
+    nodes_data, action_data = (data[0], data[1]) if len(data) == 2 else (data, [])
+    pts, nodes = [], []
+    for nd in nodes_data:
+        if len(nd) > 4:
+            n = RouteNode()
+            n.is_start_node, n.is_end_node = bool(nd[2]), bool(nd[3])
+            n.is_reverse_node, n.stop = bool(nd[4]), bool(nd[5])
+            n.turn, n.wait_time = nd[6], nd[7]
+            n.tangent = None if nd[8] is None else np.array(nd[8])
+            n.incoming_magnitude, n.outgoing_magnitude = nd[9], nd[10]
+            n.action_values = list(nd[11:])
+            nodes.append(n)
+            pts.append([in_to_px(nd[0]), in_to_px(nd[1])])
+    aps, apx = [], []
+    for ad in action_data:
+        a = RouteActionPoint(ad[2])
+        a.stop, a.wait_time = ad[3], ad[4]
+        a.action_values = list(ad[5:])
+        aps.append(a)
+        apx.append([in_to_px(ad[0]), in_to_px(ad[1])])
+    return np.array(pts, dtype=np.float64).reshape(-1, 2), nodes, aps, np.array(apx, dtype=np.float64).reshape(-1, 2)
+
+
+def px_points_to_ft(points_px) -> np.ndarray:
+    """PathWidget.update_spline (gui/path.py:365-367)."""
+    p = np.asarray(points_px, dtype=np.float64)
+    return (p / 2000 - 0.5) * PX_TO_FT
