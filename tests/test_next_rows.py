@@ -39,7 +39,8 @@ def test_splice_and_format_cpu():
     from vexautonomousplanner_b200 import export as ex
     traj = [[0, 0, 1.5, -2.0, 0.25, 12.0, 0.0], [0, np.float64(0.01), np.float64(1.25), 3.0, 0.5, 6.0, -0.125]]
     data = ex.splice_action_rows(traj, [0, 1, 2], [[7], [8], [9]], [1], [[5, 5]])
-    assert data[0] == [1, 7] and data[2] == [1, 8] and data[-1] == [1, 9] and [1, 5, 5] in data and len(data) == 6
+    # nodes rows go to map[i] + i = 0, 2, 4; the action row then to actions_map[0] + 0 = 1 (gui_manager.py:307-310)
+    assert data[0] == [1, 7] and data[1] == [1, 5, 5] and data[3] == [1, 8] and data[-1] == [1, 9] and len(data) == 6
     txt = ex.format_rows(data)
     assert txt.splitlines()[0] == "1 7 " and txt.endswith("\n")
     assert "0 0.01 1.25 3.0 0.5 6.0 -0.125 " in txt
