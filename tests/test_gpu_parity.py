@@ -428,3 +428,23 @@ def test_stream_to_host_pipeline():
                 assert np.array_equal(got[k], want[k])
         n += 1
     assert n == 5
+
+
+@pytest.mark.parametrize("kind,nn", [("cfg5", 8), ("cfg2", 8), ("cfg3", 16)])
+def test_fuzz_summaries_against_oracle(eng, ora, kind, nn):
+    """Thousands of random paths: sample counts exact, summary values within tolerance, for every path of the batch
+    (the oracle's OpenMP batch driver computes the reference summaries in a few seconds)."""
+    from vexautonomousplanner_b200 import synth
+    B = 3000 if nn == 8 else 600
+    packed = synth.mixed_paths(B, nn, seed=77) if kind == "cfg5" else synth.random_paths(B, nn, seed=78)
+    res = eng.profile(eng.upload(packed))
+    torch.cuda.synchronize()
+    got = res.summary.cpu().numpy()
+    want = ora.full_batch(packed.node_attr, packed.node_flags, packed.cons, n_ap=packed.n_ap, ap_attr=packed.ap_attr,
+                          ap_flags=packed.ap_flags, cap_d=80000, cap_t=60000)
+    assert (got[:, 4] == 0).all() and (want[:, 4] == 0).all()
+    bad = np.nonzero(got[:, 0] != want[:, 0])[0]
+    assert bad.size == 0, f"time-sample counts differ for paths {bad[:10].tolist()}"
+    np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=1e-12)        # total length
+    np.testing.assert_allclose(got[:, 2], want[:, 2], rtol=1e-6)         # t_end
+    np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=1e-6)         # max |v|
