@@ -226,6 +226,17 @@ int vap_pack_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const doub
 int vap_export_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const double* out, const int32_t* n_out,
                     const int32_t* status, int64_t* offsets, double* dst, void* stream);
 
+/* "Next" row f1, text: Python's repr(float) (= what f"{v} " writes, gui_manager.py:220-230) on the device.
+ *   vap_format_doubles: n values -> 32-byte NUL-padded slots out32[n][32] + lens[n].
+ *   vap_format_rows: export rows[R][7] -> one line per row ("0 t x y heading v omega \n", every value followed by a
+ *     blank) in slots[R][vap_row_text_stride()] + lens[R]; int_time[R] (u8, may be NULL) prints the time column as the
+ *     integer 0 (times[0] is an int in the reference).  vap_compact_rows then gathers the lines at offsets[R]
+ *     (exclusive prefix sum of lens, i64) into one contiguous text buffer.                                         */
+int vap_format_doubles(int64_t n, const double* x, char* out32, int32_t* lens, void* stream);
+int vap_row_text_stride(void);
+int vap_format_rows(int64_t R, const double* rows, const uint8_t* int_time, char* slots, int32_t* lens, void* stream);
+int vap_compact_rows(int64_t R, const char* slots, const int32_t* lens, const int64_t* offsets, char* text, void* stream);
+
 /* Test hook: counts (into the device word *bad) the pseudo-random numerators a, out of n, for which the hoisted-
  * reciprocal division used inside the time loop differs from the IEEE quotient a / b.  Must stay 0.            */
 int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* bad, void* stream);

@@ -64,14 +64,44 @@ def test_export_rows_on_device():
                          p["linear_vels"] * 12, p["angular_vels"]], axis=1)
         got = rows[offsets[b]:offsets[b + 1]]
         assert got.shape == want.shape and np.array_equal(got.view(np.int64), want.view(np.int64))
-    txt = ex.trajectory_text(eng, res, 17, [[i] for i in range(8)], [[9], [9]])
-    lines = txt.splitlines()
-    p = res.path(17)
-    assert len(lines) == len(p["times"]) + len(p["nodes_map"]) + len(p["actions_map"])
-    assert lines[0] == "1 0 "
-    first = [0, np.float64(p["times"][0]), np.float64(p["x"][0] * 12), np.float64(p["y"][0] * -12),
-             np.float64(p["headings"][0]), np.float64(p["linear_vels"][0] * 12), np.float64(p["angular_vels"][0])]
-    assert lines[1] == "".join(f"{v} " for v in first)
+    # text: the device formatter must reproduce the reference's own expression f"{v} " on the same numbers
+    wait0 = eng.upload(packed).node_attr[:, 0, 3]
+    dev_text = ex.export_text_device(eng, res, wait0)
+    for b in (0, 17, 39):
+        p = res.path(b)
+        txt = ex.trajectory_text(eng, res, b, [[i] for i in range(8)], [[9], [9]], device_text=dev_text)
+        traj = [[0, (0 if (k == 0 and int(packed.node_attr[b, 0, 3] / 0.01) == 0) else np.float64(p["times"][k])),
+                 np.float64(p["x"][k] * 12), np.float64(p["y"][k] * -12), np.float64(p["headings"][k]),
+                 np.float64(p["linear_vels"][k] * 12), np.float64(p["angular_vels"][k])] for k in range(len(p["times"]))]
+        want = ex.format_rows(ex.splice_action_rows(traj, p["nodes_map"], [[i] for i in range(8)], p["actions_map"],
+                                                    [[9], [9]]))
+        assert txt == want, b
+        assert txt.splitlines()[0] == "1 0 "
+
+
+@pytest.mark.gpu
+def test_device_repr_matches_python():
+    """The device formatter is repr(float): random bit patterns, typical trajectory magnitudes and the edge cases."""
+    import random
+    import struct
+    import torch
+    from vexautonomousplanner_b200 import export as ex
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    random.seed(11)
+    vals = [0.0, -0.0, 1.0, -1.5, 0.1, 1e16, 1e15, 9999999999999998.0, 1e-4, 1e-5, 123456789012345678.0, 5e-324,
+            2.2250738585072014e-308, 1.7976931348623157e308, float("inf"), float("-inf"), 0.3, 2 / 3, 1e22, 1e23,
+            0.30000000000000004, 9007199254740993.0, 5e-5, 0.001]
+    while len(vals) < 300000:
+        x = struct.unpack("<d", struct.pack("<Q", random.getrandbits(64)))[0]
+        if x == x:
+            vals.append(x)
+    rng = np.random.default_rng(2)
+    vals += list(rng.uniform(-80, 80, 200000)) + list(rng.uniform(-1e-3, 1e-3, 50000)) + [i * 0.01 for i in range(4000)]
+    got = ex.format_doubles_device(eng, torch.tensor(vals, dtype=torch.float64, device="cuda:0"))
+    bad = [(g, repr(float(v))) for g, v in zip(got, vals) if g != repr(float(v))]
+    assert not bad, bad[:5]
+    assert ex.format_doubles_device(eng, torch.tensor([float("nan")], dtype=torch.float64, device="cuda:0")) == ["nan"]
 
 
 @pytest.mark.gpu

@@ -15,6 +15,7 @@
 #include "vap_device.cuh"
 #include "vap_velocity.cuh"
 #include "vap_timeloop.cuh"
+#include "vap_format.cuh"
 
 static thread_local char g_err[512] = "";
 static int set_err(const char* where, cudaError_t e)
@@ -1309,5 +1310,30 @@ extern "C" int vap_export_rows(int64_t B, int64_t T_cap, int64_t out_plane_strid
     dim3 grid(blocks_for(T_cap, 256), (unsigned)B);
     k_export_rows<<<grid, 256, 0, STREAM>>>(B, n_out, status, T_cap, oplane, out, reinterpret_cast<const long long*>(offsets), dst);
     CHECK_LAUNCH("vap_export_rows");
+    return 0;
+}
+
+// ---- text of the export (repr(float)-exact) -------------------------------------------------------------------------
+extern "C" int vap_format_doubles(int64_t n, const double* x, char* out32, int32_t* lens, void* stream)
+{
+    if (n <= 0) return 0;
+    k_format_doubles<<<blocks_for(n, 256), 256, 0, STREAM>>>(n, x, out32, lens);
+    CHECK_LAUNCH("vap_format_doubles");
+    return 0;
+}
+extern "C" int vap_row_text_stride(void) { return VAP_ROW_STRIDE; }
+extern "C" int vap_format_rows(int64_t R, const double* rows, const uint8_t* int_time, char* slots, int32_t* lens, void* stream)
+{
+    if (R <= 0) return 0;
+    k_format_rows<<<blocks_for(R, 128), 128, 0, STREAM>>>(R, rows, int_time, slots, lens);
+    CHECK_LAUNCH("vap_format_rows");
+    return 0;
+}
+extern "C" int vap_compact_rows(int64_t R, const char* slots, const int32_t* lens, const int64_t* offsets, char* text,
+                                void* stream)
+{
+    if (R <= 0) return 0;
+    k_compact_rows<<<blocks_for(R * 32, 256), 256, 0, STREAM>>>(R, slots, lens, reinterpret_cast<const long long*>(offsets), text);
+    CHECK_LAUNCH("vap_compact_rows");
     return 0;
 }

@@ -37,6 +37,55 @@ def export_rows(eng: Engine, res: ProfileResult):
     return rows[:total_cap], offsets
 
 
+def format_rows_device(eng: Engine, rows: torch.Tensor, int_time: Optional[torch.Tensor] = None):
+    """Text of export rows on the device (repr(float)-exact, vap_format_rows + vap_compact_rows).
+    Returns (text uint8[total], row_offsets int64[R+1]); line r is text[row_offsets[r]:row_offsets[r+1]]."""
+    R = rows.shape[0]
+    stride = int(eng.lib.vap_row_text_stride())
+    slots = torch.empty((max(R, 1), stride), dtype=torch.uint8, device=eng.device)
+    lens = torch.zeros(max(R, 1), dtype=torch.int32, device=eng.device)
+    _lib.check(eng.lib.vap_format_rows(C.c_int64(R), _p(rows), _p(int_time), _p(slots), _p(lens), eng._stream()),
+               "vap_format_rows")
+    offsets = torch.zeros(R + 1, dtype=torch.int64, device=eng.device)
+    torch.cumsum(lens[:R], dim=0, out=offsets[1:])                 # plumbing: exclusive scan of the line lengths
+    total = int(offsets[R].item())
+    text = torch.empty(max(total, 1), dtype=torch.uint8, device=eng.device)
+    _lib.check(eng.lib.vap_compact_rows(C.c_int64(R), _p(slots), _p(lens), _p(offsets), _p(text), eng._stream()),
+               "vap_compact_rows")
+    eng.launches += 2
+    return text[:total], offsets
+
+
+def export_text_device(eng: Engine, res: ProfileResult, node0_wait: Optional[torch.Tensor] = None):
+    """Trajectory lines of every path of the batch, formatted on the device.
+    Returns (text, row_offsets, path_row_offsets): path b owns rows path_row_offsets[b] .. path_row_offsets[b+1].
+    node0_wait[B]: wait_time of node 0 (the first time stamp prints as the integer 0 when there is no prologue,
+    motion_profile_generator.py:425,459-476); None = no prologue anywhere."""
+    rows, poff = export_rows(eng, res)
+    R = rows.shape[0]
+    int_time = torch.zeros(max(R, 1), dtype=torch.uint8, device=eng.device)
+    if R:
+        has_rows = res.n_out.clamp(min=0) > 0
+        first = poff[:-1][has_rows]
+        if node0_wait is not None:
+            first = first[(node0_wait[has_rows] / eng.dt).floor() < 1]
+        int_time[first] = 1
+    text, roff = format_rows_device(eng, rows, int_time)
+    return text, roff, poff
+
+
+def format_doubles_device(eng: Engine, x: torch.Tensor) -> List[str]:
+    """repr() of every element of a device fp64 tensor (test / utility entry point of the formatter)."""
+    n = x.numel()
+    out = torch.zeros((max(n, 1), 32), dtype=torch.uint8, device=eng.device)
+    lens = torch.zeros(max(n, 1), dtype=torch.int32, device=eng.device)
+    _lib.check(eng.lib.vap_format_doubles(C.c_int64(n), _p(x.contiguous()), _p(out), _p(lens), eng._stream()),
+               "vap_format_doubles")
+    eng.launches += 1
+    o, l = out.cpu().numpy(), lens.cpu().numpy()
+    return [bytes(o[i, : l[i]]).decode() for i in range(n)]
+
+
 def splice_action_rows(traj_rows: Sequence[Sequence[float]], nodes_map: Sequence[int], node_actions: Sequence[Sequence],
                        actions_map: Sequence[int] = (), action_rows: Sequence[Sequence] = ()) -> List[list]:
     """gui_manager.py:284-310: trajectory rows with the node / action-point rows inserted at map[i] + i."""
@@ -59,15 +108,21 @@ def format_rows(nodes_data: Sequence[Sequence]) -> str:
 
 
 def trajectory_text(eng: Engine, res: ProfileResult, b: int, node_actions: Sequence[Sequence],
-                    action_rows: Sequence[Sequence] = ()) -> str:
-    """The .txt body the reference writes for path b (nodes_map includes the trailing len(times), gui/path.py:342)."""
-    rows, offsets = export_rows(eng, res)
-    lo, hi = int(offsets[b]), int(offsets[b + 1])
-    r = rows[lo:hi].cpu().numpy()
+                    action_rows: Sequence[Sequence] = (), node0_wait: Optional[torch.Tensor] = None,
+                    device_text=None) -> str:
+    """The .txt body the reference writes for path b (nodes_map includes the trailing len(times), gui/path.py:342).
+    The trajectory lines come from the device formatter; only the handful of action rows is formatted and spliced here.
+    device_text: result of export_text_device (reuse it when writing many paths of one batch)."""
+    text, roff, poff = device_text if device_text is not None else export_text_device(eng, res, node0_wait)
+    r0, r1 = int(poff[b]), int(poff[b + 1])
+    lines = bytes(text[int(roff[r0]): int(roff[r1])].cpu().numpy()).decode().splitlines(keepends=True)
     nm = res.nodes_map[b, : int(res.n_maps[b, 0])].cpu().numpy()
     am = res.actions_map[b, : int(res.n_maps[b, 1])].cpu().numpy()
-    traj = [[0] + [np.float64(v) for v in row[1:]] for row in r]
-    return format_rows(splice_action_rows(traj, nm, node_actions, am, action_rows))
+    for i in range(len(nm)):
+        lines.insert(int(nm[i] / 1) + i, format_rows([[1] + list(node_actions[i])]))
+    for i in range(len(am)):
+        lines.insert(int(am[i] / 1) + i, format_rows([[1] + list(action_rows[i])]))
+    return "".join(lines)
 
 
 # ---------------------------------------------------------------------------------------------------- f2: JSON codec
