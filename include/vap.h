@@ -221,8 +221,8 @@ int vap_pack_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const doub
 
 /* "Next" row f1: numeric rows of the trajectory export written by save_nodes_to_file (gui_manager.py:284-295):
  * dst[7*(offsets[b] + k) + {0..6}] = {0, t, x*12, y*-12, heading, v*12, omega} for every time sample k of path b;
- * offsets[B+1] as in vap_pack_rows.  The action rows ([1, *action_values], :297-310) and the text formatting are
- * host work (vexautonomousplanner_b200/export.py).                                                              */
+ * offsets[B+1] as in vap_pack_rows.  Their text is produced by vap_format_rows below; the handful of action rows
+ * ([1, *action_values], :297-310) is spliced on the host (vexautonomousplanner_b200/export.py).                 */
 int vap_export_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const double* out, const int32_t* n_out,
                     const int32_t* status, int64_t* offsets, double* dst, void* stream);
 
