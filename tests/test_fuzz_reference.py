@@ -1,0 +1,70 @@
+"""48 more pins against the UNMODIFIED reference (tests/golden/make_golden_fuzz.py): random mixed paths with turns,
+reverse, stops, waits, overrides, user tangents, sorted and unsorted action points, per-path constraints, 3..12 nodes.
+Integer outputs must be exact; sampled values of every output stream within the north-star tolerances."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN_DIR
+
+FUZZ = os.path.join(GOLDEN_DIR, "fuzz_reference.npz")
+pytestmark = pytest.mark.skipif(not os.path.exists(FUZZ), reason="fuzz fixture not generated")
+
+
+def _load():
+    return dict(np.load(FUZZ))
+
+
+def _check(f, i, D, T, L, nodes_map, actions_map, streams, vel):
+    assert D == int(f["D"][i]), (i, D, int(f["D"][i]))
+    assert T == int(f["T"][i]), (i, T, int(f["T"][i]))
+    assert list(nodes_map) == f["nodes_map"][i][: int(f["n_nm"][i])].tolist(), i
+    assert list(actions_map) == f["actions_map"][i][: int(f["n_am"][i])].tolist(), i
+    np.testing.assert_allclose(L, f["L"][i], rtol=1e-13)
+    stride = int(f["stride"])
+    idx = np.arange(0, T, stride)[:80]
+    want = f["samples"][i][:, : len(idx)]
+    got = np.stack([s[idx] for s in streams])
+    tol = {0: (1e-6, 1e-12), 1: (1e-9, 1e-10), 2: (1e-6, 1e-9), 3: (1e-6, 1e-6), 4: (1e-9, 1e-10), 5: (1e-6, 1e-9),
+           6: (1e-9, 1e-10), 7: (1e-9, 1e-10)}
+    for s in range(8):
+        np.testing.assert_allclose(got[s], want[s], rtol=tol[s][0], atol=tol[s][1], err_msg=f"case {i} stream {s}")
+    vidx = np.arange(0, D, 211)[:80]
+    np.testing.assert_allclose(vel[vidx], f["vel_samples"][i][: len(vidx)], rtol=1e-6, atol=1e-12)
+
+
+def test_oracle_against_reference_fuzz(oracle_mod):
+    o = oracle_mod
+    o.set_sq_mode(0)
+    f = _load()
+    for i in range(len(f["n"])):
+        n, A = int(f["n"][i]), int(f["n_ap"][i])
+        r = o.full(f["node_attr"][i][:n], f["node_flags"][i][:n], f["ap_attr"][i][:A], f["ap_flags"][i][:A], f["cons"][i])
+        streams = [r[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
+        _check(f, i, r["D"], r["T"], r["summary"][1], r["nodes_map"], r["actions_map"], streams, r["vel"])
+        np.testing.assert_allclose(r["summary"][2], f["t_end"][i], rtol=1e-6)
+        np.testing.assert_allclose(r["summary"][3], f["vmax"][i], rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_engine_against_reference_fuzz():
+    import torch
+    from vexautonomousplanner_b200.engine import Engine
+    from vexautonomousplanner_b200.packing import PackedPaths
+    f = _load()
+    B = len(f["n"])
+    packed = PackedPaths(np.ascontiguousarray(f["node_attr"]), np.ascontiguousarray(f["node_flags"]).astype(np.int32),
+                         f["n"].astype(np.int32), np.ascontiguousarray(f["ap_attr"]),
+                         np.ascontiguousarray(f["ap_flags"]).astype(np.int32), f["n_ap"].astype(np.int32),
+                         np.ascontiguousarray(f["cons"]))
+    for impl in (dict(), dict(velocity_impl="serial", time_impl="serial")):
+        eng = Engine("cuda:0", **impl)
+        res = eng.profile(eng.upload(packed))
+        torch.cuda.synchronize()
+        assert (res.status == 0).all()
+        for i in range(B):
+            p = res.path(i)
+            streams = [p[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
+            _check(f, i, int(res.n_samples[i]), len(p["times"]), float(res.summary[i, 1]), p["nodes_map"], p["actions_map"],
+                   streams, p["vel"])
