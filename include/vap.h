@@ -16,6 +16,8 @@
  *     Per-path failures never abort the batch: they are reported in status[B]:
  *        0 ok | -1 reference returns False | -2 reference raises IndexError
  *        -3 reference raises ValueError    | -4 caller capacity (D_cap / T_cap) too small
+ *        -5 the reference's time loop would not terminate for this input (e.g. max_dec >= 20 ft/s^2 makes a step
+ *           move backwards) or would emit more than 5e7 rows: the engine stops instead of hanging the GPU
  *   - the library keeps no global mutable state and allocates nothing.
  *
  * Packed layouts
@@ -53,6 +55,7 @@ extern "C" {
 #define VAP_ERR_INDEX (-2)
 #define VAP_ERR_VALUE (-3)
 #define VAP_ERR_CAPACITY (-4)
+#define VAP_ERR_DIVERGED (-5)
 
 int vap_version(void);
 const char* vap_last_error(void);

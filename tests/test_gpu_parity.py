@@ -448,3 +448,22 @@ def test_fuzz_summaries_against_oracle(eng, ora, kind, nn):
     np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=1e-12)        # total length
     np.testing.assert_allclose(got[:, 2], want[:, 2], rtol=1e-6)         # t_end
     np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=1e-6)         # max |v|
+
+
+def test_degenerate_inputs_never_hang(eng):
+    """Inputs for which the reference would loop forever or blow up come back with a status instead of hanging the GPU:
+    a deceleration limit so large that a step moves backwards, an absurd wait, an absurdly slow turn profile."""
+    from vexautonomousplanner_b200 import synth
+    packed = synth.random_paths(6, 6, seed=91)
+    packed.cons[1, 1] = packed.cons[1, 2] = 250.0           # dpos = 0.1*dt - 0.5*250*dt^2 < 0 near a stop: never reaches L
+    packed.node_flags[1, 2] |= 2                             # a stop node, so the profile really brakes
+    packed.node_attr[2, 2, 3] = 1e12                         # wait of 1e12 s = 1e14 rows
+    packed.node_attr[3, 2, 2] = 90.0; packed.cons[3, 1] = packed.cons[3, 2] = 1e-14   # turn profile with 1e9+ samples
+    from vexautonomousplanner_b200.packing import rotation_table
+    packed.node_attr[:, :, 10], packed.node_attr[:, :, 11] = rotation_table(packed.node_attr[:, :, 2], (packed.node_flags & 1) != 0)
+    res = eng.profile(eng.upload(packed))
+    torch.cuda.synchronize()
+    st = res.status.cpu().numpy().tolist()
+    assert st[0] == 0 and st[4] == 0 and st[5] == 0
+    assert st[2] == -5 and st[3] in (-5, -4, 0) and st[1] in (-5, 0)
+    assert int(res.n_out[2]) == 0

@@ -21,6 +21,8 @@ enum { P_T = 0, P_WAIT, P_MAXVEL, P_MAXACC };
 #define ST_INDEX (-2)
 #define ST_VALUE (-3)
 #define ST_CAPACITY (-4)
+#define ST_DIVERGED (-5)     // the reference's loop would not terminate (or would emit more than VAP_ROW_LIMIT rows)
+#define VAP_ROW_LIMIT 50000000LL
 
 #define VAP_PI 3.141592653589793
 
@@ -367,7 +369,7 @@ __device__ __forceinline__ Trapezoid trapezoid_setup(double max_velocity, double
     }
     double stop = total_time + time_step;
     double k = ceil((stop - 0.0) / time_step);    // len(np.arange(0, stop, step))
-    T.K = (k > 0.0) ? (long long)k : 0;
+    T.K = (k > 0.0) ? ((k < 9.0e18) ? (long long)k : 9000000000000000000LL) : 0;
     T.ttm = ttm; T.vmax = max_velocity; T.total_time = total_time; T.acc = max_acceleration;
     return T;
 }

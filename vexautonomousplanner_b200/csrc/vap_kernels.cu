@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
         if (na[A_TURN] != 0) st = ST_INDEX;          // headings[-1] on an empty list (:440)
         if (st == ST_OK && na[A_WAIT] > 0) {          // :459-476
             long long steps = (long long)(na[A_WAIT] / dt);
+            if (!(na[A_WAIT] / dt < (double)VAP_ROW_LIMIT)) { st = ST_DIVERGED; steps = 0; }
             double h = -1 * snap_gather(ph, 0.0, P, n, pstep, inv_pstep);
             if (is_reversed) h -= VAP_PI;
             if (h > VAP_PI) h -= 2 * VAP_PI;
@@ -722,6 +723,7 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
         const double end_param = (double)(n - 1);
         long long hint = -1;
         while (st == ST_OK && current_pos < L) {
+            if (o.T >= 16 * T_cap + 1000000 || o.T >= VAP_ROW_LIMIT) { st = ST_DIVERGED; break; }   // diverging loop
             double t = distance_to_time(ld, lt, Q, L, n, current_pos, hint);
             if (frac1(t) < frac1(prev_t) && t < end_param) {
                 nmap[nm++] = (int)o.T;
@@ -731,6 +733,7 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
                     if (!have_rows) { st = ST_INDEX; break; }
                     double angle = a[A_TURN] * (VAP_PI / 180.0);        // np.radians
                     Trapezoid tz = trapezoid_setup(V, max_acc, fabs(angle) * w / 2, dt);
+                    if (!(tz.K < VAP_ROW_LIMIT)) { st = ST_DIVERGED; break; }
                     double sgn = angle > 0 ? -1.0 : 1.0;
                     double accum = 0.0, hprev = 0.0;
                     double start_heading = last_head;
@@ -751,6 +754,7 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
                 if (nf[node_idx] & F_REVERSE) is_reversed = !is_reversed;
                 if (a[A_WAIT] > 0) {                  // handle_wait (:509-518)
                     if (!have_rows) { st = ST_INDEX; break; }
+                    if (!(a[A_WAIT] / dt < (double)VAP_ROW_LIMIT)) { st = ST_DIVERGED; break; }
                     long long steps = (long long)(a[A_WAIT] / dt);
                     for (long long i = 0; i < steps; i++)
                         o.push(current_time + (double)i * dt, 0.0, 0.0, 0.0, last_head, 0.0, last_x, last_y);
@@ -764,6 +768,7 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
                     amap[am++] = (int)o.T;
                     if (p[P_WAIT] > 0) {
                         if (!have_rows) { st = ST_INDEX; break; }
+                        if (!(p[P_WAIT] / dt < (double)VAP_ROW_LIMIT)) { st = ST_DIVERGED; break; }
                         long long steps = (long long)(p[P_WAIT] / dt);
                         for (long long i = 0; i < steps; i++)
                             o.push(current_time + (double)i * dt, 0.0, 0.0, 0.0, last_head, 0.0, last_x, last_y);

@@ -111,7 +111,9 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     const double hdt = 0.1 * dt;
     const double dlim = (double)(D - 3);
     const double ndec = -max_dec;
+    const long long k_limit = 16 * M_cap + 1000000;     // far beyond any terminating profile of this capacity class
     while (pos < L) {
+        if (k >= k_limit || k >= VAP_ROW_LIMIT) { k = -1; break; }      // diverging loop: report instead of hanging
         const bool room = k < M_cap;
         if (room) *P = pos;
         double tv1, tv2;
@@ -167,8 +169,8 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         k++;
     }
     cp_async_wait<0>();
-    if (k <= M_cap) *P = pos;
-    n_main[b] = (int)(k > 2147483647LL ? 2147483647LL : k);
+    if (k >= 0 && k <= M_cap) *P = pos;
+    n_main[b] = (int)(k > 2147483647LL ? 2147483647LL : k);      // -1: diverged
 }
 
 // exactness check of div_const against the IEEE division (test hook)
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(256) k_time_sample(
     long long b = blockIdx.y;
     if (status[b] != ST_OK) return;
     long long M = n_main[b];
-    if (M > M_cap) return;                     // capacity overflow: the caller re-runs with a larger M_cap
+    if (M > M_cap || M < 0) return;            // capacity overflow (the caller re-runs with a larger M_cap) or diverged
     long long k0 = (long long)blockIdx.x * blockDim.x;
     if (k0 >= M) return;
     long long k = k0 + threadIdx.x;
@@ -301,7 +303,8 @@ __global__ void __launch_bounds__(32) k_time_events(
         int* so = seg_off + (size_t)b * E_cap;
         int* sv = seg_rev + (size_t)b * E_cap;
         int ns = 0;
-        if (M > M_cap) st = ST_CAPACITY;
+        if (M < 0) st = ST_DIVERGED;
+        else if (M > M_cap) st = ST_CAPACITY;
         bool rev = (nf[0] & F_REVERSE) != 0;
         nmap[nm++] = 0;
         if (st == ST_OK && na[A_TURN] != 0) st = ST_INDEX;          // headings[-1] on an empty list (:440)
@@ -313,6 +316,7 @@ __global__ void __launch_bounds__(32) k_time_events(
              o_head[r_] = (h_); o_ang[r_] = (w_); o_x[r_] = (x_); o_y[r_] = (y_); } T++; } while (0)
         if (st == ST_OK && na[A_WAIT] > 0) {                          // :459-476
             long long steps = (long long)(na[A_WAIT] / dt);
+            if (!(na[A_WAIT] / dt < (double)VAP_ROW_LIMIT)) { st = ST_DIVERGED; steps = 0; }
             const long long P = (long long)spn * n;
             const double pstep = (double)(n - 1) / (double)(P - 1);
             double h = -1 * snap_gather(prop_h + (size_t)b * P_cap, 0.0, P, n, pstep, 1.0 / pstep);
@@ -379,6 +383,7 @@ __global__ void __launch_bounds__(32) k_time_events(
                     if (a[A_TURN] != 0) {                        // handle_turn (:487-507)
                         double angle = a[A_TURN] * (VAP_PI / 180.0);
                         Trapezoid tz = trapezoid_setup(V, max_acc, fabs(angle) * w / 2, dt);
+                        if (!(tz.K < VAP_ROW_LIMIT)) { st = ST_DIVERGED; break; }
                         double sgn = angle > 0 ? -1.0 : 1.0;
                         double accum = 0.0, hprev = 0.0;
                         double start_heading = last_head;
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(32) k_time_events(
                     }
                     if (nf[node_idx] & F_REVERSE) rev = !rev;
                     if (a[A_WAIT] > 0) {                         // handle_wait (:509-518)
+                        if (!(a[A_WAIT] / dt < (double)VAP_ROW_LIMIT)) { st = ST_DIVERGED; break; }
                         long long steps = (long long)(a[A_WAIT] / dt);
                         for (long long i = 0; i < steps; i++) PUSH(time + (double)i * dt, 0.0, last_head, 0.0, last_x, last_y);
                         if (steps > 0) last_pos = 0.0;
@@ -410,6 +416,7 @@ __global__ void __launch_bounds__(32) k_time_events(
                     const double* p = apa + (size_t)action_idx * APA;
                     amap[am++] = (int)T;
                     if (p[P_WAIT] > 0) {
+                        if (!(p[P_WAIT] / dt < (double)VAP_ROW_LIMIT)) { st = ST_DIVERGED; break; }
                         long long steps = (long long)(p[P_WAIT] / dt);
                         for (long long i = 0; i < steps; i++) PUSH(time + (double)i * dt, 0.0, last_head, 0.0, last_x, last_y);
                         if (steps > 0) last_pos = 0.0;
@@ -429,6 +436,7 @@ __global__ void __launch_bounds__(32) k_time_events(
         n_seg[b] = (st == ST_OK) ? ns : 0;
         if (!(st == ST_OK || st == ST_CAPACITY)) T = 0;
         if (st == ST_CAPACITY && M > M_cap) T = M;              // lower bound of the true row count
+        if (T >= VAP_ROW_LIMIT) { st = ST_DIVERGED; T = 0; }
     }
     n_out[b] = (int)T;
     n_maps[2 * b] = nm; n_maps[2 * b + 1] = am;

@@ -20,7 +20,8 @@ from . import _lib
 from .packing import PackedPaths
 
 OUT_NAMES = ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")
-ST_OK, ST_FALSE, ST_INDEX, ST_VALUE, ST_CAPACITY = 0, -1, -2, -3, -4
+ST_OK, ST_FALSE, ST_INDEX, ST_VALUE, ST_CAPACITY, ST_DIVERGED = 0, -1, -2, -3, -4, -5
+ROW_LIMIT = 1.0e7      # more time samples than this per path: treated as a non-terminating profile (status -5)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -325,15 +326,18 @@ class Engine:
         self.launches += 1
         return out, nodes_map, actions_map, n_maps, n_out, summary
 
-    def _insert_bound(self, db: DeviceBatch) -> int:
-        """Upper bound of the rows one path can insert for waits and turn profiles (sizing only)."""
+    def _insert_bound(self, db: DeviceBatch, status: Optional[torch.Tensor] = None) -> int:
+        """Upper bound of the rows one (healthy) path can insert for waits and turn profiles (sizing only)."""
         na = db.node_attr
         waits = (na[:, :, 3] / self.dt).floor().clamp(min=0).sum(dim=1) + (db.ap_attr[:, :, 1] / self.dt).floor().clamp(min=0).sum(dim=1)
         V, A, w = db.cons[:, 0:1], db.cons[:, 1:2], db.cons[:, 5:6]
         arc = (na[:, :, 2].abs() * (3.141592653589793 / 180.0)) * w / 2
         # trapezoid / triangle duration: never longer than 2 V/A + arc / V, plus two samples of slack per turn
         turn_rows = torch.where(na[:, :, 2] != 0, ((2 * V / A + arc / V) / self.dt).ceil() + 3, torch.zeros_like(arc)).sum(dim=1)
-        return int((waits + turn_rows).max().item())
+        rows = torch.nan_to_num(waits + turn_rows, nan=0.0, posinf=0.0)
+        if status is not None:
+            rows = torch.where(status == ST_OK, rows, torch.zeros_like(rows))
+        return int(rows.max().item()) if rows.numel() else 0
 
     def time_profile(self, db: DeviceBatch, g: Geometry, t: Tables, status, D_cap, n_samples, vel, T_cap,
                      outs: Optional[dict] = None):
@@ -586,8 +590,12 @@ class Engine:
         status = g.status.clone()
         vfun = self.velocity_chunked if self.velocity_impl == "chunked" else self.velocity_serial
         n_samples, vel, t_est, extra = vfun(db, g, t, status, D_cap)
+        # paths whose profile would need an absurd number of rows (the reference would effectively never return) are
+        # flagged here, so that they neither size the buffers nor spin in the time loop
+        absurd = ~(t_est < ROW_LIMIT)
+        status[absurd & (status == ST_OK)] = ST_DIVERGED
         if plan is None:
-            T_cap = int(float(t_est.max().item()) * 1.10) + 64
+            T_cap = int(float(torch.where(absurd, torch.zeros_like(t_est), t_est).max().item()) * 1.10) + 64
         else:
             T_cap = plan[1]
         status_pre = status.clone()
@@ -603,7 +611,7 @@ class Engine:
                     return self.profile(db, keep=keep, reuse_plan=False)
                 if self.time_impl == "split":
                     # n_main is exact even on overflow; inserted rows are bounded by the insert estimate
-                    T_cap = int(self._n_main.max().item()) + int(self._insert_bound(db)) + 8
+                    T_cap = int(self._n_main.max().item()) + min(int(self._insert_bound(db, status_pre)), int(ROW_LIMIT)) + 8
                 else:
                     T_cap = int(n_out.max().item()) + 8
                 status = status_pre.clone()
