@@ -138,7 +138,8 @@ int vap_fwd_bwd(int64_t B, int N_max, int A_max, const double* node_attr, const 
  *     vap_event_scratch_ints(B, N_max, A_max) elements.  ins_est[B] f32: rows the time stage will insert for
  *     waits / turn profiles (sizing only).
  *   vap_fwd_bwd_chunked: pre-pass that hoists the state-independent terms of the recurrences into one 32-byte
- *     record per sample (recF, recR: [B][D_cap][4] f64), then the forward and backward passes (:188-314) with
+ *     record per sample and direction (recF, recR: [B][D_cap][4] f64) plus the reciprocal of the wheel-acceleration
+ *     division's denominator (rg: [B][D_cap] f64), then the forward and backward passes (:188-314) with
  *     `chunks` (multiple of 32, <= 256) speculative chunks per path that are re-run until they merge bitwise with the serial evaluation.
  *     vel_f[B][D_cap]: forward result; vel[B][D_cap]: final velocities; t_est[B] f32; rounds[B][2] fix-up sweeps. */
 int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
@@ -155,8 +156,8 @@ int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, do
                         double end_vel, int64_t D_cap, const int32_t* n_samples, const double* kap, const double* th,
                         int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
                         const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
-                        const int32_t* n_vr, double* recF, double* recR, double* vel_f, double* vel, float* t_est,
-                        int32_t* rounds, int chunks, int mode, void* stream);
+                        const int32_t* n_vr, double* recF, double* recR, double* rg, double* vel_f, double* vel,
+                        float* t_est, int32_t* rounds, int chunks, int mode, void* stream);
 
 /* S6  generate_motion_profile time loop + node-0 prologue + turn / wait inserts
  *     (motion_profile_generator.py:414-628, one_dim_mp_generator.py:4-69) and S7 summary rows.
@@ -243,6 +244,8 @@ int vap_compact_rows(int64_t R, const char* slots, const int32_t* lens, const in
 /* Test hook: counts (into the device word *bad) the pseudo-random numerators a, out of n, for which the hoisted-
  * reciprocal division used inside the time loop differs from the IEEE quotient a / b.  Must stay 0.            */
 int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* bad, void* stream);
+/* test hook: mismatches between the velocity passes' pre-computed-reciprocal division and IEEE '/' over n random pairs */
+int vap_test_div_recip(int64_t n, uint64_t seed, uint64_t* bad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -309,6 +309,21 @@ def test_const_division_is_ieee():
     assert int(bad.item()) == 0
 
 
+def test_recip_division_is_ieee():
+    """The velocity passes divide by 2|dtheta| with the reciprocal made by the pre-pass and two fused residual corrections;
+    2^30 random (numerator, denominator) pairs, incl. zero denominators / numerators and all-ones significands, must give
+    the IEEE quotient bit for bit."""
+    import ctypes as C
+    from vexautonomousplanner_b200 import _lib
+    L = _lib.lib()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for seed in range(4):
+        _lib.check(L.vap_test_div_recip(C.c_int64(1 << 28), C.c_uint64(seed * 7919 + 1), C.c_void_p(bad.data_ptr()), st))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
 def test_tiled_multistream_equals_untiled():
     """Row tiles on separate CUDA streams must give the same bits as one pass over the batch."""
     from vexautonomousplanner_b200 import synth

@@ -1174,39 +1174,30 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
                                    const double* kap, const double* th, int E_cap, const double* max_accels,
                                    const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
                                    const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* recF,
-                                   double* recR, double* vel_f, double* vel, float* t_est, int32_t* rounds,
+                                   double* recR, double* rg, double* vel_f, double* vel, float* t_est, int32_t* rounds,
                                    int chunks, int mode, void* stream)
 {
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
     if (chunks < 32 || chunks > 256 || (chunks % 32) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be a multiple of 32 in [32, 256]");
+    if (D_cap > 2000000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
     dim3 grid(blocks_for(D_cap, 256), (unsigned)B);
     size_t sm = (size_t)E_cap * (2 * sizeof(double) + 4 * sizeof(int));
     k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, end_vel, D_cap, n_samples, kap, th, E_cap, max_accels, bidx, bval,
                                          n_ev, vr_idx, vr_val, st_idx, n_vr, reinterpret_cast<double4*>(recF),
-                                         reinterpret_cast<double4*>(recR));
+                                         reinterpret_cast<double4*>(recR), rg);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
-    // CTA = PB paths x `chunks` chunk threads; the fix-up re-runs of all PB paths share the CTA's first warps.
-    // Measured on 4096 x 8-node paths: PB = 1 is fastest (3.14 ms vs 3.39 ms at PB = 4): the passes are bound by the
-    // dependent-instruction latency of the longest path, and CTA-wide barriers over several paths only add waiting.
-    int PB = 1;
-    if (const char* ev = getenv("VAP_CHUNK_PB")) PB = atoi(ev);
-    if (PB < 1) PB = 1;
-    if (PB * chunks > 256) PB = 256 / chunks;
-    const int nth = PB * chunks;
-    int warm = 0;                     // warm-up steps a speculative chunk runs before its own range (tuning: VAP_CHUNK_WARM)
-    if (const char* ev = getenv("VAP_CHUNK_WARM")) warm = atoi(ev);
-    if (warm < 0) warm = 0;
-    size_t ss = (size_t)nth * (4 * sizeof(double) + sizeof(int));
-    const unsigned nblk = (unsigned)((B + PB - 1) / PB);
-    k_fwd_chunked<<<nblk, nth, ss, STREAM>>>(B, chunks, status, cons, dd, start_vel, D_cap, n_samples,
-                                             reinterpret_cast<const double4*>(recF), E_cap, max_accels, bidx, bval, n_ev,
-                                             vel_f, rounds, warm);
+    // CTA = one path, one chunk per thread.  The passes are bound by the latency of the dependent fp64 chain of a step:
+    // one-warp CTAs at <= 64 registers put 32 independent chains on every SM.
+    const size_t ss = (size_t)chunks * 4 * sizeof(double) + (size_t)E_cap * (sizeof(double) + sizeof(int));
+    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, D_cap, n_samples,
+                                                       reinterpret_cast<const double4*>(recF), rg, E_cap, max_accels, bidx,
+                                                       bval, n_ev, vel_f, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
     if (mode == 1) return 0;
-    k_bwd_chunked<<<nblk, nth, ss, STREAM>>>(B, chunks, status, cons, dd, dt, end_vel, D_cap, n_samples,
-                                             reinterpret_cast<const double4*>(recR), E_cap, max_accels, bidx, bval, n_ev,
-                                             vel_f, vel, t_est, rounds, warm);
+    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, D_cap, n_samples,
+                                                       reinterpret_cast<const double4*>(recR), rg, E_cap, max_accels, bidx,
+                                                       bval, n_ev, vel_f, vel, t_est, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
     return 0;
 }
@@ -1283,6 +1274,44 @@ extern "C" int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* 
     if (n <= 0) return 0;
     k_test_div_const<<<blocks_for(n, 256), 256, 0, STREAM>>>(n, seed, b, reinterpret_cast<unsigned long long*>(bad));
     CHECK_LAUNCH("vap_test_div_const");
+    return 0;
+}
+
+// test hook: number of (num, g) pairs (out of n pseudo-random ones) for which the pass's reciprocal division differs
+// from the IEEE quotient.  g covers 2|dtheta| (1e-17 .. 8, random significands, zeros, all-ones significands).
+__global__ void k_test_div_recip(long long n, unsigned long long seed, unsigned long long* __restrict__ bad)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto mix = [](unsigned long long z) {
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31);
+    };
+    unsigned long long z1 = mix(seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(2 * i + 1));
+    unsigned long long z2 = mix(seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(2 * i + 2));
+    // numerator: random sign, exponent in [-110, 8), random significand; every 64th one is +-0
+    int e1 = (int)((z1 >> 52) % 118) - 110 + 1023;
+    unsigned long long nb = ((z1 >> 63) << 63) | ((unsigned long long)e1 << 52) | (z1 & 0x000FFFFFFFFFFFFFULL);
+    if (((z1 >> 40) & 63) == 0) nb &= 0x8000000000000000ULL;
+    double num = __longlong_as_double((long long)nb);
+    // denominator: positive, exponent in [-57, 3); 1/32 zeros; 1/64 all-ones significands
+    int e2 = (int)((z2 >> 52) % 60) - 57 + 1023;
+    unsigned long long gb = ((unsigned long long)e2 << 52) | (z2 & 0x000FFFFFFFFFFFFFULL);
+    if (((z2 >> 40) & 63) == 1) gb |= 0x000FFFFFFFFFFFFFULL;
+    double g = __longlong_as_double((long long)gb);
+    if (((z2 >> 46) & 31) == 0) g = 0.0;
+    const double rc = recip_for_pass(g);
+    const double q1 = accel_ang_fast(num, g, rc);
+    double n2 = num, g2 = g;
+    asm volatile("" : "+d"(n2), "+d"(g2));
+    const double q2 = n2 / g2;
+    bool same = (__double_as_longlong(q1) == __double_as_longlong(q2)) || (q1 != q1 && q2 != q2) || (q1 == 0.0 && q2 == 0.0);
+    if (!same) atomicAdd(bad, 1ULL);
+}
+extern "C" int vap_test_div_recip(int64_t n, uint64_t seed, uint64_t* bad, void* stream)
+{
+    if (n <= 0) return 0;
+    k_test_div_recip<<<blocks_for(n, 256), 256, 0, STREAM>>>(n, seed, reinterpret_cast<unsigned long long*>(bad));
+    CHECK_LAUNCH("vap_test_div_recip");
     return 0;
 }
 

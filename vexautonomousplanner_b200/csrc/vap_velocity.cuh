@@ -182,6 +182,8 @@ __global__ void k_resolve_events(long long B, int N_max, int A_max, const double
     }
 }
 
+__device__ __forceinline__ double recip_for_pass(double g);   // defined with the pass kernels below
+
 // ---- pre-pass (parallel): one 32-byte record per sample and direction -----------------------------------------
 // forward  record F[i] = { |kappa_i|, 2|theta_{i+1}-theta_i| (NaN when straight), a_static_i, C_i }
 //    a_static = min(max_ang_acc/|k|, 2 acc/(w|k|+2), acc)  (acc when straight);  C_i = min(v0[i+1], vlim_i, cap_i)
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(256) k_prepass(
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
     const int* __restrict__ st_idx, const int* __restrict__ n_vr, double4* __restrict__ recF,
-    double4* __restrict__ recR)
+    double4* __restrict__ recR, double* __restrict__ rg)
 {
     extern __shared__ unsigned char s_raw[];
     long long b = blockIdx.y;
@@ -257,6 +259,8 @@ __global__ void __launch_bounds__(256) k_prepass(
     double acc_f = s_ma[s_bv[jf]];
     double dec_b = s_ma[s_bv[n_b - 1]];     // the backward pass keeps the forward pass's last max_dec
     if (i < D - 1) {
+        // reciprocal of the wheel-acceleration division's denominator for forward step i and backward step i+1
+        rg[row + i] = recip_for_pass(2 * fabs(th[row + i + 1] - th_i));
         double v0n;
         if (i + 1 == D - 1) v0n = end_vel;
         else {
@@ -296,11 +300,9 @@ __device__ __forceinline__ bool same_bits(double a, double b)
 
 // (w_i^2 - w_{i-1}^2) / (2|dtheta|) with IEEE results for every special case, but without sending the warp through the
 // slow path of the inlined division when the numerator is 0 (cruise), or the denominator is 0 (two samples snapped
-// to the same table entry) or NaN (the "straight" marker of the pre-pass).
-__device__ __forceinline__ double accel_ang_div(double num, double h2)
+// to the same table entry) or NaN (the "straight" marker of the pre-pass).  Generic path (rare inputs only).
+__device__ __noinline__ double accel_ang_div(double num, double h2)
 {
-    // ~44 % of consecutive distance samples snap to the same table entry (h2 == 0), so the special cases are the
-    // common ones and must not touch the division at all.
     bool special = !(h2 > 0.0) || num == 0.0 || !(fabs(num) < 1e300);
     double n = special ? 1.0 : num, d = special ? 1.0 : h2;
     asm volatile("" : "+d"(n), "+d"(d));   // keep nvcc from folding the selects back into the division's operands
@@ -320,408 +322,363 @@ __device__ __forceinline__ double accel_ang_div(double num, double h2)
     return qnan;                                         // NaN denominator (the pre-pass's "straight" marker)
 }
 
-// forward step i -> i+1 (motion_profile_generator.py:193-249 with the hoisted terms)
-__device__ __forceinline__ double fwd_step(const double4 r, double v, double& wp, double acc, double w, double dd)
+// Reciprocal of the division's denominator g = 2|dtheta|, made ONCE per sample by the pre-pass (it does not depend on the
+// velocity state), so that the state-dependent chain of a pass step holds one multiplication and two fused residual
+// corrections instead of a reciprocal refinement:
+//    > 0 and finite : RN(1/g), g a normal number whose significand is not all ones (Markstein's exception)
+//    +inf           : g == 0 (two samples snapped to the same heading entry; ~44 % of the samples)
+//    -1             : anything else (g NaN / subnormal / all-ones significand): the pass takes the generic division
+__device__ __forceinline__ double recip_for_pass(double g)
 {
-    double ang_vel = v * r.x;
-    double accel_ang = accel_ang_div(ang_vel * ang_vel - wp * wp, r.y);
-    double a_wheel = wheel_accel(acc, fabs(accel_ang), w);
+    const long long bits = __double_as_longlong(g);
+    const bool safe = (g >= 2.2250738585072014e-308) && (g < 1e300) &&
+                      ((bits & 0x000FFFFFFFFFFFFFLL) != 0x000FFFFFFFFFFFFFLL);
+    double d = safe ? g : 1.0;
+    asm volatile("" : "+d"(d));            // the division must never see the special values (warp-wide slow path)
+    const double r = 1.0 / d;
+    return safe ? r : ((g == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : -1.0);
+}
+
+// num / h2 given rce = recip_for_pass(h2) (or NaN when h2 is the straight marker).  q0 = num * r, then two residual
+// corrections: after the first the quotient is faithful, and with the correctly rounded reciprocal one more gives the
+// correctly rounded quotient (Markstein), i.e. exactly what '/' returns (the sign of a zero quotient is not kept; it
+// cannot reach any output).  h2 == 0 and the straight marker fall out of the multiplication: x * inf and x * NaN are
+// what x / 0 and x / NaN give.  tests/test_gpu_parity.py::test_recip_division_is_ieee checks 2^30 random pairs.
+__device__ __forceinline__ double accel_ang_fast(double num, double h2, double rce)
+{
+    const double q0 = num * rce;
+    double q = fma(fma(-h2, q0, num), rce, q0);
+    q = fma(fma(-h2, q, num), rce, q);
+    const bool corr = rce <= 1.7976931348623157e308;          // false for NaN and +inf
+    const double an = fabs(num);
+    const bool in_range = (an < 1e200) && ((an > 1e-200) || (num == 0.0));
+    if (rce < 0.0 || (corr && !in_range)) return accel_ang_div(num, h2);     // never taken on sane inputs
+    return corr ? q : q0;
+}
+
+// forward step i -> i+1 (motion_profile_generator.py:193-249 with the hoisted terms).  sq carries (v_{i-1}|k_{i-1}|)^2.
+__device__ __forceinline__ double fwd_step(const double4 r, double rc, double v, double& sq, double acc, double hw, double dd)
+{
+    const double ang_vel = v * r.x;
+    const double sqn = ang_vel * ang_vel;
+    const double rce = (r.y == r.y) ? rc : r.y;
+    const double accel_ang = accel_ang_fast(sqn - sq, r.y, rce);
+    const double x = fabs(accel_ang) * hw;                   // ang * w / 2: halving is exact, so (ang*w)/2 == ang*(w/2)
+    const double l = acc + x, rr = acc - x;                  // wheel_accel (:52-59)
+    double a_wheel = (fabs(l) < fabs(rr)) ? l : rr;
     if (a_wheel < 0) a_wheel = 0;
-    double a = pymin(r.z, a_wheel);
-    double s = sqrt(v * v + 2 * a * dd);
-    wp = ang_vel;
+    const double a = pymin(r.z, a_wheel);
+    const double s = sqrt(v * v + 2 * a * dd);
+    sq = sqn;
     return pymin(r.w, s);
 }
-// backward step i -> i-1 (:255-311)
-__device__ __forceinline__ double bwd_step(const double4 r, double v, double& wp, double acc, double w, double dd,
-                                           double vfwd_prev)
+// backward step i -> i-1 (:255-311); m = min(vel_f[i-1], G_i) (state-independent part of the three-way min)
+__device__ __forceinline__ double bwd_step(const double4 r, double rc, double v, double& sq, double acc, double hw, double dd,
+                                           double m)
 {
-    double ang_vel = v * r.x;
-    double accel_ang = accel_ang_div(ang_vel * ang_vel - wp * wp, r.y);
-    double a_wheel = wheel_accel(acc, accel_ang, w);
+    const double ang_vel = v * r.x;
+    const double sqn = ang_vel * ang_vel;
+    const double rce = (r.y == r.y) ? rc : r.y;
+    const double accel_ang = accel_ang_fast(sqn - sq, r.y, rce);
+    const double x = accel_ang * hw;
+    const double l = acc + x, rr = acc - x;
+    double a_wheel = (fabs(l) < fabs(rr)) ? l : rr;
     if (a_wheel < 0) a_wheel = 0;
-    double dcl = pymin(r.z, a_wheel);
-    double pv = sqrt(v * v + 2 * dcl * dd);
-    wp = ang_vel;
-    return pymin(pymin(pv, vfwd_prev), r.w);
+    const double dcl = pymin(r.z, a_wheel);
+    const double pv = sqrt(v * v + 2 * dcl * dd);
+    sq = sqn;
+    return pymin(pv, m);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Chunk-speculative passes, CTA = PB paths x NT chunks (thread (p, c) = path p of the CTA, chunk c).
+// Chunk-speculative passes: CTA = one path, thread c = chunk c (blockDim.x chunks).
 //
-// Sweep 1: every thread runs its own chunk from the guessed state (lockstep, all lanes busy).
-// Fix-up rounds: only a few chunks per path have to be re-run (their predecessor's end state differs bitwise from the
-// state they started from).  Those (path, chunk) items are pushed into a shared-memory queue and re-run by the FIRST
-// threads of the CTA, so that the re-runs of all PB paths share a few dense warps instead of every path keeping a
-// mostly idle warp spinning.  A re-run stops as soon as two consecutive velocities equal the stored ones bitwise.
-// Rounds end when the queue stays empty; then, by induction from the first chunk, every value is the serial value.
+// Sweep 1: every thread runs its own chunk from a guessed state (lockstep, all lanes busy).  Fix-up rounds: a chunk whose
+// predecessor's end state differs bitwise from the state it started from re-runs from the true state; the re-run stops as
+// soon as two consecutive velocities equal the stored ones bitwise (from there the old values ARE the serial values).
+// Rounds end when no chunk had to re-run; then, by induction from chunk 0, every value is the serial value.
+//
+// The kernels are bound by the latency of the dependent fp64 chain of one step, so they are written for residency
+// (<= 64 registers: 32 one-warp CTAs per SM) and a short chain: regime tables in shared memory, 32-bit indices, records
+// fetched one step ahead into two named buffers (no register rotation), the division's reciprocal from the pre-pass.
 // ------------------------------------------------------------------------------------------------------------------
-struct ChunkCtx {                 // per path; built in registers from the kernel parameters
-    long long D, Lc;
-    int nch, n_b, ok;
-    double w;
-    const double4* rec;
-    const double* vin;            // backward: forward velocities
-    double* vout;
-    const double* ma;
-    const int* bi;
-    const int* bv;
-};
+#define CH_INT_MAX 2147483647
+
+// forward chunk [lo, hi): step i reads F[i], RG[i] and writes vf[i+1]
+template <bool RERUN>
+__device__ __forceinline__ bool fwd_run(const double4* __restrict__ F, const double* __restrict__ RG, double* __restrict__ vf,
+                                        int lo, int hi, const int* s_bi, const double* s_acc, int n_b, double hw, double dd,
+                                        double& v, double& sq, bool prev_same)
+{
+    int j = 0;
+    while (j + 1 < n_b && s_bi[j + 1] <= lo) j++;
+    double acc = s_acc[j];
+    int nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX;
+    double4 ra = ldg_d4(F + lo), rb;
+    double ga = __ldg(RG + lo), gb;
+    double olda = 0.0, oldb = 0.0;
+    if (RERUN) olda = vf[lo + 1];
+    int i = lo;
+    while (true) {
+        // ---- even step: buffers a
+        rb = ldg_d4(F + i + 1); gb = __ldg(RG + i + 1);                 // rows are padded: i+1 <= D-1 < D_cap
+        if (RERUN) oldb = vf[(i + 2 <= hi) ? i + 2 : hi];
+        if (i == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
+        v = fwd_step(ra, ga, v, sq, acc, hw, dd);
+        if (RERUN) {
+            const bool same = same_bits(olda, v);
+            if (same && prev_same) return true;                         // state equals the old run's: the rest is unchanged
+            prev_same = same;
+        }
+        vf[i + 1] = v;
+        if (++i >= hi) break;
+        // ---- odd step: buffers b
+        ra = ldg_d4(F + i + 1); ga = __ldg(RG + i + 1);
+        if (RERUN) olda = vf[(i + 2 <= hi) ? i + 2 : hi];
+        if (i == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
+        v = fwd_step(rb, gb, v, sq, acc, hw, dd);
+        if (RERUN) {
+            const bool same = same_bits(oldb, v);
+            if (same && prev_same) return true;
+            prev_same = same;
+        }
+        vf[i + 1] = v;
+        if (++i >= hi) break;
+    }
+    return false;
+}
 
 // Forward pass.  Steps i = 0 .. D-2; chunk c owns steps [c*Lc, min((c+1)*Lc, D-1)); step i writes vel_f[i+1].
-__global__ void __launch_bounds__(256) k_fwd_chunked(
-    long long B, int NT, const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel,
-    long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recF, int E_cap,
+__global__ void __launch_bounds__(256, 4) k_fwd_chunked(
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, long long D_cap,
+    const int* __restrict__ n_samples, const double4* __restrict__ recF, const double* __restrict__ rg, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, double* __restrict__ vel_f, int* __restrict__ rounds_out, int warm)
+    const int* __restrict__ n_ev, double* __restrict__ vel_f, int* __restrict__ rounds_out)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
-    const int NTH = blockDim.x, PB = NTH / NT;
-    const int tid = threadIdx.x, p = tid / NT, c = tid - p * NT;
-    double* s_endv = reinterpret_cast<double*>(s_mem);           // [NTH] end state of every chunk
-    double* s_endw = s_endv + NTH;
-    double* s_usev = s_endw + NTH;                                // [NTH] start state every chunk last used
-    double* s_usew = s_usev + NTH;
-    int* s_queue = reinterpret_cast<int*>(s_usew + NTH);          // [NTH]
-    __shared__ int s_qn;
-    // path context from the kernel parameters (pointers stay provably global: ld.global.nc, no generic loads)
-    auto make_ctx = [&](int pp) -> ChunkCtx {
-        ChunkCtx x;
-        const long long bb = (long long)blockIdx.x * PB + pp;
-        x.ok = (bb < B) && status[bb] == ST_OK;
-        x.D = x.ok ? n_samples[bb] : 1;
-        long long steps = x.D - 1;
-        x.Lc = steps > 0 ? (steps + NT - 1) / NT : 1;
-        x.nch = (x.ok && steps > 0) ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
-        const long long bs = x.ok ? bb : 0;
-        x.n_b = x.ok ? n_ev[2 * bs + 1] : 0;
-        x.w = cons[bs * 6 + 5];
-        x.rec = recF + (size_t)bs * D_cap;
-        x.vin = nullptr;
-        x.vout = vel_f + (size_t)bs * D_cap;
-        x.ma = max_accels + (size_t)bs * E_cap;
-        x.bi = bidx + (size_t)bs * E_cap;
-        x.bv = bval + (size_t)bs * E_cap;
-        return x;
-    };
-    const long long b = (long long)blockIdx.x * PB + p;
-    const ChunkCtx mine = make_ctx(p);
-    if (c == 0 && mine.ok) mine.vout[0] = start_vel;
-    if (tid == 0) s_qn = 0;
+    const int NT = blockDim.x, c = threadIdx.x;
+    const long long b = blockIdx.x;
+    double* s_endv = reinterpret_cast<double*>(s_mem);           // [NT] end state of every chunk: v and (v|k|)^2
+    double* s_endw = s_endv + NT;
+    double* s_usev = s_endw + NT;                                 // [NT] start state every chunk last used
+    double* s_usew = s_usev + NT;
+    double* s_acc = s_usew + NT;                                  // [E_cap] max_acc of regime j
+    int* s_bi = reinterpret_cast<int*>(s_acc + E_cap);            // [E_cap] first sample of regime j
+    if (status[b] != ST_OK) return;                               // uniform over the CTA
+    const int D = n_samples[b];
+    const int steps = D - 1;
+    double* vf = vel_f + (size_t)b * D_cap;
+    if (c == 0) { vf[0] = start_vel; if (rounds_out) rounds_out[2 * b] = 0; }
+    if (steps <= 0) return;
+    const int n_b = n_ev[2 * b + 1];
+    for (int k = c; k < n_b; k += NT) {
+        s_bi[k] = bidx[(size_t)b * E_cap + k];
+        s_acc[k] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + k]];
+    }
+    const int Lc = (steps + NT - 1) / NT;
+    const int nch = (steps + Lc - 1) / Lc;
+    const bool active = c < nch;
+    const int lo = c * Lc;
+    const int hi = (lo + Lc < steps) ? lo + Lc : steps;
+    const double4* F = recF + (size_t)b * D_cap;
+    const double* RG = rg + (size_t)b * D_cap;
+    const double hw = cons[b * 6 + 5] * 0.5;
     __syncthreads();
 
-    // runs chunk cc of path context x from state (v, wp); mode 0: first sweep (plain stores), mode 1: re-run with
-    // bitwise merge detection against the stored velocities.  Returns true when the re-run merged (end state unchanged).
-    auto run_chunk = [&](const ChunkCtx& x, int cc, double& v, double& wp, bool rerun, bool prev_same) -> bool {
-        const long long steps = x.D - 1;
-        const long long lo = (long long)cc * x.Lc;
-        const long long hi = (lo + x.Lc < steps) ? lo + x.Lc : steps;
-        const double4* F = x.rec;
-        double* vf = x.vout;
-        int j = 1;
-        double acc = __ldg(x.ma + x.bv[0]);
-        while (j < x.n_b && x.bi[j] <= (int)lo) { acc = __ldg(x.ma + x.bv[j]); j++; }
-        int nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
-        double acc_next = (j < x.n_b) ? __ldg(x.ma + x.bv[j]) : acc;   // fetched one regime ahead: no load on the per-step path
-        double4 r = ldg_d4(F + lo);
-        double4 r1 = (lo + 1 < hi) ? ldg_d4(F + lo + 1) : r;
-        if (!rerun) {
-            for (long long i = lo; i < hi; i++) {
-                double4 r2 = (i + 2 < hi) ? ldg_d4(F + i + 2) : r1;          // records run two steps ahead of their use
-                if ((int)i == nb_next) {
-                    acc = acc_next; j++;
-                    nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
-                    acc_next = (j < x.n_b) ? __ldg(x.ma + x.bv[j]) : acc;
-                }
-                v = fwd_step(r, v, wp, acc, x.w, dd);
-                vf[i + 1] = v;
-                r = r1; r1 = r2;
-            }
-            return false;
-        }
-        double old = vf[lo + 1];
-        double old1 = (lo + 1 < hi) ? vf[lo + 2] : 0.0;
-        for (long long i = lo; i < hi; i++) {
-            double4 r2 = (i + 2 < hi) ? ldg_d4(F + i + 2) : r1;
-            double old2 = (i + 2 < hi) ? vf[i + 3] : 0.0;
-            if ((int)i == nb_next) {
-                acc = acc_next; j++;
-                nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
-                acc_next = (j < x.n_b) ? __ldg(x.ma + x.bv[j]) : acc;
-            }
-            v = fwd_step(r, v, wp, acc, x.w, dd);
-            bool same = same_bits(old, v);
-            if (same && prev_same) return true;        // state (v[i+1], v[i]*|k_i|) equals the old run's: rest is unchanged
-            vf[i + 1] = v;
-            prev_same = same;
-            r = r1; r1 = r2; old = old1; old1 = old2;
-        }
-        return false;
-    };
-
-    // ---- sweep 1.  Chunk c > 0 starts `warm` steps BEFORE its own range from the guess "the state-independent caps bind
-    // on the two samples before that point" and only computes (no stores) until it reaches its range: a wrong guess
-    // survives for at most one acceleration ramp, so after the warm-up the state is usually already the true one and the
-    // fix-up round has nothing to re-run.  (Exactness never depends on the guess: the rounds below verify bitwise.)
+    // ---- sweep 1: chunk c > 0 starts from the guess "the state-independent caps bind on the two samples before it"
     {
-        const ChunkCtx& x = mine;
-        const bool active = x.ok && c < x.nch;
-        double v = start_vel, wp = 0.0;
+        double v = start_vel, sq = 0.0;
         if (active) {
-            const long long lo = (long long)c * x.Lc;
             if (c > 0) {
-                const long long wl = (warm < lo - 2) ? warm : ((lo - 2 > 0) ? lo - 2 : 0);
-                const long long s0 = lo - wl;                       // first warm-up step (>= 2 unless lo < 2)
-                double vm1 = (s0 >= 2) ? x.rec[s0 - 2].w : start_vel;
-                double4 fm1 = x.rec[s0 - 1];
+                const double vm1 = (lo >= 2) ? F[lo - 2].w : start_vel;
+                const double4 fm1 = F[lo - 1];
                 v = fm1.w;
-                wp = vm1 * fm1.x;
-                if (wl > 0) {
-                    int j = 1;
-                    double acc = x.ma[x.bv[0]];
-                    while (j < x.n_b && x.bi[j] <= (int)s0) { acc = x.ma[x.bv[j]]; j++; }
-                    int nb_next = (j < x.n_b) ? x.bi[j] : 2147483647;
-                    double4 r = x.rec[s0];
-                    double4 r1 = (s0 + 1 < lo) ? x.rec[s0 + 1] : r;
-                    for (long long i = s0; i < lo; i++) {
-                        double4 r2 = (i + 2 < lo) ? x.rec[i + 2] : r1;
-                        if ((int)i == nb_next) { acc = x.ma[x.bv[j]]; j++; nb_next = (j < x.n_b) ? x.bi[j] : 2147483647; }
-                        v = fwd_step(r, v, wp, acc, x.w, dd);
-                        r = r1; r1 = r2;
-                    }
-                }
+                const double wp = vm1 * fm1.x;
+                sq = wp * wp;
             }
-            s_usev[tid] = v; s_usew[tid] = wp;
-            run_chunk(x, c, v, wp, false, false);
+            s_usev[c] = v; s_usew[c] = sq;
+            fwd_run<false>(F, RG, vf, lo, hi, s_bi, s_acc, n_b, hw, dd, v, sq, false);
         }
-        s_endv[tid] = v; s_endw[tid] = wp;
+        s_endv[c] = v; s_endw[c] = sq;
     }
     __syncthreads();
 
     // ---- fix-up rounds
     int rounds = 0;
     for (int round = 1; round < NT; round++) {
-        {
-            const ChunkCtx& x = mine;
-            if (x.ok && c < x.nch && c >= round) {
-                if (!(same_bits(s_endv[tid - 1], s_usev[tid]) && same_bits(s_endw[tid - 1], s_usew[tid])))
-                    s_queue[atomicAdd(&s_qn, 1)] = tid;
-            }
+        bool need = false;
+        double in_v = 0.0, in_w = 0.0;
+        if (active && c >= round) {
+            in_v = s_endv[c - 1]; in_w = s_endw[c - 1];
+            need = !(same_bits(in_v, s_usev[c]) && same_bits(in_w, s_usew[c]));
         }
-        __syncthreads();
-        const int n = s_qn;
-        if (n == 0) break;
+        if (!__syncthreads_or(need)) break;          // also orders this round's reads before its writes
         rounds = round;
-        // read the inputs of this round before anybody publishes new end states
-        int item = -1;
-        double in_v = 0.0, in_w = 0.0, old_usev = 0.0;
-        if (tid < n) { item = s_queue[tid]; in_v = s_endv[item - 1]; in_w = s_endw[item - 1]; old_usev = s_usev[item]; }
-        __syncthreads();
-        if (tid == 0) s_qn = 0;
-        if (item >= 0) {
-            const int pp = item / NT, cc = item - pp * NT;
-            const ChunkCtx x = (pp == p) ? mine : make_ctx(pp);
-            double v = in_v, wp = in_w;
-            bool merged = run_chunk(x, cc, v, wp, true, same_bits(in_v, old_usev));
-            s_usev[item] = in_v; s_usew[item] = in_w;
-            if (!merged) { s_endv[item] = v; s_endw[item] = wp; }
+        if (need) {
+            double v = in_v, sq = in_w;
+            const bool merged = fwd_run<true>(F, RG, vf, lo, hi, s_bi, s_acc, n_b, hw, dd, v, sq, same_bits(in_v, s_usev[c]));
+            s_usev[c] = in_v; s_usew[c] = in_w;
+            if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
         }
         __syncthreads();
     }
-    if (c == 0 && rounds_out && mine.ok) rounds_out[2 * b] = rounds;
+    if (c == 0 && rounds_out) rounds_out[2 * b] = rounds;
+}
+
+// backward chunk: steps i = hi, hi-1, ..., lo+1; step i reads R[i], RG[i-1], vel_f[i-1] and writes vo[i-1]
+template <bool RERUN>
+__device__ __forceinline__ bool bwd_run(const double4* __restrict__ R, const double* __restrict__ RG,
+                                        const double* __restrict__ vfw, double* __restrict__ vo, int hi, int lo,
+                                        const int* s_bi, const double* s_acc, int n_b, double acc0, double hw, double dd,
+                                        double& v, double& sq, bool prev_same)
+{
+    // regime at the chunk start (walking down from D-1): the smallest boundary index > hi was the last one applied
+    int j = n_b - 1;
+    double acc = acc0;
+    while (j >= 0 && s_bi[j] > hi) { acc = s_acc[j]; j--; }
+    int nb_next = (j >= 0) ? s_bi[j] : -1;
+    double4 ra = ldg_d4(R + hi), rb;
+    double ga = __ldg(RG + hi - 1), gb;
+    double fa = __ldg(vfw + hi - 1), fb;
+    double olda = 0.0, oldb = 0.0;
+    if (RERUN) olda = vo[hi - 1];
+    int i = hi;
+    while (true) {
+        // ---- buffers a.  Look-ahead loads are clamped to the row (i >= 1 here, so index i-1 >= 0; i-2 may be -1)
+        {
+            const int in = (i - 1 >= 1) ? i - 1 : 1;
+            rb = ldg_d4(R + in); gb = __ldg(RG + in - 1); fb = __ldg(vfw + in - 1);
+            if (RERUN) oldb = vo[in - 1];
+        }
+        if (i == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
+        v = bwd_step(ra, ga, v, sq, acc, hw, dd, pymin(fa, ra.w));
+        if (RERUN) {
+            const bool same = same_bits(olda, v);
+            if (same && prev_same) return true;
+            prev_same = same;
+        }
+        vo[i - 1] = v;
+        if (--i <= lo) break;
+        // ---- buffers b
+        {
+            const int in = (i - 1 >= 1) ? i - 1 : 1;
+            ra = ldg_d4(R + in); ga = __ldg(RG + in - 1); fa = __ldg(vfw + in - 1);
+            if (RERUN) olda = vo[in - 1];
+        }
+        if (i == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
+        v = bwd_step(rb, gb, v, sq, acc, hw, dd, pymin(fb, rb.w));
+        if (RERUN) {
+            const bool same = same_bits(oldb, v);
+            if (same && prev_same) return true;
+            prev_same = same;
+        }
+        vo[i - 1] = v;
+        if (--i <= lo) break;
+    }
+    return false;
 }
 
 // Backward pass.  Steps i = D-1 .. 1 (step i writes vel[i-1]); chunk c owns the c-th block of steps counted from the
 // end.  Reads vel_f (forward result) and writes vel (final); vel[D-1] = end_vel.  Also accumulates the travel-time
 // estimate used to size the time-domain outputs.
-__global__ void __launch_bounds__(256) k_bwd_chunked(
-    long long B, int NT, const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt,
-    double end_vel, long long D_cap, const int* __restrict__ n_samples, const double4* __restrict__ recR, int E_cap,
+__global__ void __launch_bounds__(256, 4) k_bwd_chunked(
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel, long long D_cap,
+    const int* __restrict__ n_samples, const double4* __restrict__ recR, const double* __restrict__ rg, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, const double* __restrict__ vel_f, double* __restrict__ vel,
-    float* __restrict__ t_est, int* __restrict__ rounds_out, int warm)
+    const int* __restrict__ n_ev, const double* __restrict__ vel_f, double* __restrict__ vel, float* __restrict__ t_est,
+    int* __restrict__ rounds_out)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
-    const int NTH = blockDim.x, PB = NTH / NT;
-    const int tid = threadIdx.x, p = tid / NT, c = tid - p * NT;
+    const int NT = blockDim.x, c = threadIdx.x;
+    const long long b = blockIdx.x;
     double* s_endv = reinterpret_cast<double*>(s_mem);
-    double* s_endw = s_endv + NTH;
-    double* s_usev = s_endw + NTH;
-    double* s_usew = s_usev + NTH;
-    int* s_queue = reinterpret_cast<int*>(s_usew + NTH);
-    __shared__ int s_qn;
-    auto make_ctx = [&](int pp) -> ChunkCtx {
-        ChunkCtx x;
-        const long long bb = (long long)blockIdx.x * PB + pp;
-        x.ok = (bb < B) && status[bb] == ST_OK;
-        x.D = x.ok ? n_samples[bb] : 1;
-        long long steps = x.D - 1;
-        x.Lc = steps > 0 ? (steps + NT - 1) / NT : 1;
-        x.nch = (x.ok && steps > 0) ? (int)((steps + x.Lc - 1) / x.Lc) : 0;
-        const long long bs = x.ok ? bb : 0;
-        x.n_b = x.ok ? n_ev[2 * bs + 1] : 0;
-        x.w = cons[bs * 6 + 5];
-        x.rec = recR + (size_t)bs * D_cap;
-        x.vin = vel_f + (size_t)bs * D_cap;
-        x.vout = vel + (size_t)bs * D_cap;
-        x.ma = max_accels + (size_t)bs * E_cap;
-        x.bi = bidx + (size_t)bs * E_cap;
-        x.bv = bval + (size_t)bs * E_cap;
-        return x;
-    };
-    const long long b = (long long)blockIdx.x * PB + p;
-    const ChunkCtx mine = make_ctx(p);
-    if (c == 0 && mine.ok) mine.vout[mine.D - 1] = end_vel;
-    if (tid == 0) s_qn = 0;
+    double* s_endw = s_endv + NT;
+    double* s_usev = s_endw + NT;
+    double* s_usew = s_usev + NT;
+    double* s_acc = s_usew + NT;                                  // [E_cap] max_accels[bval[j] + 1] (applied at sample bidx[j])
+    int* s_bi = reinterpret_cast<int*>(s_acc + E_cap);
+    if (c == 0 && t_est) t_est[b] = 0.f;
+    if (status[b] != ST_OK) return;
+    const int D = n_samples[b];
+    const int steps = D - 1;
+    double* vo = vel + (size_t)b * D_cap;
+    if (c == 0) { vo[D - 1] = end_vel; if (rounds_out) rounds_out[2 * b + 1] = 0; }
+    if (steps <= 0) return;
+    const int n_b = n_ev[2 * b + 1];
+    for (int k = c; k < n_b; k += NT) {
+        s_bi[k] = bidx[(size_t)b * E_cap + k];
+        s_acc[k] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + k] + 1];
+    }
+    const double acc0 = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + n_b - 1]];
+    const int Lc = (steps + NT - 1) / NT;
+    const int nch = (steps + Lc - 1) / Lc;
+    const bool active = c < nch;
+    const int hi = (D - 1) - c * Lc;
+    const int lo = (hi - Lc > 0) ? hi - Lc : 0;
+    const double4* R = recR + (size_t)b * D_cap;
+    const double* RG = rg + (size_t)b * D_cap;
+    const double* vfw = vel_f + (size_t)b * D_cap;
+    const double hw = cons[b * 6 + 5] * 0.5;
     __syncthreads();
 
-    // chunk cc: steps i = hi, hi-1, ..., lo+1 with hi = D-1 - cc*Lc, lo = max(hi - Lc, 0)
-    auto run_chunk = [&](const ChunkCtx& x, int cc, double& v, double& wp, bool rerun, bool prev_same) -> bool {
-        const long long hi = (x.D - 1) - (long long)cc * x.Lc;
-        const long long lo = (hi - x.Lc > 0) ? hi - x.Lc : 0;
-        const double4* R = x.rec;
-        const double* vf = x.vin;
-        double* vo = x.vout;
-        // regime at chunk start (walking down from D-1): the smallest boundary index > hi was the last one applied
-        double acc = __ldg(x.ma + x.bv[x.n_b - 1]);
-        int j = x.n_b - 1;
-        while (j >= 0 && x.bi[j] > (int)hi) { acc = __ldg(x.ma + x.bv[j] + 1); j--; }
-        int nb_next = (j >= 0) ? x.bi[j] : -1;
-        double acc_next = (j >= 0) ? __ldg(x.ma + x.bv[j] + 1) : acc;   // fetched one regime ahead
-        double4 r = ldg_d4(R + hi);
-        double vfp = __ldg(vf + hi - 1);
-        double4 r1 = (hi - 1 > lo) ? ldg_d4(R + hi - 1) : r;
-        double vf1 = (hi - 1 > lo) ? __ldg(vf + hi - 2) : 0.0;
-        if (!rerun) {
-            for (long long i = hi; i > lo; i--) {
-                double4 r2 = (i - 2 > lo) ? ldg_d4(R + i - 2) : r1;          // loads run two steps ahead of their use
-                double vf2 = (i - 2 > lo) ? __ldg(vf + i - 3) : 0.0;
-                if ((int)i == nb_next) {
-                    acc = acc_next; j--;
-                    nb_next = (j >= 0) ? x.bi[j] : -1;
-                    acc_next = (j >= 0) ? __ldg(x.ma + x.bv[j] + 1) : acc;
-                }
-                v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
-                vo[i - 1] = v;
-                r = r1; vfp = vf1; r1 = r2; vf1 = vf2;
-            }
-            return false;
-        }
-        double old = vo[hi - 1];
-        double old1 = (hi - 1 > lo) ? vo[hi - 2] : 0.0;
-        for (long long i = hi; i > lo; i--) {
-            double4 r2 = (i - 2 > lo) ? ldg_d4(R + i - 2) : r1;
-            double vf2 = (i - 2 > lo) ? __ldg(vf + i - 3) : 0.0;
-            double old2 = (i - 2 > lo) ? vo[i - 3] : 0.0;
-            if ((int)i == nb_next) {
-                acc = acc_next; j--;
-                nb_next = (j >= 0) ? x.bi[j] : -1;
-                acc_next = (j >= 0) ? __ldg(x.ma + x.bv[j] + 1) : acc;
-            }
-            v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
-            bool same = same_bits(old, v);
-            if (same && prev_same) return true;
-            vo[i - 1] = v;
-            prev_same = same;
-            r = r1; vfp = vf1; old = old1; r1 = r2; vf1 = vf2; old1 = old2;
-        }
-        return false;
-    };
-
-    // ---- sweep 1
+    // ---- sweep 1: guess v[hi] = min(vel_f[hi], G[hi+1]) (the state-independent part of what step hi+1 produces)
     {
-        const ChunkCtx& x = mine;
-        const bool active = x.ok && c < x.nch;
-        double v = end_vel, wp = 0.0;
+        double v = end_vel, sq = 0.0;
         if (active) {
-            const long long hi = (x.D - 1) - (long long)c * x.Lc;
             if (c > 0) {
-                // warm-up (see the forward kernel): start `warm` steps above the chunk from the guess
-                // v[s0] = min(vel_f[s0], G[s0+1]) (the state-independent part of what step s0+1 produces)
-                const long long room = (x.D - 1) - hi - 2;
-                const long long wl = (warm < room) ? warm : (room > 0 ? room : 0);
-                const long long s0 = hi + wl;
-                double4 r1 = x.rec[s0 + 1];
-                v = pymin(x.vin[s0], r1.w);
-                double vp1 = (s0 + 2 <= x.D - 1) ? pymin(x.vin[s0 + 1], x.rec[s0 + 2].w) : end_vel;
-                wp = vp1 * r1.x;
-                if (wl > 0) {
-                    double acc = x.ma[x.bv[x.n_b - 1]];
-                    int j = x.n_b - 1;
-                    while (j >= 0 && x.bi[j] > (int)s0) { acc = x.ma[x.bv[j] + 1]; j--; }
-                    int nb_next = (j >= 0) ? x.bi[j] : -1;
-                    double4 r = x.rec[s0];
-                    double vfp = x.vin[s0 - 1];
-                    double4 ra = (s0 - 1 > hi) ? x.rec[s0 - 1] : r;
-                    double vfa = (s0 - 1 > hi) ? x.vin[s0 - 2] : 0.0;
-                    for (long long i = s0; i > hi; i--) {
-                        double4 rb = (i - 2 > hi) ? x.rec[i - 2] : ra;
-                        double vfb = (i - 2 > hi) ? x.vin[i - 3] : 0.0;
-                        if ((int)i == nb_next) { acc = x.ma[x.bv[j] + 1]; j--; nb_next = (j >= 0) ? x.bi[j] : -1; }
-                        v = bwd_step(r, v, wp, acc, x.w, dd, vfp);
-                        r = ra; vfp = vfa; ra = rb; vfa = vfb;
-                    }
-                }
+                const double4 r1 = R[hi + 1];
+                v = pymin(vfw[hi], r1.w);
+                const double vp1 = (hi + 2 <= D - 1) ? pymin(vfw[hi + 1], R[hi + 2].w) : end_vel;
+                const double wp = vp1 * r1.x;
+                sq = wp * wp;
             }
-            s_usev[tid] = v; s_usew[tid] = wp;
-            run_chunk(x, c, v, wp, false, false);
+            s_usev[c] = v; s_usew[c] = sq;
+            bwd_run<false>(R, RG, vfw, vo, hi, lo, s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
         }
-        s_endv[tid] = v; s_endw[tid] = wp;
+        s_endv[c] = v; s_endw[c] = sq;
     }
     __syncthreads();
 
     // ---- fix-up rounds (states flow from chunk c-1 to chunk c, as in the forward kernel)
     int rounds = 0;
     for (int round = 1; round < NT; round++) {
-        {
-            const ChunkCtx& x = mine;
-            if (x.ok && c < x.nch && c >= round) {
-                if (!(same_bits(s_endv[tid - 1], s_usev[tid]) && same_bits(s_endw[tid - 1], s_usew[tid])))
-                    s_queue[atomicAdd(&s_qn, 1)] = tid;
-            }
+        bool need = false;
+        double in_v = 0.0, in_w = 0.0;
+        if (active && c >= round) {
+            in_v = s_endv[c - 1]; in_w = s_endw[c - 1];
+            need = !(same_bits(in_v, s_usev[c]) && same_bits(in_w, s_usew[c]));
         }
-        __syncthreads();
-        const int n = s_qn;
-        if (n == 0) break;
+        if (!__syncthreads_or(need)) break;
         rounds = round;
-        int item = -1;
-        double in_v = 0.0, in_w = 0.0, old_usev = 0.0;
-        if (tid < n) { item = s_queue[tid]; in_v = s_endv[item - 1]; in_w = s_endw[item - 1]; old_usev = s_usev[item]; }
-        __syncthreads();
-        if (tid == 0) s_qn = 0;
-        if (item >= 0) {
-            const int pp = item / NT, cc = item - pp * NT;
-            const ChunkCtx x = (pp == p) ? mine : make_ctx(pp);
-            double v = in_v, wp = in_w;
-            bool merged = run_chunk(x, cc, v, wp, true, same_bits(in_v, old_usev));
-            s_usev[item] = in_v; s_usew[item] = in_w;
-            if (!merged) { s_endv[item] = v; s_endw[item] = wp; }
+        if (need) {
+            double v = in_v, sq = in_w;
+            const bool merged = bwd_run<true>(R, RG, vfw, vo, hi, lo, s_bi, s_acc, n_b, acc0, hw, dd, v, sq,
+                                              same_bits(in_v, s_usev[c]));
+            s_usev[c] = in_v; s_usew[c] = in_w;
+            if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
         }
         __syncthreads();
     }
-    if (c == 0 && rounds_out && mine.ok) rounds_out[2 * b + 1] = rounds;
+    if (c == 0 && rounds_out) rounds_out[2 * b + 1] = rounds;
 
     // ---- travel-time estimate (single precision is plenty: it only sizes buffers)
     __syncthreads();
     float est = 0.f;
-    {
-        const ChunkCtx& x = mine;
-        if (x.ok && c < x.nch) {
-            const long long hi = (x.D - 1) - (long long)c * x.Lc;
-            const long long lo = (hi - x.Lc > 0) ? hi - x.Lc : 0;
-            for (long long i = hi; i > lo; i--) {
-                float vm = 0.5f * ((float)x.vout[i] + (float)x.vout[i - 1]);
-                est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
-            }
+    if (active) {
+        float vprev = (float)vo[hi];
+        for (int i = hi; i > lo; i--) {
+            const float vcur = (float)vo[i - 1];
+            const float vm = 0.5f * (vprev + vcur);
+            est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
+            vprev = vcur;
         }
     }
     float* s_f = reinterpret_cast<float*>(s_endv);      // end states are no longer needed
+    s_f[c] = est;
     __syncthreads();
-    s_f[tid] = est;
-    __syncthreads();
-    if (c == 0 && t_est && b < B) {
+    if (c == 0 && t_est) {
         float tot = 0.f;
-        if (mine.ok) for (int k = 0; k < NT; k++) tot += s_f[p * NT + k];
+        for (int k = 0; k < NT; k++) tot += s_f[k];
         t_est[b] = tot;
     }
 }
