@@ -1169,36 +1169,49 @@ extern "C" int64_t vap_event_scratch_ints(int64_t B, int N_max, int A_max)
     return B * N_max + B + B * Am * EV_AP_CAND + B * Am;
 }
 
+// slots per path row of the chunk-interleaved pass arrays (records, reciprocals, forward velocities)
+extern "C" int64_t vap_pass_row_slots(int64_t D_cap) { return D_cap + 512; }
+
 extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
                                    double start_vel, double end_vel, int64_t D_cap, const int32_t* n_samples,
                                    const double* kap, const double* th, int E_cap, const double* max_accels,
                                    const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
                                    const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* recF,
-                                   double* recR, double* rg, double* vel_f, double* vel, float* t_est, int32_t* rounds,
-                                   int chunks, int mode, void* stream)
+                                   double* recR, double* rg, double* vel_f, double* velT, double* vel, float* t_est,
+                                   int32_t* rounds, int chunks, int mode, void* stream)
 {
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
-    if (chunks < 32 || chunks > 256 || (chunks % 32) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be a multiple of 32 in [32, 256]");
+    if (chunks < 32 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be 32, 64, 128 or 256");
     if (D_cap > 2000000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
-    dim3 grid(blocks_for(D_cap, 256), (unsigned)B);
+    const long long RS = vap_pass_row_slots(D_cap);
+    dim3 grid(blocks_for(D_cap + chunks, 256), (unsigned)B);
     size_t sm = (size_t)E_cap * (2 * sizeof(double) + 4 * sizeof(int));
     k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, end_vel, D_cap, n_samples, kap, th, E_cap, max_accels, bidx, bval,
-                                         n_ev, vr_idx, vr_val, st_idx, n_vr, reinterpret_cast<double4*>(recF),
+                                         n_ev, vr_idx, vr_val, st_idx, n_vr, chunks, RS, reinterpret_cast<double4*>(recF),
                                          reinterpret_cast<double4*>(recR), rg);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
     // CTA = one path, one chunk per thread.  The passes are bound by the latency of the dependent fp64 chain of a step:
     // one-warp CTAs at <= 64 registers put 32 independent chains on every SM.
     const size_t ss = (size_t)chunks * 4 * sizeof(double) + (size_t)E_cap * (sizeof(double) + sizeof(int));
-    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, D_cap, n_samples,
+    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, RS, n_samples,
                                                        reinterpret_cast<const double4*>(recF), rg, E_cap, max_accels, bidx,
                                                        bval, n_ev, vel_f, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
-    if (mode == 1) return 0;
-    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, D_cap, n_samples,
+    // sample-order result: ceil(Lc_max / 32) row tiles x chunks / 32 column tiles per path
+    const long long lc_max = (D_cap + chunks - 1) / chunks + 1;
+    dim3 g2((unsigned)(((lc_max + 31) / 32) * (chunks / 32)), (unsigned)B);
+    if (mode == 1) {
+        k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, vel_f, vel);
+        CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
+        return 0;
+    }
+    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, RS, n_samples,
                                                        reinterpret_cast<const double4*>(recR), rg, E_cap, max_accels, bidx,
-                                                       bval, n_ev, vel_f, vel, t_est, rounds);
+                                                       bval, n_ev, vel_f, velT, t_est, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
+    k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, velT, vel);
+    CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
     return 0;
 }
 

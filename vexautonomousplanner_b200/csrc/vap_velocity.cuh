@@ -184,111 +184,174 @@ __global__ void k_resolve_events(long long B, int N_max, int A_max, const double
 
 __device__ __forceinline__ double recip_for_pass(double g);   // defined with the pass kernels below
 
-// ---- pre-pass (parallel): one 32-byte record per sample and direction -----------------------------------------
-// forward  record F[i] = { |kappa_i|, 2|theta_{i+1}-theta_i| (NaN when straight), a_static_i, C_i }
+// ---- chunk-interleaved layout of everything the passes stream ---------------------------------------------------------
+// A path's D-1 steps ("edges" e = 0 .. D-2: forward step e goes from sample e to e+1, backward step e+1 from sample e+1
+// to e) are cut into NT chunks of Lc = ceil((D-1)/NT) edges; chunk c owns edges [c*Lc, min((c+1)*Lc, D-1)).  Thread c of a
+// pass CTA walks chunk c, so at any moment the warp needs edge s of 32 different chunks: the per-edge data is stored at
+//      slot(e) = (e % Lc) * NT + e / Lc          (row = position inside the chunk, column = chunk)
+// which makes every warp-wide load of the passes one contiguous, fully used run of memory (1 KB of records, 256 B of
+// reciprocals / forward velocities).  Rows of RS = D_cap + 256 slots per path; slot RS-1 holds the forward velocity of
+// the last sample.
+__device__ __forceinline__ int chunk_len(int steps, int NT) { return (steps + NT - 1) / NT; }
+__device__ __forceinline__ int edge_slot(int e, int Lc, int NT) { const int c = e / Lc; return (e - c * Lc) * NT + c; }
+
+// ---- pre-pass (parallel): one 32-byte record per edge and direction ----------------------------------------------------
+// forward  record of edge e (sample i = e):     { |kappa_i|, 2|theta_{i+1}-theta_i| (NaN when straight), a_static_i, C_i }
 //    a_static = min(max_ang_acc/|k|, 2 acc/(w|k|+2), acc)  (acc when straight);  C_i = min(v0[i+1], vlim_i, cap_i)
-// backward record R[i] = { |kappa_i|, 2|theta_{i-1}-theta_i| (NaN when straight), d_static_i, G_i }
+// backward record of edge e (sample i = e + 1): { |kappa_i|, 2|theta_{i-1}-theta_i| (NaN when straight), d_static_i, G_i }
 //    d_static = min(max_ang_acc/|k|, 2 dec/(w|k|+2), dec);  G_i = min(vlim_i, cap_i)
+// rg of edge e: recip_for_pass(2|theta_{e+1}-theta_e|), shared by both directions.
 // A NaN denominator makes the wheel term NaN, which Python's min() ignores -- exactly the straight branch.
+// One thread per SLOT (coalesced stores; the 8-byte gathers of kappa / theta are 8 rows deep per CTA, so every fetched
+// sector is used by the CTA's other warps).  The thread of sample i writes the forward record of edge i and the backward
+// record of edge i-1; the thread of the last edge also makes the backward record of the final sample.
+struct PrepassTables {
+    const double* ma; const double* vv; const int* bi; const int* bv; const int* vi; const int* si;
+    int n_b, nvr, nst;
+};
+__device__ __forceinline__ int last_le(const int* a, int n, int key)      // last j in [0, n) with a[j] <= key (a[0] <= key)
+{
+    int j = 0;
+    if (n <= 8) { while (j + 1 < n && a[j + 1] <= key) j++; return j; }
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (a[mid] <= key) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+// a / b for several numerators over one denominator: y = RN(1/b) once, then per quotient one multiplication and two fused
+// residual corrections (Markstein: with the correctly rounded reciprocal the second correction gives the correctly rounded
+// quotient unless b's significand is all ones).  Operands outside the proven range take the ordinary division.
+struct SharedRecip { double b, y; bool ok; };
+__device__ __forceinline__ SharedRecip shared_recip(double b)
+{
+    SharedRecip r;
+    const long long bits = __double_as_longlong(b);
+    r.ok = (b > 1e-150) && (b < 1e150) && ((bits & 0x000FFFFFFFFFFFFFLL) != 0x000FFFFFFFFFFFFFLL);
+    r.b = b;
+    r.y = 1.0 / b;
+    return r;
+}
+__device__ __forceinline__ double div_shared(double a, const SharedRecip& r)
+{
+    const double aa = fabs(a);
+    if (!(r.ok && aa > 1e-150 && aa < 1e150)) return a / r.b;
+    double q = a * r.y;
+    q = fma(fma(-r.b, q, a), r.y, q);
+    q = fma(fma(-r.b, q, a), r.y, q);
+    return q;
+}
+__device__ __forceinline__ void prepass_sample(const PrepassTables& T, double V, double w, double max_angular_vel,
+                                               double max_angular_accel, double end_vel, int D, int i, double k,
+                                               double th_i, double th_next, double th_prev, bool wantF, bool wantR,
+                                               double4& F, double4& R)
+{
+    const double ak = fabs(k);
+    const bool straight = ak < 1e-6;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    // w|k| + 2 = 2 (1 + w|k|/2) bit for bit (halving and doubling are exact), so the wheel-speed cap
+    // |V / (1 + w|k|/2)| (:239) IS 2V / (w|k| + 2) (:214): one quotient serves both.
+    const SharedRecip rden = shared_recip(w * ak + 2);
+    const double v_kin = div_shared(2 * V, rden);
+    const double cap = fabs(v_kin);
+    double vlim, a_ang = 0.0;
+    SharedRecip rak;
+    if (straight) vlim = V;
+    else {
+        rak = shared_recip(ak);
+        double v_ang = div_shared(max_angular_vel, rak);
+        a_ang = div_shared(max_angular_accel, rak);
+        // Constraints.max_speed_at_curvature (:23-33) with 2*V/w already evaluated
+        double m = (max_angular_vel * V) / (ak * V + max_angular_vel);
+        double v_curve = pymin(m, V);
+        vlim = pymin(pymin(v_ang, v_kin), v_curve);
+    }
+    const double G = pymin(vlim, cap);
+    const double dec_b = T.ma[T.bv[T.n_b - 1]];     // the backward pass keeps the forward pass's last max_dec
+    double acc_f = dec_b, a_kin = 0.0;
+    if (wantF) {
+        if (T.n_b > 1) acc_f = T.ma[T.bv[last_le(T.bi, T.n_b, i)]];    // forward regime at step i: last boundary <= i
+        double v0n;
+        if (i + 1 == D - 1) v0n = end_vel;
+        else {
+            v0n = (T.nvr > 1) ? T.vv[last_le(T.vi, T.nvr, i + 1)] : T.vv[0];
+            for (int j = 0; j < T.nst; j++) if (T.si[j] == i + 1) v0n = 0.01;
+        }
+        double astat, h2;
+        if (straight) { astat = acc_f; h2 = qnan; }
+        else {
+            a_kin = div_shared(2 * acc_f, rden);
+            astat = pymin(pymin(a_ang, a_kin), acc_f);
+            h2 = 2 * fabs(th_next - th_i);
+        }
+        F = make_double4(ak, h2, astat, pymin(v0n, G));
+    }
+    if (wantR) {
+        double dstat, h2;
+        if (straight) { dstat = dec_b; h2 = qnan; }
+        else {
+            double d_kin = (wantF && acc_f == dec_b) ? a_kin : div_shared(2 * dec_b, rden);
+            dstat = pymin(pymin(a_ang, d_kin), dec_b);
+            h2 = 2 * fabs(th_prev - th_i);
+        }
+        R = make_double4(ak, h2, dstat, G);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_prepass(
     const int* __restrict__ status, const double* __restrict__ cons, double end_vel, long long D_cap,
     const int* __restrict__ n_samples, const double* __restrict__ kap, const double* __restrict__ th, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
-    const int* __restrict__ st_idx, const int* __restrict__ n_vr, double4* __restrict__ recF,
+    const int* __restrict__ st_idx, const int* __restrict__ n_vr, int NT, long long RS, double4* __restrict__ recF,
     double4* __restrict__ recR, double* __restrict__ rg)
 {
     extern __shared__ unsigned char s_raw[];
-    long long b = blockIdx.y;
+    const long long b = blockIdx.y;
     if (status[b] != ST_OK) return;
-    long long D = n_samples[b];
-    long long i0 = (long long)blockIdx.x * blockDim.x;
-    if (i0 >= D) return;
+    const int D = n_samples[b];
+    const int steps = D - 1;
+    if (steps <= 0) return;
+    const int Lc = chunk_len(steps, NT);
+    const int j0 = blockIdx.x * blockDim.x;
+    if (j0 >= Lc * NT) return;
     double* s_ma = reinterpret_cast<double*>(s_raw);
     double* s_vv = s_ma + E_cap;
     int* s_bi = reinterpret_cast<int*>(s_vv + E_cap);
     int* s_bv = s_bi + E_cap;
     int* s_vi = s_bv + E_cap;
     int* s_si = s_vi + E_cap;
-    const int n_acc = n_ev[2 * b], n_b = n_ev[2 * b + 1], nvr = n_vr[2 * b], nst = n_vr[2 * b + 1];
+    PrepassTables T;
+    const int n_acc = n_ev[2 * b];
+    T.n_b = n_ev[2 * b + 1]; T.nvr = n_vr[2 * b]; T.nst = n_vr[2 * b + 1];
     for (int k = threadIdx.x; k < E_cap; k += blockDim.x) {
         s_ma[k] = (k < n_acc) ? max_accels[(size_t)b * E_cap + k] : 0.0;
-        s_vv[k] = (k < nvr) ? vr_val[(size_t)b * E_cap + k] : 0.0;
-        s_bi[k] = (k < n_b) ? bidx[(size_t)b * E_cap + k] : 2147483647;
-        s_bv[k] = (k < n_b) ? bval[(size_t)b * E_cap + k] : 0;
-        s_vi[k] = (k < nvr) ? vr_idx[(size_t)b * E_cap + k] : 2147483647;
-        s_si[k] = (k < nst) ? st_idx[(size_t)b * E_cap + k] : -1;
+        s_vv[k] = (k < T.nvr) ? vr_val[(size_t)b * E_cap + k] : 0.0;
+        s_bi[k] = (k < T.n_b) ? bidx[(size_t)b * E_cap + k] : 2147483647;
+        s_bv[k] = (k < T.n_b) ? bval[(size_t)b * E_cap + k] : 0;
+        s_vi[k] = (k < T.nvr) ? vr_idx[(size_t)b * E_cap + k] : 2147483647;
+        s_si[k] = (k < T.nst) ? st_idx[(size_t)b * E_cap + k] : -1;
     }
-    // per-path constants and the block's starting positions in the (sorted) event tables: once per CTA
-    __shared__ double s_c[4];
-    __shared__ int s_j0[2];
-    if (threadIdx.x == 0) {
-        const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
-        s_c[0] = 2 * V_ / w_;                 // max_angular_vel   (:81)
-        s_c[1] = 2 * A0_ / w_;                // max_angular_accel (:82)
-        int jf = 0, jv = 0;
-        for (int j = 1; j < n_b; j++) if (s_bi[j] <= (int)i0) jf = j;
-        for (int j = 1; j < nvr; j++) if (s_vi[j] <= (int)i0 + 1) jv = j;
-        s_j0[0] = jf; s_j0[1] = jv;
-    }
+    T.ma = s_ma; T.vv = s_vv; T.bi = s_bi; T.bv = s_bv; T.vi = s_vi; T.si = s_si;
     __syncthreads();
-    long long i = i0 + threadIdx.x;
-    if (i >= D) return;
-    const double V = cons[b * 6 + 0], w = cons[b * 6 + 5];
-    const double max_angular_vel = s_c[0];
-    const double max_angular_accel = s_c[1];
-    const size_t row = (size_t)b * D_cap;
-    double k = kap[row + i], ak = fabs(k);
-    double th_i = th[row + i];
-    bool straight = ak < 1e-6;
-    double vlim, cap;
-    if (straight) vlim = V;
-    else {
-        double v_ang = max_angular_vel / ak;
-        double v_kin = 2 * V / (w * ak + 2);
-        // Constraints.max_speed_at_curvature (:23-33) with 2*V/w already evaluated
-        double m = (max_angular_vel * V) / (ak * V + max_angular_vel);
-        double v_curve = pymin(m, V);
-        vlim = pymin(pymin(v_ang, v_kin), v_curve);
-    }
-    cap = fabs(V / (1 + (w * ak / 2)));
-    double G = pymin(vlim, cap);
-    // forward regime at step i: last boundary with bidx <= i
-    int jf = s_j0[0];
-    while (jf + 1 < n_b && s_bi[jf + 1] <= (int)i) jf++;
-    double acc_f = s_ma[s_bv[jf]];
-    double dec_b = s_ma[s_bv[n_b - 1]];     // the backward pass keeps the forward pass's last max_dec
-    if (i < D - 1) {
-        // reciprocal of the wheel-acceleration division's denominator for forward step i and backward step i+1
-        rg[row + i] = recip_for_pass(2 * fabs(th[row + i + 1] - th_i));
-        double v0n;
-        if (i + 1 == D - 1) v0n = end_vel;
-        else {
-            int jv = s_j0[1];
-            while (jv + 1 < nvr && s_vi[jv + 1] <= (int)(i + 1)) jv++;
-            v0n = s_vv[jv];
-            for (int j = 0; j < nst; j++) if (s_si[j] == (int)(i + 1)) v0n = 0.01;
-        }
-        double astat, h2;
-        if (straight) { astat = acc_f; h2 = __longlong_as_double(0x7ff8000000000000LL); }
-        else {
-            double a_ang = max_angular_accel / ak;
-            double a_kin = 2 * acc_f / (w * ak + 2);
-            astat = pymin(pymin(a_ang, a_kin), acc_f);
-            h2 = 2 * fabs(th[row + i + 1] - th_i);
-        }
-        recF[row + i] = make_double4(ak, h2, astat, pymin(v0n, G));
-    }
-    if (i >= 1) {
-        double dstat, h2;
-        if (straight) { dstat = dec_b; h2 = __longlong_as_double(0x7ff8000000000000LL); }
-        else {
-            double d_ang = max_angular_accel / ak;
-            double d_kin = 2 * dec_b / (w * ak + 2);
-            dstat = pymin(pymin(d_ang, d_kin), dec_b);
-            h2 = 2 * fabs(th[row + i - 1] - th_i);
-        }
-        recR[row + i] = make_double4(ak, h2, dstat, G);
+    const int j = j0 + threadIdx.x;
+    const int s = j >> (31 - __clz(NT)), c = j & (NT - 1);      // NT is a power of two
+    const int e = c * Lc + s;                  // this slot's edge = the sample whose terms this thread evaluates
+    if (s >= Lc || e >= steps) return;
+    const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
+    const double max_angular_vel = 2 * V / w;       // (:81)
+    const double max_angular_accel = 2 * A0 / w;    // (:82)
+    const double* kr = kap + (size_t)b * D_cap;
+    const double* tr = th + (size_t)b * D_cap;
+    const size_t row = (size_t)b * RS;
+    const double th_i = tr[e], th_n = tr[e + 1];
+    const double th_p = (e >= 1) ? tr[e - 1] : 0.0;
+    double4 F, R;
+    prepass_sample(T, V, w, max_angular_vel, max_angular_accel, end_vel, D, e, kr[e], th_i, th_n, th_p, true, e >= 1, F, R);
+    recF[row + j] = F;
+    rg[row + j] = recip_for_pass(2 * fabs(th_n - th_i));
+    if (e >= 1) recR[row + ((s >= 1) ? j - NT : (Lc - 1) * NT + c - 1)] = R;     // slot of edge e-1
+    if (e == steps - 1) {                                                         // backward record of the final sample
+        prepass_sample(T, V, w, max_angular_vel, max_angular_accel, end_vel, D, D - 1, kr[D - 1], th_n, 0.0, th_i, false, true, F, R);
+        recR[row + j] = R;
     }
 }
 
@@ -404,56 +467,61 @@ __device__ __forceinline__ double bwd_step(const double4 r, double rc, double v,
 // ------------------------------------------------------------------------------------------------------------------
 #define CH_INT_MAX 2147483647
 
-// forward chunk [lo, hi): step i reads F[i], RG[i] and writes vf[i+1]
+// forward chunk of column `col`: edges lo .. lo+len-1; edge e reads slot (e-lo)*NT + col and writes the forward velocity
+// of sample e+1 into the slot of edge e+1 (the bottom of the chunk writes row 0 of the next column, or `tail`).
 template <bool RERUN>
 __device__ __forceinline__ bool fwd_run(const double4* __restrict__ F, const double* __restrict__ RG, double* __restrict__ vf,
-                                        int lo, int hi, const int* s_bi, const double* s_acc, int n_b, double hw, double dd,
-                                        double& v, double& sq, bool prev_same)
+                                        int NT, int col, int lo, int len, int last_slot, const int* s_bi, const double* s_acc,
+                                        int n_b, double hw, double dd, double& v, double& sq, bool prev_same)
 {
     int j = 0;
     while (j + 1 < n_b && s_bi[j + 1] <= lo) j++;
     double acc = s_acc[j];
     int nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX;
-    double4 ra = ldg_d4(F + lo), rb;
-    double ga = __ldg(RG + lo), gb;
+    int slot = col;                                   // slot of the current edge
+    double4 ra = ldg_d4(F + slot), rb;
+    double ga = __ldg(RG + slot), gb;
     double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = vf[lo + 1];
-    int i = lo;
+    if (RERUN) olda = vf[(len > 1) ? slot + NT : last_slot];
+    int e = lo;
+    const int hi = lo + len;
     while (true) {
-        // ---- even step: buffers a
-        rb = ldg_d4(F + i + 1); gb = __ldg(RG + i + 1);                 // rows are padded: i+1 <= D-1 < D_cap
-        if (RERUN) oldb = vf[(i + 2 <= hi) ? i + 2 : hi];
-        if (i == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
+        // ---- buffers a (look-ahead loads never leave the path's row: it is padded by NT slots)
+        rb = ldg_d4(F + slot + NT); gb = __ldg(RG + slot + NT);
+        if (RERUN) oldb = vf[(e + 2 < hi) ? slot + 2 * NT : last_slot];
+        if (e == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
         v = fwd_step(ra, ga, v, sq, acc, hw, dd);
         if (RERUN) {
             const bool same = same_bits(olda, v);
             if (same && prev_same) return true;                         // state equals the old run's: the rest is unchanged
             prev_same = same;
         }
-        vf[i + 1] = v;
-        if (++i >= hi) break;
-        // ---- odd step: buffers b
-        ra = ldg_d4(F + i + 1); ga = __ldg(RG + i + 1);
-        if (RERUN) olda = vf[(i + 2 <= hi) ? i + 2 : hi];
-        if (i == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
+        if (++e >= hi) { vf[last_slot] = v; break; }
+        slot += NT;
+        vf[slot] = v;
+        // ---- buffers b
+        ra = ldg_d4(F + slot + NT); ga = __ldg(RG + slot + NT);
+        if (RERUN) olda = vf[(e + 2 < hi) ? slot + 2 * NT : last_slot];
+        if (e == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
         v = fwd_step(rb, gb, v, sq, acc, hw, dd);
         if (RERUN) {
             const bool same = same_bits(oldb, v);
             if (same && prev_same) return true;
             prev_same = same;
         }
-        vf[i + 1] = v;
-        if (++i >= hi) break;
+        if (++e >= hi) { vf[last_slot] = v; break; }
+        slot += NT;
+        vf[slot] = v;
     }
     return false;
 }
 
-// Forward pass.  Steps i = 0 .. D-2; chunk c owns steps [c*Lc, min((c+1)*Lc, D-1)); step i writes vel_f[i+1].
-__global__ void __launch_bounds__(256, 4) k_fwd_chunked(
-    const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, long long D_cap,
+// Forward pass.  Chunk c = thread c.  vfT: forward velocities in slot order (vfT[slot(e)] = velocity at sample e).
+__global__ void __maxnreg__(72) k_fwd_chunked(
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, long long RS,
     const int* __restrict__ n_samples, const double4* __restrict__ recF, const double* __restrict__ rg, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, double* __restrict__ vel_f, int* __restrict__ rounds_out)
+    const int* __restrict__ n_ev, double* __restrict__ vfT, int* __restrict__ rounds_out)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
     const int NT = blockDim.x, c = threadIdx.x;
@@ -467,21 +535,22 @@ __global__ void __launch_bounds__(256, 4) k_fwd_chunked(
     if (status[b] != ST_OK) return;                               // uniform over the CTA
     const int D = n_samples[b];
     const int steps = D - 1;
-    double* vf = vel_f + (size_t)b * D_cap;
-    if (c == 0) { vf[0] = start_vel; if (rounds_out) rounds_out[2 * b] = 0; }
+    double* vf = vfT + (size_t)b * RS;
+    if (c == 0) { vf[0] = start_vel; vf[RS - 1] = start_vel; if (rounds_out) rounds_out[2 * b] = 0; }
     if (steps <= 0) return;
     const int n_b = n_ev[2 * b + 1];
     for (int k = c; k < n_b; k += NT) {
         s_bi[k] = bidx[(size_t)b * E_cap + k];
         s_acc[k] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + k]];
     }
-    const int Lc = (steps + NT - 1) / NT;
+    const int Lc = chunk_len(steps, NT);
     const int nch = (steps + Lc - 1) / Lc;
     const bool active = c < nch;
     const int lo = c * Lc;
-    const int hi = (lo + Lc < steps) ? lo + Lc : steps;
-    const double4* F = recF + (size_t)b * D_cap;
-    const double* RG = rg + (size_t)b * D_cap;
+    const int len = (lo + Lc < steps) ? Lc : steps - lo;
+    const int last_slot = (lo + len < steps) ? c + 1 : (int)(RS - 1);       // where the velocity of sample lo+len goes
+    const double4* F = recF + (size_t)b * RS;
+    const double* RG = rg + (size_t)b * RS;
     const double hw = cons[b * 6 + 5] * 0.5;
     __syncthreads();
 
@@ -490,14 +559,14 @@ __global__ void __launch_bounds__(256, 4) k_fwd_chunked(
         double v = start_vel, sq = 0.0;
         if (active) {
             if (c > 0) {
-                const double vm1 = (lo >= 2) ? F[lo - 2].w : start_vel;
-                const double4 fm1 = F[lo - 1];
+                const double vm1 = (lo >= 2) ? F[edge_slot(lo - 2, Lc, NT)].w : start_vel;
+                const double4 fm1 = F[edge_slot(lo - 1, Lc, NT)];
                 v = fm1.w;
                 const double wp = vm1 * fm1.x;
                 sq = wp * wp;
             }
             s_usev[c] = v; s_usew[c] = sq;
-            fwd_run<false>(F, RG, vf, lo, hi, s_bi, s_acc, n_b, hw, dd, v, sq, false);
+            fwd_run<false>(F, RG, vf, NT, c, lo, len, last_slot, s_bi, s_acc, n_b, hw, dd, v, sq, false);
         }
         s_endv[c] = v; s_endw[c] = sq;
     }
@@ -516,7 +585,8 @@ __global__ void __launch_bounds__(256, 4) k_fwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = fwd_run<true>(F, RG, vf, lo, hi, s_bi, s_acc, n_b, hw, dd, v, sq, same_bits(in_v, s_usev[c]));
+            const bool merged = fwd_run<true>(F, RG, vf, NT, c, lo, len, last_slot, s_bi, s_acc, n_b, hw, dd, v, sq,
+                                              same_bits(in_v, s_usev[c]));
             s_usev[c] = in_v; s_usew[c] = in_w;
             if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
         }
@@ -525,71 +595,77 @@ __global__ void __launch_bounds__(256, 4) k_fwd_chunked(
     if (c == 0 && rounds_out) rounds_out[2 * b] = rounds;
 }
 
-// backward chunk: steps i = hi, hi-1, ..., lo+1; step i reads R[i], RG[i-1], vel_f[i-1] and writes vo[i-1]
+// backward chunk of column `col`: edges lo+len-1 down to lo; edge e (backward step i = e+1 -> e) reads slot (e-lo)*NT + col
+// of the backward records, the reciprocals and the forward velocities, and writes the final velocity of sample e into the
+// same slot of voT.
 template <bool RERUN>
 __device__ __forceinline__ bool bwd_run(const double4* __restrict__ R, const double* __restrict__ RG,
-                                        const double* __restrict__ vfw, double* __restrict__ vo, int hi, int lo,
-                                        const int* s_bi, const double* s_acc, int n_b, double acc0, double hw, double dd,
-                                        double& v, double& sq, bool prev_same)
+                                        const double* __restrict__ vf, double* __restrict__ voT, int NT, int col, int lo,
+                                        int len, const int* s_bi, const double* s_acc, int n_b, double acc0, double hw,
+                                        double dd, double& v, double& sq, bool prev_same)
 {
-    // regime at the chunk start (walking down from D-1): the smallest boundary index > hi was the last one applied
+    // regime at the chunk start (walking down from D-1): the smallest boundary index > i was the last one applied
+    int e = lo + len - 1;                            // current edge; the reference's loop index is i = e + 1
     int j = n_b - 1;
     double acc = acc0;
-    while (j >= 0 && s_bi[j] > hi) { acc = s_acc[j]; j--; }
+    while (j >= 0 && s_bi[j] > e + 1) { acc = s_acc[j]; j--; }
     int nb_next = (j >= 0) ? s_bi[j] : -1;
-    double4 ra = ldg_d4(R + hi), rb;
-    double ga = __ldg(RG + hi - 1), gb;
-    double fa = __ldg(vfw + hi - 1), fb;
+    int slot = (len - 1) * NT + col;
+    double4 ra = ldg_d4(R + slot), rb;
+    double ga = __ldg(RG + slot), gb;
+    double fa = __ldg(vf + slot), fb;
     double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = vo[hi - 1];
-    int i = hi;
+    if (RERUN) olda = voT[slot];
     while (true) {
-        // ---- buffers a.  Look-ahead loads are clamped to the row (i >= 1 here, so index i-1 >= 0; i-2 may be -1)
+        // ---- buffers a (look-ahead slot clamped to the chunk's first row)
         {
-            const int in = (i - 1 >= 1) ? i - 1 : 1;
-            rb = ldg_d4(R + in); gb = __ldg(RG + in - 1); fb = __ldg(vfw + in - 1);
-            if (RERUN) oldb = vo[in - 1];
+            const int sn = (e > lo) ? slot - NT : slot;
+            rb = ldg_d4(R + sn); gb = __ldg(RG + sn); fb = __ldg(vf + sn);
+            if (RERUN) oldb = voT[sn];
         }
-        if (i == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
+        if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
         v = bwd_step(ra, ga, v, sq, acc, hw, dd, pymin(fa, ra.w));
         if (RERUN) {
             const bool same = same_bits(olda, v);
             if (same && prev_same) return true;
             prev_same = same;
         }
-        vo[i - 1] = v;
-        if (--i <= lo) break;
+        voT[slot] = v;
+        if (--e < lo) break;
+        slot -= NT;
         // ---- buffers b
         {
-            const int in = (i - 1 >= 1) ? i - 1 : 1;
-            ra = ldg_d4(R + in); ga = __ldg(RG + in - 1); fa = __ldg(vfw + in - 1);
-            if (RERUN) olda = vo[in - 1];
+            const int sn = (e > lo) ? slot - NT : slot;
+            ra = ldg_d4(R + sn); ga = __ldg(RG + sn); fa = __ldg(vf + sn);
+            if (RERUN) olda = voT[sn];
         }
-        if (i == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
+        if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
         v = bwd_step(rb, gb, v, sq, acc, hw, dd, pymin(fb, rb.w));
         if (RERUN) {
             const bool same = same_bits(oldb, v);
             if (same && prev_same) return true;
             prev_same = same;
         }
-        vo[i - 1] = v;
-        if (--i <= lo) break;
+        voT[slot] = v;
+        if (--e < lo) break;
+        slot -= NT;
     }
     return false;
 }
 
-// Backward pass.  Steps i = D-1 .. 1 (step i writes vel[i-1]); chunk c owns the c-th block of steps counted from the
-// end.  Reads vel_f (forward result) and writes vel (final); vel[D-1] = end_vel.  Also accumulates the travel-time
-// estimate used to size the time-domain outputs.
-__global__ void __launch_bounds__(256, 4) k_bwd_chunked(
-    const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel, long long D_cap,
-    const int* __restrict__ n_samples, const double4* __restrict__ recR, const double* __restrict__ rg, int E_cap,
-    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, const double* __restrict__ vel_f, double* __restrict__ vel, float* __restrict__ t_est,
+// Backward pass.  Thread k walks column nch-1-k (the k-th chunk counted from the end), so states flow from thread k-1 to
+// thread k as in the forward kernel.  Reads the forward velocities and writes the final ones, both in slot order
+// (velT[RS-1] = end_vel is the last sample); k_untranspose puts them into sample order.  Also accumulates the
+// travel-time estimate used to size the time-domain outputs.
+__global__ void __maxnreg__(72) k_bwd_chunked(
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel,
+    long long RS, const int* __restrict__ n_samples, const double4* __restrict__ recR, const double* __restrict__ rg,
+    int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    const int* __restrict__ n_ev, const double* __restrict__ vfT, double* __restrict__ velT, float* __restrict__ t_est,
     int* __restrict__ rounds_out)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
-    const int NT = blockDim.x, c = threadIdx.x;
+    const int NT = blockDim.x, k = threadIdx.x;
     const long long b = blockIdx.x;
     double* s_endv = reinterpret_cast<double*>(s_mem);
     double* s_endw = s_endv + NT;
@@ -597,27 +673,28 @@ __global__ void __launch_bounds__(256, 4) k_bwd_chunked(
     double* s_usew = s_usev + NT;
     double* s_acc = s_usew + NT;                                  // [E_cap] max_accels[bval[j] + 1] (applied at sample bidx[j])
     int* s_bi = reinterpret_cast<int*>(s_acc + E_cap);
-    if (c == 0 && t_est) t_est[b] = 0.f;
+    if (k == 0 && t_est) t_est[b] = 0.f;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
     const int steps = D - 1;
-    double* vo = vel + (size_t)b * D_cap;
-    if (c == 0) { vo[D - 1] = end_vel; if (rounds_out) rounds_out[2 * b + 1] = 0; }
+    double* vo = velT + (size_t)b * RS;
+    if (k == 0) { vo[RS - 1] = end_vel; if (rounds_out) rounds_out[2 * b + 1] = 0; }
     if (steps <= 0) return;
     const int n_b = n_ev[2 * b + 1];
-    for (int k = c; k < n_b; k += NT) {
-        s_bi[k] = bidx[(size_t)b * E_cap + k];
-        s_acc[k] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + k] + 1];
+    for (int q = k; q < n_b; q += NT) {
+        s_bi[q] = bidx[(size_t)b * E_cap + q];
+        s_acc[q] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + q] + 1];
     }
     const double acc0 = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + n_b - 1]];
-    const int Lc = (steps + NT - 1) / NT;
+    const int Lc = chunk_len(steps, NT);
     const int nch = (steps + Lc - 1) / Lc;
-    const bool active = c < nch;
-    const int hi = (D - 1) - c * Lc;
-    const int lo = (hi - Lc > 0) ? hi - Lc : 0;
-    const double4* R = recR + (size_t)b * D_cap;
-    const double* RG = rg + (size_t)b * D_cap;
-    const double* vfw = vel_f + (size_t)b * D_cap;
+    const bool active = k < nch;
+    const int c = nch - 1 - k;                                     // column (forward chunk index)
+    const int lo = c * Lc;
+    const int len = (lo + Lc < steps) ? Lc : steps - lo;
+    const double4* R = recR + (size_t)b * RS;
+    const double* RG = rg + (size_t)b * RS;
+    const double* vf = vfT + (size_t)b * RS;
     const double hw = cons[b * 6 + 5] * 0.5;
     __syncthreads();
 
@@ -625,60 +702,100 @@ __global__ void __launch_bounds__(256, 4) k_bwd_chunked(
     {
         double v = end_vel, sq = 0.0;
         if (active) {
-            if (c > 0) {
-                const double4 r1 = R[hi + 1];
-                v = pymin(vfw[hi], r1.w);
-                const double vp1 = (hi + 2 <= D - 1) ? pymin(vfw[hi + 1], R[hi + 2].w) : end_vel;
+            if (k > 0) {
+                const int hi = lo + len;                                   // sample at the top of this chunk (< D-1)
+                const int s1 = edge_slot(hi, Lc, NT);                      // edge hi: backward record of sample hi+1
+                const double4 r1 = R[s1];
+                v = pymin(vf[s1], r1.w);
+                double vp1 = end_vel;
+                if (hi + 2 <= D - 1) { const int s2 = edge_slot(hi + 1, Lc, NT); vp1 = pymin(vf[s2], R[s2].w); }
                 const double wp = vp1 * r1.x;
                 sq = wp * wp;
             }
-            s_usev[c] = v; s_usew[c] = sq;
-            bwd_run<false>(R, RG, vfw, vo, hi, lo, s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
+            s_usev[k] = v; s_usew[k] = sq;
+            bwd_run<false>(R, RG, vf, vo, NT, c, lo, len, s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
         }
-        s_endv[c] = v; s_endw[c] = sq;
+        s_endv[k] = v; s_endw[k] = sq;
     }
     __syncthreads();
 
-    // ---- fix-up rounds (states flow from chunk c-1 to chunk c, as in the forward kernel)
+    // ---- fix-up rounds (states flow from thread k-1 to thread k, as in the forward kernel)
     int rounds = 0;
     for (int round = 1; round < NT; round++) {
         bool need = false;
         double in_v = 0.0, in_w = 0.0;
-        if (active && c >= round) {
-            in_v = s_endv[c - 1]; in_w = s_endw[c - 1];
-            need = !(same_bits(in_v, s_usev[c]) && same_bits(in_w, s_usew[c]));
+        if (active && k >= round) {
+            in_v = s_endv[k - 1]; in_w = s_endw[k - 1];
+            need = !(same_bits(in_v, s_usev[k]) && same_bits(in_w, s_usew[k]));
         }
         if (!__syncthreads_or(need)) break;
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = bwd_run<true>(R, RG, vfw, vo, hi, lo, s_bi, s_acc, n_b, acc0, hw, dd, v, sq,
-                                              same_bits(in_v, s_usev[c]));
-            s_usev[c] = in_v; s_usew[c] = in_w;
-            if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
+            const bool merged = bwd_run<true>(R, RG, vf, vo, NT, c, lo, len, s_bi, s_acc, n_b, acc0, hw, dd, v, sq,
+                                              same_bits(in_v, s_usev[k]));
+            s_usev[k] = in_v; s_usew[k] = in_w;
+            if (!merged) { s_endv[k] = v; s_endw[k] = sq; }
         }
         __syncthreads();
     }
-    if (c == 0 && rounds_out) rounds_out[2 * b + 1] = rounds;
+    if (k == 0 && rounds_out) rounds_out[2 * b + 1] = rounds;
 
     // ---- travel-time estimate (single precision is plenty: it only sizes buffers)
     __syncthreads();
     float est = 0.f;
     if (active) {
-        float vprev = (float)vo[hi];
-        for (int i = hi; i > lo; i--) {
-            const float vcur = (float)vo[i - 1];
+        const int top = (lo + len < steps) ? c + 1 : (int)(RS - 1);       // slot of the sample above the chunk
+        float vprev = (float)vo[top];
+        for (int sl = (len - 1) * NT + c; sl >= 0; sl -= NT) {
+            const float vcur = (float)vo[sl];
             const float vm = 0.5f * (vprev + vcur);
             est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
             vprev = vcur;
         }
     }
     float* s_f = reinterpret_cast<float*>(s_endv);      // end states are no longer needed
-    s_f[c] = est;
+    s_f[k] = est;
     __syncthreads();
-    if (c == 0 && t_est) {
+    if (k == 0 && t_est) {
         float tot = 0.f;
-        for (int k = 0; k < NT; k++) tot += s_f[k];
+        for (int q = 0; q < NT; q++) tot += s_f[q];
         t_est[b] = tot;
+    }
+}
+
+// slot order -> sample order through a 32 x 32 shared-memory tile (both sides coalesced): vel[e] = vT[slot(e)], and the
+// last sample from slot RS-1.  grid = (row tiles * column tiles, B), 256 threads.
+__global__ void __launch_bounds__(256) k_untranspose(const int* __restrict__ status, const int* __restrict__ n_samples,
+                                                     long long D_cap, long long RS, int NT,
+                                                     const double* __restrict__ vT, double* __restrict__ vel)
+{
+    __shared__ double tile[32][33];
+    const long long b = blockIdx.y;
+    if (status[b] != ST_OK) return;
+    const int D = n_samples[b];
+    const int steps = D - 1;
+    const double* src = vT + (size_t)b * RS;
+    double* dst = vel + (size_t)b * D_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) dst[D - 1] = src[RS - 1];
+    if (steps <= 0) return;
+    const int Lc = chunk_len(steps, NT);
+    const int ctiles = NT >> 5;
+    const int rt = blockIdx.x / ctiles, ct = blockIdx.x - rt * ctiles;
+    const int s0 = rt * 32, c0 = ct * 32;
+    if (s0 >= Lc) return;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = wrp; r < 32; r += 8) {
+        const int s = s0 + r;
+        tile[r][lane] = (s < Lc) ? src[(size_t)s * NT + c0 + lane] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = wrp; q < 32; q += 8) {
+        const int c = c0 + q;
+        const int s = s0 + lane;
+        const int e = c * Lc + s;
+        if (s < Lc && e < steps) dst[e] = tile[lane][q];
     }
 }
