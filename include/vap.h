@@ -95,6 +95,13 @@ int vap_eval(int64_t n, const int32_t* path, const double* t, int which, int N_m
 int vap_build_lut(int64_t B, int N_max, const double* seg, const int32_t* first_node, const double* param_end,
                   const int32_t* n_splines, const int32_t* status, int samples, int64_t Q_cap, double* lut_d,
                   double* lut_t, double* total_len, void* stream);
+/* Optional accelerator of distance_to_time (spline_manager.py:291-318): an inverse index of the distance table, so that
+ *     np.searchsorted(distances, d) is one seeded lookup plus a verification against the table instead of a 10-level
+ *     binary search (identical result).  lut_inv[B][vap_lut_index_row_ints(Q_cap)] i32; pass it (or NULL) to
+ *     vap_dist_sample_events / vap_time_profile.                                                        */
+int64_t vap_lut_index_row_ints(int64_t Q_cap);
+int vap_build_lut_index(int64_t B, const int32_t* n_splines, const int32_t* status, int samples, int64_t Q_cap,
+                        const double* lut_d, const double* total_len, int32_t* lut_inv, void* stream);
 
 /* S2  precompute_path_properties (spline_manager.py:477-548): spn samples per node (default 1000).
  *     prop_k/prop_h[B][P_cap], P_cap >= spn * N_max.                                                   */
@@ -153,7 +160,7 @@ int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_a
                            int64_t D_cap, int32_t* n_samples, double* t, double* kap, double* th, int E_cap,
                            double* max_accels, int32_t* bidx, int32_t* bval, int32_t* n_ev, int32_t* vr_idx,
                            double* vr_val, int32_t* st_idx, int32_t* n_vr, double dt, float* ins_est,
-                           int32_t* ev_scratch, void* stream);
+                           int32_t* ev_scratch, const int32_t* lut_inv, void* stream);
 int64_t vap_event_scratch_ints(int64_t B, int N_max, int A_max);
 int64_t vap_pass_row_slots(int64_t D_cap);
 int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt, double start_vel,
@@ -196,7 +203,7 @@ int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, c
                      const int32_t* n_samples, const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
                      int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary, int32_t* n_main,
                      double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch, int64_t out_plane_stride,
-                     void* stream);
+                     const int32_t* lut_inv, void* stream);
 
 /* S1' QuinticHermiteSpline.get_arc_length (Gauss-Legendre, quintic_hermite_spline.py:592-644) and
  *     get_parameter_by_arc_length (:661-717) for n queries on spline `spl[q]` of path `path[q]`.

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 # every symbol include/vap.h declares (tests check the list against the header and the .so)
 SYMBOLS = [
     "vap_version", "vap_last_error", "vap_build_path", "vap_fit_splines", "vap_eval", "vap_build_lut",
-    "vap_build_props", "vap_query_tables", "vap_build_dgrid", "vap_dist_sample", "vap_fwd_bwd", "vap_resample",
+    "vap_lut_index_row_ints", "vap_build_lut_index", "vap_build_props", "vap_query_tables", "vap_build_dgrid", "vap_dist_sample", "vap_fwd_bwd", "vap_resample",
     "vap_gl", "vap_turn_profile", "vap_lerp", "vap_wheel_trajectory", "vap_dist_sample_events",
     "vap_event_scratch_ints", "vap_pass_row_slots", "vap_fwd_bwd_chunked", "vap_time_profile", "vap_pack_rows", "vap_export_rows", "vap_format_doubles", "vap_row_text_stride",
     "vap_format_rows", "vap_compact_rows", "vap_test_div_const", "vap_test_div_recip",
@@ -64,6 +64,7 @@ def lib():
             getattr(L, name).restype = C.c_int
         L.vap_event_scratch_ints.restype = C.c_int64
         L.vap_pass_row_slots.restype = C.c_int64
+        L.vap_lut_index_row_ints.restype = C.c_int64
         _lib = L
     return _lib
 

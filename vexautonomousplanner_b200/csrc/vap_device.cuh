@@ -312,6 +312,30 @@ __device__ __forceinline__ double distance_to_time32(const double* __restrict__ 
     return t0 + (t1 - t0) * (d - d0) / (d1 - d0);
 }
 
+// ---- inverse index of the distance table ("which LUT interval does distance d fall in", in O(1)) ----------------------
+// Row layout (int32): [0..1] the bits of scale = Q / total_length, [2 + m] = a LUT index at or just below
+// searchsorted(distances, m / scale) for m = 0 .. Q.  The index only seeds the search: the result is verified against the
+// table in both directions, so it is exactly np.searchsorted(distances, d) (side='left') whatever the seed.
+#define LUT_INV_HDR 2
+__device__ __forceinline__ double distance_to_time_inv(const double* __restrict__ ld, const double* __restrict__ lt,
+                                                       const int* __restrict__ inv, int Q, double total, int n, double d)
+{
+    if (d <= 0) return 0.0;
+    if (d >= total) return (double)(n - 1);
+    const double scale = __hiloint2double(__ldg(inv + 1), __ldg(inv));
+    const double e = d * scale;
+    int m = (e < (double)Q) ? __double2int_rz(e) : Q;
+    int lo = __ldg(inv + LUT_INV_HDR + m);
+    double d1 = __ldg(ld + lo);
+    while (lo < Q - 1 && d1 < d) { lo++; d1 = __ldg(ld + lo); }          // d < total = distances[Q-1]: stops inside the table
+    if (lo == 0) return lt[0];
+    double d0 = __ldg(ld + lo - 1);
+    while (lo > 1 && d0 >= d) { lo--; d1 = d0; d0 = __ldg(ld + lo - 1); }
+    if (d0 >= d) return lt[0];                                            // lo == 1 and distances[0] >= d (cannot happen for d > 0)
+    const double t0 = __ldg(lt + lo - 1), t1 = __ldg(lt + lo);
+    return t0 + (t1 - t0) * (d - d0) / (d1 - d0);
+}
+
 // lerp on xs[i] = fl(i*dd) (motion_profile_generator.py:349-386,:484): index of searchsorted(side='right') - 1
 __device__ __forceinline__ long long uniform_index(double x, double dd, double inv_dd, long long D)
 {

@@ -362,6 +362,29 @@ __global__ void __launch_bounds__(256) k_build_lut(int N_max, const double* __re
     if (threadIdx.x == 0) total_len[b] = current;
 }
 
+// inverse index of the distance table (see distance_to_time_inv): one CTA per path, one binary search per bucket
+__global__ void __launch_bounds__(256) k_build_lut_index(const int* __restrict__ n_splines, const int* __restrict__ status,
+                                                         int samples, long long Q_cap, const double* __restrict__ lut_d,
+                                                         const double* __restrict__ total_len, int* __restrict__ lut_inv)
+{
+    const long long b = blockIdx.x;
+    int* row = lut_inv + (size_t)b * (Q_cap + LUT_INV_HDR + 2);
+    const int S = n_splines[b];
+    if (status[b] != ST_OK || S <= 0 || (long long)S * samples > Q_cap) return;
+    const int Q = S * samples;
+    const double* ld = lut_d + (size_t)b * Q_cap;
+    const double L = total_len[b];
+    const double scale = (L > 0.0) ? (double)Q / L : 0.0;
+    if (threadIdx.x == 0) { row[0] = __double2loint(scale); row[1] = __double2hiint(scale); }
+    for (int m = threadIdx.x; m <= Q; m += blockDim.x) {
+        const double x = (scale > 0.0) ? (double)m / scale : 0.0;
+        int lo = 0, hi = Q;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (ld[mid] < x) lo = mid + 1; else hi = mid; }
+        lo -= 1;                                         // one below: absorbs the rounding of m = trunc(d * scale)
+        row[LUT_INV_HDR + m] = lo < 0 ? 0 : (lo > Q - 1 ? Q - 1 : lo);
+    }
+}
+
 // =====================================================================================================
 // S2  precompute_path_properties: one thread per (path, table entry)
 // =====================================================================================================
@@ -997,6 +1020,16 @@ extern "C" int vap_build_lut(int64_t B, int N_max, const double* seg, const int3
     return 0;
 }
 
+extern "C" int64_t vap_lut_index_row_ints(int64_t Q_cap) { return Q_cap + LUT_INV_HDR + 2; }
+extern "C" int vap_build_lut_index(int64_t B, const int32_t* n_splines, const int32_t* status, int samples, int64_t Q_cap,
+                                   const double* lut_d, const double* total_len, int32_t* lut_inv, void* stream)
+{
+    if (B <= 0) return 0;
+    k_build_lut_index<<<(unsigned)B, 256, 0, STREAM>>>(n_splines, status, samples, Q_cap, lut_d, total_len, lut_inv);
+    CHECK_LAUNCH("vap_build_lut_index");
+    return 0;
+}
+
 extern "C" int vap_build_props(int64_t B, int N_max, const int32_t* n_nodes, const double* seg,
                                const int32_t* first_node, const double* param_end, const int32_t* n_splines,
                                const int32_t* status, int spn, int64_t P_cap, double* prop_k, double* prop_h,
@@ -1134,7 +1167,8 @@ extern "C" int vap_dist_sample_events(int64_t B, int N_max, int A_max, const dou
                                       const double* prop_h, int64_t D_cap, int32_t* n_samples, double* t, double* kap,
                                       double* th, int E_cap, double* max_accels, int32_t* bidx, int32_t* bval,
                                       int32_t* n_ev, int32_t* vr_idx, double* vr_val, int32_t* st_idx, int32_t* n_vr,
-                                      double dt, float* ins_est, int32_t* ev_scratch, void* stream)
+                                      double dt, float* ins_est, int32_t* ev_scratch, const int32_t* lut_inv,
+                                      void* stream)
 {
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_dist_sample_events: B > 65535 per call (tile the batch)");
@@ -1154,7 +1188,7 @@ extern "C" int vap_dist_sample_events(int64_t B, int N_max, int A_max, const dou
     dim3 grid(blocks_for(D_cap, 256), (unsigned)B);
     k_dist_sample_ev<<<grid, 256, 0, STREAM>>>(N_max, Am, n_nodes, n_splines, status, ap_attr, n_ap, dgrid, samples, Q_cap,
                                                lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h, D_cap, n_samples, t,
-                                               kap, th, ev_wrap, ev_nwrap, ev_apc, ev_napc);
+                                               kap, th, ev_wrap, ev_nwrap, ev_apc, ev_napc, lut_inv);
     CHECK_LAUNCH("vap_dist_sample_events/sample");
     k_resolve_events<<<blocks_for(B, 64), 64, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, ap_flags,
                                                           n_ap, cons, status, ev_wrap, ev_nwrap, ev_apc, ev_napc, E_cap,
@@ -1186,7 +1220,9 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     if (D_cap > 2000000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
     const long long RS = vap_pass_row_slots(D_cap);
     dim3 grid(blocks_for(D_cap + chunks, 256), (unsigned)B);
-    size_t sm = (size_t)E_cap * (2 * sizeof(double) + 4 * sizeof(int));
+    // event tables + the kappa / theta tile (chunks columns x (256 / chunks + 2) rows, odd stride)
+    size_t sm = (size_t)E_cap * (2 * sizeof(double) + 4 * sizeof(int)) + 8 +
+                2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 2) | 1);
     k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, end_vel, D_cap, n_samples, kap, th, E_cap, max_accels, bidx, bval,
                                          n_ev, vr_idx, vr_val, st_idx, n_vr, chunks, RS, reinterpret_cast<double4*>(recF),
                                          reinterpret_cast<double4*>(recR), rg);
@@ -1226,7 +1262,7 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
                                 const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
                                 int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary,
                                 int32_t* n_main, double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch,
-                                int64_t out_plane_stride, void* stream)
+                                int64_t out_plane_stride, const int32_t* lut_inv, void* stream)
 {
     (void)ap_flags;
     const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
@@ -1267,7 +1303,7 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     dim3 grid(blocks_for(M_cap, 256), (unsigned)B);
     k_time_sample<<<grid, 256, 0, STREAM>>>(B, N_max, Am, n_nodes, status, ap_attr, n_ap, seg, first_node, param_end,
                                             n_splines, samples, Q_cap, lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h,
-                                            M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc, ev_napc);
+                                            M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc, ev_napc, lut_inv);
     CHECK_LAUNCH("vap_time_profile/sample");
     k_time_events<<<blocks_for(B, lanes), lanes, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, n_ap, cons,
                                                        status, dt, seg, first_node, param_end, n_splines, spn, P_cap,

@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(256) k_time_sample(
     int samples, long long Q_cap, const double* __restrict__ lut_d, const double* __restrict__ lut_t,
     const double* __restrict__ total_len, int spn, long long P_cap, const double* __restrict__ prop_k,
     const double* __restrict__ prop_h, long long M_cap, const int* __restrict__ n_main, double* __restrict__ stage,
-    int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc)
+    int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc,
+    const int* __restrict__ lut_inv)
 {
     __shared__ double s_t[257];
     long long b = blockIdx.y;
@@ -217,10 +218,12 @@ __global__ void __launch_bounds__(256) k_time_sample(
     const size_t plane = (size_t)B * (M_cap + 1);
     const size_t row = (size_t)b * (M_cap + 1);
     const PropGrid pg = prop_grid(spn, n);
+    const int* inv = lut_inv ? lut_inv + (size_t)b * (Q_cap + LUT_INV_HDR + 2) : nullptr;
+    auto d2t = [&](double d) { return inv ? distance_to_time_inv(ld, lt, inv, Q, L, n, d) : distance_to_time32(ld, lt, Q, L, n, d); };
     double t = 0.0;
     if (k < M) {
         double pos = stage[TS_POS * plane + row + k];
-        t = distance_to_time32(ld, lt, Q, L, n, pos);
+        t = d2t(pos);
         double curvature, heading, cx, cy;
         snap_gather2_32(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, pg, curvature, heading);
         eval_path<0>(g, t, cx, cy);
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(256) k_time_sample(
         stage[TS_Y * plane + row + k] = cy;
     }
     s_t[threadIdx.x + 1] = t;
-    if (threadIdx.x == 0) s_t[0] = (k0 > 0) ? distance_to_time32(ld, lt, Q, L, n, stage[TS_POS * plane + row + k0 - 1]) : 0.0;
+    if (threadIdx.x == 0) s_t[0] = (k0 > 0) ? d2t(stage[TS_POS * plane + row + k0 - 1]) : 0.0;
     __syncthreads();
     if (k >= M) return;
     double tp = s_t[threadIdx.x];

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(256) k_dist_sample_ev(
     const double* __restrict__ lut_t, const double* __restrict__ total_len, int spn, long long P_cap,
     const double* __restrict__ prop_k, const double* __restrict__ prop_h, long long D_cap,
     const int* __restrict__ n_samples, double* __restrict__ t_out, double* __restrict__ kap, double* __restrict__ th,
-    int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc)
+    int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc,
+    const int* __restrict__ lut_inv)
 {
     __shared__ double s_t[257];
     long long b = blockIdx.y;
@@ -45,16 +46,18 @@ __global__ void __launch_bounds__(256) k_dist_sample_ev(
     const int Q = samples * n_splines[b];
     const double L = total_len[b];
     const PropGrid pg = prop_grid(spn, n);
+    const int* inv = lut_inv ? lut_inv + (size_t)b * (Q_cap + LUT_INV_HDR + 2) : nullptr;
+    auto d2t = [&](double d) { return inv ? distance_to_time_inv(ld, lt, inv, Q, L, n, d) : distance_to_time32(ld, lt, Q, L, n, d); };
     double t = 0.0;
     if (i < D) {
-        t = (i == D - 1) ? (double)(n - 1) : distance_to_time32(ld, lt, Q, L, n, dgrid[i]);
+        t = (i == D - 1) ? (double)(n - 1) : d2t(dgrid[i]);
         double k, h;
         snap_gather2_32(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, pg, k, h);
         size_t o = (size_t)b * D_cap + i;
         t_out[o] = t; kap[o] = k; th[o] = h;
     }
     s_t[threadIdx.x + 1] = t;
-    if (threadIdx.x == 0) s_t[0] = (i0 > 0) ? distance_to_time32(ld, lt, Q, L, n, dgrid[i0 - 1]) : 0.0;   // prev_t of sample 0 is 0
+    if (threadIdx.x == 0) s_t[0] = (i0 > 0) ? d2t(dgrid[i0 - 1]) : 0.0;   // prev_t of sample 0 is 0
     __syncthreads();
     if (i >= D - 1) return;            // the final appended sample takes no part in the event logic
     double tp = s_t[threadIdx.x];
@@ -331,21 +334,37 @@ __global__ void __launch_bounds__(256) k_prepass(
         s_si[k] = (k < T.nst) ? st_idx[(size_t)b * E_cap + k] : -1;
     }
     T.ma = s_ma; T.vv = s_vv; T.bi = s_bi; T.bv = s_bv; T.vi = s_vi; T.si = s_si;
+    // kappa / theta of this CTA's slots: rows s0 .. s0+RW-1 of every column plus one halo row on each side, fetched with the
+    // lanes running ALONG a column (contiguous samples) into shared memory
+    const double* kr = kap + (size_t)b * D_cap;
+    const double* tr = th + (size_t)b * D_cap;
+    const int sh = 31 - __clz(NT);                   // NT is a power of two
+    const int RW = blockDim.x >> sh;                 // rows per CTA
+    const int st = (RW + 2) | 1;                     // odd tile stride
+    double* t_th = reinterpret_cast<double*>(s_si + E_cap);            // 32 * E_cap bytes in: 8-byte aligned
+    double* t_k = t_th + NT * st;
+    const int s0 = j0 >> sh;
+    for (int q = threadIdx.x; q < NT * (RW + 2); q += blockDim.x) {
+        const int cc = q / (RW + 2), r = q - cc * (RW + 2);
+        int ee = cc * Lc + s0 - 1 + r;
+        ee = ee < 0 ? 0 : (ee > D - 1 ? D - 1 : ee);
+        t_th[cc * st + r] = tr[ee];
+        if (r >= 1 && r <= RW) t_k[cc * st + r] = kr[ee];
+    }
     __syncthreads();
     const int j = j0 + threadIdx.x;
-    const int s = j >> (31 - __clz(NT)), c = j & (NT - 1);      // NT is a power of two
+    const int s = j >> sh, c = j & (NT - 1);
     const int e = c * Lc + s;                  // this slot's edge = the sample whose terms this thread evaluates
     if (s >= Lc || e >= steps) return;
     const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
     const double max_angular_vel = 2 * V / w;       // (:81)
     const double max_angular_accel = 2 * A0 / w;    // (:82)
-    const double* kr = kap + (size_t)b * D_cap;
-    const double* tr = th + (size_t)b * D_cap;
     const size_t row = (size_t)b * RS;
-    const double th_i = tr[e], th_n = tr[e + 1];
-    const double th_p = (e >= 1) ? tr[e - 1] : 0.0;
+    const int tl = c * st + (s - s0) + 1;
+    const double th_i = t_th[tl], th_n = t_th[tl + 1];
+    const double th_p = t_th[tl - 1];
     double4 F, R;
-    prepass_sample(T, V, w, max_angular_vel, max_angular_accel, end_vel, D, e, kr[e], th_i, th_n, th_p, true, e >= 1, F, R);
+    prepass_sample(T, V, w, max_angular_vel, max_angular_accel, end_vel, D, e, t_k[tl], th_i, th_n, th_p, true, e >= 1, F, R);
     recF[row + j] = F;
     rg[row + j] = recip_for_pass(2 * fabs(th_n - th_i));
     if (e >= 1) recR[row + ((s >= 1) ? j - NT : (Lc - 1) * NT + c - 1)] = R;     // slot of edge e-1
@@ -466,6 +485,10 @@ __device__ __forceinline__ double bwd_step(const double4 r, double rc, double v,
 // fetched one step ahead into two named buffers (no register rotation), the division's reciprocal from the pre-pass.
 // ------------------------------------------------------------------------------------------------------------------
 #define CH_INT_MAX 2147483647
+#ifndef CH_PF
+#define CH_PF 4          // rows the passes prefetch into L1 ahead of the row being loaded into registers
+#endif
+__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // forward chunk of column `col`: edges lo .. lo+len-1; edge e reads slot (e-lo)*NT + col and writes the forward velocity
 // of sample e+1 into the slot of edge e+1 (the bottom of the chunk writes row 0 of the next column, or `tail`).
@@ -487,6 +510,7 @@ __device__ __forceinline__ bool fwd_run(const double4* __restrict__ F, const dou
     const int hi = lo + len;
     while (true) {
         // ---- buffers a (look-ahead loads never leave the path's row: it is padded by NT slots)
+        if (e + CH_PF < hi) { pf_l1(F + slot + CH_PF * NT); pf_l1(RG + slot + CH_PF * NT); }
         rb = ldg_d4(F + slot + NT); gb = __ldg(RG + slot + NT);
         if (RERUN) oldb = vf[(e + 2 < hi) ? slot + 2 * NT : last_slot];
         if (e == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
@@ -500,6 +524,7 @@ __device__ __forceinline__ bool fwd_run(const double4* __restrict__ F, const dou
         slot += NT;
         vf[slot] = v;
         // ---- buffers b
+        if (e + CH_PF < hi) { pf_l1(F + slot + CH_PF * NT); pf_l1(RG + slot + CH_PF * NT); }
         ra = ldg_d4(F + slot + NT); ga = __ldg(RG + slot + NT);
         if (RERUN) olda = vf[(e + 2 < hi) ? slot + 2 * NT : last_slot];
         if (e == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
@@ -618,6 +643,7 @@ __device__ __forceinline__ bool bwd_run(const double4* __restrict__ R, const dou
     if (RERUN) olda = voT[slot];
     while (true) {
         // ---- buffers a (look-ahead slot clamped to the chunk's first row)
+        if (e - CH_PF >= lo) { pf_l1(R + slot - CH_PF * NT); pf_l1(RG + slot - CH_PF * NT); pf_l1(vf + slot - CH_PF * NT); }
         {
             const int sn = (e > lo) ? slot - NT : slot;
             rb = ldg_d4(R + sn); gb = __ldg(RG + sn); fb = __ldg(vf + sn);
@@ -634,6 +660,7 @@ __device__ __forceinline__ bool bwd_run(const double4* __restrict__ R, const dou
         if (--e < lo) break;
         slot -= NT;
         // ---- buffers b
+        if (e - CH_PF >= lo) { pf_l1(R + slot - CH_PF * NT); pf_l1(RG + slot - CH_PF * NT); pf_l1(vf + slot - CH_PF * NT); }
         {
             const int sn = (e > lo) ? slot - NT : slot;
             ra = ldg_d4(R + sn); ga = __ldg(RG + sn); fa = __ldg(vf + sn);
