@@ -144,14 +144,14 @@ int vap_fwd_bwd(int64_t B, int N_max, int A_max, const double* node_attr, const 
  *     vr_idx/vr_val[B][E_cap], the stop samples st_idx[B][E_cap] and n_vr[B][2].  ev_scratch: i32 scratch of
  *     vap_event_scratch_ints(B, N_max, A_max) elements.  ins_est[B] f32: rows the time stage will insert for
  *     waits / turn profiles (sizing only).
- *   vap_fwd_bwd_chunked: pre-pass that hoists the state-independent terms of the recurrences into one 32-byte
- *     record per step and direction plus the reciprocal of the wheel-acceleration division's denominator, then the
- *     forward and backward passes (:188-314) with `chunks` (32, 64, 128 or 256) speculative chunks per path that
- *     are re-run until they merge bitwise with the serial evaluation.  The arrays the passes stream are
- *     chunk-interleaved (step s of chunk c at slot s*chunks + c) so that every warp-wide access is one contiguous run:
- *     recF, recR: [B][RS][4] f64, rg, vel_f, velT: [B][RS] f64 (forward / final velocities, slot order) with
- *     RS = vap_pass_row_slots(D_cap).  vel[B][D_cap]: final velocities in sample order (mode 1: the forward
- *     velocities in sample order); t_est[B] f32; rounds[B][2] fix-up sweeps.                                */
+ *   vap_fwd_bwd_chunked: pre-pass that hoists everything of a step that depends neither on the velocity state nor on
+ *     the events (per sample |kappa|, the velocity caps, the static acceleration limit; per step the wheel-acceleration
+ *     denominator and its reciprocal), then the forward and backward passes (:188-314) with `chunks` (32, 64, 128 or 256)
+ *     speculative chunks per path that are re-run until they merge bitwise with the serial evaluation.  The arrays the
+ *     passes stream are chunk-interleaved (step s of chunk c in row s, column c) so that every warp-wide access is one
+ *     contiguous run: rec [B][RS][3] f64 (three field planes per row), gh2 [B][RS][2] f64, vel_f / velT [B][RS] f64
+ *     (forward / final velocities, slot order), RS = vap_pass_row_slots(D_cap).  vel[B][D_cap]: final velocities in
+ *     sample order (mode 1: the forward velocities in sample order); t_est[B] f32; rounds[B][2] fix-up sweeps.     */
 int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
                            const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
                            const double* cons, const int32_t* n_splines, int32_t* status, int64_t n_grid,
@@ -167,8 +167,8 @@ int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, do
                         double end_vel, int64_t D_cap, const int32_t* n_samples, const double* kap, const double* th,
                         int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
                         const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
-                        const int32_t* n_vr, double* recF, double* recR, double* rg, double* vel_f, double* velT,
-                        double* vel, float* t_est, int32_t* rounds, int chunks, int mode, void* stream);
+                        const int32_t* n_vr, double* rec, double* gh2, double* vel_f, double* velT, double* vel,
+                        float* t_est, int32_t* rounds, int chunks, int mode, void* stream);
 
 /* S6  generate_motion_profile time loop + node-0 prologue + turn / wait inserts
  *     (motion_profile_generator.py:414-628, one_dim_mp_generator.py:4-69) and S7 summary rows.

@@ -1210,29 +1210,28 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
                                    double start_vel, double end_vel, int64_t D_cap, const int32_t* n_samples,
                                    const double* kap, const double* th, int E_cap, const double* max_accels,
                                    const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
-                                   const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* recF,
-                                   double* recR, double* rg, double* vel_f, double* velT, double* vel, float* t_est,
+                                   const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* rec,
+                                   double* gh2, double* vel_f, double* velT, double* vel, float* t_est,
                                    int32_t* rounds, int chunks, int mode, void* stream)
 {
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
     if (chunks < 32 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be 32, 64, 128 or 256");
-    if (D_cap > 2000000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
+    if (D_cap > 500000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
     const long long RS = vap_pass_row_slots(D_cap);
     dim3 grid(blocks_for(D_cap + chunks, 256), (unsigned)B);
-    // event tables + the kappa / theta tile (chunks columns x (256 / chunks + 2) rows, odd stride)
-    size_t sm = (size_t)E_cap * (2 * sizeof(double) + 4 * sizeof(int)) + 8 +
-                2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 2) | 1);
-    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, end_vel, D_cap, n_samples, kap, th, E_cap, max_accels, bidx, bval,
-                                         n_ev, vr_idx, vr_val, st_idx, n_vr, chunks, RS, reinterpret_cast<double4*>(recF),
-                                         reinterpret_cast<double4*>(recR), rg);
+    // the kappa / theta tile: chunks columns x (256 / chunks + 1) rows, odd stride
+    const size_t sm = 2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 1) | 1);
+    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec,
+                                         reinterpret_cast<double2*>(gh2));
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
     // CTA = one path, one chunk per thread.  The passes are bound by the latency of the dependent fp64 chain of a step:
-    // one-warp CTAs at <= 64 registers put 32 independent chains on every SM.
-    const size_t ss = (size_t)chunks * 4 * sizeof(double) + (size_t)E_cap * (sizeof(double) + sizeof(int));
-    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, RS, n_samples,
-                                                       reinterpret_cast<const double4*>(recF), rg, E_cap, max_accels, bidx,
-                                                       bval, n_ev, vel_f, rounds);
+    // one-warp CTAs at 72 registers put 28 independent chains on every SM.
+    const size_t VC = 3 * (size_t)E_cap + 2;
+    const size_t ss = ((size_t)chunks * 4 + E_cap + VC) * sizeof(double) + (E_cap + VC) * sizeof(int);
+    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, end_vel, RS, n_samples, rec,
+                                                       reinterpret_cast<const double2*>(gh2), E_cap, max_accels, bidx, bval,
+                                                       n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
     // sample-order result: ceil(Lc_max / 32) row tiles x chunks / 32 column tiles per path
     const long long lc_max = (D_cap + chunks - 1) / chunks + 1;
@@ -1242,9 +1241,9 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
         CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
         return 0;
     }
-    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, RS, n_samples,
-                                                       reinterpret_cast<const double4*>(recR), rg, E_cap, max_accels, bidx,
-                                                       bval, n_ev, vel_f, velT, t_est, rounds);
+    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, RS, n_samples, rec,
+                                                       reinterpret_cast<const double2*>(gh2), E_cap, max_accels, bidx, bval,
+                                                       n_ev, vel_f, velT, t_est, rounds);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
     k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, velT, vel);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");

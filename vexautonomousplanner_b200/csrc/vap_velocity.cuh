@@ -198,32 +198,24 @@ __device__ __forceinline__ double recip_for_pass(double g);   // defined with th
 __device__ __forceinline__ int chunk_len(int steps, int NT) { return (steps + NT - 1) / NT; }
 __device__ __forceinline__ int edge_slot(int e, int Lc, int NT) { const int c = e / Lc; return (e - c * Lc) * NT + c; }
 
-// ---- pre-pass (parallel): one 32-byte record per edge and direction ----------------------------------------------------
-// forward  record of edge e (sample i = e):     { |kappa_i|, 2|theta_{i+1}-theta_i| (NaN when straight), a_static_i, C_i }
-//    a_static = min(max_ang_acc/|k|, 2 acc/(w|k|+2), acc)  (acc when straight);  C_i = min(v0[i+1], vlim_i, cap_i)
-// backward record of edge e (sample i = e + 1): { |kappa_i|, 2|theta_{i-1}-theta_i| (NaN when straight), d_static_i, G_i }
-//    d_static = min(max_ang_acc/|k|, 2 dec/(w|k|+2), dec);  G_i = min(vlim_i, cap_i)
-// rg of edge e: recip_for_pass(2|theta_{e+1}-theta_e|), shared by both directions.
-// A NaN denominator makes the wheel term NaN, which Python's min() ignores -- exactly the straight branch.
-// One thread per SLOT (coalesced stores; the 8-byte gathers of kappa / theta are 8 rows deep per CTA, so every fetched
-// sector is used by the CTA's other warps).  The thread of sample i writes the forward record of edge i and the backward
-// record of edge i-1; the thread of the last edge also makes the backward record of the final sample.
-struct PrepassTables {
-    const double* ma; const double* vv; const int* bi; const int* bv; const int* vi; const int* si;
-    int n_b, nvr, nst;
-};
-__device__ __forceinline__ int last_le(const int* a, int n, int key)      // last j in [0, n) with a[j] <= key (a[0] <= key)
-{
-    int j = 0;
-    if (n <= 8) { while (j + 1 < n && a[j + 1] <= key) j++; return j; }
-    int lo = 0, hi = n - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (a[mid] <= key) lo = mid; else hi = mid - 1; }
-    return lo;
-}
+// ---- pre-pass (parallel): everything of a pass step that depends neither on the velocity state nor on the events --------
+// per sample i (row / column of edge i; three field planes per row: element (row s, field f, column c) of a path is
+// rec[(3 s + f) NT + c]; the final sample D-1 sits in the last three doubles of the path's 3 RS):
+//    rec = { |kappa_i|, G_i, stat_i }
+//       G_i    = min(vlim_i, cap_i)                         velocity caps (:212-218, :239)
+//       stat_i = min(max_ang_acc/|k|, 2 A0/(w|k|+2), A0)    the state-independent acceleration limits for the path's own
+//                (A0 when straight)                         max_acc A0 -- forward a_static AND backward d_static as long as
+//                                                           no node / action point overrides max_acceleration
+// per edge e (slot order):
+//    gh2 = { 2|theta_{e+1} - theta_e|, recip_for_pass(of it) }   denominator of the wheel-acceleration term of forward
+//                                                                step e and of backward step e+1, and its reciprocal
+// What depends on the events is applied by the passes themselves from small shared-memory tables: the initial velocity
+// v0[i+1] (regimes, stops, end velocity) enters as C_i = min(v0[i+1], G_i), a max_acceleration override recomputes stat.
+// One thread per SLOT (coalesced stores); kappa / theta come through a shared-memory tile whose loads run along the columns.
+struct SharedRecip { double b, y; bool ok; };
 // a / b for several numerators over one denominator: y = RN(1/b) once, then per quotient one multiplication and two fused
 // residual corrections (Markstein: with the correctly rounded reciprocal the second correction gives the correctly rounded
 // quotient unless b's significand is all ones).  Operands outside the proven range take the ordinary division.
-struct SharedRecip { double b, y; bool ok; };
 __device__ __forceinline__ SharedRecip shared_recip(double b)
 {
     SharedRecip r;
@@ -242,72 +234,50 @@ __device__ __forceinline__ double div_shared(double a, const SharedRecip& r)
     q = fma(fma(-r.b, q, a), r.y, q);
     return q;
 }
-__device__ __forceinline__ void prepass_sample(const PrepassTables& T, double V, double w, double max_angular_vel,
-                                               double max_angular_accel, double end_vel, int D, int i, double k,
-                                               double th_i, double th_next, double th_prev, bool wantF, bool wantR,
-                                               double4& F, double4& R)
+// the state-independent acceleration limit for max_acc (or max_dec) x -- generic form, used by the passes when an override
+// makes x differ from the path's A0 (:220-225, :281-286)
+__device__ __noinline__ double accel_static(double ak, double x, double w, double max_angular_accel)
+{
+    if (ak < 1e-6) return x;
+    double a_ang = max_angular_accel / ak;
+    double a_kin = 2 * x / (w * ak + 2);
+    return pymin(pymin(a_ang, a_kin), x);
+}
+struct SampleTerms { double ak, G, stat; };
+__device__ __forceinline__ SampleTerms prepass_sample(double V, double A0, double w, double max_angular_vel,
+                                                      double max_angular_accel, double k)
 {
     const double ak = fabs(k);
     const bool straight = ak < 1e-6;
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     // w|k| + 2 = 2 (1 + w|k|/2) bit for bit (halving and doubling are exact), so the wheel-speed cap
-    // |V / (1 + w|k|/2)| (:239) IS 2V / (w|k| + 2) (:214): one quotient serves both.
+    // |V / (1 + w|k|/2)| (:239) IS |2V / (w|k| + 2)| (:214): one quotient serves both.
     const SharedRecip rden = shared_recip(w * ak + 2);
     const double v_kin = div_shared(2 * V, rden);
     const double cap = fabs(v_kin);
-    double vlim, a_ang = 0.0;
-    SharedRecip rak;
-    if (straight) vlim = V;
+    double vlim, stat;
+    if (straight) { vlim = V; stat = A0; }
     else {
-        rak = shared_recip(ak);
-        double v_ang = div_shared(max_angular_vel, rak);
-        a_ang = div_shared(max_angular_accel, rak);
+        const SharedRecip rak = shared_recip(ak);
+        const double v_ang = div_shared(max_angular_vel, rak);
+        const double a_ang = div_shared(max_angular_accel, rak);
         // Constraints.max_speed_at_curvature (:23-33) with 2*V/w already evaluated
-        double m = (max_angular_vel * V) / (ak * V + max_angular_vel);
-        double v_curve = pymin(m, V);
+        const double m = (max_angular_vel * V) / (ak * V + max_angular_vel);
+        const double v_curve = pymin(m, V);
         vlim = pymin(pymin(v_ang, v_kin), v_curve);
+        const double a_kin = div_shared(2 * A0, rden);
+        stat = pymin(pymin(a_ang, a_kin), A0);
     }
-    const double G = pymin(vlim, cap);
-    const double dec_b = T.ma[T.bv[T.n_b - 1]];     // the backward pass keeps the forward pass's last max_dec
-    double acc_f = dec_b, a_kin = 0.0;
-    if (wantF) {
-        if (T.n_b > 1) acc_f = T.ma[T.bv[last_le(T.bi, T.n_b, i)]];    // forward regime at step i: last boundary <= i
-        double v0n;
-        if (i + 1 == D - 1) v0n = end_vel;
-        else {
-            v0n = (T.nvr > 1) ? T.vv[last_le(T.vi, T.nvr, i + 1)] : T.vv[0];
-            for (int j = 0; j < T.nst; j++) if (T.si[j] == i + 1) v0n = 0.01;
-        }
-        double astat, h2;
-        if (straight) { astat = acc_f; h2 = qnan; }
-        else {
-            a_kin = div_shared(2 * acc_f, rden);
-            astat = pymin(pymin(a_ang, a_kin), acc_f);
-            h2 = 2 * fabs(th_next - th_i);
-        }
-        F = make_double4(ak, h2, astat, pymin(v0n, G));
-    }
-    if (wantR) {
-        double dstat, h2;
-        if (straight) { dstat = dec_b; h2 = qnan; }
-        else {
-            double d_kin = (wantF && acc_f == dec_b) ? a_kin : div_shared(2 * dec_b, rden);
-            dstat = pymin(pymin(a_ang, d_kin), dec_b);
-            h2 = 2 * fabs(th_prev - th_i);
-        }
-        R = make_double4(ak, h2, dstat, G);
-    }
+    SampleTerms t;
+    t.ak = ak; t.G = pymin(vlim, cap); t.stat = stat;
+    return t;
 }
 
 __global__ void __launch_bounds__(256) k_prepass(
-    const int* __restrict__ status, const double* __restrict__ cons, double end_vel, long long D_cap,
-    const int* __restrict__ n_samples, const double* __restrict__ kap, const double* __restrict__ th, int E_cap,
-    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
-    const int* __restrict__ st_idx, const int* __restrict__ n_vr, int NT, long long RS, double4* __restrict__ recF,
-    double4* __restrict__ recR, double* __restrict__ rg)
+    const int* __restrict__ status, const double* __restrict__ cons, long long D_cap, const int* __restrict__ n_samples,
+    const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec,
+    double2* __restrict__ gh2)
 {
-    extern __shared__ unsigned char s_raw[];
+    extern __shared__ double s_tile[];
     const long long b = blockIdx.y;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
@@ -316,40 +286,22 @@ __global__ void __launch_bounds__(256) k_prepass(
     const int Lc = chunk_len(steps, NT);
     const int j0 = blockIdx.x * blockDim.x;
     if (j0 >= Lc * NT) return;
-    double* s_ma = reinterpret_cast<double*>(s_raw);
-    double* s_vv = s_ma + E_cap;
-    int* s_bi = reinterpret_cast<int*>(s_vv + E_cap);
-    int* s_bv = s_bi + E_cap;
-    int* s_vi = s_bv + E_cap;
-    int* s_si = s_vi + E_cap;
-    PrepassTables T;
-    const int n_acc = n_ev[2 * b];
-    T.n_b = n_ev[2 * b + 1]; T.nvr = n_vr[2 * b]; T.nst = n_vr[2 * b + 1];
-    for (int k = threadIdx.x; k < E_cap; k += blockDim.x) {
-        s_ma[k] = (k < n_acc) ? max_accels[(size_t)b * E_cap + k] : 0.0;
-        s_vv[k] = (k < T.nvr) ? vr_val[(size_t)b * E_cap + k] : 0.0;
-        s_bi[k] = (k < T.n_b) ? bidx[(size_t)b * E_cap + k] : 2147483647;
-        s_bv[k] = (k < T.n_b) ? bval[(size_t)b * E_cap + k] : 0;
-        s_vi[k] = (k < T.nvr) ? vr_idx[(size_t)b * E_cap + k] : 2147483647;
-        s_si[k] = (k < T.nst) ? st_idx[(size_t)b * E_cap + k] : -1;
-    }
-    T.ma = s_ma; T.vv = s_vv; T.bi = s_bi; T.bv = s_bv; T.vi = s_vi; T.si = s_si;
-    // kappa / theta of this CTA's slots: rows s0 .. s0+RW-1 of every column plus one halo row on each side, fetched with the
-    // lanes running ALONG a column (contiguous samples) into shared memory
+    // kappa / theta of this CTA's slots: rows s0 .. s0+RW-1 of every column plus the row after them, fetched with the lanes
+    // running ALONG a column (contiguous samples) into shared memory
     const double* kr = kap + (size_t)b * D_cap;
     const double* tr = th + (size_t)b * D_cap;
     const int sh = 31 - __clz(NT);                   // NT is a power of two
     const int RW = blockDim.x >> sh;                 // rows per CTA
-    const int st = (RW + 2) | 1;                     // odd tile stride
-    double* t_th = reinterpret_cast<double*>(s_si + E_cap);            // 32 * E_cap bytes in: 8-byte aligned
+    const int st = (RW + 1) | 1;                     // odd tile stride
+    double* t_th = s_tile;
     double* t_k = t_th + NT * st;
     const int s0 = j0 >> sh;
-    for (int q = threadIdx.x; q < NT * (RW + 2); q += blockDim.x) {
-        const int cc = q / (RW + 2), r = q - cc * (RW + 2);
-        int ee = cc * Lc + s0 - 1 + r;
-        ee = ee < 0 ? 0 : (ee > D - 1 ? D - 1 : ee);
+    for (int q = threadIdx.x; q < NT * (RW + 1); q += blockDim.x) {
+        const int cc = q / (RW + 1), r = q - cc * (RW + 1);
+        int ee = cc * Lc + s0 + r;
+        ee = ee > D - 1 ? D - 1 : ee;
         t_th[cc * st + r] = tr[ee];
-        if (r >= 1 && r <= RW) t_k[cc * st + r] = kr[ee];
+        if (r < RW) t_k[cc * st + r] = kr[ee];
     }
     __syncthreads();
     const int j = j0 + threadIdx.x;
@@ -359,18 +311,16 @@ __global__ void __launch_bounds__(256) k_prepass(
     const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
     const double max_angular_vel = 2 * V / w;       // (:81)
     const double max_angular_accel = 2 * A0 / w;    // (:82)
-    const size_t row = (size_t)b * RS;
-    const int tl = c * st + (s - s0) + 1;
-    const double th_i = t_th[tl], th_n = t_th[tl + 1];
-    const double th_p = t_th[tl - 1];
-    double4 F, R;
-    prepass_sample(T, V, w, max_angular_vel, max_angular_accel, end_vel, D, e, t_k[tl], th_i, th_n, th_p, true, e >= 1, F, R);
-    recF[row + j] = F;
-    rg[row + j] = recip_for_pass(2 * fabs(th_n - th_i));
-    if (e >= 1) recR[row + ((s >= 1) ? j - NT : (Lc - 1) * NT + c - 1)] = R;     // slot of edge e-1
-    if (e == steps - 1) {                                                         // backward record of the final sample
-        prepass_sample(T, V, w, max_angular_vel, max_angular_accel, end_vel, D, D - 1, kr[D - 1], th_n, 0.0, th_i, false, true, F, R);
-        recR[row + j] = R;
+    const int tl = c * st + (s - s0);
+    const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
+    double* pr = rec + (size_t)b * RS * 3;
+    const SampleTerms t = prepass_sample(V, A0, w, max_angular_vel, max_angular_accel, t_k[tl]);
+    const size_t o = (size_t)s * 3 * NT + c;
+    pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat;
+    gh2[(size_t)b * RS + j] = make_double2(gh, recip_for_pass(gh));
+    if (e == steps - 1) {                           // the final sample (no edge starts there)
+        const SampleTerms u = prepass_sample(V, A0, w, max_angular_vel, max_angular_accel, kr[D - 1]);
+        pr[3 * RS - 3] = u.ak; pr[3 * RS - 2] = u.G; pr[3 * RS - 1] = u.stat;
     }
 }
 
@@ -438,38 +388,42 @@ __device__ __forceinline__ double accel_ang_fast(double num, double h2, double r
     return corr ? q : q0;
 }
 
-// forward step i -> i+1 (motion_profile_generator.py:193-249 with the hoisted terms).  sq carries (v_{i-1}|k_{i-1}|)^2.
-__device__ __forceinline__ double fwd_step(const double4 r, double rc, double v, double& sq, double acc, double hw, double dd)
+// One pass step from the hoisted terms.  ak = |kappa| of the step's sample, gh / rg the wheel-acceleration denominator and
+// its reciprocal, stat the state-independent acceleration limit, cap the state-independent velocity limit (already merged
+// with the initial / forward velocity), sq carries (v|kappa|)^2 of the previous step.
+// forward step i -> i+1 (motion_profile_generator.py:193-249): |accel_ang| into the wheel term
+__device__ __forceinline__ double fwd_step(double ak, double gh, double rg, double stat, double cap, double v, double& sq,
+                                           double acc, double hw, double dd)
 {
-    const double ang_vel = v * r.x;
+    const double ang_vel = v * ak;
     const double sqn = ang_vel * ang_vel;
-    const double rce = (r.y == r.y) ? rc : r.y;
-    const double accel_ang = accel_ang_fast(sqn - sq, r.y, rce);
+    const double rce = (ak < 1e-6) ? __longlong_as_double(0x7ff8000000000000LL) : rg;   // straight: the term is ignored
+    const double accel_ang = accel_ang_fast(sqn - sq, gh, rce);
     const double x = fabs(accel_ang) * hw;                   // ang * w / 2: halving is exact, so (ang*w)/2 == ang*(w/2)
     const double l = acc + x, rr = acc - x;                  // wheel_accel (:52-59)
     double a_wheel = (fabs(l) < fabs(rr)) ? l : rr;
     if (a_wheel < 0) a_wheel = 0;
-    const double a = pymin(r.z, a_wheel);
+    const double a = pymin(stat, a_wheel);
     const double s = sqrt(v * v + 2 * a * dd);
     sq = sqn;
-    return pymin(r.w, s);
+    return pymin(cap, s);
 }
-// backward step i -> i-1 (:255-311); m = min(vel_f[i-1], G_i) (state-independent part of the three-way min)
-__device__ __forceinline__ double bwd_step(const double4 r, double rc, double v, double& sq, double acc, double hw, double dd,
-                                           double m)
+// backward step i -> i-1 (:255-311): signed accel_ang; cap = min(vel_f[i-1], G_i)
+__device__ __forceinline__ double bwd_step(double ak, double gh, double rg, double stat, double cap, double v, double& sq,
+                                           double acc, double hw, double dd)
 {
-    const double ang_vel = v * r.x;
+    const double ang_vel = v * ak;
     const double sqn = ang_vel * ang_vel;
-    const double rce = (r.y == r.y) ? rc : r.y;
-    const double accel_ang = accel_ang_fast(sqn - sq, r.y, rce);
+    const double rce = (ak < 1e-6) ? __longlong_as_double(0x7ff8000000000000LL) : rg;
+    const double accel_ang = accel_ang_fast(sqn - sq, gh, rce);
     const double x = accel_ang * hw;
     const double l = acc + x, rr = acc - x;
     double a_wheel = (fabs(l) < fabs(rr)) ? l : rr;
     if (a_wheel < 0) a_wheel = 0;
-    const double dcl = pymin(r.z, a_wheel);
+    const double dcl = pymin(stat, a_wheel);
     const double pv = sqrt(v * v + 2 * dcl * dd);
     sq = sqn;
-    return pymin(pv, m);
+    return pymin(pv, cap);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -481,8 +435,9 @@ __device__ __forceinline__ double bwd_step(const double4 r, double rc, double v,
 // Rounds end when no chunk had to re-run; then, by induction from chunk 0, every value is the serial value.
 //
 // The kernels are bound by the latency of the dependent fp64 chain of one step, so they are written for residency
-// (<= 64 registers: 32 one-warp CTAs per SM) and a short chain: regime tables in shared memory, 32-bit indices, records
-// fetched one step ahead into two named buffers (no register rotation), the division's reciprocal from the pre-pass.
+// (72 registers: 28 one-warp CTAs per SM, 4144 >= 4096 paths in one wave) and a short chain: event tables in shared
+// memory, 32-bit indices, records fetched one step ahead into two named buffers (no register rotation), the division's
+// reciprocal from the pre-pass, coalesced slot-order streams.
 // ------------------------------------------------------------------------------------------------------------------
 #define CH_INT_MAX 2147483647
 #ifndef CH_PF
@@ -490,73 +445,90 @@ __device__ __forceinline__ double bwd_step(const double4 r, double rc, double v,
 #endif
 __device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// forward chunk of column `col`: edges lo .. lo+len-1; edge e reads slot (e-lo)*NT + col and writes the forward velocity
-// of sample e+1 into the slot of edge e+1 (the bottom of the chunk writes row 0 of the next column, or `tail`).
+// per-path event tables of the forward pass in shared memory
+struct FwdTables {
+    const int* bi; const double* acc; int n_b;       // max_acc regimes: acc[j] from sample bi[j] on
+    const int* vi; const double* vv; int n_v;        // initial velocity: vv[j] from sample vi[j] on (stops / end included)
+};
+__device__ __forceinline__ double2 ldg_d2(const double2* p) { return __ldg(p); }
+// field f of the sample in row r, column col of a path's record planes
+#define REC_AT(P_, r_, f_) __ldg((P_) + ((size_t)(r_) * 3 + (f_)) * NT + col)
+
+// forward chunk of column `col`: edges lo .. lo+len-1; edge e = lo + r reads row r of the record planes and of gh2, and
+// writes the forward velocity of sample e+1 into the slot of edge e+1 (the bottom of the chunk writes row 0 of the next
+// column, or the tail slot).
 template <bool RERUN>
-__device__ __forceinline__ bool fwd_run(const double4* __restrict__ F, const double* __restrict__ RG, double* __restrict__ vf,
-                                        int NT, int col, int lo, int len, int last_slot, const int* s_bi, const double* s_acc,
-                                        int n_b, double hw, double dd, double& v, double& sq, bool prev_same)
+__device__ __forceinline__ bool fwd_run(const double* __restrict__ P, const double2* __restrict__ GH, double* __restrict__ vf,
+                                        int NT, int col, int lo, int len, int last_slot, const FwdTables& T, double A0,
+                                        double w, double maa, double hw, double dd, double& v, double& sq, bool prev_same)
 {
     int j = 0;
-    while (j + 1 < n_b && s_bi[j + 1] <= lo) j++;
-    double acc = s_acc[j];
-    int nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX;
-    int slot = col;                                   // slot of the current edge
-    double4 ra = ldg_d4(F + slot), rb;
-    double ga = __ldg(RG + slot), gb;
+    while (j + 1 < T.n_b && T.bi[j + 1] <= lo) j++;
+    double acc = T.acc[j];
+    int nb_next = (j + 1 < T.n_b) ? T.bi[j + 1] : CH_INT_MAX;
+    int jv = 0;                                      // initial velocity of sample e+1
+    while (jv + 1 < T.n_v && T.vi[jv + 1] <= lo + 1) jv++;
+    double v0n = T.vv[jv];
+    int nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX;
+    int r = 0;                                       // row of the current edge
+    double aka = REC_AT(P, 0, 0), Ga = REC_AT(P, 0, 1), sta = REC_AT(P, 0, 2), akb, Gb, stb;
+    double2 ga = ldg_d2(GH + col), gb;
     double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = vf[(len > 1) ? slot + NT : last_slot];
+    if (RERUN) olda = vf[(len > 1) ? NT + col : last_slot];
     int e = lo;
     const int hi = lo + len;
+#define FWD_ONE(AK_, G_, ST_, GH_, OLD_)                                                                             \
+        if (e == nb_next) { j++; acc = T.acc[j]; nb_next = (j + 1 < T.n_b) ? T.bi[j + 1] : CH_INT_MAX; }              \
+        if (e + 1 == nv_next) { jv++; v0n = T.vv[jv]; nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX; }      \
+        {                                                                                                            \
+            const double stat = (acc == A0) ? ST_ : accel_static(AK_, acc, w, maa);                                 \
+            v = fwd_step(AK_, GH_.x, GH_.y, stat, pymin(v0n, G_), v, sq, acc, hw, dd);                               \
+        }                                                                                                            \
+        if (RERUN) {                                                                                                 \
+            const bool same = same_bits(OLD_, v);                                                                    \
+            if (same && prev_same) return true;       /* state equals the old run's: the rest is unchanged */        \
+            prev_same = same;                                                                                        \
+        }                                                                                                            \
+        if (++e >= hi) { vf[last_slot] = v; break; }                                                                 \
+        r++;                                                                                                         \
+        vf[r * NT + col] = v;
     while (true) {
-        // ---- buffers a (look-ahead loads never leave the path's row: it is padded by NT slots)
-        if (e + CH_PF < hi) { pf_l1(F + slot + CH_PF * NT); pf_l1(RG + slot + CH_PF * NT); }
-        rb = ldg_d4(F + slot + NT); gb = __ldg(RG + slot + NT);
-        if (RERUN) oldb = vf[(e + 2 < hi) ? slot + 2 * NT : last_slot];
-        if (e == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
-        v = fwd_step(ra, ga, v, sq, acc, hw, dd);
-        if (RERUN) {
-            const bool same = same_bits(olda, v);
-            if (same && prev_same) return true;                         // state equals the old run's: the rest is unchanged
-            prev_same = same;
-        }
-        if (++e >= hi) { vf[last_slot] = v; break; }
-        slot += NT;
-        vf[slot] = v;
+        // ---- buffers a (look-ahead loads never leave the path's rows: they are padded)
+        if (e + CH_PF < hi) { pf_l1(P + ((size_t)(r + CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r + CH_PF) * NT + col); }
+        akb = REC_AT(P, r + 1, 0); Gb = REC_AT(P, r + 1, 1); stb = REC_AT(P, r + 1, 2); gb = ldg_d2(GH + (r + 1) * NT + col);
+        if (RERUN) oldb = vf[(e + 2 < hi) ? (r + 2) * NT + col : last_slot];
+        FWD_ONE(aka, Ga, sta, ga, olda)
         // ---- buffers b
-        if (e + CH_PF < hi) { pf_l1(F + slot + CH_PF * NT); pf_l1(RG + slot + CH_PF * NT); }
-        ra = ldg_d4(F + slot + NT); ga = __ldg(RG + slot + NT);
-        if (RERUN) olda = vf[(e + 2 < hi) ? slot + 2 * NT : last_slot];
-        if (e == nb_next) { j++; acc = s_acc[j]; nb_next = (j + 1 < n_b) ? s_bi[j + 1] : CH_INT_MAX; }
-        v = fwd_step(rb, gb, v, sq, acc, hw, dd);
-        if (RERUN) {
-            const bool same = same_bits(oldb, v);
-            if (same && prev_same) return true;
-            prev_same = same;
-        }
-        if (++e >= hi) { vf[last_slot] = v; break; }
-        slot += NT;
-        vf[slot] = v;
+        if (e + CH_PF < hi) { pf_l1(P + ((size_t)(r + CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r + CH_PF) * NT + col); }
+        aka = REC_AT(P, r + 1, 0); Ga = REC_AT(P, r + 1, 1); sta = REC_AT(P, r + 1, 2); ga = ldg_d2(GH + (r + 1) * NT + col);
+        if (RERUN) olda = vf[(e + 2 < hi) ? (r + 2) * NT + col : last_slot];
+        FWD_ONE(akb, Gb, stb, gb, oldb)
     }
+#undef FWD_ONE
     return false;
 }
 
 // Forward pass.  Chunk c = thread c.  vfT: forward velocities in slot order (vfT[slot(e)] = velocity at sample e).
 __global__ void __maxnreg__(72) k_fwd_chunked(
-    const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, long long RS,
-    const int* __restrict__ n_samples, const double4* __restrict__ recF, const double* __restrict__ rg, int E_cap,
-    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, double* __restrict__ vfT, int* __restrict__ rounds_out)
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, double end_vel,
+    long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, const double2* __restrict__ gh2,
+    int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
+    const int* __restrict__ st_idx, const int* __restrict__ n_vr, double* __restrict__ vfT, int* __restrict__ rounds_out)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
     const int NT = blockDim.x, c = threadIdx.x;
     const long long b = blockIdx.x;
-    double* s_endv = reinterpret_cast<double*>(s_mem);           // [NT] end state of every chunk: v and (v|k|)^2
+    const int VC = 3 * E_cap + 2;                                  // capacity of the initial-velocity table
+    double* s_endv = reinterpret_cast<double*>(s_mem);            // [NT] end state of every chunk: v and (v|k|)^2
     double* s_endw = s_endv + NT;
     double* s_usev = s_endw + NT;                                 // [NT] start state every chunk last used
     double* s_usew = s_usev + NT;
     double* s_acc = s_usew + NT;                                  // [E_cap] max_acc of regime j
-    int* s_bi = reinterpret_cast<int*>(s_acc + E_cap);            // [E_cap] first sample of regime j
+    double* s_vv = s_acc + E_cap;                                 // [VC]
+    int* s_bi = reinterpret_cast<int*>(s_vv + VC);                // [E_cap] first sample of regime j
+    int* s_vi = s_bi + E_cap;                                     // [VC]
+    __shared__ int s_nv;
     if (status[b] != ST_OK) return;                               // uniform over the CTA
     const int D = n_samples[b];
     const int steps = D - 1;
@@ -568,30 +540,67 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
         s_bi[k] = bidx[(size_t)b * E_cap + k];
         s_acc[k] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + k]];
     }
+    if (c == 0) {
+        // initial velocity v0[x] as one sorted breakpoint table (motion_profile_generator.py:95-176): the regime value from
+        // vr_idx[j] on, 0.01 at the stop samples, end_vel at the last sample.  Three sorted streams (regime starts, stops,
+        // sample after a stop) are merged; the value at a breakpoint follows the reference's order of overwrites.
+        const int* vi = vr_idx + (size_t)b * E_cap;
+        const double* vv = vr_val + (size_t)b * E_cap;
+        const int* si = st_idx + (size_t)b * E_cap;
+        const int nvr = n_vr[2 * b], nst = n_vr[2 * b + 1];
+        int pv = 0, ps = 0, pa = 0, n = 0, reg = 0;
+        while (true) {
+            int x = CH_INT_MAX;
+            if (pv < nvr) x = vi[pv];
+            if (ps < nst && si[ps] < x) x = si[ps];
+            if (pa < nst && si[pa] + 1 < x) x = si[pa] + 1;
+            if (x >= D - 1) break;
+            bool stop = false;
+            while (pv < nvr && vi[pv] == x) { reg = pv; pv++; }
+            while (ps < nst && si[ps] == x) { stop = true; ps++; }
+            while (pa < nst && si[pa] + 1 == x) pa++;
+            s_vi[n] = x; s_vv[n] = stop ? 0.01 : vv[reg]; n++;
+        }
+        s_vi[n] = D - 1; s_vv[n] = end_vel; n++;
+        s_nv = n;
+    }
     const int Lc = chunk_len(steps, NT);
     const int nch = (steps + Lc - 1) / Lc;
     const bool active = c < nch;
     const int lo = c * Lc;
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
     const int last_slot = (lo + len < steps) ? c + 1 : (int)(RS - 1);       // where the velocity of sample lo+len goes
-    const double4* F = recF + (size_t)b * RS;
-    const double* RG = rg + (size_t)b * RS;
-    const double hw = cons[b * 6 + 5] * 0.5;
+    const double* P = rec + (size_t)b * RS * 3;
+    const double2* GH = gh2 + (size_t)b * RS;
+    const double A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
+    const double hw = w * 0.5;
+    const double maa = 2 * A0 / w;                                 // max_angular_accel (:82)
     __syncthreads();
+    FwdTables T;
+    T.bi = s_bi; T.acc = s_acc; T.n_b = n_b; T.vi = s_vi; T.vv = s_vv; T.n_v = s_nv;
+    const int col = c;
 
-    // ---- sweep 1: chunk c > 0 starts from the guess "the state-independent caps bind on the two samples before it"
+    // ---- sweep 1: chunk c > 0 starts from the guess "the state-independent caps bind on the two samples before it":
+    // v[lo] = C[lo-1] = min(v0[lo], G[lo-1]) and omega_prev = C[lo-2] |kappa[lo-1]|
     {
         double v = start_vel, sq = 0.0;
         if (active) {
             if (c > 0) {
-                const double vm1 = (lo >= 2) ? F[edge_slot(lo - 2, Lc, NT)].w : start_vel;
-                const double4 fm1 = F[edge_slot(lo - 1, Lc, NT)];
-                v = fm1.w;
-                const double wp = vm1 * fm1.x;
+                auto v0_at = [&](int x) { int q = 0; while (q + 1 < T.n_v && T.vi[q + 1] <= x) q++; return T.vv[q]; };
+                const int rm1 = Lc - 1;                              // sample lo-1: last row of the previous column
+                const double Gm1 = __ldg(P + ((size_t)rm1 * 3 + 1) * NT + col - 1);
+                const double akm1 = __ldg(P + ((size_t)rm1 * 3 + 0) * NT + col - 1);
+                double vm1 = start_vel;
+                if (lo >= 2) {
+                    const int e2 = lo - 2, c2 = e2 / Lc, r2 = e2 - c2 * Lc;
+                    vm1 = pymin(v0_at(lo - 1), __ldg(P + ((size_t)r2 * 3 + 1) * NT + c2));
+                }
+                v = pymin(v0_at(lo), Gm1);
+                const double wp = vm1 * akm1;
                 sq = wp * wp;
             }
             s_usev[c] = v; s_usew[c] = sq;
-            fwd_run<false>(F, RG, vf, NT, c, lo, len, last_slot, s_bi, s_acc, n_b, hw, dd, v, sq, false);
+            fwd_run<false>(P, GH, vf, NT, col, lo, len, last_slot, T, A0, w, maa, hw, dd, v, sq, false);
         }
         s_endv[c] = v; s_endw[c] = sq;
     }
@@ -610,7 +619,7 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = fwd_run<true>(F, RG, vf, NT, c, lo, len, last_slot, s_bi, s_acc, n_b, hw, dd, v, sq,
+            const bool merged = fwd_run<true>(P, GH, vf, NT, col, lo, len, last_slot, T, A0, w, maa, hw, dd, v, sq,
                                               same_bits(in_v, s_usev[c]));
             s_usev[c] = in_v; s_usew[c] = in_w;
             if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
@@ -620,63 +629,63 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
     if (c == 0 && rounds_out) rounds_out[2 * b] = rounds;
 }
 
-// backward chunk of column `col`: edges lo+len-1 down to lo; edge e (backward step i = e+1 -> e) reads slot (e-lo)*NT + col
-// of the backward records, the reciprocals and the forward velocities, and writes the final velocity of sample e into the
-// same slot of voT.
+// backward chunk of column `col`: edges lo+len-1 down to lo.  Edge e = lo + r (the reference's step i = e+1 -> e) uses the
+// record of sample e+1 (row r+1; for the chunk's top edge the three `top` values), gh2 / forward velocity of row r, and
+// writes the final velocity of sample e into row r of voT.
 template <bool RERUN>
-__device__ __forceinline__ bool bwd_run(const double4* __restrict__ R, const double* __restrict__ RG,
+__device__ __forceinline__ bool bwd_run(const double* __restrict__ P, const double2* __restrict__ GH,
                                         const double* __restrict__ vf, double* __restrict__ voT, int NT, int col, int lo,
-                                        int len, const int* s_bi, const double* s_acc, int n_b, double acc0, double hw,
-                                        double dd, double& v, double& sq, bool prev_same)
+                                        int len, double top_ak, double top_G, double top_st, const int* s_bi,
+                                        const double* s_acc, int n_b, double acc0, double dec_b, bool dec_default, double w,
+                                        double maa, double hw, double dd, double& v, double& sq, bool prev_same)
 {
     // regime at the chunk start (walking down from D-1): the smallest boundary index > i was the last one applied
-    int e = lo + len - 1;                            // current edge; the reference's loop index is i = e + 1
+    int r = len - 1;                                 // row of the current edge
+    int e = lo + r;                                  // current edge; the reference's loop index is i = e + 1
     int j = n_b - 1;
     double acc = acc0;
     while (j >= 0 && s_bi[j] > e + 1) { acc = s_acc[j]; j--; }
     int nb_next = (j >= 0) ? s_bi[j] : -1;
-    int slot = (len - 1) * NT + col;
-    double4 ra = ldg_d4(R + slot), rb;
-    double ga = __ldg(RG + slot), gb;
-    double fa = __ldg(vf + slot), fb;
+    double aka = top_ak, Ga = top_G, sta = top_st, akb, Gb, stb;     // record of sample e+1
+    double2 ga = ldg_d2(GH + r * NT + col), gb;
+    double fa = __ldg(vf + r * NT + col), fb;
     double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = voT[slot];
+    if (RERUN) olda = voT[r * NT + col];
+#define BWD_ONE(AK_, G_, ST_, GH_, F_, OLD_)                                                                         \
+        if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }                             \
+        {                                                                                                            \
+            const double stat = dec_default ? ST_ : accel_static(AK_, dec_b, w, maa);                               \
+            v = bwd_step(AK_, GH_.x, GH_.y, stat, pymin(F_, G_), v, sq, acc, hw, dd);                                \
+        }                                                                                                            \
+        if (RERUN) {                                                                                                 \
+            const bool same = same_bits(OLD_, v);                                                                    \
+            if (same && prev_same) return true;                                                                      \
+            prev_same = same;                                                                                        \
+        }                                                                                                            \
+        voT[r * NT + col] = v;                                                                                       \
+        if (--e < lo) break;                                                                                         \
+        r--;
     while (true) {
-        // ---- buffers a (look-ahead slot clamped to the chunk's first row)
-        if (e - CH_PF >= lo) { pf_l1(R + slot - CH_PF * NT); pf_l1(RG + slot - CH_PF * NT); pf_l1(vf + slot - CH_PF * NT); }
+        // ---- buffers a: the next step (edge e-1) needs the record of sample e (row r) and gh2 / vf / old of row r-1
+        if (r - CH_PF >= 0) { pf_l1(P + ((size_t)(r - CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r - CH_PF) * NT + col); pf_l1(vf + (r - CH_PF) * NT + col); }
         {
-            const int sn = (e > lo) ? slot - NT : slot;
-            rb = ldg_d4(R + sn); gb = __ldg(RG + sn); fb = __ldg(vf + sn);
-            if (RERUN) oldb = voT[sn];
+            const int rn = (r > 0) ? r - 1 : 0;
+            akb = REC_AT(P, r, 0); Gb = REC_AT(P, r, 1); stb = REC_AT(P, r, 2);
+            gb = ldg_d2(GH + rn * NT + col); fb = __ldg(vf + rn * NT + col);
+            if (RERUN) oldb = voT[rn * NT + col];
         }
-        if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
-        v = bwd_step(ra, ga, v, sq, acc, hw, dd, pymin(fa, ra.w));
-        if (RERUN) {
-            const bool same = same_bits(olda, v);
-            if (same && prev_same) return true;
-            prev_same = same;
-        }
-        voT[slot] = v;
-        if (--e < lo) break;
-        slot -= NT;
+        BWD_ONE(aka, Ga, sta, ga, fa, olda)
         // ---- buffers b
-        if (e - CH_PF >= lo) { pf_l1(R + slot - CH_PF * NT); pf_l1(RG + slot - CH_PF * NT); pf_l1(vf + slot - CH_PF * NT); }
+        if (r - CH_PF >= 0) { pf_l1(P + ((size_t)(r - CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r - CH_PF) * NT + col); pf_l1(vf + (r - CH_PF) * NT + col); }
         {
-            const int sn = (e > lo) ? slot - NT : slot;
-            ra = ldg_d4(R + sn); ga = __ldg(RG + sn); fa = __ldg(vf + sn);
-            if (RERUN) olda = voT[sn];
+            const int rn = (r > 0) ? r - 1 : 0;
+            aka = REC_AT(P, r, 0); Ga = REC_AT(P, r, 1); sta = REC_AT(P, r, 2);
+            ga = ldg_d2(GH + rn * NT + col); fa = __ldg(vf + rn * NT + col);
+            if (RERUN) olda = voT[rn * NT + col];
         }
-        if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }
-        v = bwd_step(rb, gb, v, sq, acc, hw, dd, pymin(fb, rb.w));
-        if (RERUN) {
-            const bool same = same_bits(oldb, v);
-            if (same && prev_same) return true;
-            prev_same = same;
-        }
-        voT[slot] = v;
-        if (--e < lo) break;
-        slot -= NT;
+        BWD_ONE(akb, Gb, stb, gb, fb, oldb)
     }
+#undef BWD_ONE
     return false;
 }
 
@@ -686,7 +695,7 @@ __device__ __forceinline__ bool bwd_run(const double4* __restrict__ R, const dou
 // travel-time estimate used to size the time-domain outputs.
 __global__ void __maxnreg__(72) k_bwd_chunked(
     const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel,
-    long long RS, const int* __restrict__ n_samples, const double4* __restrict__ recR, const double* __restrict__ rg,
+    long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, const double2* __restrict__ gh2,
     int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const double* __restrict__ vfT, double* __restrict__ velT, float* __restrict__ t_est,
     int* __restrict__ rounds_out)
@@ -713,17 +722,28 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         s_acc[q] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + q] + 1];
     }
     const double acc0 = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + n_b - 1]];
+    const double dec_b = acc0;                                     // the backward pass keeps the forward pass's last max_dec
     const int Lc = chunk_len(steps, NT);
     const int nch = (steps + Lc - 1) / Lc;
     const bool active = k < nch;
-    const int c = nch - 1 - k;                                     // column (forward chunk index)
-    const int lo = c * Lc;
+    const int col = nch - 1 - k;                                   // column (forward chunk index)
+    const int lo = col * Lc;
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
-    const double4* R = recR + (size_t)b * RS;
-    const double* RG = rg + (size_t)b * RS;
+    const double* P = rec + (size_t)b * RS * 3;
+    const double2* GH = gh2 + (size_t)b * RS;
     const double* vf = vfT + (size_t)b * RS;
-    const double hw = cons[b * 6 + 5] * 0.5;
+    const double A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
+    const double hw = w * 0.5;
+    const double maa = 2 * A0 / w;
+    const bool dec_default = (dec_b == A0);
     __syncthreads();
+
+    // record of the sample above the chunk (sample lo+len): row 0 of the next column, or the tail
+    double top_ak = 0.0, top_G = 0.0, top_st = 0.0;
+    if (active) {
+        if (lo + len < steps) { top_ak = __ldg(P + col + 1); top_G = __ldg(P + NT + col + 1); top_st = __ldg(P + 2 * NT + col + 1); }
+        else { top_ak = __ldg(P + 3 * RS - 3); top_G = __ldg(P + 3 * RS - 2); top_st = __ldg(P + 3 * RS - 1); }
+    }
 
     // ---- sweep 1: guess v[hi] = min(vel_f[hi], G[hi+1]) (the state-independent part of what step hi+1 produces)
     {
@@ -731,16 +751,22 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         if (active) {
             if (k > 0) {
                 const int hi = lo + len;                                   // sample at the top of this chunk (< D-1)
-                const int s1 = edge_slot(hi, Lc, NT);                      // edge hi: backward record of sample hi+1
-                const double4 r1 = R[s1];
-                v = pymin(vf[s1], r1.w);
+                // sample hi+1: row 1 of the next column, or (Lc == 1) row 0 of the one after, or the tail
+                auto rec_of = [&](int x, int f) {
+                    if (x >= steps) return __ldg(P + 3 * RS - 3 + f);
+                    const int cx = x / Lc, rx = x - cx * Lc;
+                    return __ldg(P + ((size_t)rx * 3 + f) * NT + cx);
+                };
+                const int s1 = edge_slot(hi, Lc, NT);
+                v = pymin(vf[s1], rec_of(hi + 1, 1));
                 double vp1 = end_vel;
-                if (hi + 2 <= D - 1) { const int s2 = edge_slot(hi + 1, Lc, NT); vp1 = pymin(vf[s2], R[s2].w); }
-                const double wp = vp1 * r1.x;
+                if (hi + 2 <= D - 1) vp1 = pymin(vf[edge_slot(hi + 1, Lc, NT)], rec_of(hi + 2, 1));
+                const double wp = vp1 * rec_of(hi + 1, 0);
                 sq = wp * wp;
             }
             s_usev[k] = v; s_usew[k] = sq;
-            bwd_run<false>(R, RG, vf, vo, NT, c, lo, len, s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
+            bwd_run<false>(P, GH, vf, vo, NT, col, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, dec_b, dec_default,
+                           w, maa, hw, dd, v, sq, false);
         }
         s_endv[k] = v; s_endw[k] = sq;
     }
@@ -759,8 +785,8 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = bwd_run<true>(R, RG, vf, vo, NT, c, lo, len, s_bi, s_acc, n_b, acc0, hw, dd, v, sq,
-                                              same_bits(in_v, s_usev[k]));
+            const bool merged = bwd_run<true>(P, GH, vf, vo, NT, col, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0,
+                                              dec_b, dec_default, w, maa, hw, dd, v, sq, same_bits(in_v, s_usev[k]));
             s_usev[k] = in_v; s_usew[k] = in_w;
             if (!merged) { s_endv[k] = v; s_endw[k] = sq; }
         }
@@ -772,9 +798,9 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     __syncthreads();
     float est = 0.f;
     if (active) {
-        const int top = (lo + len < steps) ? c + 1 : (int)(RS - 1);       // slot of the sample above the chunk
+        const int top = (lo + len < steps) ? col + 1 : (int)(RS - 1);       // slot of the sample above the chunk
         float vprev = (float)vo[top];
-        for (int sl = (len - 1) * NT + c; sl >= 0; sl -= NT) {
+        for (int sl = (len - 1) * NT + col; sl >= 0; sl -= NT) {
             const float vcur = (float)vo[sl];
             const float vm = 0.5f * (vprev + vcur);
             est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
@@ -790,6 +816,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         t_est[b] = tot;
     }
 }
+#undef REC_AT
 
 // slot order -> sample order through a 32 x 32 shared-memory tile (both sides coalesced): vel[e] = vT[slot(e)], and the
 // last sample from slot RS-1.  grid = (row tiles * column tiles, B), 256 threads.
