@@ -1206,32 +1206,54 @@ extern "C" int64_t vap_event_scratch_ints(int64_t B, int N_max, int A_max)
 // slots per path row of the chunk-interleaved pass arrays (records, reciprocals, forward velocities)
 extern "C" int64_t vap_pass_row_slots(int64_t D_cap) { return D_cap + 512; }
 
+template <int NT>
+static void launch_passes(int64_t B, size_t ss, cudaStream_t st, const double* cons, const int32_t* status, double dd, double dt,
+                          double start_vel, double end_vel, long long RS, const int32_t* n_samples, const double* rec,
+                          int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
+                          const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
+                          const int32_t* n_vr, double* vel_f, double* velT, float* t_est, int32_t* rounds, bool backward)
+{
+    if (!backward)
+        k_fwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, start_vel, end_vel, RS, n_samples, rec, E_cap,
+                                                       max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f,
+                                                       rounds);
+    else
+        k_bwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, dt, end_vel, RS, n_samples, rec, E_cap, max_accels,
+                                                       bidx, bval, n_ev, vel_f, velT, t_est, rounds);
+}
+
 extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
                                    double start_vel, double end_vel, int64_t D_cap, const int32_t* n_samples,
                                    const double* kap, const double* th, int E_cap, const double* max_accels,
                                    const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
                                    const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* rec,
-                                   double* gh2, double* vel_f, double* velT, double* vel, float* t_est,
-                                   int32_t* rounds, int chunks, int mode, void* stream)
+                                   double* vel_f, double* velT, double* vel, float* t_est, int32_t* rounds, int chunks,
+                                   int mode, void* stream)
 {
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
     if (chunks < 32 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be 32, 64, 128 or 256");
-    if (D_cap > 500000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
+    if (D_cap > 400000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
     const long long RS = vap_pass_row_slots(D_cap);
     dim3 grid(blocks_for(D_cap + chunks, 256), (unsigned)B);
     // the kappa / theta tile: chunks columns x (256 / chunks + 1) rows, odd stride
     const size_t sm = 2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 1) | 1);
-    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec,
-                                         reinterpret_cast<double2*>(gh2));
+    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
     // CTA = one path, one chunk per thread.  The passes are bound by the latency of the dependent fp64 chain of a step:
     // one-warp CTAs at 72 registers put 28 independent chains on every SM.
     const size_t VC = 3 * (size_t)E_cap + 2;
     const size_t ss = ((size_t)chunks * 4 + E_cap + VC) * sizeof(double) + (E_cap + VC) * sizeof(int);
-    k_fwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, start_vel, end_vel, RS, n_samples, rec,
-                                                       reinterpret_cast<const double2*>(gh2), E_cap, max_accels, bidx, bval,
-                                                       n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f, rounds);
+    auto passes = [&](bool backward) {
+        switch (chunks) {
+#define VAP_PASS_CASE(N_) case N_: launch_passes<N_>(B, ss, STREAM, cons, status, dd, dt, start_vel, end_vel, RS, n_samples, rec, \
+                                              E_cap, max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f, velT,    \
+                                              t_est, rounds, backward); break;
+            VAP_PASS_CASE(32) VAP_PASS_CASE(64) VAP_PASS_CASE(128) VAP_PASS_CASE(256)
+#undef VAP_PASS_CASE
+        }
+    };
+    passes(false);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
     // sample-order result: ceil(Lc_max / 32) row tiles x chunks / 32 column tiles per path
     const long long lc_max = (D_cap + chunks - 1) / chunks + 1;
@@ -1241,9 +1263,7 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
         CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
         return 0;
     }
-    k_bwd_chunked<<<(unsigned)B, chunks, ss, STREAM>>>(status, cons, dd, dt, end_vel, RS, n_samples, rec,
-                                                       reinterpret_cast<const double2*>(gh2), E_cap, max_accels, bidx, bval,
-                                                       n_ev, vel_f, velT, t_est, rounds);
+    passes(true);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
     k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, velT, vel);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");

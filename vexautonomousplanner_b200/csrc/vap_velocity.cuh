@@ -199,15 +199,16 @@ __device__ __forceinline__ int chunk_len(int steps, int NT) { return (steps + NT
 __device__ __forceinline__ int edge_slot(int e, int Lc, int NT) { const int c = e / Lc; return (e - c * Lc) * NT + c; }
 
 // ---- pre-pass (parallel): everything of a pass step that depends neither on the velocity state nor on the events --------
-// per sample i (row / column of edge i; three field planes per row: element (row s, field f, column c) of a path is
-// rec[(3 s + f) NT + c]; the final sample D-1 sits in the last three doubles of the path's 3 RS):
-//    rec = { |kappa_i|, G_i, stat_i }
+// One row of 5 NT doubles per chunk position s: five field planes of NT columns, element (row s, field f, column c) of a
+// path is rec[(5 s + f) NT + c]; the terms of the final sample D-1 sit in the last three doubles of the path's 5 RS.
+// fields 0-2, per sample i (row / column of edge i):
+//    { |kappa_i|, G_i, stat_i }
 //       G_i    = min(vlim_i, cap_i)                         velocity caps (:212-218, :239)
 //       stat_i = min(max_ang_acc/|k|, 2 A0/(w|k|+2), A0)    the state-independent acceleration limits for the path's own
 //                (A0 when straight)                         max_acc A0 -- forward a_static AND backward d_static as long as
 //                                                           no node / action point overrides max_acceleration
-// per edge e (slot order):
-//    gh2 = { 2|theta_{e+1} - theta_e|, recip_for_pass(of it) }   denominator of the wheel-acceleration term of forward
+// fields 3-4, per edge e:
+//    { gh_e = 2|theta_{e+1} - theta_e|, recip_for_pass(gh_e) }   denominator of the wheel-acceleration term of forward
 //                                                                step e and of backward step e+1, and its reciprocal
 // What depends on the events is applied by the passes themselves from small shared-memory tables: the initial velocity
 // v0[i+1] (regimes, stops, end velocity) enters as C_i = min(v0[i+1], G_i), a max_acceleration override recomputes stat.
@@ -274,8 +275,7 @@ __device__ __forceinline__ SampleTerms prepass_sample(double V, double A0, doubl
 
 __global__ void __launch_bounds__(256) k_prepass(
     const int* __restrict__ status, const double* __restrict__ cons, long long D_cap, const int* __restrict__ n_samples,
-    const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec,
-    double2* __restrict__ gh2)
+    const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec)
 {
     extern __shared__ double s_tile[];
     const long long b = blockIdx.y;
@@ -313,14 +313,13 @@ __global__ void __launch_bounds__(256) k_prepass(
     const double max_angular_accel = 2 * A0 / w;    // (:82)
     const int tl = c * st + (s - s0);
     const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
-    double* pr = rec + (size_t)b * RS * 3;
+    double* pr = rec + (size_t)b * RS * 5;
     const SampleTerms t = prepass_sample(V, A0, w, max_angular_vel, max_angular_accel, t_k[tl]);
-    const size_t o = (size_t)s * 3 * NT + c;
-    pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat;
-    gh2[(size_t)b * RS + j] = make_double2(gh, recip_for_pass(gh));
+    const size_t o = (size_t)s * 5 * NT + c;
+    pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat; pr[o + 3 * NT] = gh; pr[o + 4 * NT] = recip_for_pass(gh);
     if (e == steps - 1) {                           // the final sample (no edge starts there)
         const SampleTerms u = prepass_sample(V, A0, w, max_angular_vel, max_angular_accel, kr[D - 1]);
-        pr[3 * RS - 3] = u.ak; pr[3 * RS - 2] = u.G; pr[3 * RS - 1] = u.stat;
+        pr[5 * RS - 3] = u.ak; pr[5 * RS - 2] = u.G; pr[5 * RS - 1] = u.stat;
     }
 }
 
@@ -440,27 +439,21 @@ __device__ __forceinline__ double bwd_step(double ak, double gh, double rg, doub
 // reciprocal from the pre-pass, coalesced slot-order streams.
 // ------------------------------------------------------------------------------------------------------------------
 #define CH_INT_MAX 2147483647
-#ifndef CH_PF
-#define CH_PF 4          // rows the passes prefetch into L1 ahead of the row being loaded into registers
-#endif
-__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // per-path event tables of the forward pass in shared memory
 struct FwdTables {
     const int* bi; const double* acc; int n_b;       // max_acc regimes: acc[j] from sample bi[j] on
     const int* vi; const double* vv; int n_v;        // initial velocity: vv[j] from sample vi[j] on (stops / end included)
 };
-__device__ __forceinline__ double2 ldg_d2(const double2* p) { return __ldg(p); }
-// field f of the sample in row r, column col of a path's record planes
-#define REC_AT(P_, r_, f_) __ldg((P_) + ((size_t)(r_) * 3 + (f_)) * NT + col)
 
-// forward chunk of column `col`: edges lo .. lo+len-1; edge e = lo + r reads row r of the record planes and of gh2, and
-// writes the forward velocity of sample e+1 into the slot of edge e+1 (the bottom of the chunk writes row 0 of the next
-// column, or the tail slot).
-template <bool RERUN>
-__device__ __forceinline__ bool fwd_run(const double* __restrict__ P, const double2* __restrict__ GH, double* __restrict__ vf,
-                                        int NT, int col, int lo, int len, int last_slot, const FwdTables& T, double A0,
-                                        double w, double maa, double hw, double dd, double& v, double& sq, bool prev_same)
+// forward chunk: edges lo .. lo+len-1; p points at (row 0, field 0, own column) of the record rows, q at row 0 of the forward
+// velocities.  Edge e = lo + r reads row r and writes the forward velocity of sample e+1 into row r+1 (the bottom of the chunk
+// writes *last: row 0 of the next column, or the tail slot).  NT is a compile-time constant: every access is pointer +
+// immediate.
+template <int NT, bool RERUN>
+__device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __restrict__ q, double* __restrict__ last,
+                                        int lo, int len, const FwdTables& T, double A0, double w, double maa, double hw,
+                                        double dd, double& v, double& sq, bool prev_same)
 {
     int j = 0;
     while (j + 1 < T.n_b && T.bi[j + 1] <= lo) j++;
@@ -470,54 +463,52 @@ __device__ __forceinline__ bool fwd_run(const double* __restrict__ P, const doub
     while (jv + 1 < T.n_v && T.vi[jv + 1] <= lo + 1) jv++;
     double v0n = T.vv[jv];
     int nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX;
-    int r = 0;                                       // row of the current edge
-    double aka = REC_AT(P, 0, 0), Ga = REC_AT(P, 0, 1), sta = REC_AT(P, 0, 2), akb, Gb, stb;
-    double2 ga = ldg_d2(GH + col), gb;
+    double aka = __ldg(p), Ga = __ldg(p + NT), sta = __ldg(p + 2 * NT), gha = __ldg(p + 3 * NT), rga = __ldg(p + 4 * NT);
+    double akb, Gb, stb, ghb, rgb;
     double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = vf[(len > 1) ? NT + col : last_slot];
+    if (RERUN) olda = (len > 1) ? q[NT] : *last;
     int e = lo;
     const int hi = lo + len;
-#define FWD_ONE(AK_, G_, ST_, GH_, OLD_)                                                                             \
+#define FWD_ONE(AK_, G_, ST_, GH_, RG_, OLD_)                                                                        \
         if (e == nb_next) { j++; acc = T.acc[j]; nb_next = (j + 1 < T.n_b) ? T.bi[j + 1] : CH_INT_MAX; }              \
         if (e + 1 == nv_next) { jv++; v0n = T.vv[jv]; nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX; }      \
         {                                                                                                            \
             const double stat = (acc == A0) ? ST_ : accel_static(AK_, acc, w, maa);                                 \
-            v = fwd_step(AK_, GH_.x, GH_.y, stat, pymin(v0n, G_), v, sq, acc, hw, dd);                               \
+            v = fwd_step(AK_, GH_, RG_, stat, pymin(v0n, G_), v, sq, acc, hw, dd);                                   \
         }                                                                                                            \
         if (RERUN) {                                                                                                 \
             const bool same = same_bits(OLD_, v);                                                                    \
             if (same && prev_same) return true;       /* state equals the old run's: the rest is unchanged */        \
             prev_same = same;                                                                                        \
         }                                                                                                            \
-        if (++e >= hi) { vf[last_slot] = v; break; }                                                                 \
-        r++;                                                                                                         \
-        vf[r * NT + col] = v;
+        if (++e >= hi) { *last = v; break; }                                                                         \
+        p += 5 * NT; q += NT;                                                                                        \
+        *q = v;
     while (true) {
         // ---- buffers a (look-ahead loads never leave the path's rows: they are padded)
-        if (e + CH_PF < hi) { pf_l1(P + ((size_t)(r + CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r + CH_PF) * NT + col); }
-        akb = REC_AT(P, r + 1, 0); Gb = REC_AT(P, r + 1, 1); stb = REC_AT(P, r + 1, 2); gb = ldg_d2(GH + (r + 1) * NT + col);
-        if (RERUN) oldb = vf[(e + 2 < hi) ? (r + 2) * NT + col : last_slot];
-        FWD_ONE(aka, Ga, sta, ga, olda)
+        akb = __ldg(p + 5 * NT); Gb = __ldg(p + 6 * NT); stb = __ldg(p + 7 * NT); ghb = __ldg(p + 8 * NT); rgb = __ldg(p + 9 * NT);
+        if (RERUN) oldb = (e + 2 < hi) ? q[2 * NT] : *last;
+        FWD_ONE(aka, Ga, sta, gha, rga, olda)
         // ---- buffers b
-        if (e + CH_PF < hi) { pf_l1(P + ((size_t)(r + CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r + CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r + CH_PF) * NT + col); }
-        aka = REC_AT(P, r + 1, 0); Ga = REC_AT(P, r + 1, 1); sta = REC_AT(P, r + 1, 2); ga = ldg_d2(GH + (r + 1) * NT + col);
-        if (RERUN) olda = vf[(e + 2 < hi) ? (r + 2) * NT + col : last_slot];
-        FWD_ONE(akb, Gb, stb, gb, oldb)
+        aka = __ldg(p + 5 * NT); Ga = __ldg(p + 6 * NT); sta = __ldg(p + 7 * NT); gha = __ldg(p + 8 * NT); rga = __ldg(p + 9 * NT);
+        if (RERUN) olda = (e + 2 < hi) ? q[2 * NT] : *last;
+        FWD_ONE(akb, Gb, stb, ghb, rgb, oldb)
     }
 #undef FWD_ONE
     return false;
 }
 
 // Forward pass.  Chunk c = thread c.  vfT: forward velocities in slot order (vfT[slot(e)] = velocity at sample e).
+template <int NT>
 __global__ void __maxnreg__(72) k_fwd_chunked(
     const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, double end_vel,
-    long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, const double2* __restrict__ gh2,
-    int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
+    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
     const int* __restrict__ st_idx, const int* __restrict__ n_vr, double* __restrict__ vfT, int* __restrict__ rounds_out)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
-    const int NT = blockDim.x, c = threadIdx.x;
+    const int c = threadIdx.x;
     const long long b = blockIdx.x;
     const int VC = 3 * E_cap + 2;                                  // capacity of the initial-velocity table
     double* s_endv = reinterpret_cast<double*>(s_mem);            // [NT] end state of every chunk: v and (v|k|)^2
@@ -569,16 +560,14 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
     const bool active = c < nch;
     const int lo = c * Lc;
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
-    const int last_slot = (lo + len < steps) ? c + 1 : (int)(RS - 1);       // where the velocity of sample lo+len goes
-    const double* P = rec + (size_t)b * RS * 3;
-    const double2* GH = gh2 + (size_t)b * RS;
+    const double* P = rec + (size_t)b * RS * 5;
+    double* last = vf + ((lo + len < steps) ? c + 1 : (int)(RS - 1));       // where the velocity of sample lo+len goes
     const double A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
     const double hw = w * 0.5;
     const double maa = 2 * A0 / w;                                 // max_angular_accel (:82)
     __syncthreads();
     FwdTables T;
     T.bi = s_bi; T.acc = s_acc; T.n_b = n_b; T.vi = s_vi; T.vv = s_vv; T.n_v = s_nv;
-    const int col = c;
 
     // ---- sweep 1: chunk c > 0 starts from the guess "the state-independent caps bind on the two samples before it":
     // v[lo] = C[lo-1] = min(v0[lo], G[lo-1]) and omega_prev = C[lo-2] |kappa[lo-1]|
@@ -588,19 +577,19 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
             if (c > 0) {
                 auto v0_at = [&](int x) { int q = 0; while (q + 1 < T.n_v && T.vi[q + 1] <= x) q++; return T.vv[q]; };
                 const int rm1 = Lc - 1;                              // sample lo-1: last row of the previous column
-                const double Gm1 = __ldg(P + ((size_t)rm1 * 3 + 1) * NT + col - 1);
-                const double akm1 = __ldg(P + ((size_t)rm1 * 3 + 0) * NT + col - 1);
+                const double Gm1 = __ldg(P + ((size_t)rm1 * 5 + 1) * NT + c - 1);
+                const double akm1 = __ldg(P + ((size_t)rm1 * 5 + 0) * NT + c - 1);
                 double vm1 = start_vel;
                 if (lo >= 2) {
                     const int e2 = lo - 2, c2 = e2 / Lc, r2 = e2 - c2 * Lc;
-                    vm1 = pymin(v0_at(lo - 1), __ldg(P + ((size_t)r2 * 3 + 1) * NT + c2));
+                    vm1 = pymin(v0_at(lo - 1), __ldg(P + ((size_t)r2 * 5 + 1) * NT + c2));
                 }
                 v = pymin(v0_at(lo), Gm1);
                 const double wp = vm1 * akm1;
                 sq = wp * wp;
             }
             s_usev[c] = v; s_usew[c] = sq;
-            fwd_run<false>(P, GH, vf, NT, col, lo, len, last_slot, T, A0, w, maa, hw, dd, v, sq, false);
+            fwd_run<NT, false>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq, false);
         }
         s_endv[c] = v; s_endw[c] = sq;
     }
@@ -619,8 +608,8 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = fwd_run<true>(P, GH, vf, NT, col, lo, len, last_slot, T, A0, w, maa, hw, dd, v, sq,
-                                              same_bits(in_v, s_usev[c]));
+            const bool merged = fwd_run<NT, true>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq,
+                                                  same_bits(in_v, s_usev[c]));
             s_usev[c] = in_v; s_usew[c] = in_w;
             if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
         }
@@ -629,61 +618,53 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
     if (c == 0 && rounds_out) rounds_out[2 * b] = rounds;
 }
 
-// backward chunk of column `col`: edges lo+len-1 down to lo.  Edge e = lo + r (the reference's step i = e+1 -> e) uses the
-// record of sample e+1 (row r+1; for the chunk's top edge the three `top` values), gh2 / forward velocity of row r, and
-// writes the final velocity of sample e into row r of voT.
-template <bool RERUN>
-__device__ __forceinline__ bool bwd_run(const double* __restrict__ P, const double2* __restrict__ GH,
-                                        const double* __restrict__ vf, double* __restrict__ voT, int NT, int col, int lo,
-                                        int len, double top_ak, double top_G, double top_st, const int* s_bi,
+// backward chunk: edges lo+len-1 down to lo.  p points at (row len-1, field 0, own column) of the record rows, f / o at the
+// same row of the forward / final velocities.  Edge e = lo + r (the reference's step i = e+1 -> e) uses the terms of sample
+// e+1 (fields 0-2 of row r+1; for the chunk's top edge the three `top` values), gh / rg (fields 3-4) and the forward velocity
+// of row r, and writes the final velocity of sample e into row r of the final velocities.
+template <int NT, bool RERUN>
+__device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const double* __restrict__ f, double* __restrict__ o,
+                                        int lo, int len, double top_ak, double top_G, double top_st, const int* s_bi,
                                         const double* s_acc, int n_b, double acc0, double dec_b, bool dec_default, double w,
                                         double maa, double hw, double dd, double& v, double& sq, bool prev_same)
 {
     // regime at the chunk start (walking down from D-1): the smallest boundary index > i was the last one applied
-    int r = len - 1;                                 // row of the current edge
-    int e = lo + r;                                  // current edge; the reference's loop index is i = e + 1
+    int e = lo + len - 1;                            // current edge; the reference's loop index is i = e + 1
     int j = n_b - 1;
     double acc = acc0;
     while (j >= 0 && s_bi[j] > e + 1) { acc = s_acc[j]; j--; }
     int nb_next = (j >= 0) ? s_bi[j] : -1;
-    double aka = top_ak, Ga = top_G, sta = top_st, akb, Gb, stb;     // record of sample e+1
-    double2 ga = ldg_d2(GH + r * NT + col), gb;
-    double fa = __ldg(vf + r * NT + col), fb;
+    double aka = top_ak, Ga = top_G, sta = top_st, akb, Gb, stb;     // terms of sample e+1
+    double gha = __ldg(p + 3 * NT), rga = __ldg(p + 4 * NT), ghb, rgb;
+    double fa = __ldg(f), fb;
     double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = voT[r * NT + col];
-#define BWD_ONE(AK_, G_, ST_, GH_, F_, OLD_)                                                                         \
+    if (RERUN) olda = *o;
+#define BWD_ONE(AK_, G_, ST_, GH_, RG_, F_, OLD_)                                                                    \
         if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }                             \
         {                                                                                                            \
             const double stat = dec_default ? ST_ : accel_static(AK_, dec_b, w, maa);                               \
-            v = bwd_step(AK_, GH_.x, GH_.y, stat, pymin(F_, G_), v, sq, acc, hw, dd);                                \
+            v = bwd_step(AK_, GH_, RG_, stat, pymin(F_, G_), v, sq, acc, hw, dd);                                    \
         }                                                                                                            \
         if (RERUN) {                                                                                                 \
             const bool same = same_bits(OLD_, v);                                                                    \
             if (same && prev_same) return true;                                                                      \
             prev_same = same;                                                                                        \
         }                                                                                                            \
-        voT[r * NT + col] = v;                                                                                       \
+        *o = v;                                                                                                      \
         if (--e < lo) break;                                                                                         \
-        r--;
+        p -= 5 * NT; f -= NT; o -= NT;
     while (true) {
-        // ---- buffers a: the next step (edge e-1) needs the record of sample e (row r) and gh2 / vf / old of row r-1
-        if (r - CH_PF >= 0) { pf_l1(P + ((size_t)(r - CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r - CH_PF) * NT + col); pf_l1(vf + (r - CH_PF) * NT + col); }
-        {
-            const int rn = (r > 0) ? r - 1 : 0;
-            akb = REC_AT(P, r, 0); Gb = REC_AT(P, r, 1); stb = REC_AT(P, r, 2);
-            gb = ldg_d2(GH + rn * NT + col); fb = __ldg(vf + rn * NT + col);
-            if (RERUN) oldb = voT[rn * NT + col];
-        }
-        BWD_ONE(aka, Ga, sta, ga, fa, olda)
+        // ---- buffers a: the next step (edge e-1) needs the terms of sample e (this row) and gh / rg / vf / old of the row
+        // below (at the chunk's first row the look-ahead stays on the row: the values are not used)
+        akb = __ldg(p); Gb = __ldg(p + NT); stb = __ldg(p + 2 * NT);
+        if (e > lo) { ghb = __ldg(p - 2 * NT); rgb = __ldg(p - NT); fb = __ldg(f - NT); if (RERUN) oldb = o[-NT]; }
+        else { ghb = 0.0; rgb = 0.0; fb = 0.0; }
+        BWD_ONE(aka, Ga, sta, gha, rga, fa, olda)
         // ---- buffers b
-        if (r - CH_PF >= 0) { pf_l1(P + ((size_t)(r - CH_PF) * 3) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 1) * NT + col); pf_l1(P + ((size_t)(r - CH_PF) * 3 + 2) * NT + col); pf_l1(GH + (r - CH_PF) * NT + col); pf_l1(vf + (r - CH_PF) * NT + col); }
-        {
-            const int rn = (r > 0) ? r - 1 : 0;
-            aka = REC_AT(P, r, 0); Ga = REC_AT(P, r, 1); sta = REC_AT(P, r, 2);
-            ga = ldg_d2(GH + rn * NT + col); fa = __ldg(vf + rn * NT + col);
-            if (RERUN) olda = voT[rn * NT + col];
-        }
-        BWD_ONE(akb, Gb, stb, gb, fb, oldb)
+        aka = __ldg(p); Ga = __ldg(p + NT); sta = __ldg(p + 2 * NT);
+        if (e > lo) { gha = __ldg(p - 2 * NT); rga = __ldg(p - NT); fa = __ldg(f - NT); if (RERUN) olda = o[-NT]; }
+        else { gha = 0.0; rga = 0.0; fa = 0.0; }
+        BWD_ONE(akb, Gb, stb, ghb, rgb, fb, oldb)
     }
 #undef BWD_ONE
     return false;
@@ -693,15 +674,16 @@ __device__ __forceinline__ bool bwd_run(const double* __restrict__ P, const doub
 // thread k as in the forward kernel.  Reads the forward velocities and writes the final ones, both in slot order
 // (velT[RS-1] = end_vel is the last sample); k_untranspose puts them into sample order.  Also accumulates the
 // travel-time estimate used to size the time-domain outputs.
+template <int NT>
 __global__ void __maxnreg__(72) k_bwd_chunked(
     const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel,
-    long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, const double2* __restrict__ gh2,
-    int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
+    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const double* __restrict__ vfT, double* __restrict__ velT, float* __restrict__ t_est,
     int* __restrict__ rounds_out)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
-    const int NT = blockDim.x, k = threadIdx.x;
+    const int k = threadIdx.x;
     const long long b = blockIdx.x;
     double* s_endv = reinterpret_cast<double*>(s_mem);
     double* s_endw = s_endv + NT;
@@ -729,8 +711,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     const int col = nch - 1 - k;                                   // column (forward chunk index)
     const int lo = col * Lc;
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
-    const double* P = rec + (size_t)b * RS * 3;
-    const double2* GH = gh2 + (size_t)b * RS;
+    const double* P = rec + (size_t)b * RS * 5;
     const double* vf = vfT + (size_t)b * RS;
     const double A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
     const double hw = w * 0.5;
@@ -738,12 +719,16 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     const bool dec_default = (dec_b == A0);
     __syncthreads();
 
-    // record of the sample above the chunk (sample lo+len): row 0 of the next column, or the tail
+    // terms of the sample above the chunk (sample lo+len): row 0 of the next column, or the tail
     double top_ak = 0.0, top_G = 0.0, top_st = 0.0;
     if (active) {
         if (lo + len < steps) { top_ak = __ldg(P + col + 1); top_G = __ldg(P + NT + col + 1); top_st = __ldg(P + 2 * NT + col + 1); }
-        else { top_ak = __ldg(P + 3 * RS - 3); top_G = __ldg(P + 3 * RS - 2); top_st = __ldg(P + 3 * RS - 1); }
+        else { top_ak = __ldg(P + 5 * RS - 3); top_G = __ldg(P + 5 * RS - 2); top_st = __ldg(P + 5 * RS - 1); }
     }
+    const size_t r_top = active ? (size_t)(len - 1) : 0;           // row of the chunk's top edge
+    const double* p0 = P + r_top * 5 * NT + (active ? col : 0);
+    const double* f0 = vf + r_top * NT + (active ? col : 0);
+    double* o0 = vo + r_top * NT + (active ? col : 0);
 
     // ---- sweep 1: guess v[hi] = min(vel_f[hi], G[hi+1]) (the state-independent part of what step hi+1 produces)
     {
@@ -751,11 +736,10 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         if (active) {
             if (k > 0) {
                 const int hi = lo + len;                                   // sample at the top of this chunk (< D-1)
-                // sample hi+1: row 1 of the next column, or (Lc == 1) row 0 of the one after, or the tail
-                auto rec_of = [&](int x, int f) {
-                    if (x >= steps) return __ldg(P + 3 * RS - 3 + f);
+                auto rec_of = [&](int x, int fld) {                         // field fld of sample x
+                    if (x >= steps) return __ldg(P + 5 * RS - 3 + fld);
                     const int cx = x / Lc, rx = x - cx * Lc;
-                    return __ldg(P + ((size_t)rx * 3 + f) * NT + cx);
+                    return __ldg(P + ((size_t)rx * 5 + fld) * NT + cx);
                 };
                 const int s1 = edge_slot(hi, Lc, NT);
                 v = pymin(vf[s1], rec_of(hi + 1, 1));
@@ -765,8 +749,8 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
                 sq = wp * wp;
             }
             s_usev[k] = v; s_usew[k] = sq;
-            bwd_run<false>(P, GH, vf, vo, NT, col, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, dec_b, dec_default,
-                           w, maa, hw, dd, v, sq, false);
+            bwd_run<NT, false>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, dec_b, dec_default,
+                               w, maa, hw, dd, v, sq, false);
         }
         s_endv[k] = v; s_endw[k] = sq;
     }
@@ -785,8 +769,8 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = bwd_run<true>(P, GH, vf, vo, NT, col, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0,
-                                              dec_b, dec_default, w, maa, hw, dd, v, sq, same_bits(in_v, s_usev[k]));
+            const bool merged = bwd_run<NT, true>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0,
+                                                  dec_b, dec_default, w, maa, hw, dd, v, sq, same_bits(in_v, s_usev[k]));
             s_usev[k] = in_v; s_usew[k] = in_w;
             if (!merged) { s_endv[k] = v; s_endw[k] = sq; }
         }
@@ -816,7 +800,6 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         t_est[b] = tot;
     }
 }
-#undef REC_AT
 
 // slot order -> sample order through a 32 x 32 shared-memory tile (both sides coalesced): vel[e] = vT[slot(e)], and the
 // last sample from slot RS-1.  grid = (row tiles * column tiles, B), 256 threads.
