@@ -1211,15 +1211,16 @@ static void launch_passes(int64_t B, size_t ss, cudaStream_t st, const double* c
                           double start_vel, double end_vel, long long RS, const int32_t* n_samples, const double* rec,
                           int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
                           const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
-                          const int32_t* n_vr, double* vel_f, double* velT, float* t_est, int32_t* rounds, bool backward)
+                          const int32_t* n_vr, double* vel_f, double* velT, float* t_est, int32_t* rounds, bool backward,
+                          int warm, int max_rounds)
 {
     if (!backward)
         k_fwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, start_vel, end_vel, RS, n_samples, rec, E_cap,
                                                        max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f,
-                                                       rounds);
+                                                       rounds, warm, max_rounds);
     else
         k_bwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, dt, end_vel, RS, n_samples, rec, E_cap, max_accels,
-                                                       bidx, bval, n_ev, vel_f, velT, t_est, rounds);
+                                                       bidx, bval, n_ev, vel_f, velT, t_est, rounds, warm, max_rounds);
 }
 
 extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
@@ -1244,11 +1245,17 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     // one-warp CTAs at 72 registers put 28 independent chains on every SM.
     const size_t VC = 3 * (size_t)E_cap + 2;
     const size_t ss = ((size_t)chunks * 4 + E_cap + VC) * sizeof(double) + (E_cap + VC) * sizeof(int);
+    // warm-up steps a speculative chunk runs before its own range (tuning: VAP_CHUNK_WARM; any value gives the same bits).
+    // VAP_CHUNK_MAXROUNDS caps the fix-up rounds: a DIAGNOSTIC that breaks exactness (it times the first sweep alone).
+    int warm = 96, max_rounds = 1 << 30;
+    if (const char* ev = getenv("VAP_CHUNK_WARM")) warm = atoi(ev);
+    if (const char* ev = getenv("VAP_CHUNK_MAXROUNDS")) max_rounds = atoi(ev);
+    if (warm < 0) warm = 0;
     auto passes = [&](bool backward) {
         switch (chunks) {
 #define VAP_PASS_CASE(N_) case N_: launch_passes<N_>(B, ss, STREAM, cons, status, dd, dt, start_vel, end_vel, RS, n_samples, rec, \
                                               E_cap, max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f, velT,    \
-                                              t_est, rounds, backward); break;
+                                              t_est, rounds, backward, warm, max_rounds); break;
             VAP_PASS_CASE(32) VAP_PASS_CASE(64) VAP_PASS_CASE(128) VAP_PASS_CASE(256)
 #undef VAP_PASS_CASE
         }

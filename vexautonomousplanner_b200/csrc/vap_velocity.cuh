@@ -450,7 +450,10 @@ struct FwdTables {
 // velocities.  Edge e = lo + r reads row r and writes the forward velocity of sample e+1 into row r+1 (the bottom of the chunk
 // writes *last: row 0 of the next column, or the tail slot).  NT is a compile-time constant: every access is pointer +
 // immediate.
-template <int NT, bool RERUN>
+#define RUN_SWEEP 0     // first sweep: plain stores
+#define RUN_RERUN 1     // fix-up: bitwise merge detection against the stored velocities
+#define RUN_DRY 2       // warm-up before a speculative chunk: state only, no stores
+template <int NT, int MODE>
 __device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __restrict__ q, double* __restrict__ last,
                                         int lo, int len, const FwdTables& T, double A0, double w, double maa, double hw,
                                         double dd, double& v, double& sq, bool prev_same)
@@ -465,6 +468,8 @@ __device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __
     int nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX;
     double aka = __ldg(p), Ga = __ldg(p + NT), sta = __ldg(p + 2 * NT), gha = __ldg(p + 3 * NT), rga = __ldg(p + 4 * NT);
     double akb, Gb, stb, ghb, rgb;
+    constexpr bool RERUN = (MODE == RUN_RERUN);
+    constexpr bool DRY = (MODE == RUN_DRY);
     double olda = 0.0, oldb = 0.0;
     if (RERUN) olda = (len > 1) ? q[NT] : *last;
     int e = lo;
@@ -481,9 +486,9 @@ __device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __
             if (same && prev_same) return true;       /* state equals the old run's: the rest is unchanged */        \
             prev_same = same;                                                                                        \
         }                                                                                                            \
-        if (++e >= hi) { *last = v; break; }                                                                         \
-        p += 5 * NT; q += NT;                                                                                        \
-        *q = v;
+        if (++e >= hi) { if (!DRY) *last = v; break; }                                                               \
+        p += 5 * NT;                                                                                                 \
+        if (!DRY) { q += NT; *q = v; }
     while (true) {
         // ---- buffers a (look-ahead loads never leave the path's rows: they are padded)
         akb = __ldg(p + 5 * NT); Gb = __ldg(p + 6 * NT); stb = __ldg(p + 7 * NT); ghb = __ldg(p + 8 * NT); rgb = __ldg(p + 9 * NT);
@@ -505,7 +510,8 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
     long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
-    const int* __restrict__ st_idx, const int* __restrict__ n_vr, double* __restrict__ vfT, int* __restrict__ rounds_out)
+    const int* __restrict__ st_idx, const int* __restrict__ n_vr, double* __restrict__ vfT, int* __restrict__ rounds_out,
+    int warm, int max_rounds)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
     const int c = threadIdx.x;
@@ -569,27 +575,28 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
     FwdTables T;
     T.bi = s_bi; T.acc = s_acc; T.n_b = n_b; T.vi = s_vi; T.vv = s_vv; T.n_v = s_nv;
 
-    // ---- sweep 1: chunk c > 0 starts from the guess "the state-independent caps bind on the two samples before it":
-    // v[lo] = C[lo-1] = min(v0[lo], G[lo-1]) and omega_prev = C[lo-2] |kappa[lo-1]|
+    // ---- sweep 1: chunk c > 0 starts `wl` steps BEFORE its own range (in the previous column) from the guess "the state-
+    // independent caps bind on the two samples before that point": v[s0] = C[s0-1] = min(v0[s0], G[s0-1]) and
+    // omega_prev = C[s0-2] |kappa[s0-1]|, and only computes (no stores) until it reaches its range: a wrong guess survives for
+    // at most one acceleration ramp, so after the warm-up the state is usually the true one and the fix-up rounds have little
+    // to re-run.  (Exactness never depends on the guess: the rounds below verify bitwise.)
     {
         double v = start_vel, sq = 0.0;
         if (active) {
             if (c > 0) {
                 auto v0_at = [&](int x) { int q = 0; while (q + 1 < T.n_v && T.vi[q + 1] <= x) q++; return T.vv[q]; };
-                const int rm1 = Lc - 1;                              // sample lo-1: last row of the previous column
-                const double Gm1 = __ldg(P + ((size_t)rm1 * 5 + 1) * NT + c - 1);
-                const double akm1 = __ldg(P + ((size_t)rm1 * 5 + 0) * NT + c - 1);
-                double vm1 = start_vel;
-                if (lo >= 2) {
-                    const int e2 = lo - 2, c2 = e2 / Lc, r2 = e2 - c2 * Lc;
-                    vm1 = pymin(v0_at(lo - 1), __ldg(P + ((size_t)r2 * 5 + 1) * NT + c2));
-                }
-                v = pymin(v0_at(lo), Gm1);
-                const double wp = vm1 * akm1;
+                auto term = [&](int x, int fld) { const int cx = x / Lc, rx = x - cx * Lc; return __ldg(P + ((size_t)rx * 5 + fld) * NT + cx); };
+                int wl = warm < Lc ? warm : Lc;                      // the warm-up stays inside the previous column
+                if (wl > lo - 2) wl = lo - 2 > 0 ? lo - 2 : 0;
+                const int s0 = lo - wl;
+                const double vm1 = (s0 >= 2) ? pymin(v0_at(s0 - 1), term(s0 - 2, 1)) : start_vel;
+                v = pymin(v0_at(s0), term(s0 - 1, 1));
+                const double wp = vm1 * term(s0 - 1, 0);
                 sq = wp * wp;
+                if (wl > 0) fwd_run<NT, RUN_DRY>(P + (size_t)(Lc - wl) * 5 * NT + c - 1, nullptr, nullptr, s0, wl, T, A0, w, maa, hw, dd, v, sq, false);
             }
             s_usev[c] = v; s_usew[c] = sq;
-            fwd_run<NT, false>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq, false);
+            fwd_run<NT, RUN_SWEEP>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq, false);
         }
         s_endv[c] = v; s_endw[c] = sq;
     }
@@ -597,7 +604,7 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
 
     // ---- fix-up rounds
     int rounds = 0;
-    for (int round = 1; round < NT; round++) {
+    for (int round = 1; round < NT && round <= max_rounds; round++) {
         bool need = false;
         double in_v = 0.0, in_w = 0.0;
         if (active && c >= round) {
@@ -608,7 +615,7 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = fwd_run<NT, true>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq,
+            const bool merged = fwd_run<NT, RUN_RERUN>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq,
                                                   same_bits(in_v, s_usev[c]));
             s_usev[c] = in_v; s_usew[c] = in_w;
             if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
@@ -622,7 +629,7 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
 // same row of the forward / final velocities.  Edge e = lo + r (the reference's step i = e+1 -> e) uses the terms of sample
 // e+1 (fields 0-2 of row r+1; for the chunk's top edge the three `top` values), gh / rg (fields 3-4) and the forward velocity
 // of row r, and writes the final velocity of sample e into row r of the final velocities.
-template <int NT, bool RERUN>
+template <int NT, int MODE>
 __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const double* __restrict__ f, double* __restrict__ o,
                                         int lo, int len, double top_ak, double top_G, double top_st, const int* s_bi,
                                         const double* s_acc, int n_b, double acc0, double dec_b, bool dec_default, double w,
@@ -636,6 +643,8 @@ __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const doub
     int nb_next = (j >= 0) ? s_bi[j] : -1;
     double aka = top_ak, Ga = top_G, sta = top_st, akb, Gb, stb;     // terms of sample e+1
     double gha = __ldg(p + 3 * NT), rga = __ldg(p + 4 * NT), ghb, rgb;
+    constexpr bool RERUN = (MODE == RUN_RERUN);
+    constexpr bool DRY = (MODE == RUN_DRY);
     double fa = __ldg(f), fb;
     double olda = 0.0, oldb = 0.0;
     if (RERUN) olda = *o;
@@ -650,9 +659,10 @@ __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const doub
             if (same && prev_same) return true;                                                                      \
             prev_same = same;                                                                                        \
         }                                                                                                            \
-        *o = v;                                                                                                      \
+        if (!DRY) *o = v;                                                                                            \
         if (--e < lo) break;                                                                                         \
-        p -= 5 * NT; f -= NT; o -= NT;
+        p -= 5 * NT; f -= NT;                                                                                        \
+        if (!DRY) o -= NT;
     while (true) {
         // ---- buffers a: the next step (edge e-1) needs the terms of sample e (this row) and gh / rg / vf / old of the row
         // below (at the chunk's first row the look-ahead stays on the row: the values are not used)
@@ -680,7 +690,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const double* __restrict__ vfT, double* __restrict__ velT, float* __restrict__ t_est,
-    int* __restrict__ rounds_out)
+    int* __restrict__ rounds_out, int warm, int max_rounds)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
     const int k = threadIdx.x;
@@ -730,7 +740,9 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     const double* f0 = vf + r_top * NT + (active ? col : 0);
     double* o0 = vo + r_top * NT + (active ? col : 0);
 
-    // ---- sweep 1: guess v[hi] = min(vel_f[hi], G[hi+1]) (the state-independent part of what step hi+1 produces)
+    // ---- sweep 1: thread k > 0 starts `wl` steps ABOVE its chunk (in the next column) from the guess
+    // v[s0] = min(vel_f[s0], G[s0+1]) (the state-independent part of what step s0+1 produces) and only computes until it
+    // reaches its own range (see the forward kernel)
     {
         double v = end_vel, sq = 0.0;
         if (active) {
@@ -741,15 +753,26 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
                     const int cx = x / Lc, rx = x - cx * Lc;
                     return __ldg(P + ((size_t)rx * 5 + fld) * NT + cx);
                 };
-                const int s1 = edge_slot(hi, Lc, NT);
-                v = pymin(vf[s1], rec_of(hi + 1, 1));
+                const int len_up = (hi + Lc < steps) ? Lc : steps - hi;    // edges of the column above
+                int wl = warm < len_up ? warm : len_up;
+                if (hi + wl + 2 > D - 1) wl = (D - 1) - hi - 2 > 0 ? (D - 1) - hi - 2 : 0;
+                const int s0 = hi + wl;                                    // sample the guess is made at
+                const int s1 = edge_slot(s0, Lc, NT);
+                v = pymin(vf[s1], rec_of(s0 + 1, 1));
                 double vp1 = end_vel;
-                if (hi + 2 <= D - 1) vp1 = pymin(vf[edge_slot(hi + 1, Lc, NT)], rec_of(hi + 2, 1));
-                const double wp = vp1 * rec_of(hi + 1, 0);
+                if (s0 + 2 <= D - 1) vp1 = pymin(vf[edge_slot(s0 + 1, Lc, NT)], rec_of(s0 + 2, 1));
+                const double wp = vp1 * rec_of(s0 + 1, 0);
                 sq = wp * wp;
+                if (wl > 0) {
+                    // edges s0-1 .. hi of column col+1 (rows wl-1 .. 0); the terms above the first of them are sample s0's
+                    const size_t rw = (size_t)(wl - 1);
+                    bwd_run<NT, RUN_DRY>(P + rw * 5 * NT + col + 1, vf + rw * NT + col + 1, nullptr, hi, wl, rec_of(s0, 0),
+                                         rec_of(s0, 1), rec_of(s0, 2), s_bi, s_acc, n_b, acc0, dec_b, dec_default, w, maa, hw,
+                                         dd, v, sq, false);
+                }
             }
             s_usev[k] = v; s_usew[k] = sq;
-            bwd_run<NT, false>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, dec_b, dec_default,
+            bwd_run<NT, RUN_SWEEP>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, dec_b, dec_default,
                                w, maa, hw, dd, v, sq, false);
         }
         s_endv[k] = v; s_endw[k] = sq;
@@ -758,7 +781,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
 
     // ---- fix-up rounds (states flow from thread k-1 to thread k, as in the forward kernel)
     int rounds = 0;
-    for (int round = 1; round < NT; round++) {
+    for (int round = 1; round < NT && round <= max_rounds; round++) {
         bool need = false;
         double in_v = 0.0, in_w = 0.0;
         if (active && k >= round) {
@@ -769,7 +792,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = bwd_run<NT, true>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0,
+            const bool merged = bwd_run<NT, RUN_RERUN>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0,
                                                   dec_b, dec_default, w, maa, hw, dd, v, sq, same_bits(in_v, s_usev[k]));
             s_usev[k] = in_v; s_usew[k] = in_w;
             if (!merged) { s_endv[k] = v; s_endw[k] = sq; }

@@ -262,7 +262,7 @@ class Engine:
         return vel, ma, bidx, bval, n_ev, t_est
 
     def velocity_chunked(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0,
-                         outs: Optional[dict] = None, after_sample=None):
+                         outs: Optional[dict] = None):
         """S3 + events + S4 + S5, fast path: sample-parallel events, hoisted pre-pass, chunk-speculative passes."""
         B = db.B
         if B > 65535:
@@ -385,7 +385,7 @@ class Engine:
     # ------------------------------------------------------------------ tiled, multi-stream execution
     def _profile_tiled(self, db: DeviceBatch, D_cap: int, T_cap: int, tiles: int, host: "Optional[HostResult]" = None,
                        dense: Optional[torch.Tensor] = None, events: Optional[list] = None,
-                       stagger: bool = False) -> ProfileResult:
+                       stagger: bool = True) -> ProfileResult:
         """The fast path over `tiles` row slices of the batch, each on its own CUDA stream.
 
         The serial chains (time loop, chunked velocity passes) are latency-bound and leave most issue slots idle,
@@ -408,15 +408,16 @@ class Engine:
             k = len(self._streams)
             self._streams.append(torch.cuda.Stream(device=self.device, priority=max(-5, -(5 - min(k, 5)))))
         bounds = [(B * k // tiles, B * (k + 1) // tiles) for k in range(tiles)]
-        sampled = None          # event: the previous tile's sample-parallel front (S0-S3) has been issued and finished
+        sampled = None          # event: the previous tile's throughput-bound front (tables, sampling, velocity passes) is done
         for k, (lo, hi) in enumerate(bounds):
             if hi <= lo:
                 continue
             s = self._streams[k]
             s.wait_stream(main)
             if sampled is not None and stagger:
-                # software pipeline: the throughput-bound front of tile k runs while the latency-bound chains of the
-                # earlier tiles are in flight; early tiles finish (and stream their rows to the host) first
+                # software pipeline: the throughput-bound front of tile k starts when tile k-1 enters its latency-bound
+                # time loop (one thread per path, a few warps per SM), so the two overlap instead of running in lockstep;
+                # early tiles finish (and start streaming their rows to the host) first
                 s.wait_event(sampled)
             sampled = torch.cuda.Event()
             with torch.cuda.stream(s):
@@ -429,9 +430,8 @@ class Engine:
                 t = self.build_lut(sub, g)
                 self.build_props(sub, g, t)
                 outs["status"].copy_(g.status)
-                ev = sampled
-                n_samples, vel, _, _ = self.velocity_chunked(sub, g, t, outs["status"], D_cap, outs=outs,
-                                                             after_sample=lambda: ev.record(s))
+                n_samples, vel, _, _ = self.velocity_chunked(sub, g, t, outs["status"], D_cap, outs=outs)
+                sampled.record(s)
                 outs["status_pre"].copy_(outs["status"])
                 self.time_profile(sub, g, t, outs["status"], D_cap, n_samples, vel, T_cap, outs=outs)
                 if host is not None:
@@ -694,13 +694,15 @@ class GraphedProfile:
             self.host = HostResult(eng, db.B, db.N_max, db.A_max, self.T_cap, self.tiles)
             self.host_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
                             (db.node_attr, db.node_flags, db.n_nodes, db.ap_attr, db.ap_flags, db.n_ap, db.cons)]
+        l0 = eng.launches
         eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles, host=self.host)   # warm the per-stream allocator pools
+        self._launches_warm = eng.launches - l0                # kernels of one step (what a replay launches)
         torch.cuda.synchronize(eng.device)
         del warm
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.res = eng._profile_tiled(db, self.D_cap, self.T_cap, self.tiles, host=self.host)
-        self.launches_per_run = (13 + (2 if to_host else 0)) * self.tiles
+        self.launches_per_run = self._launches_warm
 
     def run(self, new_db: Optional[DeviceBatch] = None, check: bool = True) -> ProfileResult:
         if new_db is not None:
