@@ -203,7 +203,11 @@ int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, c
                      const int32_t* n_samples, const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
                      int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary, int32_t* n_main,
                      double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch, int64_t out_plane_stride,
-                     const int32_t* lut_inv, void* stream);
+                     const int32_t* lut_inv, const double* rden, int64_t n_rden, void* stream);
+/* Optional accelerator of the time loop's lerp (motion_profile_generator.py:349-386 on xs[i] = i*dd, :484): rden[i] =
+ *     1 / (xs[i+1] - xs[i]) for i < n, path-independent (depends on dd only).  With it the loop divides by one
+ *     multiplication and two fused residual corrections (the IEEE quotient, bit for bit); pass NULL to divide directly. */
+int vap_build_lerp_recip(int64_t n, double dd, double* rden, void* stream);
 
 /* S1' QuinticHermiteSpline.get_arc_length (Gauss-Legendre, quintic_hermite_spline.py:592-644) and
  *     get_parameter_by_arc_length (:661-717) for n queries on spline `spl[q]` of path `path[q]`.

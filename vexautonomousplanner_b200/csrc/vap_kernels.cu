@@ -1064,6 +1064,14 @@ extern "C" int vap_build_dgrid(int64_t n, double dd, double* dgrid, void* stream
     return 0;
 }
 
+extern "C" int vap_build_lerp_recip(int64_t n, double dd, double* rden, void* stream)
+{
+    if (n <= 0) return 0;
+    k_build_lerp_recip<<<blocks_for(n, 256), 256, 0, STREAM>>>(n, dd, rden);
+    CHECK_LAUNCH("vap_build_lerp_recip");
+    return 0;
+}
+
 extern "C" int vap_dist_sample(int64_t B, const int32_t* n_nodes, const int32_t* n_splines, int32_t* status,
                                int64_t n_grid, const double* dgrid, int samples, int64_t Q_cap, const double* lut_d,
                                const double* lut_t, const double* total_len, int spn, int64_t P_cap,
@@ -1288,7 +1296,8 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
                                 const double* vel, int64_t T_cap, double* out, int32_t* nodes_map,
                                 int32_t* actions_map, int32_t* n_maps, int32_t* n_out, double* summary,
                                 int32_t* n_main, double* stage, int E_cap, int32_t* seg_tab, int32_t* ev_scratch,
-                                int64_t out_plane_stride, const int32_t* lut_inv, void* stream)
+                                int64_t out_plane_stride, const int32_t* lut_inv, const double* rden, int64_t n_rden,
+                                void* stream)
 {
     (void)ap_flags;
     const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
@@ -1324,7 +1333,7 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
         attr_set = true;
     }
     k_time_state<<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
-                                                                     vel, M_cap, stage, n_main);
+                                                                     vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);
     CHECK_LAUNCH("vap_time_profile/state");
     dim3 grid(blocks_for(M_cap, 256), (unsigned)B);
     k_time_sample<<<grid, 256, 0, STREAM>>>(B, N_max, Am, n_nodes, status, ap_attr, n_ap, seg, first_node, param_end,

@@ -55,7 +55,8 @@ __device__ __forceinline__ double div_const(double a, double b, double r)
 
 #define TS_BLK 128                 // samples per staged block of the velocity row
 #define TS_RING (2 * TS_BLK)       // two blocks resident per thread
-#define TS_STRIDE (TS_RING + 2)    // per-thread ring stride in doubles (16-byte aligned, spreads banks)
+#define TS_STRIDE (2 * TS_RING + 4) // per-thread stride in doubles: velocity ring + reciprocal ring (16-byte aligned, spreads banks)
+#define TS_RDEN (TS_RING + 2)      // offset of the reciprocal ring inside a thread's slice
 
 // index of np.searchsorted(xs, x, side='right') - 1 on xs[i] = fl(i*dd), 32-bit arithmetic
 __device__ __forceinline__ int uniform_index32(double x, double dd, double inv_dd, int D)
@@ -67,13 +68,51 @@ __device__ __forceinline__ int uniform_index32(double x, double dd, double inv_d
     return k;
 }
 
+// reciprocals of the lerp denominators xs[i+1] - xs[i], xs[i] = fl(i*dd) (path-independent, like the distance grid): the
+// time loop divides by them with one multiplication and two residual corrections (div_const) instead of a division.
+// An entry is 0 when the denominator is outside the range where that is proven exact: the step then takes the generic path.
+__global__ void k_build_lerp_recip(long long n, double dd, double* __restrict__ rden)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = (double)(i + 1) * dd - (double)i * dd;
+    const long long bits = __double_as_longlong(d);
+    const bool safe = (d > 1e-150) && (d < 1e150) && ((bits & 0x000FFFFFFFFFFFFFLL) != 0x000FFFFFFFFFFFFFLL);
+    rden[i] = safe ? 1.0 / d : 0.0;
+}
+
+// a / b given r = RN(1/b): one multiplication and two fused residual corrections (see div_const); branch-free.  The caller
+// guarantees 1e-280 < |a| < 1e280 or a == 0 (a zero numerator gives a zero quotient; its sign is not kept).
+__device__ __forceinline__ double div_recip(double a, double b, double r)
+{
+    double q = a * r;
+    q = fma(fma(-b, q, a), r, q);
+    q = fma(fma(-b, q, a), r, q);
+    return q;
+}
+__device__ __forceinline__ bool recip_safe_num(double a)
+{
+    const double aa = fabs(a);
+    return (aa < 1e280) && ((aa > 1e-280) || (a == 0.0));
+}
+
 // A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row is
 // staged through a per-thread shared-memory ring with cp.async two blocks ahead, so the loop never waits on HBM.
+//
+// The kernel runs ONE warp per scheduler with a few paths per warp, so its time is the dependent-instruction latency of a
+// step times the step count of the longest path (measured on B200: 8.2 cycles per dependent DADD/DMUL/DFMA, 18 per
+// double<->int conversion, 29 per shared-memory load, ~100 for an inlined division whose reciprocal refinement sits on the
+// chain, and instructions issue in order, so independent work placed after a stalled instruction does not start early).
+// The common step is therefore written as one straight-line block: the interval index comes from trunc() in the fp domain
+// (no int->double round trip), both lerp divisions and the division by dt use tabulated / hoisted reciprocals (five
+// dependent operations each, no slow-path branch inside the chain), every validity condition of the fast path is
+// evaluated off the chain and tested ONCE; a step that fails the test is redone on the generic path.
 __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
                                                    const int* __restrict__ status, double dt, double dd,
                                                    const double* __restrict__ total_len, long long D_cap,
                                                    const int* __restrict__ n_samples, const double* __restrict__ vel,
-                                                   long long M_cap, double* __restrict__ stage, int* __restrict__ n_main)
+                                                   long long M_cap, double* __restrict__ stage, int* __restrict__ n_main,
+                                                   const double* __restrict__ rden, long long n_rden)
 {
     extern __shared__ __align__(16) double s_ring[];
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,6 +129,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     double* Ao = stage + TS_ACC * plane + (size_t)b * (M_cap + 1);
     double* To = stage + TS_TV * plane + (size_t)b * (M_cap + 1);
     double* ring = s_ring + (size_t)threadIdx.x * TS_STRIDE;
+    if (rden == nullptr) n_rden = 0;                   // no table: the fast path is disabled
     const int nblk = (int)((D_cap + TS_BLK - 1) / TS_BLK);
     auto stage_block = [&](int blk) {          // rows are padded to a multiple of TS_BLK samples by the host
         if (blk < nblk) {
@@ -97,6 +137,12 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
             double* dst = ring + (blk & 1) * TS_BLK;
 #pragma unroll 8
             for (int j = 0; j < TS_BLK; j += 2) cp_async16(dst + j, src + j);
+            if ((long long)(blk + 1) * TS_BLK <= n_rden) {       // the same block of the lerp reciprocals
+                const double* rs = rden + (size_t)blk * TS_BLK;
+                double* rd = dst + TS_RDEN;
+#pragma unroll 8
+                for (int j = 0; j < TS_BLK; j += 2) cp_async16(rd + j, rs + j);
+            }
         }
         cp_async_commit();
     };
@@ -109,11 +155,16 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     const double vlast = vv[D - 1];
     long long k = 0;
     const double hdt = 0.1 * dt;
-    const double dlim = (double)(D - 3);
+    // fast-path index range: i1 <= D-4 (both lerps strictly inside the row) and i1 + 1 inside the reciprocal table
+    const long long nr = (n_rden / TS_BLK) * TS_BLK;    // the reciprocals are staged in whole blocks
+    const long long il = ((long long)D - 3 < nr - 2) ? (long long)D - 3 : nr - 2;
+    const int ilim = il > 0 ? (int)il : 0;             // index clamp (memory safety only)
+    const double dlim = (double)ilim;                  // fast path: 0 <= pos / dd < ilim
     const double ndec = -max_dec;
-    const long long k_limit = 16 * M_cap + 1000000;     // far beyond any terminating profile of this capacity class
+    long long k_limit = 16 * M_cap + 1000000;           // far beyond any terminating profile of this capacity class
+    if (k_limit > VAP_ROW_LIMIT) k_limit = VAP_ROW_LIMIT;
     while (pos < L) {
-        if (k >= k_limit || k >= VAP_ROW_LIMIT) { k = -1; break; }      // diverging loop: report instead of hanging
+        if (k >= k_limit) { k = -1; break; }                           // diverging loop: report instead of hanging
         const bool room = k < M_cap;
         if (room) *P = pos;
         double tv1, tv2;
@@ -122,11 +173,12 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         // definition of np.searchsorted(side='right') - 1), and lerp(pos + dd) is verified to fall in the next interval;
         // anything else (first / last samples, a guess off by one, a position that moved backwards) takes the generic path.
         const double e = pos * inv_dd;
-        const int i1 = (e < dlim) ? __double2int_rz(e) : 0;
-        const double x0 = (double)i1 * dd, x1 = (double)(i1 + 1) * dd, xx2 = (double)(i1 + 2) * dd;
-        const bool fast = (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) & (i1 >= blk_lo * TS_BLK);
-        if (fast) {
-            // Invariant: block blk_lo is complete; block blk_lo+1 is complete unless `pending`.
+        const double ef = trunc(e);
+        int i1 = __double2int_rz(e);                                   // = (int)ef whenever the fast path applies
+        i1 = i1 < 0 ? 0 : (i1 > ilim ? ilim : i1);                      // memory-safe whatever pos is
+        const double x0 = ef * dd, x1 = (ef + 1.0) * dd, xx2 = (ef + 2.0) * dd;      // (double)(i1 + k) == ef + k exactly
+        // Invariant: block blk_lo is complete; block blk_lo+1 is complete unless `pending`.
+        if (i1 + 2 >= (blk_lo + 1) * TS_BLK) {
             if (i1 >= (blk_lo + 1) * TS_BLK) {
                 if (pending) { cp_async_wait<0>(); pending = false; }
                 int adv = 0;
@@ -135,10 +187,17 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 else cp_async_wait<0>();
             }
             if (pending && i1 + 2 >= (blk_lo + 1) * TS_BLK) { cp_async_wait<0>(); pending = false; }
-            const double y0 = ring[i1 & (TS_RING - 1)], y1 = ring[(i1 + 1) & (TS_RING - 1)], y2 = ring[(i1 + 2) & (TS_RING - 1)];
-            tv1 = y0 + div_pos((pos - x0) * (y1 - y0), x1 - x0);
-            tv2 = y1 + div_pos((x2 - x1) * (y2 - y1), xx2 - x1);
-        } else {
+        }
+        // everything below is computed unconditionally (the loads are safe for any index); `fast` collects, off the
+        // dependent chain, every condition under which the values are the reference's
+        const double y0 = ring[i1 & (TS_RING - 1)], y1 = ring[(i1 + 1) & (TS_RING - 1)], y2 = ring[(i1 + 2) & (TS_RING - 1)];
+        const double r1 = ring[TS_RDEN + (i1 & (TS_RING - 1))], r2 = ring[TS_RDEN + ((i1 + 1) & (TS_RING - 1))];
+        const double n1 = (pos - x0) * (y1 - y0), n2 = (x2 - x1) * (y2 - y1);
+        tv1 = y0 + div_recip(n1, x1 - x0, r1);
+        tv2 = y1 + div_recip(n2, xx2 - x1, r2);
+        const bool fast = (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
+                          (i1 >= blk_lo * TS_BLK) & (r1 > 0.0) & (r2 > 0.0) & recip_safe_num(n1) & recip_safe_num(n2);
+        if (!fast) {
             const int j1 = uniform_index32(pos, dd, inv_dd, D);
             const int j2 = uniform_index32(x2, dd, inv_dd, D);
             if (j1 < 0) tv1 = vv[0];
@@ -156,7 +215,10 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         }
         const double tvm = (tv1 + tv2) / 2;
         const double tv = (0.001 > tvm) ? 0.001 : tvm;                 // max(tvm, 0.001)
-        double accel = div_const(tv - v, dt, inv_dt);
+        const double da = tv - v;
+        double accel = div_recip(da, dt, inv_dt);
+        if (!recip_safe_num(da)) accel = div_pos(da, dt);              // tiny / huge / non-finite numerators (never on sane input)
+        accel = (da == 0.0) ? da : accel;
         accel = (accel > ndec) ? accel : ndec;                         // np.clip(accel, -max_dec, max_acc)
         accel = (accel < max_acc) ? accel : max_acc;
         double vn = v + accel * dt;

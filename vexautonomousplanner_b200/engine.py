@@ -140,6 +140,7 @@ class Engine:
             raise ValueError("time_impl must be 'split' or 'serial'")
         self.time_impl = time_impl
         self._dgrid: Optional[torch.Tensor] = None
+        self._rden: Optional[torch.Tensor] = None
         self._plan: Dict[tuple, tuple] = {}
         self._streams: list = []
         self._host_slots: Dict[int, list] = {}
@@ -177,6 +178,16 @@ class Engine:
             self.launches += 1
             self._dgrid = g
         return self._dgrid
+
+    def lerp_recip(self, n: int) -> torch.Tensor:
+        """1 / (xs[i+1] - xs[i]) on xs[i] = fl(i*dd) (the time loop's lerp denominators), cached and grown geometrically."""
+        if self._rden is None or self._rden.numel() < n:
+            m = max(int(n * 1.5), 1 << 14)
+            r = self._empty((m,))
+            _lib.check(self.lib.vap_build_lerp_recip(C.c_int64(m), C.c_double(self.dd), _p(r), self._stream()), "vap_build_lerp_recip")
+            self.launches += 1
+            self._rden = r
+        return self._rden
 
     # ------------------------------------------------------------------ stages
     def build_geometry(self, db: DeviceBatch, with_params: bool = False) -> Geometry:
@@ -366,6 +377,7 @@ class Engine:
             n_out = self._empty((B,), torch.int32)
             summary = self._empty((B, 5))
             n_main = self._empty((B,), torch.int32)
+        rden = self.lerp_recip(D_cap + 2)
         stage = self._empty((8, B, T_cap + 1))
         seg_tab = self._empty((3 * B * E_cap + B,), torch.int32)
         nscr = int(self.lib.vap_event_scratch_ints(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max)))
@@ -377,7 +389,7 @@ class Engine:
             _p(t.lut_d), _p(t.lut_t), _p(t.total_len), C.c_int(t.spn), C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h),
             C.c_int64(D_cap), _p(n_samples), _p(vel), C.c_int64(T_cap), _p(out), _p(nodes_map), _p(actions_map), _p(n_maps),
             _p(n_out), _p(summary), _p(n_main), _p(stage), C.c_int(E_cap), _p(seg_tab), _p(scr), C.c_int64(plane_stride),
-            _p(t.lut_inv), self._stream()), "vap_time_profile")
+            _p(t.lut_inv), _p(rden), C.c_int64(rden.numel()), self._stream()), "vap_time_profile")
         self.launches += 4
         self._n_main = n_main
         return out, nodes_map, actions_map, n_maps, n_out, summary
@@ -401,7 +413,8 @@ class Engine:
                      n_out=self._empty((B,), torch.int32), summary=self._empty((B, 5)), n_main=self._empty((B,), torch.int32),
                      n_samples=self._empty((B,), torch.int32), vel=self._empty((B, D_cap)),
                      status=self._empty((B,), torch.int32), status_pre=self._empty((B,), torch.int32))
-        self.dgrid(D_cap + 2)                      # make sure the shared grid exists before the side streams read it
+        self.dgrid(D_cap + 2)                      # make sure the shared tables exist before the side streams read them
+        self.lerp_recip(D_cap + 2)
         while len(self._streams) < tiles:
             # earlier tiles get higher stream priority, so that they finish (and start streaming their rows to the host)
             # while later tiles still compute, instead of all tiles finishing together
