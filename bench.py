@@ -240,7 +240,7 @@ def run_b200(args):
     hstate = None
     e2e_ms = []
     if args.e2e_mode == "stream":
-        # K batches through the 2-deep pipeline of Engine.stream_to_host (fill and drain inside the timed region)
+        # K batches through the 3-deep pipeline of Engine.stream_to_host (fill and drain inside the timed region)
         for hres in eng.stream_to_host([packed] * 3, tiles=args.e2e_tiles):
             pass
         torch.cuda.synchronize()
@@ -278,11 +278,11 @@ def run_b200(args):
                                  packed.n_ap, packed.cons))
     e2e = {"value": world * B / (e2e_step_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": hres.bytes_per_step(), "ms_per_step": e2e_step_ms,
-           "how": (f"host numpy node tables -> pinned -> device, {args.e2e_tiles} tiles on separate streams, dense result "
+           "how": (f"host numpy node tables -> pinned -> device, {args.e2e_tiles} tile(s), dense result "
                    "rows " + ("written to pinned host memory by the pack kernels inside one CUDA graph"
                               if g2h is not None else "packed on the device and moved by the copy engine tile by tile")
-                   + (f"; {args.steps} batches streamed through a 2-deep pipeline (batch n+1 computes while batch n crosses "
-                      "PCIe), wall clock of the whole stream incl. fill and drain / batches"
+                   + (f"; {args.steps} batches streamed through a 3-deep pipeline (batch n+1 computes and batch n+2 is enqueued "
+                      "while batch n crosses PCIe), wall clock of the whole stream incl. fill and drain / batches"
                       if args.e2e_mode == "stream" else ", one batch at a time, wall clock incl. the final sync"))}
 
     cpu = None
@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=32, help="speculative chunks per path in the velocity passes")
     ap.add_argument("--tiles", type=int, default=1, help="row tiles of the batch, one CUDA stream each")
     ap.add_argument("--e2e-mode", default="stream", choices=["stream", "copy", "graph"])
-    ap.add_argument("--e2e-tiles", type=int, default=2, help="tiles of the end-to-end (host in / host out) run")
+    ap.add_argument("--e2e-tiles", type=int, default=1, help="tiles of the end-to-end (host in / host out) run")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -516,8 +516,9 @@ class Engine:
         self._profile_tiled(db, st["D_cap"], st["T_cap"], st["tiles"], host=st["host"], dense=st["dense"],
                             events=st["events"], stagger=True)
 
-    def _host_collect(self, st: dict) -> "HostResult":
-        """As each tile's row count reaches the host, let the copy engine move exactly those bytes; wait for all."""
+    def _host_issue_d2h(self, st: dict) -> None:
+        """As each tile's row count reaches the host, queue the copy of exactly those bytes on the copy stream (the copy
+        engine is the bottleneck of the host-out path: nothing else may delay these enqueues)."""
         host, T_cap, cs = st["host"], st["T_cap"], st["copy_stream"]
         for k, (lo, hi) in enumerate(host.bounds):
             if hi <= lo:
@@ -527,9 +528,19 @@ class Engine:
             a = 8 * lo * T_cap
             with torch.cuda.stream(cs):
                 host.packed[a: a + 8 * total].copy_(st["dense"][a: a + 8 * total], non_blocking=True)
-        cs.synchronize()
+        if st.get("d2h_done") is None:
+            st["d2h_done"] = torch.cuda.Event()
+        st["d2h_done"].record(cs)
+
+    def _host_wait(self, st: dict) -> "HostResult":
+        st["d2h_done"].synchronize()
+        host = st["host"]
         host.state = st
         return host
+
+    def _host_collect(self, st: dict) -> "HostResult":
+        self._host_issue_d2h(st)
+        return self._host_wait(st)
 
     def profile_to_host(self, packed: PackedPaths, tiles: int = 8, state: Optional[dict] = None) -> "HostResult":
         """Host buffers in, host buffers out: every tile packs its valid rows densely on the device; as soon as a tile's
@@ -545,28 +556,39 @@ class Engine:
             return self.profile_to_host(packed, tiles, st)
         return host
 
-    def stream_to_host(self, batches, tiles: int = 4, depth: int = 2):
+    def stream_to_host(self, batches, tiles: int = 4, depth: int = 3):
         """Bulk jobs: a generator over HostResults for an iterable of same-shape PackedPaths batches, software-pipelined
-        `depth` deep -- batch n+1's kernels are already in flight while batch n's rows cross PCIe.  A yielded HostResult
-        stays valid until `depth` more batches have been submitted."""
+        three deep: while batch n's rows cross PCIe, batch n+1's kernels run and batch n+2 is being enqueued.  The copy
+        engine is the bottleneck, so the order per step is: enqueue the next batch's kernels, queue the device -> host copy
+        of the batch that just finished computing, and only then wait for the copy before it -- the copy stream never runs
+        dry behind host-side launch work.  A yielded HostResult is valid until the generator is advanced."""
+        depth = max(int(depth), 3)
         slots = self._host_slots.setdefault(depth, [None] * depth)   # pinned buffers are expensive: kept across calls
-        inflight = []                                            # (slot index, batch) in submission order
+        submitted, copying = [], []                              # (slot index, batch): kernels in flight / copy in flight
         n = 0
         for packed in batches:
             k = n % depth
-            if len(inflight) == depth:                           # the slot is still owned by an older batch: finish it
-                ks, pk = inflight.pop(0)
-                yield self._finish_streamed(slots, ks, pk, tiles)
             slots[k] = self._host_state(packed, tiles, slots[k])
             self._host_submit(packed, slots[k])
-            inflight.append((k, packed))
+            submitted.append((k, packed))
             n += 1
-        while inflight:
-            ks, pk = inflight.pop(0)
+            while len(submitted) > 1:
+                ks, pk = submitted.pop(0)
+                self._host_issue_d2h(slots[ks])
+                copying.append((ks, pk))
+            while len(copying) > 1:
+                ks, pk = copying.pop(0)
+                yield self._finish_streamed(slots, ks, pk, tiles)
+        while submitted:
+            ks, pk = submitted.pop(0)
+            self._host_issue_d2h(slots[ks])
+            copying.append((ks, pk))
+        while copying:
+            ks, pk = copying.pop(0)
             yield self._finish_streamed(slots, ks, pk, tiles)
 
     def _finish_streamed(self, slots, k, packed, tiles):
-        host = self._host_collect(slots[k])
+        host = self._host_wait(slots[k])
         if bool((host.status == ST_CAPACITY).any()):             # rare: plan too small -> exact, unpipelined redo
             host = self.profile_to_host(packed, tiles, None)
         return host
