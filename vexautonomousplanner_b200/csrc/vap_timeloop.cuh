@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     if (k_limit > VAP_ROW_LIMIT) k_limit = VAP_ROW_LIMIT;
     while (pos < L) {
         if (k >= k_limit) { k = -1; break; }                           // diverging loop: report instead of hanging
-        const bool room = k < M_cap;
-        if (room) *P = pos;
+        // rows have M_cap + 1 slots: steps beyond the capacity (the path is then re-run with a larger one) all land in the
+        // last slot, so the stores need no predicate
+        const long long ks = k < M_cap ? k : M_cap;
+        P[ks] = pos;
         double tv1, tv2;
         const double x2 = pos + dd;
         // Fast path: the interval index is guessed as trunc(pos / dd) and VERIFIED against xs[i] = fl(i*dd) (that is the
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         tv1 = y0 + div_recip(n1, x1 - x0, r1);
         tv2 = y1 + div_recip(n2, xx2 - x1, r2);
         const bool fast = (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
-                          (i1 >= blk_lo * TS_BLK) & (r1 > 0.0) & (r2 > 0.0) & recip_safe_num(n1) & recip_safe_num(n2);
+                          (i1 >= blk_lo * TS_BLK) & (r1 * r2 > 0.0) & recip_safe_num(n1) & recip_safe_num(n2);
         if (!fast) {
             const int j1 = uniform_index32(pos, dd, inv_dd, D);
             const int j2 = uniform_index32(x2, dd, inv_dd, D);
@@ -227,11 +229,11 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         const double half = 0.5 * accel * dt * dt;
         const double dpos = ((v <= 0.1) ? hdt : v * dt) + half;
         pos += dpos;
-        if (room) { *Vo = v; *Ao = accel; *To = tv; P++; Vo++; Ao++; To++; }
+        Vo[ks] = v; Ao[ks] = accel; To[ks] = tv;
         k++;
     }
     cp_async_wait<0>();
-    if (k >= 0 && k <= M_cap) *P = pos;
+    if (k >= 0 && k <= M_cap) P[k] = pos;
     n_main[b] = (int)(k > 2147483647LL ? 2147483647LL : k);      // -1: diverged
 }
 
