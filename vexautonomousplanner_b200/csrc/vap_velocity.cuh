@@ -282,26 +282,31 @@ __global__ void __launch_bounds__(256) k_prepass(
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
     const int steps = D - 1;
-    if (steps <= 0) return;
-    const int Lc = chunk_len(steps, NT);
+    const int sh = 31 - __clz(NT);                   // NT is a power of two: every index split below is a shift
+    const int Lc = (steps + NT - 1) >> sh;           // chunk_len(steps, NT)
     const int j0 = blockIdx.x * blockDim.x;
-    if (j0 >= Lc * NT) return;
+    if (steps <= 0 || j0 >= (Lc << sh)) return;
     // kappa / theta of this CTA's slots: rows s0 .. s0+RW-1 of every column plus the row after them, fetched with the lanes
     // running ALONG a column (contiguous samples) into shared memory
     const double* kr = kap + (size_t)b * D_cap;
     const double* tr = th + (size_t)b * D_cap;
-    const int sh = 31 - __clz(NT);                   // NT is a power of two
-    const int RW = blockDim.x >> sh;                 // rows per CTA
+    const int rsh = 8 - sh;                          // blockDim.x == 256: RW = 256 / NT rows per CTA
+    const int RW = 1 << rsh;
     const int st = (RW + 1) | 1;                     // odd tile stride
     double* t_th = s_tile;
     double* t_k = t_th + NT * st;
     const int s0 = j0 >> sh;
-    for (int q = threadIdx.x; q < NT * (RW + 1); q += blockDim.x) {
-        const int cc = q / (RW + 1), r = q - cc * (RW + 1);
+    {
+        const int cc = threadIdx.x >> rsh, r = threadIdx.x & (RW - 1);
         int ee = cc * Lc + s0 + r;
         ee = ee > D - 1 ? D - 1 : ee;
         t_th[cc * st + r] = tr[ee];
-        if (r < RW) t_k[cc * st + r] = kr[ee];
+        t_k[cc * st + r] = kr[ee];
+        if (threadIdx.x < NT) {                      // the halo row
+            int eh = threadIdx.x * Lc + s0 + RW;
+            eh = eh > D - 1 ? D - 1 : eh;
+            t_th[threadIdx.x * st + RW] = tr[eh];
+        }
     }
     __syncthreads();
     const int j = j0 + threadIdx.x;
