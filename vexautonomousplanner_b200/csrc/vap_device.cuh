@@ -313,8 +313,8 @@ __device__ __forceinline__ double distance_to_time32(const double* __restrict__ 
 }
 
 // ---- inverse index of the distance table ("which LUT interval does distance d fall in", in O(1)) ----------------------
-// Row layout (int32): [0..1] the bits of scale = Q / total_length, [2 + m] = a LUT index at or just below
-// searchsorted(distances, m / scale) for m = 0 .. Q.  The index only seeds the search: the result is verified against the
+// Row layout (int32): [0..1] the bits of scale = Q / total_length, [2 + m] = searchsorted(distances, m / scale) for
+// m = 0 .. Q (the lower edge of bucket m).  The index only seeds the search: the result is verified against the
 // table in both directions, so it is exactly np.searchsorted(distances, d) (side='left') whatever the seed.
 #define LUT_INV_HDR 2
 __device__ __forceinline__ double distance_to_time_inv(const double* __restrict__ ld, const double* __restrict__ lt,

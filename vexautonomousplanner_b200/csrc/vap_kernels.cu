@@ -380,8 +380,7 @@ __global__ void __launch_bounds__(256) k_build_lut_index(const int* __restrict__
         const double x = (scale > 0.0) ? (double)m / scale : 0.0;
         int lo = 0, hi = Q;
         while (lo < hi) { int mid = (lo + hi) >> 1; if (ld[mid] < x) lo = mid + 1; else hi = mid; }
-        lo -= 1;                                         // one below: absorbs the rounding of m = trunc(d * scale)
-        row[LUT_INV_HDR + m] = lo < 0 ? 0 : (lo > Q - 1 ? Q - 1 : lo);
+        row[LUT_INV_HDR + m] = lo > Q - 1 ? Q - 1 : lo;       // exact for the bucket's lower edge; the lookup verifies both ways
     }
 }
 
