@@ -218,21 +218,24 @@ def run_b200(args):
     dom = max(stage_ms, key=stage_ms.get)
     achieved = stage_bytes[dom] / 1e9 / (stage_ms[dom] * 1e-3)
     total_bytes = sum(stage_bytes.values())
-    # measured DRAM traffic of the dominant stage from the committed ncu capture (profiles/, same workload), if present
-    traffic = None
+    # measured DRAM traffic of the dominant stage from the committed ncu capture (profiles/, same workload), if present,
+    # and what ncu measured per kernel (real DRAM bytes, not the algorithmic model) next to it
+    traffic, ncu_kernels, prof_name = None, None, "profiles/r01b_kernel_table.json"
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_kernel_table.json")) as f:
+        with open(os.path.join(ROOT, prof_name)) as f:
             prof = json.load(f)
         if (B, N) == (4096, 8):
             traffic = prof["stages"][dom]["dram_bytes_per_step"]
+            ncu_kernels = {k: {"ms": v["ms"], "dram_GBps": v["dram_GBps"], "dram_frac_of_peak": round(v["dram_GBps"] / peak, 3),
+                               "fp64_pipe_pct": v["fp64_pipe_pct"]} for k, v in prof["kernels"].items() if v["ms"] >= 0.05}
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "traffic_source": "profiles/r01_kernel_table.json (ncu dram__bytes_read+write, sum over the stage's kernels)",
+                "traffic_source": prof_name + " (ncu dram__bytes_read+write, sum over the stage's kernels)",
                 "whole_step": {"alg_GB": total_bytes / 1e9, "GBps": total_bytes / 1e9 / (ms_per_step * 1e-3),
                                "frac": total_bytes / 1e9 / (ms_per_step * 1e-3) / peak},
-                "stages": stages}
+                "stages": stages, "ncu_kernels": ncu_kernels}
 
     # ---------------- end to end through the public API with HOST buffers (h2d + d2h inside the timed region):
     # numpy node tables on the host -> Engine -> every output stream of every path back in (pinned) host memory
