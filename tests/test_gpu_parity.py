@@ -324,6 +324,31 @@ def test_recip_division_is_ieee():
     assert int(bad.item()) == 0
 
 
+def test_accelerators_do_not_change_bits():
+    """The inverse LUT index (seeded searchsorted) and the tabulated lerp reciprocals are pure accelerators: with NULL passed
+    for both, the kernels fall back to the binary search / the plain divisions and must produce the same bits."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    fast = Engine("cuda:0")
+    plain = Engine("cuda:0", accelerators=False)
+    for packed in (synth.random_paths(300, 8, seed=31), synth.mixed_paths(200, 8, seed=32), synth.random_paths(40, 16, seed=33)):
+        a = fast.profile(fast.upload(packed), keep=True)
+        b = plain.profile(plain.upload(packed), keep=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a.n_out, b.n_out) and torch.equal(a.status, b.status) and torch.equal(a.n_samples, b.n_samples)
+        D = a.n_samples.long()
+        md = torch.arange(a.vel.shape[1], device=D.device)[None, :] < D[:, None]
+        for name in ("t", "kap", "th"):
+            assert torch.equal(a.extra[name][md].view(torch.int64), b.extra[name][md].view(torch.int64)), name
+        assert torch.equal(a.vel[md].view(torch.int64), b.vel[md].view(torch.int64))
+        n = a.n_out.long()
+        Tm = min(a.T_cap, b.T_cap)
+        mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+        for i in range(8):
+            assert torch.equal(a.out[i][:, :Tm][mt].view(torch.int64), b.out[i][:, :Tm][mt].view(torch.int64)), i
+        assert torch.equal(a.summary.view(torch.int64), b.summary.view(torch.int64))
+
+
 def test_tiled_multistream_equals_untiled():
     """Row tiles on separate CUDA streams must give the same bits as one pass over the batch."""
     from vexautonomousplanner_b200 import synth

@@ -125,7 +125,7 @@ class Engine:
 
     def __init__(self, device="cuda:0", dt: float = 0.01, dd: float = 0.005, lut_samples: int = 1000,
                  samples_per_node: int = 1000, start_vel: float = 0.01, end_vel: float = 0.01,
-                 velocity_impl: str = "chunked", chunks: int = 32, time_impl: str = "split"):
+                 velocity_impl: str = "chunked", chunks: int = 32, time_impl: str = "split", accelerators: bool = True):
         if not torch.cuda.is_available():
             raise _lib.VapError("no CUDA device: vexautonomousplanner_b200 has no CPU fallback")
         self.lib = _lib.lib()
@@ -139,6 +139,9 @@ class Engine:
         if time_impl not in ("split", "serial"):
             raise ValueError("time_impl must be 'split' or 'serial'")
         self.time_impl = time_impl
+        # accelerators=False passes NULL for the inverse LUT index and the lerp reciprocals (binary search / plain division
+        # instead: same bits, slower); tests use it to pin the equivalence
+        self.accelerators = bool(accelerators)
         self._dgrid: Optional[torch.Tensor] = None
         self._rden: Optional[torch.Tensor] = None
         self._plan: Dict[tuple, tuple] = {}
@@ -296,7 +299,8 @@ class Engine:
                 C.c_int64(grid.numel()), _p(grid), C.c_int(t.samples), C.c_int64(t.Q_cap), _p(t.lut_d), _p(t.lut_t),
                 _p(t.total_len), C.c_int(t.spn), C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h), C.c_int64(D_cap),
                 _p(n_samples), _p(tq), _p(kap), _p(th), C.c_int(E_cap), _p(ma), _p(bidx), _p(bval), _p(n_ev), _p(vr_idx),
-                _p(vr_val), _p(st_idx), _p(n_vr), C.c_double(self.dt), _p(ins_est), _p(scr), _p(t.lut_inv), self._stream()),
+                _p(vr_val), _p(st_idx), _p(n_vr), C.c_double(self.dt), _p(ins_est), _p(scr),
+                _p(t.lut_inv if self.accelerators else None), self._stream()),
                 "vap_dist_sample_events")
             self.launches += 3
         chunks = self.chunks if D_cap <= 65536 else 256
@@ -389,7 +393,8 @@ class Engine:
             _p(t.lut_d), _p(t.lut_t), _p(t.total_len), C.c_int(t.spn), C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h),
             C.c_int64(D_cap), _p(n_samples), _p(vel), C.c_int64(T_cap), _p(out), _p(nodes_map), _p(actions_map), _p(n_maps),
             _p(n_out), _p(summary), _p(n_main), _p(stage), C.c_int(E_cap), _p(seg_tab), _p(scr), C.c_int64(plane_stride),
-            _p(t.lut_inv), _p(rden), C.c_int64(rden.numel()), self._stream()), "vap_time_profile")
+            _p(t.lut_inv if self.accelerators else None), _p(rden if self.accelerators else None), C.c_int64(rden.numel()),
+            self._stream()), "vap_time_profile")
         self.launches += 4
         self._n_main = n_main
         return out, nodes_map, actions_map, n_maps, n_out, summary
