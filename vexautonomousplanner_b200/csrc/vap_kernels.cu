@@ -1324,10 +1324,10 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     int lanes = (int)((B + 591) / 592);
     if (const char* ev = getenv("VAP_STATE_LANES")) lanes = atoi(ev);
     lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
-    const size_t ring_bytes = (size_t)lanes * TS_STRIDE * sizeof(double);
+    const size_t ring_bytes = (size_t)lanes * (TS_STRIDE * sizeof(double) + 16);     // rings + two mbarriers per path
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * TS_STRIDE * sizeof(double)));
+        cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * (TS_STRIDE * sizeof(double) + 16)));
         if (ea != cudaSuccess) return set_err("vap_time_profile/attr", ea);
         attr_set = true;
     }

@@ -68,6 +68,33 @@ __device__ __forceinline__ int uniform_index32(double x, double dd, double inv_d
     return k;
 }
 
+// ---- TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): one instruction moves a whole 1 KB
+// block of a thread's ring, instead of 64 LDGSTS.  Every thread owns its two barriers (one per ring slot).
+__device__ __forceinline__ void mbar_init(unsigned a, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(a), "r"(parity) : "memory");
+}
+
 // reciprocals of the lerp denominators xs[i+1] - xs[i], xs[i] = fl(i*dd) (path-independent, like the distance grid): the
 // time loop divides by them with one multiplication and two residual corrections (div_const) instead of a division.
 // An entry is 0 when the denominator is outside the range where that is proven exact: the step then takes the generic path.
@@ -96,8 +123,9 @@ __device__ __forceinline__ bool recip_safe_num(double a)
     return (aa < 1e280) && ((aa > 1e-280) || (a == 0.0));
 }
 
-// A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row is
-// staged through a per-thread shared-memory ring with cp.async two blocks ahead, so the loop never waits on HBM.
+// A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row (and the lerp
+// reciprocals) are staged through a per-thread shared-memory ring by TMA bulk copies two 128-sample blocks ahead, so the loop
+// never waits on HBM.
 //
 // The kernel runs ONE warp per scheduler with a few paths per warp, so its time is the dependent-instruction latency of a
 // step times the step count of the longest path (measured on B200: 8.2 cycles per dependent DADD/DMUL/DFMA, 18 per
@@ -115,6 +143,12 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                                                    const double* __restrict__ rden, long long n_rden)
 {
     extern __shared__ __align__(16) double s_ring[];
+    // this thread's two mbarriers (one per ring slot) live behind the rings
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(s_ring + (size_t)blockDim.x * TS_STRIDE + 2 * threadIdx.x);
+    mbar_init(mb, 1);
+    mbar_init(mb + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     if (status[b] != ST_OK) { n_main[b] = 0; return; }
@@ -129,28 +163,35 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     double* Ao = stage + TS_ACC * plane + (size_t)b * (M_cap + 1);
     double* To = stage + TS_TV * plane + (size_t)b * (M_cap + 1);
     double* ring = s_ring + (size_t)threadIdx.x * TS_STRIDE;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     if (rden == nullptr) n_rden = 0;                   // no table: the fast path is disabled
     const int nblk = (int)((D_cap + TS_BLK - 1) / TS_BLK);
-    auto stage_block = [&](int blk) {          // rows are padded to a multiple of TS_BLK samples by the host
-        if (blk < nblk) {
-            const double* src = vv + (size_t)blk * TS_BLK;
-            double* dst = ring + (blk & 1) * TS_BLK;
-#pragma unroll 8
-            for (int j = 0; j < TS_BLK; j += 2) cp_async16(dst + j, src + j);
-            if ((long long)(blk + 1) * TS_BLK <= n_rden) {       // the same block of the lerp reciprocals
-                const double* rs = rden + (size_t)blk * TS_BLK;
-                double* rd = dst + TS_RDEN;
-#pragma unroll 8
-                for (int j = 0; j < TS_BLK; j += 2) cp_async16(rd + j, rs + j);
-            }
+    unsigned phase = 0, pend = 0;                      // per slot: parity to wait for / a copy is in flight
+    auto wait_slot = [&](int sl) {
+        if ((pend >> sl) & 1u) {
+            mbar_wait(mb + 8 * sl, (phase >> sl) & 1u);
+            phase ^= 1u << sl;
+            pend &= ~(1u << sl);
         }
-        cp_async_commit();
     };
-    int blk_lo = 0;                             // blocks blk_lo and blk_lo+1 are resident
-    bool pending = false;
+    auto stage_block = [&](int blk) {          // rows are padded to a multiple of TS_BLK samples by the host
+        const int sl = blk & 1;
+        wait_slot(sl);                          // never two copies in flight on one barrier
+        if (blk < nblk) {
+            const bool with_r = (long long)(blk + 1) * TS_BLK <= n_rden;      // the same block of the lerp reciprocals
+            const unsigned bytes = TS_BLK * sizeof(double);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier reads of the slot precede the TMA writes
+            mbar_expect_tx(mb + 8 * sl, with_r ? 2 * bytes : bytes);
+            bulk_g2s(ring_s + sl * bytes, vv + (size_t)blk * TS_BLK, bytes, mb + 8 * sl);
+            if (with_r) bulk_g2s(ring_s + TS_RDEN * sizeof(double) + sl * bytes, rden + (size_t)blk * TS_BLK, bytes, mb + 8 * sl);
+            pend |= 1u << sl;
+        }
+    };
+    int blk_lo = 0;                             // blocks blk_lo and blk_lo+1 are resident (or in flight: `pend`)
     stage_block(0);
     stage_block(1);
-    cp_async_wait<0>();
+    wait_slot(0);
+    wait_slot(1);
     double pos = 0.0, v = vv[0];
     const double vlast = vv[D - 1];
     long long k = 0;
@@ -179,16 +220,13 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         int i1 = __double2int_rz(e);                                   // = (int)ef whenever the fast path applies
         i1 = i1 < 0 ? 0 : (i1 > ilim ? ilim : i1);                      // memory-safe whatever pos is
         const double x0 = ef * dd, x1 = (ef + 1.0) * dd, xx2 = (ef + 2.0) * dd;      // (double)(i1 + k) == ef + k exactly
-        // Invariant: block blk_lo is complete; block blk_lo+1 is complete unless `pending`.
+        // Invariant: block blk_lo is complete; block blk_lo+1 is complete unless its slot is still pending.
         if (i1 + 2 >= (blk_lo + 1) * TS_BLK) {
             if (i1 >= (blk_lo + 1) * TS_BLK) {
-                if (pending) { cp_async_wait<0>(); pending = false; }
-                int adv = 0;
-                while (i1 >= (blk_lo + 1) * TS_BLK) { blk_lo++; stage_block(blk_lo + 1); adv++; }
-                if (adv == 1) pending = true;          // the block after the current one streams in behind us
-                else cp_async_wait<0>();
+                while (i1 >= (blk_lo + 1) * TS_BLK) { blk_lo++; stage_block(blk_lo + 1); }
+                wait_slot(blk_lo & 1);                   // the block the position is in now
             }
-            if (pending && i1 + 2 >= (blk_lo + 1) * TS_BLK) { cp_async_wait<0>(); pending = false; }
+            if (i1 + 2 >= (blk_lo + 1) * TS_BLK) wait_slot((blk_lo + 1) & 1);
         }
         // everything below is computed unconditionally (the loads are safe for any index); `fast` collects, off the
         // dependent chain, every condition under which the values are the reference's
@@ -232,7 +270,8 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         Vo[ks] = v; Ao[ks] = accel; To[ks] = tv;
         k++;
     }
-    cp_async_wait<0>();
+    wait_slot(0);                                // no TMA write may be in flight when the CTA's shared memory is released
+    wait_slot(1);
     if (k >= 0 && k <= M_cap) P[k] = pos;
     n_main[b] = (int)(k > 2147483647LL ? 2147483647LL : k);      // -1: diverged
 }
