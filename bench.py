@@ -195,16 +195,23 @@ def run_b200(args):
     value = world * B / (ms_per_step * 1e-3)
     assert bool((res.status == 0).all().item())
 
-    # ---------------- per-stage device times (separate pass, same command, CUDA events on the launch stream)
-    eng.stage_events = []
-    for _ in range(args.steps):
-        flush.zero_()
-        res = eng.profile(db, reuse_plan=True)
+    # ---------------- per-stage device times (separate eager pass, same command, CUDA events on the launch stream).
+    # One untimed eager step first (it fills the allocator pools of the eager path); per stage the MEDIAN over the steps,
+    # because these intervals also contain host-side launch gaps (a graph replay has none).
+    eng.profile(db, reuse_plan=True)
     torch.cuda.synchronize()
-    stage_ms = {}
-    for name, s, e in eng.stage_events:
-        stage_ms[name] = stage_ms.get(name, 0.0) + s.elapsed_time(e) / args.steps
+    per_step = []
+    for _ in range(max(args.steps, 3)):
+        flush.zero_()
+        eng.stage_events = []
+        res = eng.profile(db, reuse_plan=True)
+        torch.cuda.synchronize()
+        acc = {}
+        for name, s, e in eng.stage_events:
+            acc[name] = acc.get(name, 0.0) + s.elapsed_time(e)
+        per_step.append(acc)
     eng.stage_events = None
+    stage_ms = {k: float(np.median([a[k] for a in per_step])) for k in per_step[0]}
     # algorithmic bytes per stage: 8 B per fp64 element, each array once per stage that must touch it
     Dsum = float(res.n_samples.double().sum().item())
     Tsum = float(res.n_out.double().sum().item())
