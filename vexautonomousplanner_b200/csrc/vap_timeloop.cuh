@@ -294,7 +294,7 @@ __global__ void k_test_div_const(long long n, unsigned long long seed, double b,
 }
 
 // B1: per-step lookups + event candidates
-__global__ void __launch_bounds__(256) k_time_sample(
+__global__ void __launch_bounds__(256, 8) k_time_sample(
     long long B, int N_max, int A_max, const int* __restrict__ n_nodes, const int* __restrict__ status,
     const double* __restrict__ ap_attr, const int* __restrict__ n_ap, const double* __restrict__ seg,
     const int* __restrict__ first_node, const double* __restrict__ param_end, const int* __restrict__ n_splines,

@@ -23,7 +23,7 @@ __device__ __forceinline__ double4 ldg_d4(const double4* p)
 // ---- S3 (parallel): t, kappa, theta per distance sample + event candidates -----------------------------------
 // wrap candidates: samples with frac(t[i-1]) > frac(t[i]) and t[i] < N-1  (motion_profile_generator.py:124)
 // action candidates: samples with t[i-1] < ap.t <= t[i]                   (:142-146)
-__global__ void __launch_bounds__(256) k_dist_sample_ev(
+__global__ void __launch_bounds__(256, 8) k_dist_sample_ev(
     int N_max, int A_max, const int* __restrict__ n_nodes, const int* __restrict__ n_splines,
     const int* __restrict__ status, const double* __restrict__ ap_attr, const int* __restrict__ n_ap,
     const double* __restrict__ dgrid, int samples, long long Q_cap, const double* __restrict__ lut_d,
@@ -273,7 +273,7 @@ __device__ __forceinline__ SampleTerms prepass_sample(double V, double A0, doubl
     return t;
 }
 
-__global__ void __launch_bounds__(256) k_prepass(
+__global__ void __launch_bounds__(256, 8) k_prepass(
     const int* __restrict__ status, const double* __restrict__ cons, long long D_cap, const int* __restrict__ n_samples,
     const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec)
 {
