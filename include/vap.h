@@ -141,7 +141,8 @@ int vap_fwd_bwd(int64_t B, int N_max, int A_max, const double* node_attr, const 
 /* v2 of S3 + S4 + S5 (same results, bit for bit, as vap_dist_sample + vap_fwd_bwd; this is the fast path).
  *   vap_dist_sample_events: distance sampling plus sample-parallel event detection and a per-path replay of the
  *     sampling loop's event logic (motion_profile_generator.py:93-176).  Adds the initial-velocity regimes
- *     vr_idx/vr_val[B][E_cap], the stop samples st_idx[B][E_cap] and n_vr[B][2].  ev_scratch: i32 scratch of
+ *     vr_idx/vr_val[B][E_cap], the stop samples st_idx[B][E_cap] and n_vr[B][2].  t may be NULL (the parameters
+ *     are not needed downstream).  ev_scratch: i32 scratch of
  *     vap_event_scratch_ints(B, N_max, A_max) elements.  ins_est[B] f32: rows the time stage will insert for
  *     waits / turn profiles (sizing only).
  *   vap_fwd_bwd_chunked: pre-pass that hoists everything of a step that depends neither on the velocity state nor on

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     wait_slot(1);
     double pos = 0.0, v = vv[0];
     const double vlast = vv[D - 1];
-    long long k = 0;
+    int k = 0;                                          // 32-bit: the row limit is far below 2^31
     const double hdt = 0.1 * dt;
     // fast-path index range: i1 <= D-4 (both lerps strictly inside the row) and i1 + 1 inside the reciprocal table
     const long long nr = (n_rden / TS_BLK) * TS_BLK;    // the reciprocals are staged in whole blocks
@@ -202,13 +202,15 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     const int ilim = il > 0 ? (int)il : 0;             // index clamp (memory safety only)
     const double dlim = (double)ilim;                  // fast path: 0 <= pos / dd < ilim
     const double ndec = -max_dec;
-    long long k_limit = 16 * M_cap + 1000000;           // far beyond any terminating profile of this capacity class
-    if (k_limit > VAP_ROW_LIMIT) k_limit = VAP_ROW_LIMIT;
+    long long k_lim64 = 16 * M_cap + 1000000;           // far beyond any terminating profile of this capacity class
+    if (k_lim64 > VAP_ROW_LIMIT) k_lim64 = VAP_ROW_LIMIT;
+    const int k_limit = (int)k_lim64;
+    const int m_cap = (int)(M_cap < 2147483647LL ? M_cap : 2147483647LL);
     while (pos < L) {
         if (k >= k_limit) { k = -1; break; }                           // diverging loop: report instead of hanging
         // rows have M_cap + 1 slots: steps beyond the capacity (the path is then re-run with a larger one) all land in the
         // last slot, so the stores need no predicate
-        const long long ks = k < M_cap ? k : M_cap;
+        const int ks = k < m_cap ? k : m_cap;
         P[ks] = pos;
         double tv1, tv2;
         const double x2 = pos + dd;
@@ -272,8 +274,8 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     }
     wait_slot(0);                                // no TMA write may be in flight when the CTA's shared memory is released
     wait_slot(1);
-    if (k >= 0 && k <= M_cap) P[k] = pos;
-    n_main[b] = (int)(k > 2147483647LL ? 2147483647LL : k);      // -1: diverged
+    if (k >= 0 && k <= m_cap) P[k] = pos;
+    n_main[b] = k;                                      // -1: diverged
 }
 
 // exactness check of div_const against the IEEE division (test hook)

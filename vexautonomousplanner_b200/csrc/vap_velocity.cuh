@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(256, 8) k_dist_sample_ev(
         double k, h;
         snap_gather2_32(prop_k + (size_t)b * P_cap, prop_h + (size_t)b * P_cap, t, pg, k, h);
         size_t o = (size_t)b * D_cap + i;
-        t_out[o] = t; kap[o] = k; th[o] = h;
+        if (t_out) t_out[o] = t;           // the parameters themselves are only an inspection output
+        kap[o] = k; th[o] = h;
     }
     s_t[threadIdx.x + 1] = t;
     if (threadIdx.x == 0) s_t[0] = (i0 > 0) ? d2t(dgrid[i0 - 1]) : 0.0;   // prev_t of sample 0 is 0

@@ -276,7 +276,7 @@ class Engine:
         return vel, ma, bidx, bval, n_ev, t_est
 
     def velocity_chunked(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0,
-                         outs: Optional[dict] = None):
+                         outs: Optional[dict] = None, want_t: bool = True):
         """S3 + events + S4 + S5, fast path: sample-parallel events, hoisted pre-pass, chunk-speculative passes."""
         B = db.B
         if B > 65535:
@@ -284,7 +284,8 @@ class Engine:
         E_cap = db.N_max + db.A_max + 2
         grid = self.dgrid(D_cap + 2)
         n_samples = outs["n_samples"] if outs else self._empty((B,), torch.int32)
-        tq, kap, th = self._empty((B, D_cap)), self._empty((B, D_cap)), self._empty((B, D_cap))
+        tq = self._empty((B, D_cap)) if want_t else None      # t per distance sample: an inspection output only
+        kap, th = self._empty((B, D_cap)), self._empty((B, D_cap))
         ma = self._empty((B, E_cap)); bidx = self._empty((B, E_cap), torch.int32); bval = self._empty((B, E_cap), torch.int32)
         n_ev = self._empty((B, 2), torch.int32)
         vr_idx = self._empty((B, E_cap), torch.int32); vr_val = self._empty((B, E_cap))
@@ -448,7 +449,7 @@ class Engine:
                 t = self.build_lut(sub, g)
                 self.build_props(sub, g, t)
                 outs["status"].copy_(g.status)
-                n_samples, vel, _, _ = self.velocity_chunked(sub, g, t, outs["status"], D_cap, outs=outs)
+                n_samples, vel, _, _ = self.velocity_chunked(sub, g, t, outs["status"], D_cap, outs=outs, want_t=False)
                 sampled.record(s)
                 outs["status_pre"].copy_(outs["status"])
                 self.time_profile(sub, g, t, outs["status"], D_cap, n_samples, vel, T_cap, outs=outs)
@@ -636,7 +637,8 @@ class Engine:
         D_cap = (D_cap + 127) // 128 * 128
         status = g.status.clone()
         vfun = self.velocity_chunked if self.velocity_impl == "chunked" else self.velocity_serial
-        n_samples, vel, t_est, extra = vfun(db, g, t, status, D_cap)
+        n_samples, vel, t_est, extra = (vfun(db, g, t, status, D_cap, want_t=keep) if self.velocity_impl == "chunked"
+                                        else vfun(db, g, t, status, D_cap))
         # paths whose profile would need an absurd number of rows (the reference would effectively never return) are
         # flagged here, so that they neither size the buffers nor spin in the time loop
         absurd = ~(t_est < ROW_LIMIT)
