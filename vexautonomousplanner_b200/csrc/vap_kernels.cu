@@ -1253,10 +1253,12 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     const size_t VC = 3 * (size_t)E_cap + 2;
     const size_t ss = ((size_t)chunks * 4 + E_cap + VC) * sizeof(double) + (E_cap + VC) * sizeof(int);
     // warm-up steps a speculative chunk runs before its own range (tuning: VAP_CHUNK_WARM; any value gives the same bits).
-    // VAP_CHUNK_MAXROUNDS caps the fix-up rounds: a DIAGNOSTIC that breaks exactness (it times the first sweep alone).
+    // max_rounds only ever caps the fix-up rounds in profiling builds (-DVAP_DIAG_MAXROUNDS): it breaks exactness.
     int warm = 96, max_rounds = 1 << 30;
     if (const char* ev = getenv("VAP_CHUNK_WARM")) warm = atoi(ev);
+#ifdef VAP_DIAG_MAXROUNDS
     if (const char* ev = getenv("VAP_CHUNK_MAXROUNDS")) max_rounds = atoi(ev);
+#endif
     if (warm < 0) warm = 0;
     auto passes = [&](bool backward) {
         switch (chunks) {
