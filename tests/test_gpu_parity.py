@@ -277,6 +277,49 @@ def test_chunked_equals_serial_bitwise():
             assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64))
 
 
+def test_short_paths_and_chunk_edges():
+    """Paths far shorter than the chunk count (one step per chunk, idle chunks), lengths around multiples of the chunk
+    count, a stop node (exact reset of the forward pass) and every warm-up length: fast == serial bit for bit."""
+    import os
+    import vexautonomousplanner_b200 as vap
+    from vexautonomousplanner_b200.engine import Engine
+    cons = [4.0, 8.0, 8.0, 0.8, 16.0, 12.5 / 12]
+    paths = []
+    for L in (0.012, 0.05, 0.155, 0.16, 0.165, 0.32, 0.645, 1.0, 1.285, 2.0):       # 3 .. 400 distance samples
+        paths.append(np.array([[1.0, 1.0], [1.0 + L, 1.0 + 0.3 * L]]))
+    paths.append(np.array([[0.0, 0.0], [0.4, 0.1], [0.7, -0.2]]))
+    N = max(len(p) for p in paths)
+    pts = np.zeros((len(paths), N, 2)); nn = np.zeros(len(paths), dtype=np.int32)
+    for b, p in enumerate(paths):
+        pts[b, :len(p)] = p; pts[b, len(p):] = p[-1] + np.arange(1, N - len(p) + 1)[:, None] * 0.5; nn[b] = len(p)
+    stop = np.zeros((len(paths), N), dtype=bool); stop[-1, 1] = True
+    packed = vap.pack_arrays(pts, cons, n_nodes=nn, stop=stop)
+    ser = Engine("cuda:0", velocity_impl="serial", time_impl="serial")
+    ref = ser.profile(ser.upload(packed), keep=True)
+    assert bool((ref.status == 0).all())
+    old = os.environ.get("VAP_CHUNK_WARM")
+    try:
+        for warm in ("0", "1", "7", "96", "1000"):
+            os.environ["VAP_CHUNK_WARM"] = warm
+            for chunks in (32, 128):
+                got = Engine("cuda:0", chunks=chunks).profile(ser.upload(packed), keep=True)
+                torch.cuda.synchronize()
+                assert torch.equal(ref.n_samples, got.n_samples) and torch.equal(ref.n_out, got.n_out)
+                D = ref.n_samples.long()
+                m = torch.arange(ref.vel.shape[1], device=D.device)[None, :] < D[:, None]
+                assert torch.equal(ref.vel[m].view(torch.int64), got.vel[m].view(torch.int64)), (warm, chunks)
+                n = ref.n_out.long()
+                Tm = min(ref.T_cap, got.T_cap)
+                mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+                for i in range(8):
+                    assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64)), (warm, chunks, i)
+    finally:
+        if old is None:
+            os.environ.pop("VAP_CHUNK_WARM", None)
+        else:
+            os.environ["VAP_CHUNK_WARM"] = old
+
+
 def test_capacity_retry():
     """A deliberately undersized plan must be detected on the device and redone exactly."""
     from vexautonomousplanner_b200 import synth

@@ -144,6 +144,7 @@ class Engine:
         self.accelerators = bool(accelerators)
         self._dgrid: Optional[torch.Tensor] = None
         self._rden: Optional[torch.Tensor] = None
+        self._retired: list = []                # outgrown path-independent tables, kept alive for captured graphs
         self._plan: Dict[tuple, tuple] = {}
         self._streams: list = []
         self._host_slots: Dict[int, list] = {}
@@ -179,6 +180,8 @@ class Engine:
             g = self._empty((m,))
             _lib.check(self.lib.vap_build_dgrid(C.c_int64(m), C.c_double(self.dd), _p(g), self._stream()), "vap_build_dgrid")
             self.launches += 1
+            if self._dgrid is not None:
+                self._retired.append(self._dgrid)      # captured graphs may still read the smaller table
             self._dgrid = g
         return self._dgrid
 
@@ -189,6 +192,8 @@ class Engine:
             r = self._empty((m,))
             _lib.check(self.lib.vap_build_lerp_recip(C.c_int64(m), C.c_double(self.dd), _p(r), self._stream()), "vap_build_lerp_recip")
             self.launches += 1
+            if self._rden is not None:
+                self._retired.append(self._rden)
             self._rden = r
         return self._rden
 
