@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256) k_build_lut(int N_max, const double* __re
                                                    int samples, long long Q_cap, double* __restrict__ lut_d,
                                                    double* __restrict__ lut_t, double* __restrict__ total_len)
 {
-    extern __shared__ double sm[];   // [samples]
+    extern __shared__ double sm[];   // [2 * samples]: magnitudes / cumulative sums, trapezoid increments
     long long b = blockIdx.x;
     PathGeo g = path_geo(b, N_max, seg, first_node, param_end, n_splines);
     double* od = lut_d + (size_t)b * Q_cap;
@@ -338,16 +338,23 @@ __global__ void __launch_bounds__(256) k_build_lut(int N_max, const double* __re
             sm[j] = norm_ax1(dx, dy);
         }
         __syncthreads();
+        // trapezoid increments in parallel (same operations as the reference's vector expression), so that the serial
+        // np.cumsum chain below is one dependent addition per entry
+        double* inc = sm + samples;
+        for (int j = threadIdx.x + 1; j < samples; j += blockDim.x) inc[j] = (sm[j - 1] + sm[j]) * 0.5 * dtp;
+        __syncthreads();
         if (threadIdx.x == 0) {
-            double c = 0.0, mprev = sm[0];
+            double c = 0.0;
             sm[0] = 0.0;
-            for (int j = 1; j < samples; j++) {
-                double m = sm[j];
-                double inc = (mprev + m) * 0.5 * dtp;
-                c = c + inc;
-                sm[j] = c;
-                mprev = m;
+            int j = 1;
+            for (; j + 8 <= samples; j += 8) {           // eight increments in registers ahead of the dependent additions
+                double a[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) a[q] = inc[j + q];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { c = c + a[q]; sm[j + q] = c; }
             }
+            for (; j < samples; j++) { c = c + inc[j]; sm[j] = c; }
         }
         __syncthreads();
         for (int j = threadIdx.x; j < samples; j += blockDim.x) {
@@ -1012,7 +1019,9 @@ extern "C" int vap_build_lut(int64_t B, int N_max, const double* seg, const int3
 {
     if (B <= 0) return 0;
     if (samples < 2 || samples > 6000) return arg_err("vap_build_lut: samples must be in [2, 6000]");
-    k_build_lut<<<(unsigned)B, 256, (size_t)samples * sizeof(double), STREAM>>>(N_max, seg, first_node, param_end,
+    const size_t lut_sm = 2 * (size_t)samples * sizeof(double);
+    if (lut_sm > 48 * 1024) cudaFuncSetAttribute(k_build_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_sm);
+    k_build_lut<<<(unsigned)B, 256, lut_sm, STREAM>>>(N_max, seg, first_node, param_end,
                                                                                n_splines, status, samples, Q_cap,
                                                                                lut_d, lut_t, total_len);
     CHECK_LAUNCH("vap_build_lut");
