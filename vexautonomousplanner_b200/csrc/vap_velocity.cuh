@@ -309,14 +309,20 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
             t_th[threadIdx.x * st + RW] = tr[eh];
         }
     }
+    __shared__ double s_c[2];                        // per-path constants: one thread divides, not all 256
+    if (threadIdx.x == 0) {
+        const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
+        s_c[0] = 2 * V_ / w_;                        // max_angular_vel   (:81)
+        s_c[1] = 2 * A0_ / w_;                       // max_angular_accel (:82)
+    }
     __syncthreads();
     const int j = j0 + threadIdx.x;
     const int s = j >> sh, c = j & (NT - 1);
     const int e = c * Lc + s;                  // this slot's edge = the sample whose terms this thread evaluates
     if (s >= Lc || e >= steps) return;
     const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
-    const double max_angular_vel = 2 * V / w;       // (:81)
-    const double max_angular_accel = 2 * A0 / w;    // (:82)
+    const double max_angular_vel = s_c[0];
+    const double max_angular_accel = s_c[1];
     const int tl = c * st + (s - s0);
     const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
     double* pr = rec + (size_t)b * RS * 5;
