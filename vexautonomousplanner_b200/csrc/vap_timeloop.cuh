@@ -3,7 +3,8 @@
 // The reference's loop carries only (current_pos, current_vel) from one iteration to the next; everything else
 // it appends (parameter, heading, curvature, coordinates, angular velocity) is a pure function of the position
 // before the step, and the node / action-point events only insert rows and flip signs.  So the stage is split:
-//   A  k_time_state     one thread per path: the exact (pos, vel) recurrence alone (3 divisions per step)
+//   A  k_time_state     one thread per path: the exact (pos, vel) recurrence alone (3 divisions per step, each one
+//                       multiplication + two residual corrections with a tabulated / hoisted reciprocal; TMA-staged rows)
 //   B1 k_time_sample    one thread per (path, step): t = distance_to_time(pos), snap gathers, point evaluation,
 //                       omega, and the event candidates (frac wrap of t, action-point crossings)
 //   C  k_time_events    one thread per path: replay of the event logic over the candidates only (turn / wait

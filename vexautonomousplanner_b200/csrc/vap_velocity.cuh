@@ -1,6 +1,7 @@
-// vap_velocity.cuh -- v2 of stages S3-events / S4 / S5: sample-parallel event detection, a pre-pass that hoists
-// every state-independent term of the forward / backward recurrences into one 32-byte record per sample, and
-// chunk-speculative kernels that run the exact serial recurrences on many chunks of one path at once.
+// vap_velocity.cuh -- stages S3-events / S4 / S5: sample-parallel event detection, a pre-pass that hoists every term of
+// the forward / backward recurrences that depends neither on the velocity state nor on the events into five values per
+// sample (chunk-interleaved rows, written once), and chunk-speculative kernels that run the exact serial recurrences on
+// many chunks of one path at once over coalesced streams.
 //
 // Exactness: the recurrences of motion_profile_generator.py:188-311 are NOT associative (the wheel-acceleration
 // term depends on v[i] and v[i-1]), so no scan is used.  A chunk starts from a guessed state, and
