@@ -150,8 +150,9 @@ int vap_fwd_bwd(int64_t B, int N_max, int A_max, const double* node_attr, const 
  *     denominator and its reciprocal), then the forward and backward passes (:188-314) with `chunks` (32, 64, 128 or 256)
  *     speculative chunks per path that are re-run until they merge bitwise with the serial evaluation.  The arrays the
  *     passes stream are chunk-interleaved (step s of chunk c in row s, column c) so that every warp-wide access is one
- *     contiguous run: rec [B][RS][5] f64 (rows of five field planes of `chunks` columns), vel_f / velT [B][RS] f64
- *     (forward / final velocities, slot order), RS = vap_pass_row_slots(D_cap).  vel[B][D_cap]: final velocities in
+ *     contiguous run: rec [B][RS][5] f64 (rows of five field planes of `chunks` columns), statB / vel_f / velT [B][RS] f64
+ *     (the backward pass's static acceleration limit, touched only for paths with max_acceleration overrides; forward /
+ *     final velocities; all slot order), RS = vap_pass_row_slots(D_cap).  vel[B][D_cap]: final velocities in
  *     sample order (mode 1: the forward velocities in sample order); t_est[B] f32; rounds[B][2] fix-up sweeps.     */
 int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
                            const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
@@ -168,8 +169,8 @@ int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, do
                         double end_vel, int64_t D_cap, const int32_t* n_samples, const double* kap, const double* th,
                         int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
                         const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
-                        const int32_t* n_vr, double* rec, double* vel_f, double* velT, double* vel, float* t_est,
-                        int32_t* rounds, int chunks, int mode, void* stream);
+                        const int32_t* n_vr, double* rec, double* statB, double* vel_f, double* velT, double* vel,
+                        float* t_est, int32_t* rounds, int chunks, int mode, void* stream);
 
 /* S6  generate_motion_profile time loop + node-0 prologue + turn / wait inserts
  *     (motion_profile_generator.py:414-628, one_dim_mp_generator.py:4-69) and S7 summary rows.

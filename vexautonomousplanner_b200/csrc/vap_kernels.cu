@@ -1228,7 +1228,7 @@ static void launch_passes(int64_t B, size_t ss, cudaStream_t st, const double* c
                           int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
                           const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
                           const int32_t* n_vr, double* vel_f, double* velT, float* t_est, int32_t* rounds, bool backward,
-                          int warm, int max_rounds)
+                          int warm, int max_rounds, const double* statB)
 {
     if (!backward)
         k_fwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, start_vel, end_vel, RS, n_samples, rec, E_cap,
@@ -1236,7 +1236,7 @@ static void launch_passes(int64_t B, size_t ss, cudaStream_t st, const double* c
                                                        rounds, warm, max_rounds);
     else
         k_bwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, dt, end_vel, RS, n_samples, rec, E_cap, max_accels,
-                                                       bidx, bval, n_ev, vel_f, velT, t_est, rounds, warm, max_rounds);
+                                                       bidx, bval, n_ev, vel_f, velT, t_est, rounds, warm, max_rounds, statB);
 }
 
 extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
@@ -1244,8 +1244,8 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
                                    const double* kap, const double* th, int E_cap, const double* max_accels,
                                    const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
                                    const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* rec,
-                                   double* vel_f, double* velT, double* vel, float* t_est, int32_t* rounds, int chunks,
-                                   int mode, void* stream)
+                                   double* statB, double* vel_f, double* velT, double* vel, float* t_est, int32_t* rounds,
+                                   int chunks, int mode, void* stream)
 {
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
@@ -1255,7 +1255,8 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     dim3 grid(blocks_for(D_cap + chunks, 256), (unsigned)B);
     // the kappa / theta tile: chunks columns x (256 / chunks + 1) rows, odd stride
     const size_t sm = 2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 1) | 1);
-    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec);
+    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec, E_cap, max_accels, bidx,
+                                         bval, n_ev, statB);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
     // CTA = one path, one chunk per thread.  The passes are bound by the latency of the dependent fp64 chain of a step:
     // one-warp CTAs at 72 registers put 28 independent chains on every SM.
@@ -1273,7 +1274,7 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
         switch (chunks) {
 #define VAP_PASS_CASE(N_) case N_: launch_passes<N_>(B, ss, STREAM, cons, status, dd, dt, start_vel, end_vel, RS, n_samples, rec, \
                                               E_cap, max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f, velT,    \
-                                              t_est, rounds, backward, warm, max_rounds); break;
+                                              t_est, rounds, backward, warm, max_rounds, statB); break;
             VAP_PASS_CASE(32) VAP_PASS_CASE(64) VAP_PASS_CASE(128) VAP_PASS_CASE(256)
 #undef VAP_PASS_CASE
         }

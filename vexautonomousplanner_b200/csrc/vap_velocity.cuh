@@ -213,7 +213,9 @@ __device__ __forceinline__ int edge_slot(int e, int Lc, int NT) { const int c = 
 //    { gh_e = 2|theta_{e+1} - theta_e|, recip_for_pass(gh_e) }   denominator of the wheel-acceleration term of forward
 //                                                                step e and of backward step e+1, and its reciprocal
 // What depends on the events is applied by the passes themselves from small shared-memory tables: the initial velocity
-// v0[i+1] (regimes, stops, end velocity) enters as C_i = min(v0[i+1], G_i), a max_acceleration override recomputes stat.
+// v0[i+1] (regimes, stops, end velocity) enters as C_i = min(v0[i+1], G_i).  Only a path with max_acceleration overrides
+// makes the pre-pass look at the regime table: stat then uses the forward regime's max_acc and the backward pass's limit
+// (its max_dec) goes to a slot-order array of its own, statB.
 // One thread per SLOT (coalesced stores); kappa / theta come through a shared-memory tile whose loads run along the columns.
 struct SharedRecip { double b, y; bool ok; };
 // a / b for several numerators over one denominator: y = RN(1/b) once, then per quotient one multiplication and two fused
@@ -237,17 +239,24 @@ __device__ __forceinline__ double div_shared(double a, const SharedRecip& r)
     q = fma(fma(-r.b, q, a), r.y, q);
     return q;
 }
-// the state-independent acceleration limit for max_acc (or max_dec) x -- generic form, used by the passes when an override
-// makes x differ from the path's A0 (:220-225, :281-286)
-__device__ __noinline__ double accel_static(double ak, double x, double w, double max_angular_accel)
+// does any regime of the path use a max_acc other than the path's own A0?  (max_accels[0 .. n_acc): the sampling loop's list)
+__device__ __forceinline__ int pass_has_override(const double* __restrict__ ma, int n_acc, double A0)
 {
-    if (ak < 1e-6) return x;
-    double a_ang = max_angular_accel / ak;
-    double a_kin = 2 * x / (w * ak + 2);
-    return pymin(pymin(a_ang, a_kin), x);
+    int f = 0;
+    for (int j = 0; j < n_acc; j++) f |= (ma[j] != A0);
+    return f;
 }
-struct SampleTerms { double ak, G, stat; };
-__device__ __forceinline__ SampleTerms prepass_sample(double V, double A0, double w, double max_angular_vel,
+__device__ __forceinline__ int last_le(const int* __restrict__ a, int n, int key)      // last j in [0, n) with a[j] <= key
+{
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a[mid] <= key) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+struct SampleTerms { double ak, G, stat, stat_b; };
+// acc_f: max_acc of the forward regime the sample lies in; dec_b: the backward pass's max_dec (both the path's A0 unless a
+// node / action point overrides max_acceleration)
+template <bool OVR>
+__device__ __forceinline__ SampleTerms prepass_sample(double V, double acc_f, double dec_b, double w, double max_angular_vel,
                                                       double max_angular_accel, double k)
 {
     const double ak = fabs(k);
@@ -257,8 +266,8 @@ __device__ __forceinline__ SampleTerms prepass_sample(double V, double A0, doubl
     const SharedRecip rden = shared_recip(w * ak + 2);
     const double v_kin = div_shared(2 * V, rden);
     const double cap = fabs(v_kin);
-    double vlim, stat;
-    if (straight) { vlim = V; stat = A0; }
+    double vlim, stat, stat_b;
+    if (straight) { vlim = V; stat = acc_f; stat_b = dec_b; }
     else {
         const SharedRecip rak = shared_recip(ak);
         const double v_ang = div_shared(max_angular_vel, rak);
@@ -267,22 +276,57 @@ __device__ __forceinline__ SampleTerms prepass_sample(double V, double A0, doubl
         const double m = (max_angular_vel * V) / (ak * V + max_angular_vel);
         const double v_curve = pymin(m, V);
         vlim = pymin(pymin(v_ang, v_kin), v_curve);
-        const double a_kin = div_shared(2 * A0, rden);
-        stat = pymin(pymin(a_ang, a_kin), A0);
+        const double a_kin = div_shared(2 * acc_f, rden);
+        stat = pymin(pymin(a_ang, a_kin), acc_f);
+        stat_b = stat;
+        if (OVR && dec_b != acc_f) {
+            const double d_kin = div_shared(2 * dec_b, rden);
+            stat_b = pymin(pymin(a_ang, d_kin), dec_b);
+        }
     }
     SampleTerms t;
-    t.ak = ak; t.G = pymin(vlim, cap); t.stat = stat;
+    t.ak = ak; t.G = pymin(vlim, cap); t.stat = stat; t.stat_b = stat_b;
     return t;
+}
+
+// per-slot work of the pre-pass for a path WITH max_acceleration overrides: the forward regime of the sample is looked up and
+// the backward limit goes to its own array.  Out of line: the common (override-free) path keeps its 32 registers.
+__device__ __noinline__ void prepass_slot_ovr(long long b, int e, int j, int steps, int D, int NT, long long RS, int E_cap,
+                                             double V, double w, double max_angular_vel, double max_angular_accel,
+                                             double k_e, double k_last, double gh,
+                                             const double* __restrict__ max_accels, const int* __restrict__ bidx,
+                                             const int* __restrict__ bval, const int* __restrict__ n_ev,
+                                             double* __restrict__ pr, size_t o, double* __restrict__ statB)
+{
+    const int nb = n_ev[2 * b + 1];
+    const double dec_b = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + nb - 1]];       // backward max_dec
+    const double acc_f = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + last_le(bidx + (size_t)b * E_cap, nb, e)]];
+    const SampleTerms t = prepass_sample<true>(V, acc_f, dec_b, w, max_angular_vel, max_angular_accel, k_e);
+    pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat; pr[o + 3 * NT] = gh; pr[o + 4 * NT] = recip_for_pass(gh);
+    statB[(size_t)b * RS + j] = t.stat_b;
+    if (e == steps - 1) {
+        const SampleTerms u = prepass_sample<true>(V, dec_b, dec_b, w, max_angular_vel, max_angular_accel, k_last);
+        pr[5 * RS - 3] = u.ak; pr[5 * RS - 2] = u.G; pr[5 * RS - 1] = u.stat;
+        statB[(size_t)b * RS + RS - 1] = u.stat_b;
+    }
 }
 
 __global__ void __launch_bounds__(256, 8) k_prepass(
     const int* __restrict__ status, const double* __restrict__ cons, long long D_cap, const int* __restrict__ n_samples,
-    const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec)
+    const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec,
+    int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    const int* __restrict__ n_ev, double* __restrict__ statB)
 {
     extern __shared__ double s_tile[];
     const long long b = blockIdx.y;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
+    // does some node / action point override max_acceleration?  One regime per thread, loaded here and compared at the
+    // barrier, so that the latency overlaps the tile's (paths with more than blockDim.x regimes: a loop for the rest)
+    const bool o_in = (int)threadIdx.x < E_cap;
+    const int o_n = n_ev[2 * b];
+    const double o_ma = o_in ? max_accels[(size_t)b * E_cap + threadIdx.x] : 0.0;
+    const double o_A0 = cons[b * 6 + 1];
     const int steps = D - 1;
     const int sh = 31 - __clz(NT);                   // NT is a power of two: every index split below is a shift
     const int Lc = (steps + NT - 1) >> sh;           // chunk_len(steps, NT)
@@ -316,7 +360,9 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
         s_c[0] = 2 * V_ / w_;                        // max_angular_vel   (:81)
         s_c[1] = 2 * A0_ / w_;                       // max_angular_accel (:82)
     }
-    __syncthreads();
+    int p_ovr = o_in & ((int)threadIdx.x < o_n) & (o_ma != o_A0);
+    for (int q = threadIdx.x + blockDim.x; q < o_n; q += blockDim.x) p_ovr |= (max_accels[(size_t)b * E_cap + q] != o_A0);
+    const int ovr = __syncthreads_or(p_ovr);
     const int j = j0 + threadIdx.x;
     const int s = j >> sh, c = j & (NT - 1);
     const int e = c * Lc + s;                  // this slot's edge = the sample whose terms this thread evaluates
@@ -327,11 +373,18 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     const int tl = c * st + (s - s0);
     const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
     double* pr = rec + (size_t)b * RS * 5;
-    const SampleTerms t = prepass_sample(V, A0, w, max_angular_vel, max_angular_accel, t_k[tl]);
+    // without overrides both passes use the path's A0 (the common case, kept free of any table code); with them the forward
+    // regime of this sample is looked up and the backward limit goes to its own slot-order array
     const size_t o = (size_t)s * 5 * NT + c;
+    if (ovr) {                                      // uniform over the CTA; rare
+        prepass_slot_ovr(b, e, j, steps, D, NT, RS, E_cap, V, w, max_angular_vel, max_angular_accel, t_k[tl], kr[D - 1],
+                         gh, max_accels, bidx, bval, n_ev, pr, o, statB);
+        return;
+    }
+    const SampleTerms t = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, t_k[tl]);
     pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat; pr[o + 3 * NT] = gh; pr[o + 4 * NT] = recip_for_pass(gh);
-    if (e == steps - 1) {                           // the final sample (no edge starts there)
-        const SampleTerms u = prepass_sample(V, A0, w, max_angular_vel, max_angular_accel, kr[D - 1]);
+    if (e == steps - 1) {                           // the final sample (no edge starts there): the backward pass starts on it
+        const SampleTerms u = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, kr[D - 1]);
         pr[5 * RS - 3] = u.ak; pr[5 * RS - 2] = u.G; pr[5 * RS - 1] = u.stat;
     }
 }
@@ -468,7 +521,7 @@ struct FwdTables {
 #define RUN_DRY 2       // warm-up before a speculative chunk: state only, no stores
 template <int NT, int MODE>
 __device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __restrict__ q, double* __restrict__ last,
-                                        int lo, int len, const FwdTables& T, double A0, double w, double maa, double hw,
+                                        int lo, int len, const FwdTables& T, double hw,
                                         double dd, double& v, double& sq, bool prev_same)
 {
     int j = 0;
@@ -491,8 +544,7 @@ __device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __
         if (e == nb_next) { j++; acc = T.acc[j]; nb_next = (j + 1 < T.n_b) ? T.bi[j + 1] : CH_INT_MAX; }              \
         if (e + 1 == nv_next) { jv++; v0n = T.vv[jv]; nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX; }      \
         {                                                                                                            \
-            const double stat = (acc == A0) ? ST_ : accel_static(AK_, acc, w, maa);                                 \
-            v = fwd_step(AK_, GH_, RG_, stat, pymin(v0n, G_), v, sq, acc, hw, dd);                                   \
+            v = fwd_step(AK_, GH_, RG_, ST_, pymin(v0n, G_), v, sq, acc, hw, dd);                                    \
         }                                                                                                            \
         if (RERUN) {                                                                                                 \
             const bool same = same_bits(OLD_, v);                                                                    \
@@ -581,9 +633,7 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
     const double* P = rec + (size_t)b * RS * 5;
     double* last = vf + ((lo + len < steps) ? c + 1 : (int)(RS - 1));       // where the velocity of sample lo+len goes
-    const double A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
-    const double hw = w * 0.5;
-    const double maa = 2 * A0 / w;                                 // max_angular_accel (:82)
+    const double hw = cons[b * 6 + 5] * 0.5;
     __syncthreads();
     FwdTables T;
     T.bi = s_bi; T.acc = s_acc; T.n_b = n_b; T.vi = s_vi; T.vv = s_vv; T.n_v = s_nv;
@@ -606,10 +656,10 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
                 v = pymin(v0_at(s0), term(s0 - 1, 1));
                 const double wp = vm1 * term(s0 - 1, 0);
                 sq = wp * wp;
-                if (wl > 0) fwd_run<NT, RUN_DRY>(P + (size_t)(Lc - wl) * 5 * NT + c - 1, nullptr, nullptr, s0, wl, T, A0, w, maa, hw, dd, v, sq, false);
+                if (wl > 0) fwd_run<NT, RUN_DRY>(P + (size_t)(Lc - wl) * 5 * NT + c - 1, nullptr, nullptr, s0, wl, T, hw, dd, v, sq, false);
             }
             s_usev[c] = v; s_usew[c] = sq;
-            fwd_run<NT, RUN_SWEEP>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq, false);
+            fwd_run<NT, RUN_SWEEP>(P + c, vf + c, last, lo, len, T, hw, dd, v, sq, false);
         }
         s_endv[c] = v; s_endw[c] = sq;
     }
@@ -628,7 +678,7 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = fwd_run<NT, RUN_RERUN>(P + c, vf + c, last, lo, len, T, A0, w, maa, hw, dd, v, sq,
+            const bool merged = fwd_run<NT, RUN_RERUN>(P + c, vf + c, last, lo, len, T, hw, dd, v, sq,
                                                   same_bits(in_v, s_usev[c]));
             s_usev[c] = in_v; s_usew[c] = in_w;
             if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
@@ -642,11 +692,13 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
 // same row of the forward / final velocities.  Edge e = lo + r (the reference's step i = e+1 -> e) uses the terms of sample
 // e+1 (fields 0-2 of row r+1; for the chunk's top edge the three `top` values), gh / rg (fields 3-4) and the forward velocity
 // of row r, and writes the final velocity of sample e into row r of the final velocities.
-template <int NT, int MODE>
+// OVR: the path has max_acceleration overrides; the static limit of the backward pass then comes from its own slot-order
+// array `sb` (same slots as the forward velocities) instead of field 2 of the record rows.
+template <int NT, int MODE, bool OVR>
 __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const double* __restrict__ f, double* __restrict__ o,
-                                        int lo, int len, double top_ak, double top_G, double top_st, const int* s_bi,
-                                        const double* s_acc, int n_b, double acc0, double dec_b, bool dec_default, double w,
-                                        double maa, double hw, double dd, double& v, double& sq, bool prev_same)
+                                        const double* __restrict__ sb, int lo, int len, double top_ak, double top_G,
+                                        double top_st, const int* s_bi, const double* s_acc, int n_b, double acc0, double hw,
+                                        double dd, double& v, double& sq, bool prev_same)
 {
     // regime at the chunk start (walking down from D-1): the smallest boundary index > i was the last one applied
     int e = lo + len - 1;                            // current edge; the reference's loop index is i = e + 1
@@ -663,10 +715,7 @@ __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const doub
     if (RERUN) olda = *o;
 #define BWD_ONE(AK_, G_, ST_, GH_, RG_, F_, OLD_)                                                                    \
         if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }                             \
-        {                                                                                                            \
-            const double stat = dec_default ? ST_ : accel_static(AK_, dec_b, w, maa);                               \
-            v = bwd_step(AK_, GH_, RG_, stat, pymin(F_, G_), v, sq, acc, hw, dd);                                    \
-        }                                                                                                            \
+        v = bwd_step(AK_, GH_, RG_, ST_, pymin(F_, G_), v, sq, acc, hw, dd);                                         \
         if (RERUN) {                                                                                                 \
             const bool same = same_bits(OLD_, v);                                                                    \
             if (same && prev_same) return true;                                                                      \
@@ -675,16 +724,17 @@ __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const doub
         if (!DRY) *o = v;                                                                                            \
         if (--e < lo) break;                                                                                         \
         p -= 5 * NT; f -= NT;                                                                                        \
+        if (OVR) sb -= NT;                                                                                           \
         if (!DRY) o -= NT;
     while (true) {
         // ---- buffers a: the next step (edge e-1) needs the terms of sample e (this row) and gh / rg / vf / old of the row
         // below (at the chunk's first row the look-ahead stays on the row: the values are not used)
-        akb = __ldg(p); Gb = __ldg(p + NT); stb = __ldg(p + 2 * NT);
+        akb = __ldg(p); Gb = __ldg(p + NT); stb = OVR ? __ldg(sb) : __ldg(p + 2 * NT);
         if (e > lo) { ghb = __ldg(p - 2 * NT); rgb = __ldg(p - NT); fb = __ldg(f - NT); if (RERUN) oldb = o[-NT]; }
         else { ghb = 0.0; rgb = 0.0; fb = 0.0; }
         BWD_ONE(aka, Ga, sta, gha, rga, fa, olda)
         // ---- buffers b
-        aka = __ldg(p); Ga = __ldg(p + NT); sta = __ldg(p + 2 * NT);
+        aka = __ldg(p); Ga = __ldg(p + NT); sta = OVR ? __ldg(sb) : __ldg(p + 2 * NT);
         if (e > lo) { gha = __ldg(p - 2 * NT); rga = __ldg(p - NT); fa = __ldg(f - NT); if (RERUN) olda = o[-NT]; }
         else { gha = 0.0; rga = 0.0; fa = 0.0; }
         BWD_ONE(akb, Gb, stb, ghb, rgb, fb, oldb)
@@ -703,7 +753,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const double* __restrict__ vfT, double* __restrict__ velT, float* __restrict__ t_est,
-    int* __restrict__ rounds_out, int warm, int max_rounds)
+    int* __restrict__ rounds_out, int warm, int max_rounds, const double* __restrict__ statB)
 {
     extern __shared__ __align__(16) unsigned char s_mem[];
     const int k = threadIdx.x;
@@ -727,7 +777,6 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         s_acc[q] = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + q] + 1];
     }
     const double acc0 = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + n_b - 1]];
-    const double dec_b = acc0;                                     // the backward pass keeps the forward pass's last max_dec
     const int Lc = chunk_len(steps, NT);
     const int nch = (steps + Lc - 1) / Lc;
     const bool active = k < nch;
@@ -736,21 +785,27 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
     const double* P = rec + (size_t)b * RS * 5;
     const double* vf = vfT + (size_t)b * RS;
-    const double A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
-    const double hw = w * 0.5;
-    const double maa = 2 * A0 / w;
-    const bool dec_default = (dec_b == A0);
+    const double hw = cons[b * 6 + 5] * 0.5;
+    // with max_acceleration overrides the static limit of this pass is in statB (slot order, written by the pre-pass)
+    const bool ovr = pass_has_override(max_accels + (size_t)b * E_cap, n_ev[2 * b], cons[b * 6 + 1]) != 0;
+    const double* SB = statB + (size_t)b * RS;
     __syncthreads();
 
     // terms of the sample above the chunk (sample lo+len): row 0 of the next column, or the tail
     double top_ak = 0.0, top_G = 0.0, top_st = 0.0;
     if (active) {
-        if (lo + len < steps) { top_ak = __ldg(P + col + 1); top_G = __ldg(P + NT + col + 1); top_st = __ldg(P + 2 * NT + col + 1); }
-        else { top_ak = __ldg(P + 5 * RS - 3); top_G = __ldg(P + 5 * RS - 2); top_st = __ldg(P + 5 * RS - 1); }
+        if (lo + len < steps) {
+            top_ak = __ldg(P + col + 1); top_G = __ldg(P + NT + col + 1);
+            top_st = ovr ? __ldg(SB + col + 1) : __ldg(P + 2 * NT + col + 1);
+        } else {
+            top_ak = __ldg(P + 5 * RS - 3); top_G = __ldg(P + 5 * RS - 2);
+            top_st = ovr ? __ldg(SB + RS - 1) : __ldg(P + 5 * RS - 1);
+        }
     }
     const size_t r_top = active ? (size_t)(len - 1) : 0;           // row of the chunk's top edge
     const double* p0 = P + r_top * 5 * NT + (active ? col : 0);
     const double* f0 = vf + r_top * NT + (active ? col : 0);
+    const double* sb0 = SB + r_top * NT + (active ? col : 0);
     double* o0 = vo + r_top * NT + (active ? col : 0);
 
     // ---- sweep 1: thread k > 0 starts `wl` steps ABOVE its chunk (in the next column) from the guess
@@ -762,6 +817,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
             if (k > 0) {
                 const int hi = lo + len;                                   // sample at the top of this chunk (< D-1)
                 auto rec_of = [&](int x, int fld) {                         // field fld of sample x
+                    if (fld == 2 && ovr) return __ldg(SB + (x >= steps ? (int)(RS - 1) : edge_slot(x, Lc, NT)));
                     if (x >= steps) return __ldg(P + 5 * RS - 3 + fld);
                     const int cx = x / Lc, rx = x - cx * Lc;
                     return __ldg(P + ((size_t)rx * 5 + fld) * NT + cx);
@@ -779,14 +835,20 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
                 if (wl > 0) {
                     // edges s0-1 .. hi of column col+1 (rows wl-1 .. 0); the terms above the first of them are sample s0's
                     const size_t rw = (size_t)(wl - 1);
-                    bwd_run<NT, RUN_DRY>(P + rw * 5 * NT + col + 1, vf + rw * NT + col + 1, nullptr, hi, wl, rec_of(s0, 0),
-                                         rec_of(s0, 1), rec_of(s0, 2), s_bi, s_acc, n_b, acc0, dec_b, dec_default, w, maa, hw,
-                                         dd, v, sq, false);
+                    const double* pd = P + rw * 5 * NT + col + 1;
+                    const double* fd = vf + rw * NT + col + 1;
+                    const double* sd = SB + rw * NT + col + 1;
+                    if (ovr) bwd_run<NT, RUN_DRY, true>(pd, fd, nullptr, sd, hi, wl, rec_of(s0, 0), rec_of(s0, 1), rec_of(s0, 2),
+                                                        s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
+                    else bwd_run<NT, RUN_DRY, false>(pd, fd, nullptr, sd, hi, wl, rec_of(s0, 0), rec_of(s0, 1), rec_of(s0, 2),
+                                                     s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
                 }
             }
             s_usev[k] = v; s_usew[k] = sq;
-            bwd_run<NT, RUN_SWEEP>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, dec_b, dec_default,
-                               w, maa, hw, dd, v, sq, false);
+            if (ovr) bwd_run<NT, RUN_SWEEP, true>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw, dd,
+                                                  v, sq, false);
+            else bwd_run<NT, RUN_SWEEP, false>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw, dd,
+                                               v, sq, false);
         }
         s_endv[k] = v; s_endw[k] = sq;
     }
@@ -805,8 +867,11 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         rounds = round;
         if (need) {
             double v = in_v, sq = in_w;
-            const bool merged = bwd_run<NT, RUN_RERUN>(p0, f0, o0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0,
-                                                  dec_b, dec_default, w, maa, hw, dd, v, sq, same_bits(in_v, s_usev[k]));
+            const bool ps = same_bits(in_v, s_usev[k]);
+            const bool merged = ovr ? bwd_run<NT, RUN_RERUN, true>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc,
+                                                                   n_b, acc0, hw, dd, v, sq, ps)
+                                    : bwd_run<NT, RUN_RERUN, false>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc,
+                                                                    n_b, acc0, hw, dd, v, sq, ps);
             s_usev[k] = in_v; s_usew[k] = in_w;
             if (!merged) { s_endv[k] = v; s_endw[k] = sq; }
         }
