@@ -478,6 +478,30 @@ def test_cfg4_single_long_path(ora):
     assert int(res.extra["rounds"].max()) < 256
 
 
+def test_late_acceleration_override_on_long_path(ora):
+    """A 300-node path whose nodes all carry max_acceleration = the path's own value except node 280: more regimes than
+    one pre-pass CTA has threads, and the only real override sits past the 256th.  Every stage bit-exact against the oracle."""
+    import numpy as np
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.packing import pack_arrays
+    from vexautonomousplanner_b200.engine import Engine
+    rng = np.random.default_rng(11)
+    N = 300
+    cons = np.array(synth.FACTORY, dtype=np.float64)
+    ma = np.full((1, N), cons[1])
+    ma[0, 280] = 0.5 * cons[1]
+    packed = pack_arrays(synth.px_to_ft(synth.random_pixels(rng, 1, N)), cons, max_acceleration=ma)
+    eng = Engine("cuda:0")
+    res = eng.profile(eng.upload(packed), keep=True)
+    torch.cuda.synchronize()
+    assert int(res.status[0]) == 0
+    stagewise_check(ora, packed, res, 0)
+    plain = pack_arrays(synth.px_to_ft(synth.random_pixels(np.random.default_rng(11), 1, N)), cons)
+    res2 = eng.profile(eng.upload(plain), keep=True)
+    torch.cuda.synchronize()
+    assert int(res.n_out[0]) != int(res2.n_out[0])          # the override took effect
+
+
 def test_cfg3_tiled_job_summaries(ora):
     """BASELINE configs[2] in miniature: a job bigger than one call is tiled by profile_many; summaries match the oracle."""
     from vexautonomousplanner_b200 import synth
