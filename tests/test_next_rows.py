@@ -46,6 +46,26 @@ def test_splice_and_format_cpu():
     assert "0 0.01 1.25 3.0 0.5 6.0 -0.125 " in txt
 
 
+def test_routes_header_writer_cpu(tmp_path):
+    """f1, legacy routes.h export: identical files to the reference's own fill_template (gui_manager.py:442-507) on the
+    committed cases (tests/golden/gen_routes_header.py ran the reference method itself): new file, second route appended
+    before #endif, route replaced in place, empty file, file without #endif (entry dropped, as the reference does),
+    indented declaration."""
+    import os
+    from vexautonomousplanner_b200.export import update_routes_header, write_routes_header, routes_header_entry
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "routes_header.json")))
+    assert len(cases) == 6
+    for c in cases:
+        before = None if c["before"] is None else c["before"].splitlines(keepends=True)
+        assert "".join(update_routes_header(before, c["name"], c["rows"])) == c["after"], c["tag"]
+        path = tmp_path / (c["tag"] + ".h")
+        if c["before"] is not None:
+            path.write_text(c["before"])
+        write_routes_header(str(path), c["name"], c["rows"])
+        assert path.read_text() == c["after"], c["tag"]
+    assert routes_header_entry("r", [[1, 2]]) == "std::vector<std::vector<double>> r = {{1, 2}};\n"
+
+
 @pytest.mark.gpu
 def test_export_rows_on_device():
     import torch

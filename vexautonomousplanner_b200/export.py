@@ -125,6 +125,52 @@ def trajectory_text(eng: Engine, res: ProfileResult, b: int, node_actions: Seque
     return "".join(lines)
 
 
+ROUTES_DECL = "std::vector<std::vector<double>> "
+ROUTES_SKELETON = ("#ifndef ROUTES_H\n", "#define ROUTES_H\n", "#include <vector>\n", "\n", None, "\n", "#endif\n")
+
+
+def routes_header_entry(name: str, nodes_data: Sequence[Sequence]) -> str:
+    """The one-line C++ initialiser the legacy routes.h export holds per route (fill_template, gui_manager.py:442-454):
+    rows of more than two values as "{a, b, c}", shorter rows as "{row[0], row[1]}", values printed like f"{v}"."""
+    rows = []
+    for row in nodes_data:
+        vals = row if len(row) > 2 else (row[0], row[1])
+        rows.append("{" + ", ".join(f"{v}" for v in vals) + "}")
+    return f"{ROUTES_DECL}{name} = {{{', '.join(rows)}}};\n"
+
+
+def update_routes_header(lines: Optional[Sequence[str]], name: str, nodes_data: Sequence[Sequence]) -> List[str]:
+    """New content of routes.h (gui_manager.py:456-500).  lines: the current file as readlines() gives it, None when
+    the file does not exist, empty when it is empty.  An existing declaration of `name` is replaced in place; otherwise
+    the entry goes in front of the "#endif" line (and, like the reference, nowhere if there is none); a missing or
+    empty file becomes the include-guard skeleton around the entry."""
+    entry = routes_header_entry(name, nodes_data)
+    if not lines:
+        return [entry if x is None else x for x in ROUTES_SKELETON]
+    out = list(lines)
+    head = f"{ROUTES_DECL}{name} ="
+    for i, line in enumerate(out):
+        if line.strip().startswith(head):
+            out[i] = entry
+            return out
+    for i, line in enumerate(out):
+        if line.strip() == "#endif":
+            out.insert(i, entry)
+            break
+    return out
+
+
+def write_routes_header(path: str, name: str, nodes_data: Sequence[Sequence]) -> None:
+    """fill_template's file handling: read, update, write back (a zero-length file counts as missing, :488-491)."""
+    import os
+    lines = None
+    if os.path.exists(path) and os.stat(path).st_size > 0:
+        with open(path, "r") as f:
+            lines = f.readlines()
+    with open(path, "w") as f:
+        f.writelines(update_routes_header(lines, name, nodes_data))
+
+
 # ---------------------------------------------------------------------------------------------------- f2: JSON codec
 def px_to_in(px: float) -> float:
     return ((px / 2000) - 0.5) * PX_TO_IN          # Node.get_abs_x (gui/node.py:53-55)
