@@ -1252,9 +1252,9 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     if (chunks < 32 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be 32, 64, 128 or 256");
     if (D_cap > 400000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
     const long long RS = vap_pass_row_slots(D_cap);
-    dim3 grid(blocks_for(D_cap + chunks, 256), (unsigned)B);
-    // the kappa / theta tile: chunks columns x (256 / chunks + 1) rows, odd stride
-    const size_t sm = 2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 1) | 1);
+    dim3 grid(blocks_for(D_cap + chunks, 256 * PP_TILES), (unsigned)B);
+    // the kappa / theta tile: chunks columns x (256 / chunks + 1) rows, odd stride; two buffers
+    const size_t sm = 2 * 2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 1) | 1);
     k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec, E_cap, max_accels, bidx,
                                          bval, n_ev, statB);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");

@@ -311,13 +311,14 @@ __device__ __noinline__ void prepass_slot_ovr(long long b, int e, int j, int ste
     }
 }
 
+#define PP_TILES 4          // 256-slot tiles per pre-pass CTA: the per-path preamble (status, sizes, override test, constants) is paid once
 __global__ void __launch_bounds__(256, 8) k_prepass(
     const int* __restrict__ status, const double* __restrict__ cons, long long D_cap, const int* __restrict__ n_samples,
     const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec,
     int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, double* __restrict__ statB)
 {
-    extern __shared__ double s_tile[];
+    extern __shared__ double s_tile[];               // two tile buffers: one barrier per tile
     const long long b = blockIdx.y;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
@@ -330,30 +331,16 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     const int steps = D - 1;
     const int sh = 31 - __clz(NT);                   // NT is a power of two: every index split below is a shift
     const int Lc = (steps + NT - 1) >> sh;           // chunk_len(steps, NT)
-    const int j0 = blockIdx.x * blockDim.x;
-    if (steps <= 0 || j0 >= (Lc << sh)) return;
-    // kappa / theta of this CTA's slots: rows s0 .. s0+RW-1 of every column plus the row after them, fetched with the lanes
+    const int jend = Lc << sh;
+    int j0 = blockIdx.x * (blockDim.x * PP_TILES);
+    if (steps <= 0 || j0 >= jend) return;
+    // kappa / theta of a tile's slots: rows s0 .. s0+RW-1 of every column plus the row after them, fetched with the lanes
     // running ALONG a column (contiguous samples) into shared memory
     const double* kr = kap + (size_t)b * D_cap;
     const double* tr = th + (size_t)b * D_cap;
-    const int rsh = 8 - sh;                          // blockDim.x == 256: RW = 256 / NT rows per CTA
+    const int rsh = 8 - sh;                          // blockDim.x == 256: RW = 256 / NT rows per tile
     const int RW = 1 << rsh;
     const int st = (RW + 1) | 1;                     // odd tile stride
-    double* t_th = s_tile;
-    double* t_k = t_th + NT * st;
-    const int s0 = j0 >> sh;
-    {
-        const int cc = threadIdx.x >> rsh, r = threadIdx.x & (RW - 1);
-        int ee = cc * Lc + s0 + r;
-        ee = ee > D - 1 ? D - 1 : ee;
-        t_th[cc * st + r] = tr[ee];
-        t_k[cc * st + r] = kr[ee];
-        if (threadIdx.x < NT) {                      // the halo row
-            int eh = threadIdx.x * Lc + s0 + RW;
-            eh = eh > D - 1 ? D - 1 : eh;
-            t_th[threadIdx.x * st + RW] = tr[eh];
-        }
-    }
     __shared__ double s_c[2];                        // per-path constants: one thread divides, not all 256
     if (threadIdx.x == 0) {
         const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
@@ -362,30 +349,50 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     }
     int p_ovr = o_in & ((int)threadIdx.x < o_n) & (o_ma != o_A0);
     for (int q = threadIdx.x + blockDim.x; q < o_n; q += blockDim.x) p_ovr |= (max_accels[(size_t)b * E_cap + q] != o_A0);
-    const int ovr = __syncthreads_or(p_ovr);
-    const int j = j0 + threadIdx.x;
-    const int s = j >> sh, c = j & (NT - 1);
-    const int e = c * Lc + s;                  // this slot's edge = the sample whose terms this thread evaluates
-    if (s >= Lc || e >= steps) return;
     const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
-    const double max_angular_vel = s_c[0];
-    const double max_angular_accel = s_c[1];
-    const int tl = c * st + (s - s0);
-    const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
     double* pr = rec + (size_t)b * RS * 5;
-    // without overrides both passes use the path's A0 (the common case, kept free of any table code); with them the forward
-    // regime of this sample is looked up and the backward limit goes to its own slot-order array
-    const size_t o = (size_t)s * 5 * NT + c;
-    if (ovr) {                                      // uniform over the CTA; rare
-        prepass_slot_ovr(b, e, j, steps, D, NT, RS, E_cap, V, w, max_angular_vel, max_angular_accel, t_k[tl], kr[D - 1],
-                         gh, max_accels, bidx, bval, n_ev, pr, o, statB);
-        return;
-    }
-    const SampleTerms t = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, t_k[tl]);
-    pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat; pr[o + 3 * NT] = gh; pr[o + 4 * NT] = recip_for_pass(gh);
-    if (e == steps - 1) {                           // the final sample (no edge starts there): the backward pass starts on it
-        const SampleTerms u = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, kr[D - 1]);
-        pr[5 * RS - 3] = u.ak; pr[5 * RS - 2] = u.G; pr[5 * RS - 1] = u.stat;
+    int ovr = 0;
+    for (int it = 0; it < PP_TILES && j0 < jend; ++it, j0 += blockDim.x) {
+        double* t_th = s_tile + (it & 1) * (2 * NT * st);
+        double* t_k = t_th + NT * st;
+        const int s0 = j0 >> sh;
+        {
+            const int cc = threadIdx.x >> rsh, r = threadIdx.x & (RW - 1);
+            int ee = cc * Lc + s0 + r;
+            ee = ee > D - 1 ? D - 1 : ee;
+            t_th[cc * st + r] = tr[ee];
+            t_k[cc * st + r] = kr[ee];
+            if (threadIdx.x < NT) {                  // the halo row
+                int eh = threadIdx.x * Lc + s0 + RW;
+                eh = eh > D - 1 ? D - 1 : eh;
+                t_th[threadIdx.x * st + RW] = tr[eh];
+            }
+        }
+        // the barrier of the first tile also carries the override vote and publishes s_c; the other buffer is free again
+        // one barrier later, when every thread has left the tile before
+        if (it == 0) ovr = __syncthreads_or(p_ovr); else __syncthreads();
+        const int j = j0 + threadIdx.x;
+        const int s = j >> sh, c = j & (NT - 1);
+        const int e = c * Lc + s;              // this slot's edge = the sample whose terms this thread evaluates
+        if (s >= Lc || e >= steps) continue;
+        const double max_angular_vel = s_c[0];
+        const double max_angular_accel = s_c[1];
+        const int tl = c * st + (s - s0);
+        const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
+        // without overrides both passes use the path's A0 (the common case, kept free of any table code); with them the
+        // forward regime of this sample is looked up and the backward limit goes to its own slot-order array
+        const size_t o = (size_t)s * 5 * NT + c;
+        if (ovr) {                                  // uniform over the CTA; rare
+            prepass_slot_ovr(b, e, j, steps, D, NT, RS, E_cap, V, w, max_angular_vel, max_angular_accel, t_k[tl], kr[D - 1],
+                             gh, max_accels, bidx, bval, n_ev, pr, o, statB);
+            continue;
+        }
+        const SampleTerms t = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, t_k[tl]);
+        pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat; pr[o + 3 * NT] = gh; pr[o + 4 * NT] = recip_for_pass(gh);
+        if (e == steps - 1) {                       // the final sample (no edge starts there): the backward pass starts on it
+            const SampleTerms u = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, kr[D - 1]);
+            pr[5 * RS - 3] = u.ak; pr[5 * RS - 2] = u.G; pr[5 * RS - 1] = u.stat;
+        }
     }
 }
 
