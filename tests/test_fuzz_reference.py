@@ -47,6 +47,36 @@ def test_oracle_against_reference_fuzz(oracle_mod):
         np.testing.assert_allclose(r["summary"][3], f["vmax"][i], rtol=1e-6)
 
 
+MANY = os.path.join(GOLDEN_DIR, "many_regimes_reference.npz")
+
+
+def test_oracle_against_reference_many_regimes(oracle_mod):
+    """Two 300-node paths (tests/golden/make_golden_many_regimes.py, the reference itself): one acceleration regime per
+    node, the only real overrides behind the 256th node (a stop before one of them, an action-point override after the
+    other).  Head AND tail samples of every stream: the overrides act at the end of the path."""
+    o = oracle_mod
+    o.set_sq_mode(0)
+    f = dict(np.load(MANY))
+    stride = int(f["stride"])
+    tol = {0: (1e-6, 1e-12), 1: (1e-9, 1e-10), 2: (1e-6, 1e-9), 3: (1e-6, 1e-6), 4: (1e-9, 1e-10), 5: (1e-6, 1e-9),
+           6: (1e-9, 1e-10), 7: (1e-9, 1e-10)}
+    for i in range(len(f["n"])):
+        n, A = int(f["n"][i]), int(f["n_ap"][i])
+        assert n == 300
+        r = o.full(f["node_attr"][i][:n], f["node_flags"][i][:n], f["ap_attr"][i][:A], f["ap_flags"][i][:A], f["cons"][i])
+        streams = [r[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
+        _check(f, i, r["D"], r["T"], r["summary"][1], r["nodes_map"], r["actions_map"], streams, r["vel"])
+        T, D = r["T"], r["D"]
+        tidx = np.arange(T - 1, -1, -stride)[:80]
+        for s_ in range(8):
+            np.testing.assert_allclose(streams[s_][tidx], f["tail_samples"][i][s_][: len(tidx)], rtol=tol[s_][0],
+                                       atol=tol[s_][1], err_msg=f"case {i} tail stream {s_}")
+        tvi = np.arange(D - 1, -1, -211)[:80]
+        np.testing.assert_allclose(r["vel"][tvi], f["tail_vel_samples"][i][: len(tvi)], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(r["summary"][2], f["t_end"][i], rtol=1e-6)
+        np.testing.assert_allclose(r["summary"][3], f["vmax"][i], rtol=1e-6)
+
+
 @pytest.mark.gpu
 def test_engine_against_reference_fuzz():
     import torch
@@ -68,3 +98,26 @@ def test_engine_against_reference_fuzz():
             streams = [p[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
             _check(f, i, int(res.n_samples[i]), len(p["times"]), float(res.summary[i, 1]), p["nodes_map"], p["actions_map"],
                    streams, p["vel"])
+
+
+@pytest.mark.gpu
+def test_engine_against_reference_many_regimes():
+    """The same two 300-node paths through the engine: more regimes than a pre-pass CTA has threads, real overrides only
+    behind the 256th; integer outputs exact, sampled streams within the north-star tolerances."""
+    import torch
+    from vexautonomousplanner_b200.engine import Engine
+    from vexautonomousplanner_b200.packing import PackedPaths
+    f = dict(np.load(MANY))
+    packed = PackedPaths(np.ascontiguousarray(f["node_attr"]), np.ascontiguousarray(f["node_flags"]).astype(np.int32),
+                         f["n"].astype(np.int32), np.ascontiguousarray(f["ap_attr"]),
+                         np.ascontiguousarray(f["ap_flags"]).astype(np.int32), f["n_ap"].astype(np.int32),
+                         np.ascontiguousarray(f["cons"]))
+    eng = Engine("cuda:0")
+    res = eng.profile(eng.upload(packed))
+    torch.cuda.synchronize()
+    assert (res.status == 0).all()
+    for i in range(len(f["n"])):
+        p = res.path(i)
+        streams = [p[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
+        _check(f, i, int(res.n_samples[i]), len(p["times"]), float(res.summary[i, 1]), p["nodes_map"], p["actions_map"],
+               streams, p["vel"])
