@@ -253,7 +253,7 @@ def test_chunked_equals_serial_bitwise():
     for packed in batches:
         db = ser.upload(packed)
         ref = ser.profile(db, keep=True)
-        for chunks in (32, 64, 256):
+        for chunks in (8, 16, 32, 64, 256):
             chk = Engine("cuda:0", velocity_impl="chunked", chunks=chunks, time_impl="split")
             got = chk.profile(db, keep=True)
             torch.cuda.synchronize()
@@ -301,7 +301,7 @@ def test_short_paths_and_chunk_edges():
     try:
         for warm in ("0", "1", "7", "96", "1000"):
             os.environ["VAP_CHUNK_WARM"] = warm
-            for chunks in (32, 128):
+            for chunks in (8, 16, 32, 128):
                 got = Engine("cuda:0", chunks=chunks).profile(ser.upload(packed), keep=True)
                 torch.cuda.synchronize()
                 assert torch.equal(ref.n_samples, got.n_samples) and torch.equal(ref.n_out, got.n_out)

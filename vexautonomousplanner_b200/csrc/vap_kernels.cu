@@ -1249,7 +1249,7 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
 {
     if (B <= 0) return 0;
     if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
-    if (chunks < 32 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be 32, 64, 128 or 256");
+    if (chunks < 8 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be a power of two in 8 .. 256");
     if (D_cap > 400000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
     const long long RS = vap_pass_row_slots(D_cap);
     dim3 grid(blocks_for(D_cap + chunks, 256 * PP_TILES), (unsigned)B);
@@ -1275,7 +1275,7 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
 #define VAP_PASS_CASE(N_) case N_: launch_passes<N_>(B, ss, STREAM, cons, status, dd, dt, start_vel, end_vel, RS, n_samples, rec, \
                                               E_cap, max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f, velT,    \
                                               t_est, rounds, backward, warm, max_rounds, statB); break;
-            VAP_PASS_CASE(32) VAP_PASS_CASE(64) VAP_PASS_CASE(128) VAP_PASS_CASE(256)
+            VAP_PASS_CASE(8) VAP_PASS_CASE(16) VAP_PASS_CASE(32) VAP_PASS_CASE(64) VAP_PASS_CASE(128) VAP_PASS_CASE(256)
 #undef VAP_PASS_CASE
         }
     };
@@ -1283,7 +1283,7 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
     // sample-order result: ceil(Lc_max / 32) row tiles x chunks / 32 column tiles per path
     const long long lc_max = (D_cap + chunks - 1) / chunks + 1;
-    dim3 g2((unsigned)(((lc_max + 31) / 32) * (chunks / 32)), (unsigned)B);
+    dim3 g2((unsigned)(((lc_max + 31) / 32) * ((chunks + 31) / 32)), (unsigned)B);
     if (mode == 1) {
         k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, vel_f, vel);
         CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");

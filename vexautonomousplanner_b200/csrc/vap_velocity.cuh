@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(256) k_untranspose(const int* __restrict__ sta
     if (blockIdx.x == 0 && threadIdx.x == 0) dst[D - 1] = src[RS - 1];
     if (steps <= 0) return;
     const int Lc = chunk_len(steps, NT);
-    const int ctiles = NT >> 5;
+    const int ctiles = (NT + 31) >> 5;
     const int rt = blockIdx.x / ctiles, ct = blockIdx.x - rt * ctiles;
     const int s0 = rt * 32, c0 = ct * 32;
     if (s0 >= Lc) return;
@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(256) k_untranspose(const int* __restrict__ sta
 #pragma unroll
     for (int r = wrp; r < 32; r += 8) {
         const int s = s0 + r;
-        tile[r][lane] = (s < Lc) ? src[(size_t)s * NT + c0 + lane] : 0.0;
+        tile[r][lane] = (s < Lc && c0 + lane < NT) ? src[(size_t)s * NT + c0 + lane] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -941,6 +941,6 @@ __global__ void __launch_bounds__(256) k_untranspose(const int* __restrict__ sta
         const int c = c0 + q;
         const int s = s0 + lane;
         const int e = c * Lc + s;
-        if (s < Lc && e < steps) dst[e] = tile[lane][q];
+        if (s < Lc && c < NT && e < steps) dst[e] = tile[lane][q];
     }
 }
