@@ -250,12 +250,21 @@ int vap_export_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride, const do
 /* "Next" row f1, text: Python's repr(float) (= what f"{v} " writes, gui_manager.py:220-230) on the device.
  *   vap_format_doubles: n values -> 32-byte NUL-padded slots out32[n][32] + lens[n].
  *   vap_format_rows: export rows[R][7] -> one line per row ("0 t x y heading v omega \n", every value followed by a
- *     blank) in slots[R][vap_row_text_stride()] + lens[R]; int_time[R] (u8, may be NULL) prints the time column as the
- *     integer 0 (times[0] is an int in the reference).  vap_compact_rows then gathers the lines at offsets[R]
- *     (exclusive prefix sum of lens, i64) into one contiguous text buffer.                                         */
+ *     blank) in slots[R][vap_row_text_stride()] + lens[R]; kinds[R] (u8 bit set from vap_row_kinds, may be NULL) prints
+ *     the columns that hold a Python int in the reference as "0" instead of "0.0".  vap_compact_rows then gathers the
+ *     lines at offsets[R] (exclusive prefix sum of lens, i64) into one contiguous text buffer.
+ *   vap_row_kinds: per result row of every path, which entries of generate_motion_profile's lists are Python ints
+ *     (motion_profile_generator.py:425, 448-453, 459-476, 487-518, 548-553): bit 1 times[r] (row 0 without a prologue),
+ *     bit 2 linear_vels / accelerations (inserted turn / wait rows), bit 4 angular_vels (wait rows, first turn row),
+ *     bit 8 positions (wait rows).  kinds row of path b starts at offsets[b] (the dense rows of vap_export_rows) or at
+ *     b * T_cap when offsets is NULL; n_kinds = bytes of `kinds` (cleared by the call).                            */
+int vap_row_kinds(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* n_nodes, const double* ap_attr,
+                  const int32_t* n_ap, const double* cons, const int32_t* status, double dt, const int32_t* nodes_map,
+                  const int32_t* actions_map, const int32_t* n_maps, const int32_t* n_out, int64_t T_cap,
+                  const int64_t* offsets, int64_t n_kinds, uint8_t* kinds, void* stream);
 int vap_format_doubles(int64_t n, const double* x, char* out32, int32_t* lens, void* stream);
 int vap_row_text_stride(void);
-int vap_format_rows(int64_t R, const double* rows, const uint8_t* int_time, char* slots, int32_t* lens, void* stream);
+int vap_format_rows(int64_t R, const double* rows, const uint8_t* kinds, char* slots, int32_t* lens, void* stream);
 int vap_compact_rows(int64_t R, const char* slots, const int32_t* lens, const int64_t* offsets, char* text, void* stream);
 
 /* Test hook: counts (into the device word *bad) the pseudo-random numerators a, out of n, for which the hoisted-

@@ -89,6 +89,8 @@ def lib():
         L.ora_full.restype = C.c_long
         L.ora_full_batch.argtypes = [C.c_long, C.c_int, _dp, _ip, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp,
                                      C.c_double, C.c_double, C.c_long, C.c_long, _dp]
+        L.ora_full_batch_ex.argtypes = [C.c_long, C.c_int, _dp, _ip, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp,
+                                        C.c_double, C.c_double, C.c_long, C.c_long, _dp, _lp, _dp]
         _lib = L
     return _lib
 
@@ -316,3 +318,31 @@ def full_batch(node_attr, node_flags, cons, n_ap=None, ap_attr=None, ap_flags=No
         L.ora_full_batch(B, n, na.reshape(-1), nf.reshape(-1), 0, None, None, None, cons.reshape(-1), dt, dd, cap_d,
                          cap_t, summ.reshape(-1))
     return summ
+
+
+def full_batch_ex(node_attr, node_flags, cons, n_ap=None, ap_attr=None, ap_flags=None, dt=0.01, dd=0.005,
+                  cap_d=60000, cap_t=40000, threads=None):
+    """full_batch that also returns the integer outputs: (summaries[B,5], ints[B,K], checks[B,4]) with
+    ints = D, len(nodes_map), len(actions_map), nodes_map (n+1 slots, -1 padded), actions_map (Amax slots);
+    checks = sums of the velocity row, of times, of x, of y."""
+    L = lib()
+    na = np.ascontiguousarray(node_attr, dtype=np.float64)
+    B, n = na.shape[0], na.shape[1]
+    nf = np.ascontiguousarray(node_flags, dtype=np.int32)
+    cons = np.ascontiguousarray(cons, dtype=np.float64).reshape(B, 6)
+    if threads:
+        L.ora_set_threads(int(threads))
+    summ = np.zeros((B, 5))
+    if ap_attr is not None:
+        apa = np.ascontiguousarray(ap_attr, dtype=np.float64)
+        apf = np.ascontiguousarray(ap_flags, dtype=np.int32)
+        nap = np.ascontiguousarray(n_ap, dtype=np.int32)
+        Amax = apa.shape[1]
+        ptrs = (nap.ctypes.data, apa.ctypes.data, apf.ctypes.data)
+    else:
+        Amax, ptrs = 0, (None, None, None)
+    ints = np.zeros((B, 3 + (n + 1) + Amax), dtype=np.int64)
+    checks = np.zeros((B, 4))
+    L.ora_full_batch_ex(B, n, na.reshape(-1), nf.reshape(-1), Amax, *ptrs, cons.reshape(-1), dt, dd, cap_d, cap_t,
+                        summ.reshape(-1), ints.reshape(-1), checks.reshape(-1))
+    return summ, ints, checks

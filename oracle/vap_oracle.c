@@ -940,3 +940,44 @@ void ora_full_batch(long B, int n, const double* na, const int* nf, int Amax, co
         free(buf); free(nmap); free(amap);
     }
 }
+
+/* Like ora_full_batch, but also keeps every INTEGER output of each path (tests compare them between arithmetic
+ * modes / against the engine at scale): ints[b][0..2] = D, len(nodes_map), len(actions_map), then nodes_map
+ * (n + 1 slots) and actions_map (Amax slots); K = 3 + (n + 1) + Amax longs per path.  checks[b][0..3] = sums of
+ * the velocity row, of times, of x and of y (cheap value fingerprints). */
+void ora_full_batch_ex(long B, int n, const double* na, const int* nf, int Amax, const int* n_ap, const double* apa,
+                       const int* apf, const double* cons, double dt, double dd, long cap_d, long cap_t,
+                       double* summaries, long* ints, double* checks)
+{
+    const long K = 3 + (n + 1) + Amax;
+#pragma omp parallel
+    {
+        double* buf = (double*)malloc(sizeof(double) * (size_t)(cap_d + 8 * cap_t));
+        long* nmap = (long*)malloc(sizeof(long) * (size_t)(n + 2));
+        long* amap = (long*)malloc(sizeof(long) * (size_t)(Amax + 2));
+#pragma omp for schedule(dynamic, 1)
+        for (long b = 0; b < B; b++) {
+            double* v = buf;
+            double* o = buf + cap_d;
+            long D = 0;
+            int nnm = 0, nam = 0;
+            long T = ora_full(n, na + (size_t)b * n * NA, nf + (size_t)b * n, n_ap ? n_ap[b] : 0,
+                              apa ? apa + (size_t)b * Amax * APA : NULL, apf ? apf + (size_t)b * Amax : NULL,
+                              cons + (size_t)b * 6, dt, dd, cap_d, cap_t, v, &D, o, o + cap_t, o + 2 * cap_t,
+                              o + 3 * cap_t, o + 4 * cap_t, o + 5 * cap_t, o + 6 * cap_t, o + 7 * cap_t, nmap, &nnm,
+                              amap, &nam, summaries + (size_t)b * 5);
+            long* r = ints + (size_t)b * K;
+            for (long q = 0; q < K; q++) r[q] = -1;
+            r[0] = D; r[1] = nnm; r[2] = nam;
+            for (int q = 0; q < nnm && q < n + 1; q++) r[3 + q] = nmap[q];
+            for (int q = 0; q < nam && q < Amax; q++) r[3 + (n + 1) + q] = amap[q];
+            double* c = checks + (size_t)b * 4;
+            c[0] = c[1] = c[2] = c[3] = 0.0;
+            if (T > 0) {
+                for (long i = 0; i < D; i++) c[0] += v[i];
+                for (long i = 0; i < T; i++) { c[1] += o[i]; c[2] += o[6 * cap_t + i]; c[3] += o[7 * cap_t + i]; }
+            }
+        }
+        free(buf); free(nmap); free(amap);
+    }
+}

@@ -143,6 +143,7 @@ def run_case(name, px, node_kw=None, aps=None, cons=FACTORY, dt=0.01, dd=0.005, 
                         friction_coef=0.8, max_jerk=cons["max_jerk"], track_width=cons["track_width"])
     out = {}
     out["points_ft"] = pts
+    out["points_px"] = np.asarray(px, dtype=float)      # the GUI works in pixels (mirror_nodes, gui/path.py:596-600)
     out["n_reverse"] = np.array([bool(nd.is_reverse_node) for nd in nodes])
     out["n_turn"] = np.array([float(nd.turn) for nd in nodes])
     out["n_wait"] = np.array([float(nd.wait_time) for nd in nodes])

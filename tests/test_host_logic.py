@@ -99,8 +99,57 @@ def test_pack_paths_layout_and_rotation_table():
                     ap_max_velocity=[[2.0]])
     assert np.array_equal(q.node_attr[0], p.node_attr[0]) and np.array_equal(q.node_flags[0], p.node_flags[0])
     assert np.array_equal(q.ap_attr[0], p.ap_attr[0]) and np.array_equal(q.ap_flags[0], p.ap_flags[0])
-    m = q.mirrored()
-    assert np.array_equal(m.node_attr[:, :, 0], -q.node_attr[:, :, 0]) and m.node_attr[0, 1, 2] == -45.0
+    with pytest.raises(ValueError):
+        q.mirrored()                  # packed from feet: the reference mirrors in pixel space (gui/path.py:596-600)
+
+
+def test_mirrored_is_the_reference_transform():
+    """f4: PackedPaths.mirrored() against the reference's own mirror_nodes (gui/path.py:596-600).  (a) the golden pairs
+    mixed8_k / mixed8_k_mirror (inputs of the latter were built as 2000 - x_px, -turn and run through the unmodified
+    reference): mirroring the packed first case must give the packed twin BIT FOR BIT, tangents untouched;
+    (b) gui_reference.json: node pixels / turns after the reference's PathWidget.mirror_nodes ran headless."""
+    import json
+    import os
+    from golden_util import GOLDEN_DIR, load_case
+    from vexautonomousplanner_b200.packing import mirror_nodes_px, pack_arrays
+
+    def pack(c):
+        tg = np.where(c["n_has_tangent"][:, None], c["n_tangent"], np.nan)
+        return pack_arrays(None, c["constraints"], reverse=c["n_reverse"][None], stop=c["n_stop"][None],
+                           turn=c["n_turn"][None], wait=c["n_wait"][None], max_velocity=c["n_maxvel"][None],
+                           max_acceleration=c["n_maxacc"][None], tangent=tg[None], in_mag=c["n_inmag"][None],
+                           out_mag=c["n_outmag"][None], ap_t=c["ap_t"][None] if len(c["ap_t"]) else None,
+                           ap_stop=c["ap_stop"][None] if len(c["ap_t"]) else None,
+                           ap_wait=c["ap_wait"][None] if len(c["ap_t"]) else None,
+                           ap_max_velocity=c["ap_maxvel"][None] if len(c["ap_t"]) else None,
+                           ap_max_acceleration=c["ap_maxacc"][None] if len(c["ap_t"]) else None,
+                           points_px=c["points_px"][None])
+
+    for k in (0, 1):
+        a, b = load_case(f"mixed8_{k}"), load_case(f"mixed8_{k}_mirror")
+        pa = pack(a)
+        assert np.array_equal(pa.node_attr[0], a["node_attr"]) and np.array_equal(pa.node_flags[0], a["node_flags"])
+        m = pa.mirrored()
+        assert np.array_equal(m.points_px[0], b["points_px"])
+        assert m.node_attr[0].tobytes() == b["node_attr"].tobytes()          # feet, turn, rotation table, tangents: all bits
+        assert np.array_equal(m.node_flags[0], b["node_flags"]) and np.array_equal(m.ap_attr[0], b["ap_attr"])
+        np.testing.assert_allclose(m.mirrored().points_px, pa.points_px, rtol=0, atol=1e-9)   # an involution up to rounding
+    # a node with a user tangent keeps it (the reference's mirror does not touch tangents)
+    t = load_case("tangents")
+    pt = pack(t)
+    assert pt.node_flags[0].tolist() == t["node_flags"].tolist() and (pt.node_flags[0] & 4).any()
+    mt = pt.mirrored()
+    assert np.array_equal(mt.node_attr[0, :, 6:10], pt.node_attr[0, :, 6:10])
+    # the reference's own mirror_nodes, run headless (tests/golden/make_golden_gui.py)
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "gui_reference.json")))
+    for name, r in ref.items():
+        if "mirrored" not in r:
+            continue
+        px0 = np.array([n["px"] for n in r["loaded"]["nodes"]]); tu0 = np.array([n["turn"] for n in r["loaded"]["nodes"]], dtype=float)
+        px1, tu1 = mirror_nodes_px(px0, tu0)
+        assert px1.tolist() == [n["px"] for n in r["mirrored"]["nodes"]], name
+        assert tu1.tolist() == [float(n["turn"]) for n in r["mirrored"]["nodes"]], name
+        assert [n["tangent"] for n in r["mirrored"]["nodes"]] == [n["tangent"] for n in r["loaded"]["nodes"]]
 
 
 def test_synthetic_workloads_follow_the_spec():

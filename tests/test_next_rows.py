@@ -85,18 +85,26 @@ def test_export_rows_on_device():
         got = rows[offsets[b]:offsets[b + 1]]
         assert got.shape == want.shape and np.array_equal(got.view(np.int64), want.view(np.int64))
     # text: the device formatter must reproduce the reference's own expression f"{v} " on the same numbers
-    wait0 = eng.upload(packed).node_attr[:, 0, 3]
-    dev_text = ex.export_text_device(eng, res, wait0)
+    db = eng.upload(packed)
+    dev_text = ex.export_text_device(eng, res, db)
+    kinds = ex.row_kinds(eng, res, db).cpu().numpy()
+    n_int = 0
     for b in (0, 17, 39):
         p = res.path(b)
         txt = ex.trajectory_text(eng, res, b, [[i] for i in range(8)], [[9], [9]], device_text=dev_text)
-        traj = [[0, (0 if (k == 0 and int(packed.node_attr[b, 0, 3] / 0.01) == 0) else np.float64(p["times"][k])),
+        kb = kinds[b]
+        n_int += int(((kb[: len(p["times"])] & ex.RK_INSERTED) != 0).sum())
+        # the expression of save_nodes_to_file (gui_manager.py:284-295) on the reference's element types: int 0 where
+        # the reference's lists hold ints (0 * 12 is the int 0), numpy floats elsewhere
+        traj = [[0, (0 if kb[k] & ex.RK_TIME_INT else np.float64(p["times"][k])),
                  np.float64(p["x"][k] * 12), np.float64(p["y"][k] * -12), np.float64(p["headings"][k]),
-                 np.float64(p["linear_vels"][k] * 12), np.float64(p["angular_vels"][k])] for k in range(len(p["times"]))]
+                 (0 * 12 if kb[k] & ex.RK_INSERTED else np.float64(p["linear_vels"][k] * 12)),
+                 (0 if kb[k] & ex.RK_OMEGA_INT else np.float64(p["angular_vels"][k]))] for k in range(len(p["times"]))]
         want = ex.format_rows(ex.splice_action_rows(traj, p["nodes_map"], [[i] for i in range(8)], p["actions_map"],
                                                     [[9], [9]]))
         assert txt == want, b
         assert txt.splitlines()[0] == "1 0 "
+    assert n_int > 0          # the sampled paths do contain inserted rows
 
 
 @pytest.mark.gpu
@@ -157,3 +165,151 @@ def test_interactive_queries():
             best, best_t, best_pt = d, t, pt
     assert got_t == best_t
     assert np.array_equal(got_px, (best_pt / 12.1090395251 + 0.5) * 2000)
+
+
+def _gui_ref():
+    import os
+    from golden_util import GOLDEN_DIR
+    return json.load(open(os.path.join(GOLDEN_DIR, "gui_reference.json")))
+
+
+def _route_objects(state):
+    """RouteNode / RouteActionPoint lists from a fixture snapshot (attribute-for-attribute what the GUI objects held)."""
+    from vexautonomousplanner_b200 import export as ex
+    nodes = []
+    for d in state["nodes"]:
+        n = ex.RouteNode()
+        n.px = d["px"]; n.is_start_node, n.is_end_node = d["start"], d["end"]
+        n.is_reverse_node, n.stop, n.turn, n.wait_time = d["reverse"], d["stop"], d["turn"], d["wait"]
+        n.tangent = None if d["tangent"] is None else np.array(d["tangent"])
+        n.incoming_magnitude, n.outgoing_magnitude, n.action_values = d["in_mag"], d["out_mag"], d["actions"]
+        nodes.append(n)
+    aps = []
+    for d in state["action_points"]:
+        a = ex.RouteActionPoint(d["t"]); a.px = d["px"]; a.stop, a.wait_time, a.action_values = d["stop"], d["wait"], d["actions"]
+        aps.append(a)
+    return nodes, aps
+
+
+def test_json_codec_against_the_reference_gui_cpu():
+    """f2 pinned to the reference: tests/golden/make_golden_gui.py ran the unmodified PathWidget.load_nodes /
+    convert_point (gui/path.py:590-644) and AutonomousPlannerGUIManager.convert_nodes (gui_manager.py:388-427) headless.
+    nodes_to_json must emit the reference's string byte for byte; load_nodes must land every node on the same pixel
+    doubles, attributes, list order and build_path point order; a second convert must reproduce the reference's too."""
+    from vexautonomousplanner_b200 import export as ex
+    ref = _gui_ref()
+    for name, r in ref.items():
+        if "built" not in r:
+            continue
+        for stage in ("built", "loaded", "mirrored"):
+            st = r[stage]
+            nodes, aps = _route_objects(st)
+            # convert_nodes ran BEFORE the path update moved the action points: the fixture holds their pixels at that moment
+            s = ex.nodes_to_json([n.px for n in nodes], nodes, aps, st["ap_px_at_convert"])
+            assert s == st["json"], (name, stage)                      # the reference's string, byte for byte
+            assert ex.nodes_to_json([n.px for n in nodes], nodes, aps, st["ap_px_at_convert"], as_list=True) == st["as_list"]
+        pts, nodes, aps, apx = ex.load_nodes(r["built"]["json"])
+        L = r["loaded"]
+        assert [n.px for n in nodes] == [d["px"] for d in L["nodes"]], name               # bit-equal pixel doubles
+        assert pts.tolist() == L["ordered_px"], name
+        for n, d in zip(nodes, L["nodes"]):
+            assert (n.is_start_node, n.is_end_node, n.is_reverse_node, n.stop) == (d["start"], d["end"], d["reverse"], d["stop"])
+            assert (n.turn, n.wait_time, n.incoming_magnitude, n.outgoing_magnitude) == (d["turn"], d["wait"], d["in_mag"], d["out_mag"])
+            assert (None if n.tangent is None else n.tangent.tolist()) == d["tangent"]
+            assert list(n.action_values) == d["actions"]
+        assert [(a.t, a.stop, a.wait_time, list(a.action_values)) for a in aps] == \
+               [(d["t"], d["stop"], d["wait"], d["actions"]) for d in L["action_points"]]
+    # legacy single-list file (gui/path.py:604-609)
+    pts, nodes, aps, _ = ex.load_nodes(ref["legacy_single_list"]["json"])
+    assert [n.px for n in nodes] == [d["px"] for d in ref["legacy_single_list"]["nodes"]] and aps == []
+
+
+@pytest.mark.gpu
+def test_interactive_queries_against_the_reference_gui():
+    """f3 pinned to the reference: the 25*N preview polyline returned by PathWidget.update_spline (gui/path.py:356-390)
+    and the two-pass find_closest_point_on_path (gui/path.py:658-727), both run headless on the unmodified reference by
+    tests/golden/make_golden_gui.py, for four routes (plain, turn / reverse / wait with action points, user tangents,
+    8 random nodes), each also after load_nodes and after mirror_nodes, five mouse positions each."""
+    from vexautonomousplanner_b200 import export as ex, queries
+    from vexautonomousplanner_b200.splines.spline_manager import QuinticHermiteSplineManager
+    ref = _gui_ref()
+    n_q = 0
+    for name, r in ref.items():
+        if "built" not in r:
+            continue
+        for stage in ("built", "loaded", "mirrored"):
+            st = r[stage]
+            nodes, aps = _route_objects(st)
+            sm = QuinticHermiteSplineManager()
+            assert sm.build_path(ex.px_points_to_ft(st["ordered_px"]), nodes, aps)
+            n = len(nodes)
+            poly = queries.preview_polyline(sm, n)
+            want = np.array(st["polyline"])
+            assert poly.shape == want.shape == (25 * n, 2)
+            np.testing.assert_allclose(poly, want, rtol=1e-12, atol=1e-9)          # pixels; 1e-9 px = 6e-12 ft
+            for c in st["closest"]:
+                got_px, got_t = queries.find_closest_point_on_path(sm, np.array(c["query"]), n)
+                assert got_t == c["parameter"], (name, stage, c["query"])          # same sample wins: an index-like result
+                np.testing.assert_allclose(got_px, c["px"], rtol=1e-12, atol=1e-9)
+                n_q += 1
+            # the action points land where _execute_update_path puts them (path.py:416-420)
+            if aps:
+                at = np.array([sm.get_point_at_parameter(a.t) for a in aps])
+                np.testing.assert_allclose((at / 12.1090395251 + 0.5) * 2000, st["ap_px_after_update"], rtol=1e-12, atol=1e-9)
+    assert n_q == 60
+
+
+@pytest.mark.gpu
+def test_trajectory_txt_against_the_reference_save_path():
+    """f1 pinned to the reference's own save path: tests/golden/make_golden_gui.py ran the unmodified
+    save_nodes_to_file + fill_txt_file (gui_manager.py:220-316) headless on two routes with turns, waits (also on node 0),
+    reversal, stop and action points.  The engine's .txt body must have the same lines in the same places, print the
+    SAME TOKEN wherever the reference printed an integer (row markers, action values, and the int 0 the reference's
+    lists hold on inserted rows: "0", never "0.0"), and agree on every float within the north-star tolerances."""
+    import gzip
+    import os
+    from golden_util import GOLDEN_DIR
+    from vexautonomousplanner_b200 import export as ex
+    from vexautonomousplanner_b200.engine import Engine
+    from vexautonomousplanner_b200.packing import pack_paths
+    from vexautonomousplanner_b200.synth import FACTORY
+    ref = _gui_ref()
+    eng = Engine("cuda:0")
+    for name in ("turn_reverse_wait", "node0_wait"):
+        st = ref[name]["built"]
+        nodes, aps = _route_objects(st)
+        want = gzip.open(os.path.join(GOLDEN_DIR, f"save_txt_{name}.txt.gz"), "rt").read()
+        assert want.count("\n") == st["save_txt_lines"]
+        packed = pack_paths([(ex.px_points_to_ft(st["ordered_px"]), nodes, aps)], FACTORY)
+        db = eng.upload(packed)
+        res = eng.profile(db)
+        assert int(res.status[0]) == 0
+        got = ex.trajectory_text(eng, res, 0, [n.action_values for n in nodes], [a.action_values for a in aps], db=db)
+        gl, wl = got.splitlines(), want.splitlines()
+        assert len(gl) == len(wl), name
+        n_int_tokens = 0
+        for r, (g, w) in enumerate(zip(gl, wl)):
+            gt, wt = g.split(" "), w.split(" ")
+            assert len(gt) == len(wt), (name, r, g, w)
+            for c, (a, b) in enumerate(zip(gt, wt)):
+                is_int = b.lstrip("-").isdigit()
+                if is_int or b == "":
+                    assert a == b, (name, r, c, g, w)              # ints print identically ("0", not "0.0")
+                    n_int_tokens += is_int
+                else:
+                    assert not a.lstrip("-").isdigit(), (name, r, c, g, w)
+                    tol = dict(rtol=1e-9, atol=1e-9) if c in (2, 3, 4) else dict(rtol=1e-6, atol=1e-6)
+                    np.testing.assert_allclose(float(a), float(b), err_msg=f"{name} row {r} col {c}", **tol)
+        assert n_int_tokens > len(wl)                               # column 0 plus the inserted rows' ints
+    # the Python mirror returns the same element types as the reference (ints on inserted rows)
+    from vexautonomousplanner_b200.motion_profiling_v2.motion_profile_generator import Constraints, generate_motion_profile
+    from vexautonomousplanner_b200.splines.spline_manager import QuinticHermiteSplineManager
+    st = ref["node0_wait"]["built"]
+    nodes, aps = _route_objects(st)
+    sm = QuinticHermiteSplineManager()
+    assert sm.build_path(ex.px_points_to_ft(st["ordered_px"]), nodes, aps)
+    out = generate_motion_profile(sm, Constraints(4.0, 8.0, 8.0, 0.8, 16.0, 12.5 / 12))
+    times, positions, lin, acc, head, ang = out[:6]
+    assert isinstance(times[0], np.float64) and times[0] == 0.0          # node 0 waits: current_time is a float by then
+    assert lin[0] == 0 and isinstance(lin[0], int) and isinstance(ang[0], int) and isinstance(positions[0], int)
+    assert isinstance(lin[40], np.float64) and isinstance(acc[0], int) and isinstance(head[0], np.float64)

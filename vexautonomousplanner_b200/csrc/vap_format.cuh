@@ -189,12 +189,18 @@ __global__ void __launch_bounds__(256) k_format_doubles(long long n, const doubl
 }
 
 // Export rows -> text.  rows[R][7] = {0, t, x*12, y*-12, heading, v*12, omega}; every value is followed by one blank, the
-// row ends with '\n' (fill_txt_file).  Column 0 is the integer 0; int_time[r] != 0 prints the time as the integer 0 as well
-// (times[0] is the int 0 when the path has no prologue, motion_profile_generator.py:425).
+// row ends with '\n' (fill_txt_file).  Column 0 is the integer 0.  kinds[r] (the RK_* bits of k_row_kinds) says which other
+// columns hold a Python int in the reference and therefore print as "0", not "0.0": the time of row 0 when the path has no
+// prologue (motion_profile_generator.py:425), v*12 on every inserted turn / wait row (0 * 12 is the int 0, :448-453,
+// 500-503, 511-515), omega on wait rows and on the first row of a turn (:343, :451, :514).
 // Pass 1: row text into fixed VAP_ROW_STRIDE-byte slots + lengths.  Pass 2 (after an exclusive scan of the lengths): compact.
 #define VAP_ROW_STRIDE 176
+#define RK_TIME_INT 1    // times[r] is the int 0 (row 0 of a path whose node 0 has no wait: current_time starts as an int)
+#define RK_INSERTED 2    // turn / wait row: linear_vels[r] and accelerations[r] are the int 0
+#define RK_OMEGA_INT 4   // angular_vels[r] is the int 0 (wait rows; first row of a turn profile)
+#define RK_POS_INT 8     // positions[r] is the int 0 (wait rows)
 __global__ void __launch_bounds__(128) k_format_rows(long long R, const double* __restrict__ rows,
-                                                     const unsigned char* __restrict__ int_time, char* __restrict__ slots,
+                                                     const unsigned char* __restrict__ kinds, char* __restrict__ slots,
                                                      int* __restrict__ lens)
 {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,8 +209,10 @@ __global__ void __launch_bounds__(128) k_format_rows(long long R, const double* 
     int n = 0;
     o[n++] = '0'; o[n++] = ' ';
     const double* v = rows + (size_t)r * 7;
+    const unsigned kind = kinds ? kinds[r] : 0u;
     for (int c = 1; c < 7; c++) {
-        if (c == 1 && int_time && int_time[r]) { o[n++] = '0'; }
+        const bool as_int = (c == 1 && (kind & RK_TIME_INT)) || (c == 5 && (kind & RK_INSERTED)) || (c == 6 && (kind & RK_OMEGA_INT));
+        if (as_int) { o[n++] = '0'; }
         else n += format_repr(v[c], o + n);
         o[n++] = ' ';
     }

@@ -1451,6 +1451,68 @@ extern "C" int vap_format_doubles(int64_t n, const double* x, char* out32, int32
     return 0;
 }
 extern "C" int vap_row_text_stride(void) { return VAP_ROW_STRIDE; }
+// Which entries of the result lists are Python ints in the reference (one thread per path): replays where
+// generate_motion_profile inserted rows -- node 0's wait (:459-476), per crossed node i = 1 .. its turn profile (K rows,
+// handle_turn :487-507) then its wait (handle_wait :509-518), per fired action point its wait (:548-553) -- from the maps
+// the time stage wrote.  kinds row of path b starts at offsets[b] (dense export rows) or b * T_cap (offsets == NULL).
+__global__ void k_row_kinds(long long B, int N_max, int A_max, const double* __restrict__ node_attr,
+                            const int* __restrict__ n_nodes, const double* __restrict__ ap_attr, const int* __restrict__ n_ap,
+                            const double* __restrict__ cons, const int* __restrict__ status, double dt,
+                            const int* __restrict__ nodes_map, const int* __restrict__ actions_map,
+                            const int* __restrict__ n_maps, const int* __restrict__ n_out, long long T_cap,
+                            const long long* __restrict__ offsets, unsigned char* __restrict__ kinds)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || status[b] != ST_OK) return;
+    long long T = n_out[b];
+    if (T > T_cap) T = T_cap;
+    unsigned char* kr = kinds + (offsets ? offsets[b] : b * T_cap);
+    auto mark = [&](long long r0, long long cnt, unsigned char k) {
+        for (long long r = r0; r < r0 + cnt && r < T; r++) if (r >= 0) kr[r] |= k;
+    };
+    const double* na = node_attr + (size_t)b * N_max * NA;
+    const double V = cons[b * 6 + 0], max_acc = cons[b * 6 + 1], w = cons[b * 6 + 5];
+    if (na[A_WAIT] > 0) mark(0, (long long)(na[A_WAIT] / dt), RK_INSERTED | RK_OMEGA_INT | RK_POS_INT);
+    else if (T > 0) kr[0] |= RK_TIME_INT;
+    const int nm = n_maps[2 * b], am = n_maps[2 * b + 1];
+    const int* nmap = nodes_map + (size_t)b * (N_max + 1);
+    const int n = n_nodes[b];
+    for (int i = 1; i < nm - 1 && i < n; i++) {              // entry 0 is the start, the last one is len(times)
+        const double* a = na + (size_t)i * NA;
+        long long r = nmap[i];
+        if (a[A_TURN] != 0) {
+            const double angle = a[A_TURN] * (VAP_PI / 180.0);
+            const Trapezoid tz = trapezoid_setup(V, max_acc, fabs(angle) * w / 2, dt);
+            mark(r, 1, RK_INSERTED | RK_OMEGA_INT);
+            mark(r + 1, tz.K - 1, RK_INSERTED);
+            r += tz.K;
+        }
+        if (a[A_WAIT] > 0) mark(r, (long long)(a[A_WAIT] / dt), RK_INSERTED | RK_OMEGA_INT | RK_POS_INT);
+    }
+    const int* amap = actions_map + (size_t)b * (A_max > 0 ? A_max : 1);
+    const int A = n_ap ? n_ap[b] : 0;
+    for (int j = 0; j < am && j < A; j++) {
+        const double wt = ap_attr[((size_t)b * A_max + j) * APA + P_WAIT];
+        if (wt > 0) mark(amap[j], (long long)(wt / dt), RK_INSERTED | RK_OMEGA_INT | RK_POS_INT);
+    }
+}
+
+extern "C" int vap_row_kinds(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* n_nodes,
+                             const double* ap_attr, const int32_t* n_ap, const double* cons, const int32_t* status,
+                             double dt, const int32_t* nodes_map, const int32_t* actions_map, const int32_t* n_maps,
+                             const int32_t* n_out, int64_t T_cap, const int64_t* offsets, int64_t n_kinds, uint8_t* kinds,
+                             void* stream)
+{
+    if (B <= 0 || n_kinds <= 0) return 0;
+    cudaError_t e = cudaMemsetAsync(kinds, 0, (size_t)n_kinds, STREAM);
+    if (e != cudaSuccess) return set_err("vap_row_kinds/memset", e);
+    k_row_kinds<<<blocks_for(B, 64), 64, 0, STREAM>>>(B, N_max, A_max, node_attr, n_nodes, ap_attr, n_ap, cons, status, dt,
+                                                     nodes_map, actions_map, n_maps, n_out, T_cap,
+                                                     reinterpret_cast<const long long*>(offsets), kinds);
+    CHECK_LAUNCH("vap_row_kinds");
+    return 0;
+}
+
 extern "C" int vap_format_rows(int64_t R, const double* rows, const uint8_t* int_time, char* slots, int32_t* lens, void* stream)
 {
     if (R <= 0) return 0;

@@ -245,6 +245,26 @@ class Engine:
             self.launches += 1
         return t
 
+    def gl_queries(self, g: Geometry, path, spl, a, b, mode: int = 0, num_points: int = 20, max_iter: int = 50):
+        """Batched Gauss-Legendre arc length (mode 0: a, b = t_start, t_end) or its bisection inverse (mode 1: a = arc
+        length, b = tolerance) on spline spl[q] of path path[q] (quintic_hermite_spline.py:592-717): one thread per
+        query.  Returns (values[n] f64, qstatus[n] i32: 0 ok, -3 where the reference raises ValueError)."""
+        path = torch.as_tensor(path, dtype=torch.int32).to(self.device)
+        spl = torch.as_tensor(spl, dtype=torch.int32).to(self.device)
+        a = torch.as_tensor(a, dtype=torch.float64).to(self.device)
+        b = torch.as_tensor(b, dtype=torch.float64).to(self.device).expand_as(a).contiguous()
+        n = int(a.numel())
+        pts, wts = np.polynomial.legendre.leggauss(num_points)     # the reference's own nodes / weights (:628)
+        dp, dw = torch.from_numpy(pts).to(self.device), torch.from_numpy(wts).to(self.device)
+        out = self._empty((n,)); qst = self._empty((n,), torch.int32)
+        N_max = g.param_end.shape[1]
+        _lib.check(self.lib.vap_gl(C.c_int64(n), _p(path), _p(spl), _p(a), _p(b), C.c_int(mode), C.c_int(max_iter),
+                                   C.c_int(num_points), _p(dp), _p(dw), C.c_int(N_max), _p(g.seg), _p(g.first_node),
+                                   _p(g.param_end), _p(out), _p(qst), self._stream()), "vap_gl")
+        self.launches += 1
+        torch.cuda.current_stream(self.device).synchronize()     # dp / dw / the converted inputs die with this frame
+        return out, qst
+
     def dist_sample(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int):
         B = db.B
         grid = self.dgrid(D_cap + 2)

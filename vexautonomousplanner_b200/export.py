@@ -38,7 +38,8 @@ def export_rows(eng: Engine, res: ProfileResult):
 
 
 def format_rows_device(eng: Engine, rows: torch.Tensor, int_time: Optional[torch.Tensor] = None):
-    """Text of export rows on the device (repr(float)-exact, vap_format_rows + vap_compact_rows).
+    """Text of export rows on the device (repr(float)-exact, vap_format_rows + vap_compact_rows); int_time: the u8 row
+    kinds of row_kinds() (bit 1 alone = "the time prints as the int 0").
     Returns (text uint8[total], row_offsets int64[R+1]); line r is text[row_offsets[r]:row_offsets[r+1]]."""
     R = rows.shape[0]
     stride = int(eng.lib.vap_row_text_stride())
@@ -56,21 +57,39 @@ def format_rows_device(eng: Engine, rows: torch.Tensor, int_time: Optional[torch
     return text[:total], offsets
 
 
-def export_text_device(eng: Engine, res: ProfileResult, node0_wait: Optional[torch.Tensor] = None):
+RK_TIME_INT, RK_INSERTED, RK_OMEGA_INT, RK_POS_INT = 1, 2, 4, 8
+
+
+def row_kinds(eng: Engine, res: ProfileResult, db, offsets: Optional[torch.Tensor] = None, n_rows: Optional[int] = None):
+    """Which entries of the reference's result lists are Python ints (vap_row_kinds): u8 bit set per result row --
+    RK_TIME_INT times[r], RK_INSERTED linear_vels / accelerations, RK_OMEGA_INT angular_vels, RK_POS_INT positions.
+    With `offsets` (from export_rows) the rows are the dense export rows, else a [B, T_cap] array."""
+    B, T_cap = res.B, res.T_cap
+    n = int(n_rows) if offsets is not None else B * T_cap
+    kinds = torch.empty(max(n, 1), dtype=torch.uint8, device=eng.device)
+    _lib.check(eng.lib.vap_row_kinds(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max), _p(db.node_attr), _p(db.n_nodes),
+                                     _p(db.ap_attr), _p(db.n_ap), _p(db.cons), _p(res.status), C.c_double(eng.dt),
+                                     _p(res.nodes_map), _p(res.actions_map), _p(res.n_maps), _p(res.n_out), C.c_int64(T_cap),
+                                     _p(offsets), C.c_int64(n), _p(kinds), eng._stream()), "vap_row_kinds")
+    eng.launches += 1
+    return kinds if offsets is not None else kinds.view(B, T_cap)
+
+
+def export_text_device(eng: Engine, res: ProfileResult, db=None):
     """Trajectory lines of every path of the batch, formatted on the device.
     Returns (text, row_offsets, path_row_offsets): path b owns rows path_row_offsets[b] .. path_row_offsets[b+1].
-    node0_wait[B]: wait_time of node 0 (the first time stamp prints as the integer 0 when there is no prologue,
-    motion_profile_generator.py:425,459-476); None = no prologue anywhere."""
+    db: the DeviceBatch the result was profiled from.  It tells which columns hold a Python int in the reference and
+    print as "0" (times[0] without a prologue; v*12 and omega on inserted turn / wait rows,
+    motion_profile_generator.py:425,448-453,500-515); None = plain paths without waits / turns (only times[0] is an int)."""
     rows, poff = export_rows(eng, res)
     R = rows.shape[0]
-    int_time = torch.zeros(max(R, 1), dtype=torch.uint8, device=eng.device)
-    if R:
-        has_rows = res.n_out.clamp(min=0) > 0
-        first = poff[:-1][has_rows]
-        if node0_wait is not None:
-            first = first[(node0_wait[has_rows] / eng.dt).floor() < 1]
-        int_time[first] = 1
-    text, roff = format_rows_device(eng, rows, int_time)
+    if db is not None:
+        kinds = row_kinds(eng, res, db, offsets=poff, n_rows=R)
+    else:
+        kinds = torch.zeros(max(R, 1), dtype=torch.uint8, device=eng.device)
+        if R:
+            kinds[poff[:-1][res.n_out.clamp(min=0) > 0]] = RK_TIME_INT
+    text, roff = format_rows_device(eng, rows, kinds)
     return text, roff, poff
 
 
@@ -108,12 +127,11 @@ def format_rows(nodes_data: Sequence[Sequence]) -> str:
 
 
 def trajectory_text(eng: Engine, res: ProfileResult, b: int, node_actions: Sequence[Sequence],
-                    action_rows: Sequence[Sequence] = (), node0_wait: Optional[torch.Tensor] = None,
-                    device_text=None) -> str:
+                    action_rows: Sequence[Sequence] = (), db=None, device_text=None) -> str:
     """The .txt body the reference writes for path b (nodes_map includes the trailing len(times), gui/path.py:342).
     The trajectory lines come from the device formatter; only the handful of action rows is formatted and spliced here.
     device_text: result of export_text_device (reuse it when writing many paths of one batch)."""
-    text, roff, poff = device_text if device_text is not None else export_text_device(eng, res, node0_wait)
+    text, roff, poff = device_text if device_text is not None else export_text_device(eng, res, db)
     r0, r1 = int(poff[b]), int(poff[b + 1])
     lines = bytes(text[int(roff[r0]): int(roff[r1])].cpu().numpy()).decode().splitlines(keepends=True)
     nm = res.nodes_map[b, : int(res.n_maps[b, 0])].cpu().numpy()
@@ -205,40 +223,56 @@ class RouteNode:
         self.is_start_node = False; self.is_end_node = False; self.is_reverse_node = False; self.stop = False
         self.turn = 0; self.wait_time = 0; self.tangent = None; self.incoming_magnitude = None
         self.outgoing_magnitude = None; self.max_velocity = 0; self.max_acceleration = 0; self.action_values = []
+        self.px = None
 
 
 class RouteActionPoint:
     def __init__(self, t):
         self.t = t; self.stop = False; self.wait_time = 0; self.max_velocity = 0; self.max_acceleration = 0
-        self.action_values = []
+        self.action_values = []; self.px = None
 
 
 def load_nodes(node_str: str):
     """load_nodes (gui/path.py:602-644) without Qt: returns (points_px[N,2], nodes, action_points, action_px[A,2]).
-    Like the GUI, the start node is moved to the front and the end node to the back of the point list
-    (PathWidget._execute_update_path, gui/path.py:407-413)."""
+
+    `nodes` is the widget's node LIST, built with add_node's insertion rule (path.py:439-446: once an end node exists,
+    every further node goes in front of the last list element); `points_px` is the point order
+    _execute_update_path hands to build_path together with that list (path.py:403-413: the start node, every node that
+    is flagged neither start nor end, the end node) -- empty unless a start node, an end node and two nodes exist.
+    Each node also carries its own pixel position as `.px`.  Action points are kept sorted by t (path.py:459-471)."""
     data = json.loads(node_str)
     nodes_data, action_data = (data[0], data[1]) if len(data) == 2 else (data, [])
-    pts, nodes = [], []
+    nodes, start_node, end_node = [], None, None
     for nd in nodes_data:
         if len(nd) > 4:
             n = RouteNode()
-            n.is_start_node, n.is_end_node = bool(nd[2]), bool(nd[3])
+            n.px = [in_to_px(nd[0]), in_to_px(nd[1])]
+            if end_node is not None:
+                nodes.insert(len(nodes) - 1, n)
+            else:
+                nodes.append(n)
+            start_node = n if bool(nd[2]) else start_node
+            n.is_start_node = bool(nd[2])
+            end_node = n if bool(nd[3]) else end_node
+            n.is_end_node = bool(nd[3])
             n.is_reverse_node, n.stop = bool(nd[4]), bool(nd[5])
             n.turn, n.wait_time = nd[6], nd[7]
             n.tangent = None if nd[8] is None else np.array(nd[8])
             n.incoming_magnitude, n.outgoing_magnitude = nd[9], nd[10]
             n.action_values = list(nd[11:])
-            nodes.append(n)
-            pts.append([in_to_px(nd[0]), in_to_px(nd[1])])
-    aps, apx = [], []
+    aps = []
     for ad in action_data:
         a = RouteActionPoint(ad[2])
+        a.px = [in_to_px(ad[0]), in_to_px(ad[1])]
         a.stop, a.wait_time = ad[3], ad[4]
         a.action_values = list(ad[5:])
-        aps.append(a)
-        apx.append([in_to_px(ad[0]), in_to_px(ad[1])])
-    return np.array(pts, dtype=np.float64).reshape(-1, 2), nodes, aps, np.array(apx, dtype=np.float64).reshape(-1, 2)
+        k = next((i for i, o in enumerate(aps) if o.t > a.t), len(aps))
+        aps.insert(k, a)
+    pts = []
+    if start_node is not None and end_node is not None and len(nodes) > 1:
+        pts = [start_node.px] + [n.px for n in nodes if not (n.is_end_node or n.is_start_node)] + [end_node.px]
+    return (np.array(pts, dtype=np.float64).reshape(-1, 2), nodes, aps,
+            np.array([a.px for a in aps], dtype=np.float64).reshape(-1, 2))
 
 
 def px_points_to_ft(points_px) -> np.ndarray:

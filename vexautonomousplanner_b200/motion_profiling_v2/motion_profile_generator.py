@@ -141,20 +141,24 @@ def generate_motion_profile(spline_manager, constraints: Constraints, dt: float 
     logger.info("Generating motion profile")
     if hasattr(spline_manager, "rebuild_tables") and hasattr(spline_manager, "_db"):
         spline_manager.rebuild_tables()                      # same side effect as the reference (:402)
-    res = eng.profile(eng.upload(_pack(spline_manager, constraints)))
+    from ..export import RK_INSERTED, RK_OMEGA_INT, RK_POS_INT, RK_TIME_INT, row_kinds
+    db = eng.upload(_pack(spline_manager, constraints))
+    res = eng.profile(db)
     _raise_for(int(res.status.item()))
     p = res.path(0)
     T = len(p["times"])
-    times = [np.float64(v) for v in p["times"]]
-    nodes = spline_manager.nodes
-    if T and not (nodes[0].wait_time > 0 and int(nodes[0].wait_time / dt) > 0):
-        times[0] = 0                                         # current_time starts as the int 0 (:425)
+    # the entries the reference appends as Python ints: current_time starts as the int 0 (:425); inserted turn / wait rows
+    # extend the lists with the int 0 (:448-453, 500-503, 511-515) and the first angular velocity of a turn is 0 (:343)
+    kinds = row_kinds(eng, res, db)[0, :T].cpu().numpy()
+
+    def col(name, bit):
+        return [0 if (k & bit) else np.float64(v) for v, k in zip(p[name], kinds)]
+
     coords = [np.array([x, y]) for x, y in zip(p["x"], p["y"])]
     logger.info(f"Generated {T} points")
-    return (times, [np.float64(v) for v in p["positions"]], [np.float64(v) for v in p["linear_vels"]],
-            [np.float64(v) for v in p["accelerations"]], [np.float64(v) for v in p["headings"]],
-            [np.float64(v) for v in p["angular_vels"]], [int(v) for v in p["nodes_map"][:-1]],
-            [int(v) for v in p["actions_map"]], coords)
+    return (col("times", RK_TIME_INT), col("positions", RK_POS_INT), col("linear_vels", RK_INSERTED),
+            col("accelerations", RK_INSERTED), [np.float64(v) for v in p["headings"]], col("angular_vels", RK_OMEGA_INT),
+            [int(v) for v in p["nodes_map"][:-1]], [int(v) for v in p["actions_map"]], coords)
 
 
 def get_wheel_trajectory(linear_vels: List[float], angular_vels: List[float], track_width: float):

@@ -62,6 +62,7 @@ class PackedPaths:
     ap_flags: np.ndarray        # [B, A_max] i32
     n_ap: np.ndarray            # [B] i32
     cons: np.ndarray            # [B, 6] f64
+    points_px: Optional[np.ndarray] = None   # [B, N_max, 2] GUI pixel coordinates, when the batch was packed from pixels
 
     @property
     def B(self):
@@ -85,18 +86,32 @@ class PackedPaths:
     def slice(self, lo: int, hi: int) -> "PackedPaths":
         return PackedPaths(*(np.ascontiguousarray(a[lo:hi]) for a in
                              (self.node_attr, self.node_flags, self.n_nodes, self.ap_attr, self.ap_flags, self.n_ap,
-                              self.cons)))
+                              self.cons)),
+                           points_px=None if self.points_px is None else np.ascontiguousarray(self.points_px[lo:hi]))
 
     def mirrored(self) -> "PackedPaths":
-        """PathWidget.mirror_nodes (gui/path.py:596-600) in field coordinates: x -> -x, turn -> -turn."""
+        """PathWidget.mirror_nodes (gui/path.py:596-600), exactly: every node moves to pixel x -> 2000 - x and gets
+        turn -> -turn; NOTHING else changes (user tangents keep their direction, as in the reference).  The GUI mirrors
+        in PIXEL space and only then converts to feet (path.py:365-367), which is not the same double as negating the
+        feet, so the batch must have been packed from pixels (pack_arrays(points_px=...))."""
+        if self.points_px is None:
+            raise ValueError("mirrored() needs the pixel coordinates: pack the batch with pack_arrays(points_px=...) "
+                             "(the reference mirrors in pixel space, gui/path.py:596-600)")
+        px, turn = mirror_nodes_px(self.points_px, self.node_attr[:, :, A_TURN])
         na = self.node_attr.copy()
-        na[:, :, A_X] = -na[:, :, A_X]
-        na[:, :, A_TURN] = -na[:, :, A_TURN]
-        na[:, :, A_TX] = -na[:, :, A_TX]
-        rc, rs = rotation_table(na[:, :, A_TURN], (self.node_flags & F_REVERSE) != 0)
+        na[:, :, 0:2] = px_to_ft(px)
+        na[:, :, A_TURN] = turn
+        rc, rs = rotation_table(turn, (self.node_flags & F_REVERSE) != 0)
         na[:, :, A_RCOS], na[:, :, A_RSIN] = rc, rs
         return PackedPaths(na, self.node_flags.copy(), self.n_nodes.copy(), self.ap_attr.copy(), self.ap_flags.copy(),
-                           self.n_ap.copy(), self.cons.copy())
+                           self.n_ap.copy(), self.cons.copy(), points_px=px)
+
+
+def mirror_nodes_px(points_px, turn):
+    """The transform of PathWidget.mirror_nodes (gui/path.py:596-600) on arrays: setPos(2000 - x, y), turn = -turn."""
+    px = np.array(points_px, dtype=np.float64, copy=True)
+    px[..., 0] = 2000 - px[..., 0]
+    return px, 0.0 - np.asarray(turn, dtype=np.float64)     # the GUI's turn is an int: -0 is 0, never -0.0
 
 
 def constraints_row(c) -> np.ndarray:
@@ -109,9 +124,14 @@ def constraints_row(c) -> np.ndarray:
 def pack_arrays(points_ft, cons, reverse=None, stop=None, turn=None, wait=None, max_velocity=None,
                 max_acceleration=None, tangent=None, in_mag=None, out_mag=None, n_nodes=None,
                 ap_t=None, ap_stop=None, ap_wait=None, ap_max_velocity=None, ap_max_acceleration=None,
-                n_ap=None) -> PackedPaths:
-    """Vectorised packing from plain arrays: points_ft[B,N,2]; optional per-node arrays [B,N];
-    tangent[B,N,2] with NaN rows meaning "not set"; action-point arrays [B,A]; cons [6] or [B,6]."""
+                n_ap=None, points_px=None) -> PackedPaths:
+    """Vectorised packing from plain arrays: points_ft[B,N,2] (or None with points_px[B,N,2]: GUI pixels, converted
+    as gui/path.py:365-367 does and kept for mirrored()); optional per-node arrays [B,N]; tangent[B,N,2] with NaN rows
+    meaning "not set"; action-point arrays [B,A]; cons [6] or [B,6]."""
+    if points_px is not None:
+        points_px = np.ascontiguousarray(points_px, dtype=np.float64)
+        if points_ft is None:
+            points_ft = px_to_ft(points_px)
     pts = np.asarray(points_ft, dtype=np.float64)
     B, N = pts.shape[0], pts.shape[1]
     na = np.zeros((B, N, NA))
@@ -157,7 +177,8 @@ def pack_arrays(points_ft, cons, reverse=None, stop=None, turn=None, wait=None, 
         nap = np.full(B, A, dtype=np.int32) if n_ap is None else np.asarray(n_ap, dtype=np.int32).reshape(B)
     cons = np.asarray(cons, dtype=np.float64)
     cons = np.tile(cons.reshape(1, 6), (B, 1)) if cons.size == 6 else cons.reshape(B, 6)
-    return PackedPaths(np.ascontiguousarray(na), nf, nn, np.ascontiguousarray(apa), apf, nap, np.ascontiguousarray(cons))
+    return PackedPaths(np.ascontiguousarray(na), nf, nn, np.ascontiguousarray(apa), apf, nap, np.ascontiguousarray(cons),
+                       points_px=points_px)
 
 
 def pack_paths(paths: Sequence, constraints) -> PackedPaths:

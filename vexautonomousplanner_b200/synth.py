@@ -33,7 +33,7 @@ def cfg1(constraints=REPO_ROOT) -> PackedPaths:
 def random_paths(B: int, N: int, seed: int, constraints=FACTORY) -> PackedPaths:
     """cfg2 (B=4096, N=8, seed 0) and cfg3 (B=2**20, N=16, seed 1): plain random-node paths, no actions."""
     rng = np.random.default_rng(seed)
-    return pack_arrays(px_to_ft(random_pixels(rng, B, N)), constraints)
+    return pack_arrays(None, constraints, points_px=random_pixels(rng, B, N))
 
 
 def mixed_paths(B: int, N: int = 8, seed: int = 3) -> PackedPaths:
@@ -67,18 +67,16 @@ def mixed_paths(B: int, N: int = 8, seed: int = 3) -> PackedPaths:
     cons[:, 4] = 16.0
     cons[:, 5] = rng.uniform(9.0, 15.0, H) / 12
     turn[:, 0] = 0.0                      # never: turn at node 0, turn/reverse at the last node (reference crashes)
-    first = pack_arrays(px_to_ft(px), cons, reverse=rev, stop=stop, turn=turn, wait=wait, max_velocity=mv,
+    first = pack_arrays(None, cons, reverse=rev, stop=stop, turn=turn, wait=wait, max_velocity=mv,
                         max_acceleration=ma, ap_t=ap_t, ap_stop=ap_stop, ap_wait=ap_wait, ap_max_velocity=ap_mv,
-                        ap_max_acceleration=ap_ma, n_ap=n_ap)
-    pxm = px.copy()
-    pxm[:, :, 0] = 2000 - pxm[:, :, 0]
-    second = pack_arrays(px_to_ft(pxm), cons, reverse=rev, stop=stop, turn=-turn, wait=wait, max_velocity=mv,
-                         max_acceleration=ma, ap_t=ap_t, ap_stop=ap_stop, ap_wait=ap_wait, ap_max_velocity=ap_mv,
-                         ap_max_acceleration=ap_ma, n_ap=n_ap)
+                        ap_max_acceleration=ap_ma, n_ap=n_ap, points_px=px)
+    second = first.mirrored()           # pixel-space mirror, turn -> -turn, nothing else (gui/path.py:596-600)
     cat = [np.concatenate([a, b])[:B] for a, b in zip(
-        (first.node_attr, first.node_flags, first.n_nodes, first.ap_attr, first.ap_flags, first.n_ap, first.cons),
-        (second.node_attr, second.node_flags, second.n_nodes, second.ap_attr, second.ap_flags, second.n_ap, second.cons))]
-    return PackedPaths(*[np.ascontiguousarray(a) for a in cat])
+        (first.node_attr, first.node_flags, first.n_nodes, first.ap_attr, first.ap_flags, first.n_ap, first.cons,
+         first.points_px),
+        (second.node_attr, second.node_flags, second.n_nodes, second.ap_attr, second.ap_flags, second.n_ap, second.cons,
+         second.points_px))]
+    return PackedPaths(*[np.ascontiguousarray(a) for a in cat[:7]], points_px=np.ascontiguousarray(cat[7]))
 
 
 def long_path(N: int = 801, seed: int = 2, constraints=FACTORY) -> PackedPaths:
