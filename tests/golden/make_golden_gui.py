@@ -66,7 +66,7 @@ class _InertMeta(type):
 
 class QPointF:
     def __init__(self, x=0.0, y=0.0):
-        self._x, self._y = x, y
+        self._x, self._y = float(x), float(y)          # Qt's qreal: coordinates are always doubles
 
     def x(self):
         return self._x
@@ -75,10 +75,10 @@ class QPointF:
         return self._y
 
     def setX(self, v):
-        self._x = v
+        self._x = float(v)
 
     def setY(self, v):
-        self._y = v
+        self._y = float(v)
 
 
 class QGraphicsItem(metaclass=_InertMeta):
