@@ -256,7 +256,7 @@ def test_interactive_queries_against_the_reference_gui():
             if aps:
                 at = np.array([sm.get_point_at_parameter(a.t) for a in aps])
                 np.testing.assert_allclose((at / 12.1090395251 + 0.5) * 2000, st["ap_px_after_update"], rtol=1e-12, atol=1e-9)
-    assert n_q == 60
+    assert n_q == 75
 
 
 @pytest.mark.gpu
