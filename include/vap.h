@@ -18,6 +18,8 @@
  *        -3 reference raises ValueError    | -4 caller capacity (D_cap / T_cap) too small
  *        -5 the reference's time loop would not terminate for this input (e.g. max_dec >= 20 ft/s^2 makes a step
  *           move backwards) or would emit more than 5e7 rows: the engine stops instead of hanging the GPU
+ *        -6 more node crossings / action-point candidates than the per-path event tables hold (N_max wraps,
+ *           4 candidate samples per action point): a permanent condition, unlike -4 it does not go away on a retry
  *   - the library keeps no global mutable state and allocates nothing.
  *
  * Packed layouts
@@ -56,6 +58,7 @@ extern "C" {
 #define VAP_ERR_VALUE (-3)
 #define VAP_ERR_CAPACITY (-4)
 #define VAP_ERR_DIVERGED (-5)
+#define VAP_ERR_EVENTS (-6)
 
 int vap_version(void);
 const char* vap_last_error(void);

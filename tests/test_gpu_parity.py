@@ -649,3 +649,30 @@ def test_gl_arclength_and_inverse_batched_bit_exact(ora):
     assert sb.cpu().numpy().tolist() == [-3, -3, -3]
     bad, sb = eng.gl_queries(g, [0, 0], [0, 0], [-1.0, 1e9], 1e-6, mode=1)
     assert sb.cpu().numpy().tolist() == [-3, -3]
+
+
+def test_bad_lengths_do_not_break_the_batch():
+    """Sizing is per batch, status is per path: a NaN coordinate (the reference's loops then simply do not run), an
+    absurdly long path (5e8 distance samples: the reference would run out of memory) and a path with an infinite length
+    neither raise during sizing nor size the buffers of the healthy paths; repeated calls (plan reuse) keep working."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    eng = Engine("cuda:0")
+    packed = synth.random_paths(6, 6, seed=92)
+    packed.node_attr[1, 2, 0] = np.nan
+    packed.node_attr[2, 3, 0:2] = [2.5e6, -2.5e6]          # > 5e7 samples at dd = 0.005
+    packed.node_attr[3, 1, 1] = np.inf
+    db = eng.upload(packed)
+    ref = eng.profile(eng.upload(synth.random_paths(6, 6, seed=92)))
+    for reuse in (False, True, True):
+        res = eng.profile(db, reuse_plan=reuse)
+        torch.cuda.synchronize()
+        st = res.status.cpu().numpy().tolist()
+        assert st[0] == 0 and st[4] == 0 and st[5] == 0, st
+        assert st[2] == -5, st
+        assert st[1] != -4 and st[3] != -4, st              # never a capacity retry loop
+        assert int(res.n_out[1]) == 0 and int(res.n_out[2]) == 0 and int(res.n_out[3]) == 0
+        for b in (0, 4, 5):
+            assert int(res.n_out[b]) == int(ref.n_out[b])
+            assert torch.equal(res.out[:, b, : int(res.n_out[b])], ref.out[:, b, : int(ref.n_out[b])])
+        assert res.vel.shape[1] < 40000                     # the outliers did not size the distance-domain rows

@@ -22,6 +22,7 @@ enum { P_T = 0, P_WAIT, P_MAXVEL, P_MAXACC };
 #define ST_VALUE (-3)
 #define ST_CAPACITY (-4)
 #define ST_DIVERGED (-5)     // the reference's loop would not terminate (or would emit more than VAP_ROW_LIMIT rows)
+#define ST_EVENTS (-6)       // more node-crossing / action-point candidates than the event tables hold (never goes away on a retry)
 #define VAP_ROW_LIMIT 50000000LL
 
 #define VAP_PI 3.141592653589793

@@ -1337,11 +1337,9 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     if (const char* ev = getenv("VAP_STATE_LANES")) lanes = atoi(ev);
     lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
     const size_t ring_bytes = (size_t)lanes * (TS_STRIDE * sizeof(double) + 16);     // rings + two mbarriers per path
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (ring_bytes > 48 * 1024) {      // per device and cheap: no process-global "already set" flag (the library keeps no state)
         cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * (TS_STRIDE * sizeof(double) + 16)));
         if (ea != cudaSuccess) return set_err("vap_time_profile/attr", ea);
-        attr_set = true;
     }
     k_time_state<<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
                                                                      vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);

@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(32) k_time_events(
             // events in step order: node crossing first, then the action point of the same step
             int* wr = ev_wrap + (size_t)b * N_max;
             int nw = ev_nwrap[b];
-            if (nw > N_max) st = ST_CAPACITY;
+            if (nw > N_max) st = ST_EVENTS;
             for (int i = 1; i < nw && st == ST_OK; i++) {
                 int x = wr[i], j = i - 1;
                 while (j >= 0 && wr[j] > x) { wr[j + 1] = wr[j]; j--; }
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(32) k_time_events(
                 int ai = 2147483647;
                 if (!actions_dead && action_idx < A) {
                     int nc = ev_napc[(size_t)b * A_max + action_idx];
-                    if (nc > EV_AP_CAND) { st = ST_CAPACITY; break; }
+                    if (nc > EV_AP_CAND) { st = ST_EVENTS; break; }
                     const int* c = ev_apc + ((size_t)b * A_max + action_idx) * EV_AP_CAND;
                     for (int q = 0; q < nc; q++) if (c[q] > last_fire && c[q] < ai) ai = c[q];
                     if (ai == 2147483647) actions_dead = true;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(32) k_time_events(
                     last_fire = (int)ke;
                 }
                 if (ns < E_cap) { sk[ns] = (int)ke; so[ns] = (int)off; sv[ns] = rev ? 1 : 0; ns++; }
-                else st = ST_CAPACITY;
+                else st = ST_EVENTS;
             }
             if (st == ST_OK) nmap[nm++] = (int)T;                 // gui/path.py:342
             if (st == ST_OK && T > T_cap) st = ST_CAPACITY;

@@ -112,7 +112,7 @@ __global__ void k_resolve_events(long long B, int N_max, int A_max, const double
     int* si = st_idx + (size_t)b * E_cap;
     int* wr = ev_wrap + (size_t)b * N_max;
     int nw = ev_nwrap[b];
-    if (nw > N_max) { status[b] = ST_CAPACITY; return; }
+    if (nw > N_max) { status[b] = ST_EVENTS; return; }
     for (int i = 1; i < nw; i++) {           // sort wrap samples ascending
         int x = wr[i], j = i - 1;
         while (j >= 0 && wr[j] > x) { wr[j + 1] = wr[j]; j--; }
@@ -131,7 +131,7 @@ __global__ void k_resolve_events(long long B, int N_max, int A_max, const double
         int ai = 2147483647;
         if (!actions_dead && action_idx < A) {
             int nc = ev_napc[(size_t)b * A_max + action_idx];
-            if (nc > EV_AP_CAND) { status[b] = ST_CAPACITY; return; }
+            if (nc > EV_AP_CAND) { status[b] = ST_EVENTS; return; }
             const int* c = ev_apc + ((size_t)b * A_max + action_idx) * EV_AP_CAND;
             for (int k = 0; k < nc; k++) if (c[k] > last_fire && c[k] < ai) ai = c[k];
             if (ai == 2147483647) actions_dead = true;      // this action point never fires -> none after it does

@@ -20,8 +20,10 @@ from . import _lib
 from .packing import PackedPaths
 
 OUT_NAMES = ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")
-ST_OK, ST_FALSE, ST_INDEX, ST_VALUE, ST_CAPACITY, ST_DIVERGED = 0, -1, -2, -3, -4, -5
+ST_OK, ST_FALSE, ST_INDEX, ST_VALUE, ST_CAPACITY, ST_DIVERGED, ST_EVENTS = 0, -1, -2, -3, -4, -5, -6
 ROW_LIMIT = 1.0e7      # more time samples than this per path: treated as a non-terminating profile (status -5)
+DIST_LIMIT = 5.0e7     # more distance samples than this per path (L / dd; an infinite length too): status -5
+MAX_RETRIES = 2        # exact re-runs after a capacity overflow; a status that survives them is returned as it is
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -573,7 +575,8 @@ class Engine:
         self._host_issue_d2h(st)
         return self._host_wait(st)
 
-    def profile_to_host(self, packed: PackedPaths, tiles: int = 8, state: Optional[dict] = None) -> "HostResult":
+    def profile_to_host(self, packed: PackedPaths, tiles: int = 8, state: Optional[dict] = None,
+                        _retry: int = 0) -> "HostResult":
         """Host buffers in, host buffers out: every tile packs its valid rows densely on the device; as soon as a tile's
         row count has reached the host, the copy engine moves exactly those bytes into pinned memory while later tiles
         are still computing.  `state` (returned in HostResult.state) carries the reusable buffers."""
@@ -581,10 +584,10 @@ class Engine:
         self._host_submit(packed, st)
         host = self._host_collect(st)
         torch.cuda.current_stream(self.device).synchronize()
-        if bool((host.status == ST_CAPACITY).any()):
+        if bool((host.status == ST_CAPACITY).any()) and _retry < MAX_RETRIES:
             self._plan.pop((packed.B, st["db"].N_max, st["db"].A_max, st["db"].max_splines), None)
             st["key"] = None
-            return self.profile_to_host(packed, tiles, st)
+            return self.profile_to_host(packed, tiles, st, _retry=_retry + 1)
         return host
 
     def stream_to_host(self, batches, tiles: int = 4, depth: int = 3):
@@ -630,7 +633,27 @@ class Engine:
         return GraphedProfile(self, db, tiles, to_host=to_host)
 
     # ------------------------------------------------------------------ whole path
-    def profile(self, db: DeviceBatch, keep: bool = False, reuse_plan: bool = False, tiles: int = 1) -> ProfileResult:
+    def _plan_distance(self, t: Tables, status: torch.Tensor) -> int:
+        """D_cap from the longest healthy path.  Paths whose length is infinite or absurd (the reference's sampling loop
+        `while d < total_length` would never end / never fit in memory) are flagged ST_DIVERGED here, so that neither they
+        nor a NaN length (for which the reference's loops simply do not run: empty result lists) size the buffers."""
+        L = t.total_len
+        absurd = (L / self.dd > DIST_LIMIT) & (status == ST_OK)          # false for NaN
+        status[absurd] = ST_DIVERGED
+        ok_len = torch.where((status == ST_OK) & torch.isfinite(L), L, torch.zeros_like(L))
+        Lmax = float(ok_len.max().item()) if ok_len.numel() else 0.0
+        D_cap = (int(Lmax / self.dd) + 8 + 127) // 128 * 128             # rows padded to whole 128-sample blocks
+        need = 12 * 8 * D_cap * max(int(L.numel()), 1)                   # ~12 [B, D_cap] fp64 arrays live at the peak
+        free, _ = torch.cuda.mem_get_info(self.device)
+        reusable = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        if need > free + reusable:
+            raise _lib.VapError(f"batch needs about {need / 2**30:.1f} GiB of distance-domain scratch (longest path: {Lmax:.1f} ft = "
+                                f"{D_cap} samples x {L.numel()} paths) but only {(free + reusable) / 2**30:.1f} GiB are free: "
+                                "tile the batch (Engine.profile_many) or bucket the paths by length")
+        return D_cap
+
+    def profile(self, db: DeviceBatch, keep: bool = False, reuse_plan: bool = False, tiles: int = 1,
+                _retry: int = 0) -> ProfileResult:
         """build_path + generate_motion_profile for every path of the batch.
 
         keep: also return geometry / tables / distance-domain intermediates.
@@ -643,9 +666,9 @@ class Engine:
                 and self.velocity_impl == "chunked" and self.time_impl == "split"):
             D_cap, T_cap = self._plan[key]
             res = self._profile_tiled(db, D_cap, T_cap, min(tiles, B))
-            if bool((res.status == ST_CAPACITY).any().item()):     # undersized plan: redo exactly, untiled
+            if bool((res.status == ST_CAPACITY).any().item()) and _retry < MAX_RETRIES:   # undersized plan: redo exactly, untiled
                 self._plan.pop(key, None)
-                return self.profile(db, keep=keep, reuse_plan=False)
+                return self.profile(db, keep=keep, reuse_plan=False, _retry=_retry + 1)
             return res
         with self._stage("S0_build_path"):
             g = self.build_geometry(db)
@@ -654,13 +677,13 @@ class Engine:
         with self._stage("S2_props"):
             self.build_props(db, g, t)
         plan = self._plan.get(key) if reuse_plan else None
+        status = g.status.clone()
         if plan is None:
-            Lmax = float(t.total_len.max().item())
-            D_cap = (int(Lmax / self.dd) + 8 + 127) // 128 * 128      # rows padded to whole 128-sample blocks
+            D_cap = self._plan_distance(t, status)
         else:
             D_cap = plan[0]
+            status[(t.total_len / self.dd > DIST_LIMIT) & (status == ST_OK)] = ST_DIVERGED
         D_cap = (D_cap + 127) // 128 * 128
-        status = g.status.clone()
         vfun = self.velocity_chunked if self.velocity_impl == "chunked" else self.velocity_serial
         n_samples, vel, t_est, extra = (vfun(db, g, t, status, D_cap, want_t=keep) if self.velocity_impl == "chunked"
                                         else vfun(db, g, t, status, D_cap))
@@ -680,9 +703,11 @@ class Engine:
             # capacity check (one small read-back; also what a caller needs to trim the rows)
             if bool((status == ST_CAPACITY).any().item()):
                 if bool((status_pre == ST_CAPACITY).any().item()):
-                    # distance capacity was too small: drop the plan and redo with exact sizing
+                    # distance capacity was too small: drop the plan and redo with exact sizing (bounded: a status that
+                    # survives the exact re-runs is reported, never retried forever)
                     self._plan.pop(key, None)
-                    return self.profile(db, keep=keep, reuse_plan=False)
+                    if _retry < MAX_RETRIES:
+                        return self.profile(db, keep=keep, reuse_plan=False, _retry=_retry + 1)
                 if self.time_impl == "split":
                     # n_main is exact even on overflow; inserted rows are bounded by the insert estimate
                     T_cap = int(self._n_main.max().item()) + min(int(self._insert_bound(db, status_pre)), int(ROW_LIMIT)) + 8

@@ -99,6 +99,10 @@ class QuinticHermiteSplineManager:
         self.arc_length = None
         self.lookup_table = None
         self._tables = None
+        # The reference clears only lookup_table here (spline_manager.py:170-171) and would answer get_heading /
+        # get_curvature from the PREVIOUS path's property tables until rebuild_tables() runs; the device tables are
+        # keyed to this path's geometry, so the stale cache is dropped and the next query rebuilds it.
+        self._precomputed_properties = None
         return True
 
     def _need(self):
@@ -200,6 +204,8 @@ class QuinticHermiteSplineManager:
 
     def _query(self, what: int, x: float) -> float:
         eng = get_engine()
+        if self._tables is None or (what != 0 and self._tables.prop_k is None):
+            self.precompute_path_properties()
         t = self._tables
         out = eng._empty((1,))
         z = torch.zeros(1, dtype=torch.int32, device=eng.device)
