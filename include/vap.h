@@ -270,6 +270,11 @@ int vap_row_text_stride(void);
 int vap_format_rows(int64_t R, const double* rows, const uint8_t* kinds, char* slots, int32_t* lens, void* stream);
 int vap_compact_rows(int64_t R, const char* slots, const int32_t* lens, const int64_t* offsets, char* text, void* stream);
 
+/* Measurement hook: `ctas` CTAs of 256 threads run `iters` rounds of 8 independent fp64 FMA chains each
+ * (flops = ctas * 256 * iters * 16); bench.py times it to report the MEASURED fp64 peak that fp64-pipe
+ * utilisations are quoted against.  out: one device double (never written).        */
+int vap_bench_dfma(int64_t ctas, int64_t iters, double* out, void* stream);
+
 /* Test hook: counts (into the device word *bad) the pseudo-random numerators a, out of n, for which the hoisted-
  * reciprocal division used inside the time loop differs from the IEEE quotient a / b.  Must stay 0.            */
 int vap_test_div_const(int64_t n, uint64_t seed, double b, uint64_t* bad, void* stream);

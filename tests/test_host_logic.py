@@ -183,6 +183,17 @@ def test_shard_bounds_cover_and_balance():
     assert max(loads) / min(loads) < 1.05
     sub, (lo, hi) = local_shard(p, 1, 4)
     assert sub.B == hi - lo and np.array_equal(sub.node_attr, p.node_attr[lo:hi])
+    # plain paths: the weight is the chord sum in samples; mixed paths (cfg5) add the rows of waits and turn profiles
+    d = np.diff(p.node_attr[:, :, 0:2], axis=1)
+    np.testing.assert_allclose(w, np.hypot(d[:, :, 0], d[:, :, 1]).sum(axis=1) / 0.005, rtol=1e-12)
+    m = synth.mixed_paths(256, 8, seed=3)
+    wm = chord_weights(m)
+    dm = np.diff(m.node_attr[:, :, 0:2], axis=1)
+    base = np.hypot(dm[:, :, 0], dm[:, :, 1]).sum(axis=1) / 0.005
+    has_insert = ((m.node_attr[:, :, 2] != 0) | (m.node_attr[:, :, 3] > 0)).any(axis=1) | (m.ap_attr[:, :, 1] > 0).any(axis=1)
+    assert np.all(wm[~has_insert & (m.n_ap == 0)] == base[~has_insert & (m.n_ap == 0)])
+    assert np.all(wm[(m.node_attr[:, :, 3] > 0).any(axis=1)] > base[(m.node_attr[:, :, 3] > 0).any(axis=1)] + 9)
+    assert np.all(wm[(m.node_attr[:, :, 2] != 0).any(axis=1)] > base[(m.node_attr[:, :, 2] != 0).any(axis=1)] + 50)
 
 
 _GLOO_WORKER = r"""
@@ -190,7 +201,7 @@ import os, sys
 sys.path.insert(0, %(root)r)
 import numpy as np, torch, torch.distributed as dist
 from vexautonomousplanner_b200 import synth
-from vexautonomousplanner_b200.sharding import gather_summaries, local_shard
+from vexautonomousplanner_b200.sharding import SummaryGatherer, gather_summaries, local_shard, shard_bounds, chord_weights
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
 packed = synth.random_paths(37, 6, seed=2)
@@ -202,6 +213,14 @@ allrows = gather_summaries(rows)
 assert allrows.shape == (37, 5), allrows.shape
 assert torch.equal(allrows[:, 0], torch.arange(37, dtype=torch.float64))
 assert torch.equal(allrows[:, 1], torch.tensor(packed.node_attr[:, 0, 0]))
+# the preallocated gatherer the bench uses (ragged shard sizes, several steps through the slot ring)
+counts = [b - a for a, b in shard_bounds(packed.B, world, chord_weights(packed))]
+sg = SummaryGatherer(counts, "cpu")
+for step in range(6):
+    slot = sg.submit(rows + step)
+    sg.wait()
+    got = sg.rows(slot)
+    assert got.shape == (37, 5) and torch.equal(got[:, 0], torch.arange(37, dtype=torch.float64) + step), step
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")

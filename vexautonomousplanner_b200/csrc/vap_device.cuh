@@ -37,6 +37,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Kernels whose grid is (tiles of one path) x (paths) are launched on a 1-D grid of tiles_x * B CTAs (grid.y stops at
+// 65535 paths); a CTA finds its path and its tile with one division.  Tiles of a path stay adjacent in launch order.
+struct PathTile { long long b; unsigned x; };
+__device__ __forceinline__ PathTile path_tile(unsigned tiles_x)
+{
+    PathTile p;
+    const unsigned q = blockIdx.x / tiles_x;
+    p.b = q; p.x = blockIdx.x - q * tiles_x;
+    return p;
+}
+
 // Python builtin min / max on floats: the first argument survives unless a later one is strictly smaller / larger.
 __device__ __forceinline__ double pymin(double a, double b) { return (b < a) ? b : a; }
 __device__ __forceinline__ double pymax(double a, double b) { return (b > a) ? b : a; }

@@ -400,10 +400,12 @@ __global__ void __launch_bounds__(256) k_build_props(int N_max, const int* __res
                                                      const double* __restrict__ param_end,
                                                      const int* __restrict__ n_splines,
                                                      const int* __restrict__ status, int spn, long long P_cap,
-                                                     double* __restrict__ prop_k, double* __restrict__ prop_h)
+                                                     double* __restrict__ prop_k, double* __restrict__ prop_h,
+                                                     unsigned tiles_x)
 {
-    long long b = blockIdx.y;
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const PathTile pt = path_tile(tiles_x);
+    long long b = pt.b;
+    long long j = (long long)pt.x * blockDim.x + threadIdx.x;
     int n = n_nodes[b];
     long long P = (long long)spn * n;
     if (status[b] != ST_OK || j >= P || P > P_cap) return;
@@ -480,10 +482,11 @@ __global__ void __launch_bounds__(256) k_dist_sample(const int* __restrict__ n_n
                                                      const double* __restrict__ prop_k,
                                                      const double* __restrict__ prop_h, long long D_cap,
                                                      const int* __restrict__ n_samples, double* __restrict__ t_out,
-                                                     double* __restrict__ kap, double* __restrict__ th)
+                                                     double* __restrict__ kap, double* __restrict__ th, unsigned tiles_x)
 {
-    long long b = blockIdx.y;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const PathTile pt = path_tile(tiles_x);
+    long long b = pt.b;
+    long long i = (long long)pt.x * blockDim.x + threadIdx.x;
     if (status[b] != ST_OK) return;
     long long D = n_samples[b];
     if (i >= D) return;
@@ -1044,10 +1047,11 @@ extern "C" int vap_build_props(int64_t B, int N_max, const int32_t* n_nodes, con
                                void* stream)
 {
     if (B <= 0) return 0;
-    if (B > 65535) return arg_err("vap_build_props: B > 65535 per call (tile the batch)");
-    dim3 grid(blocks_for(P_cap, 256), (unsigned)B);
+    const unsigned tx = blocks_for(P_cap, 256);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_build_props: more than 2^31 CTAs (tile the batch)");
+    const unsigned grid = tx * (unsigned)B;
     k_build_props<<<grid, 256, 0, STREAM>>>(N_max, n_nodes, seg, first_node, param_end, n_splines, status, spn, P_cap,
-                                            prop_k, prop_h);
+                                            prop_k, prop_h, tx);
     CHECK_LAUNCH("vap_build_props");
     return 0;
 }
@@ -1087,12 +1091,13 @@ extern "C" int vap_dist_sample(int64_t B, const int32_t* n_nodes, const int32_t*
                                double* t, double* kap, double* th, void* stream)
 {
     if (B <= 0) return 0;
-    if (B > 65535) return arg_err("vap_dist_sample: B > 65535 per call (tile the batch)");
     k_count_samples<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, status, status, n_grid, dgrid, total_len, D_cap, n_samples);
     CHECK_LAUNCH("vap_dist_sample/count");
-    dim3 grid(blocks_for(D_cap, 256), (unsigned)B);
+    const unsigned tx = blocks_for(D_cap, 256);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_dist_sample: more than 2^31 CTAs (tile the batch)");
+    const unsigned grid = tx * (unsigned)B;
     k_dist_sample<<<grid, 256, 0, STREAM>>>(n_nodes, n_splines, status, dgrid, samples, Q_cap, lut_d, lut_t, total_len,
-                                            spn, P_cap, prop_k, prop_h, D_cap, n_samples, t, kap, th);
+                                            spn, P_cap, prop_k, prop_h, D_cap, n_samples, t, kap, th, tx);
     CHECK_LAUNCH("vap_dist_sample");
     return 0;
 }
@@ -1187,7 +1192,6 @@ extern "C" int vap_dist_sample_events(int64_t B, int N_max, int A_max, const dou
                                       void* stream)
 {
     if (B <= 0) return 0;
-    if (B > 65535) return arg_err("vap_dist_sample_events: B > 65535 per call (tile the batch)");
     if (E_cap < N_max + A_max + 2) return arg_err("vap_dist_sample_events: E_cap < N_max + A_max + 2");
     int Am = A_max > 0 ? A_max : 1;
     // ev_scratch: wrap[B][N_max] | nwrap[B] | apc[B][Am][EV_AP_CAND] | napc[B][Am]
@@ -1201,10 +1205,12 @@ extern "C" int vap_dist_sample_events(int64_t B, int N_max, int A_max, const dou
     if (e != cudaSuccess) return set_err("vap_dist_sample_events/memset", e);
     k_count_samples<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, status, status, n_grid, dgrid, total_len, D_cap, n_samples);
     CHECK_LAUNCH("vap_dist_sample_events/count");
-    dim3 grid(blocks_for(D_cap, 256), (unsigned)B);
+    const unsigned tx = blocks_for(D_cap, 256);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_dist_sample_events: more than 2^31 CTAs (tile the batch)");
+    const unsigned grid = tx * (unsigned)B;
     k_dist_sample_ev<<<grid, 256, 0, STREAM>>>(N_max, Am, n_nodes, n_splines, status, ap_attr, n_ap, dgrid, samples, Q_cap,
                                                lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h, D_cap, n_samples, t,
-                                               kap, th, ev_wrap, ev_nwrap, ev_apc, ev_napc, lut_inv);
+                                               kap, th, ev_wrap, ev_nwrap, ev_apc, ev_napc, lut_inv, tx);
     CHECK_LAUNCH("vap_dist_sample_events/sample");
     k_resolve_events<<<blocks_for(B, 64), 64, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, ap_flags,
                                                           n_ap, cons, status, ev_wrap, ev_nwrap, ev_apc, ev_napc, E_cap,
@@ -1248,15 +1254,16 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
                                    int chunks, int mode, void* stream)
 {
     if (B <= 0) return 0;
-    if (B > 65535) return arg_err("vap_fwd_bwd_chunked: B > 65535 per call (tile the batch)");
     if (chunks < 8 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be a power of two in 8 .. 256");
     if (D_cap > 400000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
     const long long RS = vap_pass_row_slots(D_cap);
-    dim3 grid(blocks_for(D_cap + chunks, 256 * PP_TILES), (unsigned)B);
+    const unsigned tx = blocks_for(D_cap + chunks, 256 * PP_TILES);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_fwd_bwd_chunked: more than 2^31 CTAs (tile the batch)");
+    const unsigned grid = tx * (unsigned)B;
     // the kappa / theta tile: chunks columns x (256 / chunks + 1) rows, odd stride; two buffers
     const size_t sm = 2 * 2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 1) | 1);
     k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec, E_cap, max_accels, bidx,
-                                         bval, n_ev, statB);
+                                         bval, n_ev, statB, tx);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
     // CTA = one path, one chunk per thread.  The passes are bound by the latency of the dependent fp64 chain of a step:
     // one-warp CTAs at 72 registers put 28 independent chains on every SM.
@@ -1283,15 +1290,17 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
     // sample-order result: ceil(Lc_max / 32) row tiles x chunks / 32 column tiles per path
     const long long lc_max = (D_cap + chunks - 1) / chunks + 1;
-    dim3 g2((unsigned)(((lc_max + 31) / 32) * ((chunks + 31) / 32)), (unsigned)B);
+    const unsigned tx2 = (unsigned)(((lc_max + 31) / 32) * ((chunks + 31) / 32));
+    if ((long long)tx2 * B > 2147483647LL) return arg_err("vap_fwd_bwd_chunked: more than 2^31 CTAs (tile the batch)");
+    const unsigned g2 = tx2 * (unsigned)B;
     if (mode == 1) {
-        k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, vel_f, vel);
+        k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, vel_f, vel, tx2);
         CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
         return 0;
     }
     passes(true);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
-    k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, velT, vel);
+    k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, velT, vel, tx2);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
     return 0;
 }
@@ -1313,7 +1322,6 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     (void)ap_flags;
     const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
     if (B <= 0) return 0;
-    if (B > 65535) return arg_err("vap_time_profile: B > 65535 per call (tile the batch)");
     if (E_cap < N_max + A_max + 2) return arg_err("vap_time_profile: E_cap < N_max + A_max + 2");
     int Am = A_max > 0 ? A_max : 1;
     const int64_t M_cap = T_cap;
@@ -1344,10 +1352,12 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     k_time_state<<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
                                                                      vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);
     CHECK_LAUNCH("vap_time_profile/state");
-    dim3 grid(blocks_for(M_cap, 256), (unsigned)B);
+    const unsigned tx = blocks_for(M_cap, 256);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_time_profile: more than 2^31 CTAs (tile the batch)");
+    const unsigned grid = tx * (unsigned)B;
     k_time_sample<<<grid, 256, 0, STREAM>>>(B, N_max, Am, n_nodes, status, ap_attr, n_ap, seg, first_node, param_end,
                                             n_splines, samples, Q_cap, lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h,
-                                            M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc, ev_napc, lut_inv);
+                                            M_cap, n_main, stage, ev_wrap, ev_nwrap, ev_apc, ev_napc, lut_inv, tx);
     CHECK_LAUNCH("vap_time_profile/sample");
     k_time_events<<<blocks_for(B, lanes), lanes, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, n_ap, cons,
                                                        status, dt, seg, first_node, param_end, n_splines, spn, P_cap,
@@ -1356,8 +1366,34 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
                                                        out, nodes_map, actions_map, n_maps, n_out, summary);
     CHECK_LAUNCH("vap_time_profile/events");
     k_time_finalize<<<grid, 256, 0, STREAM>>>(B, status, M_cap, n_main, stage, E_cap, seg_k, seg_off, seg_rev, n_seg,
-                                              T_cap, oplane, out, summary);
+                                              T_cap, oplane, out, summary, tx);
     CHECK_LAUNCH("vap_time_profile/finalize");
+    return 0;
+}
+
+// Measurement hook: fp64 FMA peak of the device (BASELINE.md section 3 asks for a measured DFMA figure before any fp64
+// utilisation is quoted).  Every thread runs 8 independent dependent-FMA chains (more than the 8.2-cycle DFMA latency needs
+// at 8 warps per scheduler); flops = ctas * 256 * iters * 8 * 2.
+__global__ void __launch_bounds__(256) k_bench_dfma(long long iters, double* __restrict__ out)
+{
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + 1e-9 * (double)(threadIdx.x + 37 * k);
+    const double m = 0.9999999, c = 1e-7;
+    for (long long i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fma(a[k], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == 123456.789) out[0] = s;          // never true: keeps the chains alive
+}
+extern "C" int vap_bench_dfma(int64_t ctas, int64_t iters, double* out, void* stream)
+{
+    if (ctas <= 0 || iters <= 0) return 0;
+    k_bench_dfma<<<(unsigned)ctas, 256, 0, STREAM>>>(iters, out);
+    CHECK_LAUNCH("vap_bench_dfma");
     return 0;
 }
 
@@ -1413,7 +1449,6 @@ extern "C" int vap_pack_rows(int64_t B, int64_t T_cap, int64_t out_plane_stride,
                              const int32_t* status, int64_t* offsets, double* dst, void* stream)
 {
     if (B <= 0) return 0;
-    if (B > 65535) return arg_err("vap_pack_rows: B > 65535 per call (tile the batch)");
     const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
     k_row_offsets<<<1, 1024, 0, STREAM>>>(B, n_out, status, T_cap, reinterpret_cast<long long*>(offsets));
     CHECK_LAUNCH("vap_pack_rows/offsets");
@@ -1430,12 +1465,13 @@ extern "C" int vap_export_rows(int64_t B, int64_t T_cap, int64_t out_plane_strid
                                const int32_t* status, int64_t* offsets, double* dst, void* stream)
 {
     if (B <= 0) return 0;
-    if (B > 65535) return arg_err("vap_export_rows: B > 65535 per call (tile the batch)");
     const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
     k_row_offsets<<<1, 1024, 0, STREAM>>>(B, n_out, status, T_cap, reinterpret_cast<long long*>(offsets));
     CHECK_LAUNCH("vap_export_rows/offsets");
-    dim3 grid(blocks_for(T_cap, 256), (unsigned)B);
-    k_export_rows<<<grid, 256, 0, STREAM>>>(B, n_out, status, T_cap, oplane, out, reinterpret_cast<const long long*>(offsets), dst);
+    const unsigned tx = blocks_for(T_cap, 256);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_export_rows: more than 2^31 CTAs (tile the batch)");
+    const unsigned grid = tx * (unsigned)B;
+    k_export_rows<<<grid, 256, 0, STREAM>>>(B, n_out, status, T_cap, oplane, out, reinterpret_cast<const long long*>(offsets), dst, tx);
     CHECK_LAUNCH("vap_export_rows");
     return 0;
 }

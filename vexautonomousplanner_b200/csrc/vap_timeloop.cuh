@@ -305,14 +305,15 @@ __global__ void __launch_bounds__(256, 8) k_time_sample(
     const double* __restrict__ total_len, int spn, long long P_cap, const double* __restrict__ prop_k,
     const double* __restrict__ prop_h, long long M_cap, const int* __restrict__ n_main, double* __restrict__ stage,
     int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc,
-    const int* __restrict__ lut_inv)
+    const int* __restrict__ lut_inv, unsigned tiles_x)
 {
     __shared__ double s_t[257];
-    long long b = blockIdx.y;
+    const PathTile pt = path_tile(tiles_x);
+    long long b = pt.b;
     if (status[b] != ST_OK) return;
     long long M = n_main[b];
     if (M > M_cap || M < 0) return;            // capacity overflow (the caller re-runs with a larger M_cap) or diverged
-    long long k0 = (long long)blockIdx.x * blockDim.x;
+    long long k0 = (long long)pt.x * blockDim.x;
     if (k0 >= M) return;
     long long k = k0 + threadIdx.x;
     const int n = n_nodes[b];
@@ -560,13 +561,14 @@ __global__ void __launch_bounds__(256) k_time_finalize(long long B, const int* _
                                                        const int* __restrict__ seg_off, const int* __restrict__ seg_rev,
                                                        const int* __restrict__ n_seg, long long T_cap,
                                                        long long oplane, double* __restrict__ out,
-                                                       double* __restrict__ summary)
+                                                       double* __restrict__ summary, unsigned tiles_x)
 {
     __shared__ double s_max[8];
-    long long b = blockIdx.y;
+    const PathTile pt = path_tile(tiles_x);
+    long long b = pt.b;
     if (status[b] != ST_OK) return;
     long long M = n_main[b];
-    long long k0 = (long long)blockIdx.x * blockDim.x;
+    long long k0 = (long long)pt.x * blockDim.x;
     if (k0 >= M) return;
     long long k = k0 + threadIdx.x;
     const int ns = n_seg[b];
@@ -668,13 +670,15 @@ __global__ void __launch_bounds__(256) k_pack_rows(long long B, const int* __res
 __global__ void __launch_bounds__(256) k_export_rows(long long B, const int* __restrict__ n_out,
                                                      const int* __restrict__ status, long long T_cap, long long oplane,
                                                      const double* __restrict__ out,
-                                                     const long long* __restrict__ offsets, double* __restrict__ dst)
+                                                     const long long* __restrict__ offsets, double* __restrict__ dst,
+                                                     unsigned tiles_x)
 {
-    long long b = blockIdx.y;
+    const PathTile pt = path_tile(tiles_x);
+    long long b = pt.b;
     if (status[b] != ST_OK) return;
     long long n = n_out[b];
     if (n > T_cap) n = T_cap;
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long k = (long long)pt.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const double* src = out + (size_t)b * T_cap + k;
     double* d = dst + 7 * (offsets[b] + k);

@@ -32,13 +32,14 @@ __global__ void __launch_bounds__(256, 8) k_dist_sample_ev(
     const double* __restrict__ prop_k, const double* __restrict__ prop_h, long long D_cap,
     const int* __restrict__ n_samples, double* __restrict__ t_out, double* __restrict__ kap, double* __restrict__ th,
     int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc,
-    const int* __restrict__ lut_inv)
+    const int* __restrict__ lut_inv, unsigned tiles_x)
 {
     __shared__ double s_t[257];
-    long long b = blockIdx.y;
+    const PathTile pt = path_tile(tiles_x);
+    long long b = pt.b;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
-    const int i0 = blockIdx.x * blockDim.x;
+    const int i0 = pt.x * blockDim.x;
     if (i0 >= D) return;
     const int i = i0 + threadIdx.x;
     const int n = n_nodes[b];
@@ -316,10 +317,11 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     const int* __restrict__ status, const double* __restrict__ cons, long long D_cap, const int* __restrict__ n_samples,
     const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec,
     int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, double* __restrict__ statB)
+    const int* __restrict__ n_ev, double* __restrict__ statB, unsigned tiles_x)
 {
     extern __shared__ double s_tile[];               // two tile buffers: one barrier per tile
-    const long long b = blockIdx.y;
+    const PathTile pt = path_tile(tiles_x);
+    const long long b = pt.b;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
     // does some node / action point override max_acceleration?  One regime per thread, loaded here and compared at the
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     const int sh = 31 - __clz(NT);                   // NT is a power of two: every index split below is a shift
     const int Lc = (steps + NT - 1) >> sh;           // chunk_len(steps, NT)
     const int jend = Lc << sh;
-    int j0 = blockIdx.x * (blockDim.x * PP_TILES);
+    int j0 = pt.x * (blockDim.x * PP_TILES);
     if (steps <= 0 || j0 >= jend) return;
     // kappa / theta of a tile's slots: rows s0 .. s0+RW-1 of every column plus the row after them, fetched with the lanes
     // running ALONG a column (contiguous samples) into shared memory
@@ -913,20 +915,22 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
 // last sample from slot RS-1.  grid = (row tiles * column tiles, B), 256 threads.
 __global__ void __launch_bounds__(256) k_untranspose(const int* __restrict__ status, const int* __restrict__ n_samples,
                                                      long long D_cap, long long RS, int NT,
-                                                     const double* __restrict__ vT, double* __restrict__ vel)
+                                                     const double* __restrict__ vT, double* __restrict__ vel,
+                                                     unsigned tiles_x)
 {
     __shared__ double tile[32][33];
-    const long long b = blockIdx.y;
+    const PathTile pt = path_tile(tiles_x);
+    const long long b = pt.b;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
     const int steps = D - 1;
     const double* src = vT + (size_t)b * RS;
     double* dst = vel + (size_t)b * D_cap;
-    if (blockIdx.x == 0 && threadIdx.x == 0) dst[D - 1] = src[RS - 1];
+    if (pt.x == 0 && threadIdx.x == 0) dst[D - 1] = src[RS - 1];
     if (steps <= 0) return;
     const int Lc = chunk_len(steps, NT);
     const int ctiles = (NT + 31) >> 5;
-    const int rt = blockIdx.x / ctiles, ct = blockIdx.x - rt * ctiles;
+    const int rt = pt.x / ctiles, ct = pt.x - rt * ctiles;
     const int s0 = rt * 32, c0 = ct * 32;
     if (s0 >= Lc) return;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;

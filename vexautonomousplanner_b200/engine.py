@@ -238,13 +238,10 @@ class Engine:
         t.P_cap = spn * db.N_max
         t.prop_k = self._empty((B, t.P_cap))
         t.prop_h = self._empty((B, t.P_cap))
-        for lo in range(0, B, 65535):
-            hi = min(B, lo + 65535)
-            _lib.check(self.lib.vap_build_props(C.c_int64(hi - lo), C.c_int(db.N_max), _p(db.n_nodes[lo:hi]), _p(g.seg[lo:hi]),
-                                                _p(g.first_node[lo:hi]), _p(g.param_end[lo:hi]), _p(g.n_splines[lo:hi]),
-                                                _p(g.status[lo:hi]), C.c_int(spn), C.c_int64(t.P_cap), _p(t.prop_k[lo:hi]),
-                                                _p(t.prop_h[lo:hi]), self._stream()), "vap_build_props")
-            self.launches += 1
+        _lib.check(self.lib.vap_build_props(C.c_int64(B), C.c_int(db.N_max), _p(db.n_nodes), _p(g.seg), _p(g.first_node),
+                                            _p(g.param_end), _p(g.n_splines), _p(g.status), C.c_int(spn), C.c_int64(t.P_cap),
+                                            _p(t.prop_k), _p(t.prop_h), self._stream()), "vap_build_props")
+        self.launches += 1
         return t
 
     def gl_queries(self, g: Geometry, path, spl, a, b, mode: int = 0, num_points: int = 20, max_iter: int = 50):
@@ -272,16 +269,12 @@ class Engine:
         grid = self.dgrid(D_cap + 2)
         n_samples = self._empty((B,), torch.int32)
         tq, kap, th = self._empty((B, D_cap)), self._empty((B, D_cap)), self._empty((B, D_cap))
-        for lo in range(0, B, 65535):
-            hi = min(B, lo + 65535)
-            _lib.check(self.lib.vap_dist_sample(C.c_int64(hi - lo), _p(db.n_nodes[lo:hi]), _p(g.n_splines[lo:hi]),
-                                                _p(status[lo:hi]), C.c_int64(grid.numel()), _p(grid), C.c_int(t.samples),
-                                                C.c_int64(t.Q_cap), _p(t.lut_d[lo:hi]), _p(t.lut_t[lo:hi]),
-                                                _p(t.total_len[lo:hi]), C.c_int(t.spn), C.c_int64(t.P_cap),
-                                                _p(t.prop_k[lo:hi]), _p(t.prop_h[lo:hi]), C.c_int64(D_cap),
-                                                _p(n_samples[lo:hi]), _p(tq[lo:hi]), _p(kap[lo:hi]), _p(th[lo:hi]),
-                                                self._stream()), "vap_dist_sample")
-            self.launches += 2
+        _lib.check(self.lib.vap_dist_sample(C.c_int64(B), _p(db.n_nodes), _p(g.n_splines), _p(status), C.c_int64(grid.numel()),
+                                            _p(grid), C.c_int(t.samples), C.c_int64(t.Q_cap), _p(t.lut_d), _p(t.lut_t),
+                                            _p(t.total_len), C.c_int(t.spn), C.c_int64(t.P_cap), _p(t.prop_k), _p(t.prop_h),
+                                            C.c_int64(D_cap), _p(n_samples), _p(tq), _p(kap), _p(th), self._stream()),
+                   "vap_dist_sample")
+        self.launches += 2
         return n_samples, tq, kap, th
 
     def fwd_bwd(self, db: DeviceBatch, status, D_cap, n_samples, tq, kap, th, mode: int = 0):
@@ -306,8 +299,6 @@ class Engine:
                          outs: Optional[dict] = None, want_t: bool = True):
         """S3 + events + S4 + S5, fast path: sample-parallel events, hoisted pre-pass, chunk-speculative passes."""
         B = db.B
-        if B > 65535:
-            raise _lib.VapError("tile the batch: at most 65535 paths per profile() call")
         E_cap = db.N_max + db.A_max + 2
         grid = self.dgrid(D_cap + 2)
         n_samples = outs["n_samples"] if outs else self._empty((B,), torch.int32)
@@ -393,8 +384,6 @@ class Engine:
                      outs: Optional[dict] = None):
         """S6 + S7, fast path (vap_time_profile): state recurrence / parallel lookups / event replay / scatter."""
         B = db.B
-        if B > 65535:
-            raise _lib.VapError("tile the batch: at most 65535 paths per profile() call")
         E_cap = db.N_max + db.A_max + 2
         plane_stride = 0
         if outs:
@@ -627,10 +616,12 @@ class Engine:
             host = self.profile_to_host(packed, tiles, None)
         return host
 
-    def capture(self, db: DeviceBatch, tiles: int = 4, to_host: bool = False) -> "GraphedProfile":
+    def capture(self, db: DeviceBatch, tiles: int = 4, to_host: bool = False, margin: float = 1.0) -> "GraphedProfile":
         """Capture the tiled fast path for this batch shape into a CUDA graph (one launch per step afterwards).
-        to_host=True adds the pack kernels that stream the dense result rows into pinned host memory."""
-        return GraphedProfile(self, db, tiles, to_host=to_host)
+        to_host=True adds the pack kernels that stream the dense result rows into pinned host memory.
+        margin > 1 enlarges the capacities planned from `db`, for graphs that will be fed OTHER batches of the same shape
+        (run(new_db)); a batch that still does not fit is detected on the device and redone exactly, outside the graph."""
+        return GraphedProfile(self, db, tiles, to_host=to_host, margin=margin)
 
     # ------------------------------------------------------------------ whole path
     def _plan_distance(self, t: Tables, status: torch.Tensor) -> int:
@@ -774,7 +765,7 @@ class GraphedProfile:
     An undersized plan is detected after the replay and the step is redone exactly through Engine.profile.
     """
 
-    def __init__(self, eng: Engine, db: DeviceBatch, tiles: int = 4, to_host: bool = False):
+    def __init__(self, eng: Engine, db: DeviceBatch, tiles: int = 4, to_host: bool = False, margin: float = 1.0):
         if eng.velocity_impl != "chunked" or eng.time_impl != "split":
             raise ValueError("graph capture needs the fast path (velocity_impl='chunked', time_impl='split')")
         self.eng, self.db, self.tiles = eng, db, max(1, min(tiles, db.B))
@@ -782,6 +773,10 @@ class GraphedProfile:
         key = (db.B, db.N_max, db.A_max, db.max_splines)
         warm = eng.profile(db, reuse_plan=True)                # sizes the plan, builds the distance grid
         self.D_cap, self.T_cap = eng._plan[key]
+        if margin > 1.0:
+            self.D_cap = (int(self.D_cap * margin) + 127) // 128 * 128
+            self.T_cap = int(self.T_cap * margin) + 64
+            eng._plan[key] = (max(self.D_cap, eng._plan[key][0]), max(self.T_cap, eng._plan[key][1]))
         if to_host:
             self.host = HostResult(eng, db.B, db.N_max, db.A_max, self.T_cap, self.tiles)
             self.host_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
@@ -826,3 +821,48 @@ class GraphedProfile:
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.host_in)
+
+
+class PipelinedProfiler:
+    """Independent batches of one shape, software-pipelined on the device: `depth` CUDA graphs (each with its own static
+    inputs, scratch and outputs) are replayed round-robin on `depth` streams, so that the latency-bound tails of batch n
+    (the per-path time loop runs one warp per scheduler and uses ~6 % of the warp slots, the event replays a few threads)
+    overlap the bandwidth-bound front of batch n+1 instead of leaving the GPU idle.  Every batch still runs every kernel.
+
+    submit(new_db, consume): enqueue one batch -- copy `new_db` (None: the slot keeps its inputs) into the slot's static
+    inputs, replay, then call consume(result) with the slot's stream current, so that whatever it enqueues (a copy of the
+    summary rows, an export kernel, a device->host copy ...) is ordered before the slot is reused.  drain() joins all
+    streams back into the caller's stream.  Capacity overflows are reported in the status / summary rows as usual
+    (ST_CAPACITY); the caller redoes those batches through Engine.profile.
+    """
+
+    def __init__(self, eng: Engine, db: DeviceBatch, depth: int = 2, margin: float = 1.0):
+        self.eng, self.depth = eng, max(1, int(depth))
+
+        def clone(d: DeviceBatch) -> DeviceBatch:
+            return DeviceBatch(d.node_attr.clone(), d.node_flags.clone(), d.n_nodes.clone(), d.ap_attr.clone(),
+                               d.ap_flags.clone(), d.n_ap.clone(), d.cons.clone(), d.max_splines)
+        self.graphs = [eng.capture(db if k == 0 else clone(db), tiles=1, margin=margin) for k in range(self.depth)]
+        self.streams = [torch.cuda.Stream(device=eng.device) for _ in range(self.depth)]
+        self.n = 0
+
+    def submit(self, new_db: Optional[DeviceBatch] = None, consume=None) -> ProfileResult:
+        k = self.n % self.depth
+        g, st = self.graphs[k], self.streams[k]
+        st.wait_stream(torch.cuda.current_stream(self.eng.device))          # inputs prepared on the caller's stream
+        with torch.cuda.stream(st):
+            if new_db is not None:
+                for name in ("node_attr", "node_flags", "n_nodes", "ap_attr", "ap_flags", "n_ap", "cons"):
+                    getattr(g.db, name).copy_(getattr(new_db, name), non_blocking=True)
+            g.graph.replay()
+            if consume is not None:
+                consume(g.res)
+        self.eng.launches += g.launches_per_run
+        self.n += 1
+        return g.res
+
+    def drain(self) -> None:
+        main = torch.cuda.current_stream(self.eng.device)
+        for st in self.streams:
+            main.wait_stream(st)
+        self.n = 0
