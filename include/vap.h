@@ -152,11 +152,13 @@ int vap_fwd_bwd(int64_t B, int N_max, int A_max, const double* node_attr, const 
  *     the events (per sample |kappa|, the velocity caps, the static acceleration limit; per step the wheel-acceleration
  *     denominator and its reciprocal), then the forward and backward passes (:188-314) with `chunks` (32, 64, 128 or 256)
  *     speculative chunks per path that are re-run until they merge bitwise with the serial evaluation.  The arrays the
- *     passes stream are chunk-interleaved (step s of chunk c in row s, column c) so that every warp-wide access is one
- *     contiguous run: rec [B][RS][5] f64 (rows of five field planes of `chunks` columns), statB / vel_f / velT [B][RS] f64
- *     (the backward pass's static acceleration limit, touched only for paths with max_acceleration overrides; forward /
- *     final velocities; all slot order), RS = vap_pass_row_slots(D_cap).  vel[B][D_cap]: final velocities in
- *     sample order (mode 1: the forward velocities in sample order); t_est[B] f32; rounds[B][2] fix-up sweeps.     */
+ *     passes stream are chunk-interleaved in blocks of four steps (steps 4k .. 4k+3 of chunk c are one 32-byte sector;
+ *     sector (k, c) follows sector (k, c-1)) so that every warp-wide access is one contiguous run and a chunk re-run
+ *     alone fetches only bytes it uses: rec [B][RS][5] f64 (per block five field planes of 4 x `chunks` doubles),
+ *     statB / vel_f [B][RS] f64 (the backward pass's static acceleration limit, touched only for paths with
+ *     max_acceleration overrides; forward velocities; both slot order), RS = vap_pass_row_slots(D_cap, chunks).
+ *     vel[B][D_cap] (D_cap even): final velocities in sample order, written by the backward pass itself (mode 1: the
+ *     forward velocities in sample order); t_est[B] f32; rounds[B][2] fix-up sweeps.     */
 int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
                            const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
                            const double* cons, const int32_t* n_splines, int32_t* status, int64_t n_grid,
@@ -167,13 +169,13 @@ int vap_dist_sample_events(int64_t B, int N_max, int A_max, const double* node_a
                            double* vr_val, int32_t* st_idx, int32_t* n_vr, double dt, float* ins_est,
                            int32_t* ev_scratch, const int32_t* lut_inv, void* stream);
 int64_t vap_event_scratch_ints(int64_t B, int N_max, int A_max);
-int64_t vap_pass_row_slots(int64_t D_cap);
+int64_t vap_pass_row_slots(int64_t D_cap, int chunks);
 int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt, double start_vel,
                         double end_vel, int64_t D_cap, const int32_t* n_samples, const double* kap, const double* th,
                         int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
                         const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
-                        const int32_t* n_vr, double* rec, double* statB, double* vel_f, double* velT, double* vel,
-                        float* t_est, int32_t* rounds, int chunks, int mode, void* stream);
+                        const int32_t* n_vr, double* rec, double* statB, double* vel_f, double* vel, float* t_est,
+                        int32_t* rounds, int chunks, int mode, void* stream);
 
 /* S6  generate_motion_profile time loop + node-0 prologue + turn / wait inserts
  *     (motion_profile_generator.py:414-628, one_dim_mp_generator.py:4-69) and S7 summary rows.

@@ -9,12 +9,12 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libvap.so")
+SO_PATH = os.environ.get("VAP_LIB_PATH") or os.path.join(_HERE, "libvap.so")   # VAP_LIB_PATH: A/B builds of the engine
 SRC_DIR = os.path.join(_HERE, "csrc")
 SOURCES = ["vap_kernels.cu"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "vap.h")
 
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+NVCC_FLAGS = os.environ.get("VAP_NVCC_EXTRA", "").split() + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false",            # load-bearing: the reference never fuses multiply-add
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -37,6 +37,37 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): one instruction moves a whole
+// contiguous block (a 1 KB block of a time-loop thread's ring, a 1 KB plane of a pass warp's block row) instead of 64 LDGSTS.
+__device__ __forceinline__ void mbar_init(unsigned a, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy reads of a shared-memory slot must precede the async-proxy (TMA) writes that refill it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Kernels whose grid is (tiles of one path) x (paths) are launched on a 1-D grid of tiles_x * B CTAs (grid.y stops at
 // 65535 paths); a CTA finds its path and its tile with one division.  Tiles of a path stay adjacent in launch order.
 struct PathTile { long long b; unsigned x; };

@@ -1225,24 +1225,43 @@ extern "C" int64_t vap_event_scratch_ints(int64_t B, int N_max, int A_max)
     return B * N_max + B + B * Am * EV_AP_CAND + B * Am;
 }
 
-// slots per path row of the chunk-interleaved pass arrays (records, reciprocals, forward velocities)
-extern "C" int64_t vap_pass_row_slots(int64_t D_cap) { return D_cap + 512; }
+// slots per path row of the chunk-interleaved pass arrays (records, override limits, forward velocities): the samples, one
+// block of four rows per chunk for rounding the chunk length up, one more for the passes' look-ahead loads, the tail slot
+extern "C" int64_t vap_pass_row_slots(int64_t D_cap, int chunks) { return ((D_cap + 8 * (int64_t)chunks + 64 + 1) / 2) * 2; }
 
-template <int NT>
-static void launch_passes(int64_t B, size_t ss, cudaStream_t st, const double* cons, const int32_t* status, double dd, double dt,
-                          double start_vel, double end_vel, long long RS, const int32_t* n_samples, const double* rec,
-                          int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
-                          const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
-                          const int32_t* n_vr, double* vel_f, double* velT, float* t_est, int32_t* rounds, bool backward,
-                          int warm, int max_rounds, const double* statB)
+template <int NT, bool TMA>
+static int launch_passes_v(int64_t B, size_t ss, cudaStream_t st, const double* cons, const int32_t* status, double dd, double dt,
+                           double start_vel, double end_vel, long long RS, long long D_cap, const int32_t* n_samples,
+                           const double* rec, int E_cap, const double* max_accels, const int32_t* bidx, const int32_t* bval,
+                           const int32_t* n_ev, const int32_t* vr_idx, const double* vr_val, const int32_t* st_idx,
+                           const int32_t* n_vr, double* vel_f, double* vel, float* t_est, int32_t* rounds, bool backward,
+                           int warm, int max_rounds, const double* statB)
 {
-    if (!backward)
-        k_fwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, start_vel, end_vel, RS, n_samples, rec, E_cap,
-                                                       max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f,
-                                                       rounds, warm, max_rounds);
-    else
-        k_bwd_chunked<NT><<<(unsigned)B, NT, ss, st>>>(status, cons, dd, dt, end_vel, RS, n_samples, rec, E_cap, max_accels,
-                                                       bidx, bval, n_ev, vel_f, velT, t_est, rounds, warm, max_rounds, statB);
+    // TMA variant: behind the tables every warp has a two-stage ring of 5 (forward) / 6 (backward) planes of 1 KB + 2 mbarriers
+    const int warps = (NT + 31) / 32;
+    const int ring_off = (int)((ss + 127) / 128 * 128);
+    const int planes = backward ? 6 : 5;
+    const size_t smem = TMA ? (size_t)ring_off + (size_t)warps * (2 * planes * TMA_PLANE_DOUBLES * 8 + 16) : ss;
+    cudaError_t e = cudaSuccess;
+    if (!backward) {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_fwd_chunked<NT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_err("vap_fwd_bwd_chunked/attr", e);
+        k_fwd_chunked<NT, TMA><<<(unsigned)B, NT, smem, st>>>(status, cons, dd, start_vel, end_vel, RS, n_samples, rec, E_cap,
+                                                             max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f,
+                                                             rounds, warm, max_rounds, ring_off);
+    } else {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bwd_chunked<NT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_err("vap_fwd_bwd_chunked/attr", e);
+        k_bwd_chunked<NT, TMA><<<(unsigned)B, NT, smem, st>>>(status, cons, dd, dt, end_vel, RS, D_cap, n_samples, rec, E_cap,
+                                                             max_accels, bidx, bval, n_ev, vel_f, vel, t_est, rounds, warm,
+                                                             max_rounds, statB, ring_off);
+    }
+    return 0;
+}
+template <int NT, typename... Args>
+static int launch_passes(bool tma, Args... args)
+{
+    return tma ? launch_passes_v<NT, true>(args...) : launch_passes_v<NT, false>(args...);
 }
 
 extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
@@ -1250,58 +1269,57 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
                                    const double* kap, const double* th, int E_cap, const double* max_accels,
                                    const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
                                    const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* rec,
-                                   double* statB, double* vel_f, double* velT, double* vel, float* t_est, int32_t* rounds,
+                                   double* statB, double* vel_f, double* vel, float* t_est, int32_t* rounds,
                                    int chunks, int mode, void* stream)
 {
     if (B <= 0) return 0;
     if (chunks < 8 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be a power of two in 8 .. 256");
     if (D_cap > 400000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
-    const long long RS = vap_pass_row_slots(D_cap);
-    const unsigned tx = blocks_for(D_cap + chunks, 256 * PP_TILES);
+    if (D_cap & 1) return arg_err("vap_fwd_bwd_chunked: D_cap must be even (the passes move 16-byte pairs)");
+    const long long RS = vap_pass_row_slots(D_cap, chunks);
+    const unsigned tx = blocks_for(D_cap + 4 * chunks, 256 * PP_TILES);
     if ((long long)tx * B > 2147483647LL) return arg_err("vap_fwd_bwd_chunked: more than 2^31 CTAs (tile the batch)");
     const unsigned grid = tx * (unsigned)B;
-    // the kappa / theta tile: chunks columns x (256 / chunks + 1) rows, odd stride; two buffers
-    const size_t sm = 2 * 2 * sizeof(double) * (size_t)chunks * (((256 / chunks) + 1) | 1);
+    // the kappa / theta tile: min(chunks, 64) columns x (256 / columns + 1) rows, odd stride; two buffers
+    const size_t sm = 2 * 2 * sizeof(double) * (size_t)prepass_tile_cols(chunks) * prepass_tile_stride(chunks);
     k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec, E_cap, max_accels, bidx,
                                          bval, n_ev, statB, tx);
     CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
-    // CTA = one path, one chunk per thread.  The passes are bound by the latency of the dependent fp64 chain of a step:
-    // one-warp CTAs at 72 registers put 28 independent chains on every SM.
+    // CTA = one path, one chunk per thread.  One-warp CTAs at 72 registers put 28 independent chains on every SM.
     const size_t VC = 3 * (size_t)E_cap + 2;
     const size_t ss = ((size_t)chunks * 4 + E_cap + VC) * sizeof(double) + (E_cap + VC) * sizeof(int);
     // warm-up steps a speculative chunk runs before its own range (tuning: VAP_CHUNK_WARM; any value gives the same bits).
     // max_rounds only ever caps the fix-up rounds in profiling builds (-DVAP_DIAG_MAXROUNDS): it breaks exactness.
-    int warm = 96, max_rounds = 1 << 30;
+    int warm = 0, max_rounds = 1 << 30;
     if (const char* ev = getenv("VAP_CHUNK_WARM")) warm = atoi(ev);
 #ifdef VAP_DIAG_MAXROUNDS
     if (const char* ev = getenv("VAP_CHUNK_MAXROUNDS")) max_rounds = atoi(ev);
 #endif
     if (warm < 0) warm = 0;
-    auto passes = [&](bool backward) {
+    // first sweeps staged through shared memory by TMA bulk copies (default) or loaded by the lanes (VAP_PASS_TMA=0; same bits)
+    bool tma = true;
+    if (const char* ev = getenv("VAP_PASS_TMA")) tma = atoi(ev) != 0;
+    auto passes = [&](bool backward) -> int {
         switch (chunks) {
-#define VAP_PASS_CASE(N_) case N_: launch_passes<N_>(B, ss, STREAM, cons, status, dd, dt, start_vel, end_vel, RS, n_samples, rec, \
-                                              E_cap, max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, vel_f, velT,    \
-                                              t_est, rounds, backward, warm, max_rounds, statB); break;
+#define VAP_PASS_CASE(N_) case N_: return launch_passes<N_>(tma, B, ss, STREAM, cons, status, dd, dt, start_vel, end_vel, RS, D_cap,   \
+                                              n_samples, rec, E_cap, max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr,  \
+                                              vel_f, vel, t_est, rounds, backward, warm, max_rounds, statB);
             VAP_PASS_CASE(8) VAP_PASS_CASE(16) VAP_PASS_CASE(32) VAP_PASS_CASE(64) VAP_PASS_CASE(128) VAP_PASS_CASE(256)
 #undef VAP_PASS_CASE
         }
+        return 0;
     };
-    passes(false);
+    if (int rc = passes(false)) return rc;
     CHECK_LAUNCH("vap_fwd_bwd_chunked/fwd");
-    // sample-order result: ceil(Lc_max / 32) row tiles x chunks / 32 column tiles per path
-    const long long lc_max = (D_cap + chunks - 1) / chunks + 1;
-    const unsigned tx2 = (unsigned)(((lc_max + 31) / 32) * ((chunks + 31) / 32));
-    if ((long long)tx2 * B > 2147483647LL) return arg_err("vap_fwd_bwd_chunked: more than 2^31 CTAs (tile the batch)");
-    const unsigned g2 = tx2 * (unsigned)B;
-    if (mode == 1) {
-        k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, vel_f, vel, tx2);
+    if (mode == 1) {                 // forward velocities only: slot order -> sample order
+        const unsigned tx2 = blocks_for(D_cap, 256);
+        if ((long long)tx2 * B > 2147483647LL) return arg_err("vap_fwd_bwd_chunked: more than 2^31 CTAs (tile the batch)");
+        k_untranspose<<<tx2 * (unsigned)B, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, vel_f, vel, tx2);
         CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
         return 0;
     }
-    passes(true);
+    if (int rc = passes(true)) return rc;      // writes vel in sample order itself
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
-    k_untranspose<<<g2, 256, 0, STREAM>>>(status, n_samples, D_cap, RS, chunks, velT, vel, tx2);
-    CHECK_LAUNCH("vap_fwd_bwd_chunked/untranspose");
     return 0;
 }
 

@@ -69,32 +69,7 @@ __device__ __forceinline__ int uniform_index32(double x, double dd, double inv_d
     return k;
 }
 
-// ---- TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): one instruction moves a whole 1 KB
-// block of a thread's ring, instead of 64 LDGSTS.  Every thread owns its two barriers (one per ring slot).
-__device__ __forceinline__ void mbar_init(unsigned a, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity)
-{
-    asm volatile("{\n"
-                 ".reg .pred P1;\n"
-                 "LAB_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-                 "@P1 bra DONE;\n"
-                 "bra LAB_WAIT;\n"
-                 "DONE:\n"
-                 "}" ::"r"(a), "r"(parity) : "memory");
-}
+// (the TMA bulk-copy / mbarrier helpers live in vap_device.cuh)
 
 // reciprocals of the lerp denominators xs[i+1] - xs[i], xs[i] = fl(i*dd) (path-independent, like the distance grid): the
 // time loop divides by them with one multiplication and two residual corrections (div_const) instead of a division.

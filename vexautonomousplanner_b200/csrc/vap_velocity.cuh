@@ -190,20 +190,34 @@ __global__ void k_resolve_events(long long B, int N_max, int A_max, const double
 
 __device__ __forceinline__ double recip_for_pass(double g);   // defined with the pass kernels below
 
-// ---- chunk-interleaved layout of everything the passes stream ---------------------------------------------------------
+// ---- chunk-interleaved, block-of-four layout of everything the passes stream ------------------------------------------
 // A path's D-1 steps ("edges" e = 0 .. D-2: forward step e goes from sample e to e+1, backward step e+1 from sample e+1
-// to e) are cut into NT chunks of Lc = ceil((D-1)/NT) edges; chunk c owns edges [c*Lc, min((c+1)*Lc, D-1)).  Thread c of a
-// pass CTA walks chunk c, so at any moment the warp needs edge s of 32 different chunks: the per-edge data is stored at
-//      slot(e) = (e % Lc) * NT + e / Lc          (row = position inside the chunk, column = chunk)
-// which makes every warp-wide load of the passes one contiguous, fully used run of memory (1 KB of records, 256 B of
-// reciprocals / forward velocities).  Rows of RS = D_cap + 256 slots per path; slot RS-1 holds the forward velocity of
+// to e) are cut into NT chunks of Lc edges (Lc = ceil((D-1)/NT) rounded up to a multiple of PB = 4); chunk c owns edges
+// [c*Lc, min((c+1)*Lc, D-1)).  Thread c of a pass CTA walks chunk c, so at any moment the warp needs edge s of 32 different
+// chunks.  The per-edge data is stored in BLOCKS of four consecutive rows of one chunk:
+//      slot(e) = ((r / 4) * NT + c) * 4 + r % 4          r = e % Lc (row = position inside the chunk), c = e / Lc (column)
+// so a lane's four consecutive steps are one 32-byte sector (fetched with two 16-byte loads), a warp-wide load is one
+// contiguous run of memory, and -- what the earlier row-interleaved layout (slot = r * NT + c) could not give -- a lane that
+// re-runs ALONE in a fix-up round fetches only sectors it uses entirely: measured with ncu on cfg2, the lone lanes of the
+// fix-up rounds cost 1.2 GB per pass in that layout (8 bytes used of every 64 fetched), as much as the 96-step warm-up
+// that avoids them.  Rows of RS = vap_pass_row_slots(D_cap, NT) slots per path; slot RS-1 holds the forward velocity of
 // the last sample.
-__device__ __forceinline__ int chunk_len(int steps, int NT) { return (steps + NT - 1) / NT; }
-__device__ __forceinline__ int edge_slot(int e, int Lc, int NT) { const int c = e / Lc; return (e - c * Lc) * NT + c; }
+#define PB 4
+__device__ __forceinline__ int chunk_len(int steps, int NT) { return (((steps + NT - 1) / NT) + PB - 1) & ~(PB - 1); }
+__device__ __forceinline__ int edge_slot(int e, int Lc, int NT)
+{
+    const int c = e / Lc, r = e - c * Lc;
+    return ((r >> 2) * NT + c) * PB + (r & 3);
+}
+// record element (row r, field f, column c) of a path: rec[((r / 4) * 5 + f) * 4 NT + 4 c + r % 4]
+__device__ __forceinline__ size_t rec_index(int r, int f, int c, int NT)
+{
+    return ((size_t)(r >> 2) * 5 + f) * (PB * NT) + (size_t)c * PB + (r & 3);
+}
 
 // ---- pre-pass (parallel): everything of a pass step that depends neither on the velocity state nor on the events --------
-// One row of 5 NT doubles per chunk position s: five field planes of NT columns, element (row s, field f, column c) of a
-// path is rec[(5 s + f) NT + c]; the terms of the final sample D-1 sit in the last three doubles of the path's 5 RS.
+// Per block of four chunk positions five field planes of 4 NT doubles: element (row s, field f, column c) of a path is
+// rec[rec_index(s, f, c)]; the terms of the final sample D-1 sit in the last three doubles of the path's 5 RS.
 // fields 0-2, per sample i (row / column of edge i):
 //    { |kappa_i|, G_i, stat_i }
 //       G_i    = min(vlim_i, cap_i)                         velocity caps (:212-218, :239)
@@ -303,7 +317,8 @@ __device__ __noinline__ void prepass_slot_ovr(long long b, int e, int j, int ste
     const double dec_b = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + nb - 1]];       // backward max_dec
     const double acc_f = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + last_le(bidx + (size_t)b * E_cap, nb, e)]];
     const SampleTerms t = prepass_sample<true>(V, acc_f, dec_b, w, max_angular_vel, max_angular_accel, k_e);
-    pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat; pr[o + 3 * NT] = gh; pr[o + 4 * NT] = recip_for_pass(gh);
+    const int PS = PB * NT;
+    pr[o] = t.ak; pr[o + PS] = t.G; pr[o + 2 * PS] = t.stat; pr[o + 3 * PS] = gh; pr[o + 4 * PS] = recip_for_pass(gh);
     statB[(size_t)b * RS + j] = t.stat_b;
     if (e == steps - 1) {
         const SampleTerms u = prepass_sample<true>(V, dec_b, dec_b, w, max_angular_vel, max_angular_accel, k_last);
@@ -312,7 +327,12 @@ __device__ __noinline__ void prepass_slot_ovr(long long b, int e, int j, int ste
     }
 }
 
+// One thread per SLOT (coalesced stores: 256 consecutive slots are whole 32-byte blocks of min(NT, 64) columns); kappa /
+// theta come through a shared-memory tile of TC = min(NT, 64) columns x TR = 256 / TC rows (+ one halo row for the heading
+// difference) whose loads run ALONG the columns (contiguous samples).
 #define PP_TILES 4          // 256-slot tiles per pre-pass CTA: the per-path preamble (status, sizes, override test, constants) is paid once
+__host__ __device__ __forceinline__ int prepass_tile_cols(int NT) { return NT < 64 ? NT : 64; }
+__host__ __device__ __forceinline__ int prepass_tile_stride(int NT) { return ((256 / prepass_tile_cols(NT)) + 1) | 1; }   // odd
 __global__ void __launch_bounds__(256, 8) k_prepass(
     const int* __restrict__ status, const double* __restrict__ cons, long long D_cap, const int* __restrict__ n_samples,
     const double* __restrict__ kap, const double* __restrict__ th, int NT, long long RS, double* __restrict__ rec,
@@ -332,17 +352,17 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     const double o_A0 = cons[b * 6 + 1];
     const int steps = D - 1;
     const int sh = 31 - __clz(NT);                   // NT is a power of two: every index split below is a shift
-    const int Lc = (steps + NT - 1) >> sh;           // chunk_len(steps, NT)
+    const int Lc = chunk_len(steps, NT);
     const int jend = Lc << sh;
     int j0 = pt.x * (blockDim.x * PP_TILES);
     if (steps <= 0 || j0 >= jend) return;
-    // kappa / theta of a tile's slots: rows s0 .. s0+RW-1 of every column plus the row after them, fetched with the lanes
-    // running ALONG a column (contiguous samples) into shared memory
     const double* kr = kap + (size_t)b * D_cap;
     const double* tr = th + (size_t)b * D_cap;
-    const int rsh = 8 - sh;                          // blockDim.x == 256: RW = 256 / NT rows per tile
-    const int RW = 1 << rsh;
-    const int st = (RW + 1) | 1;                     // odd tile stride
+    const int tcsh = sh < 6 ? sh : 6;                // blockDim.x == 256: TC = min(NT, 64) columns x TR = 256 / TC rows per tile
+    const int TC = 1 << tcsh;
+    const int trsh = 8 - tcsh;
+    const int TR = 1 << trsh;
+    const int st = (TR + 1) | 1;                     // odd tile stride
     __shared__ double s_c[2];                        // per-path constants: one thread divides, not all 256
     if (threadIdx.x == 0) {
         const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
@@ -353,44 +373,47 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     for (int q = threadIdx.x + blockDim.x; q < o_n; q += blockDim.x) p_ovr |= (max_accels[(size_t)b * E_cap + q] != o_A0);
     const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
     double* pr = rec + (size_t)b * RS * 5;
+    const int PS = PB * NT;                          // plane stride inside a block
     int ovr = 0;
     for (int it = 0; it < PP_TILES && j0 < jend; ++it, j0 += blockDim.x) {
-        double* t_th = s_tile + (it & 1) * (2 * NT * st);
-        double* t_k = t_th + NT * st;
-        const int s0 = j0 >> sh;
+        double* t_th = s_tile + (it & 1) * (2 * TC * st);
+        double* t_k = t_th + TC * st;
+        const int c0 = (j0 >> 2) & (NT - 1);         // first column of the tile (0 unless NT > 64)
+        const int s0 = (j0 >> (sh + 2)) << 2;        // first row of the tile
         {
-            const int cc = threadIdx.x >> rsh, r = threadIdx.x & (RW - 1);
-            int ee = cc * Lc + s0 + r;
+            const int cc = threadIdx.x >> trsh, r = threadIdx.x & (TR - 1);
+            int ee = (c0 + cc) * Lc + s0 + r;
             ee = ee > D - 1 ? D - 1 : ee;
             t_th[cc * st + r] = tr[ee];
             t_k[cc * st + r] = kr[ee];
-            if (threadIdx.x < NT) {                  // the halo row
-                int eh = threadIdx.x * Lc + s0 + RW;
+            if ((int)threadIdx.x < TC) {             // the halo row
+                int eh = (c0 + threadIdx.x) * Lc + s0 + TR;
                 eh = eh > D - 1 ? D - 1 : eh;
-                t_th[threadIdx.x * st + RW] = tr[eh];
+                t_th[threadIdx.x * st + TR] = tr[eh];
             }
         }
         // the barrier of the first tile also carries the override vote and publishes s_c; the other buffer is free again
         // one barrier later, when every thread has left the tile before
         if (it == 0) ovr = __syncthreads_or(p_ovr); else __syncthreads();
         const int j = j0 + threadIdx.x;
-        const int s = j >> sh, c = j & (NT - 1);
+        const int c = (j >> 2) & (NT - 1);
+        const int s = ((j >> (sh + 2)) << 2) + (j & 3);
         const int e = c * Lc + s;              // this slot's edge = the sample whose terms this thread evaluates
         if (s >= Lc || e >= steps) continue;
         const double max_angular_vel = s_c[0];
         const double max_angular_accel = s_c[1];
-        const int tl = c * st + (s - s0);
+        const int tl = (c - c0) * st + (s - s0);
         const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
         // without overrides both passes use the path's A0 (the common case, kept free of any table code); with them the
         // forward regime of this sample is looked up and the backward limit goes to its own slot-order array
-        const size_t o = (size_t)s * 5 * NT + c;
+        const size_t o = (size_t)(j >> (sh + 2)) * (5 * PS) + (size_t)(j & (PS - 1));
         if (ovr) {                                  // uniform over the CTA; rare
             prepass_slot_ovr(b, e, j, steps, D, NT, RS, E_cap, V, w, max_angular_vel, max_angular_accel, t_k[tl], kr[D - 1],
                              gh, max_accels, bidx, bval, n_ev, pr, o, statB);
             continue;
         }
         const SampleTerms t = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, t_k[tl]);
-        pr[o] = t.ak; pr[o + NT] = t.G; pr[o + 2 * NT] = t.stat; pr[o + 3 * NT] = gh; pr[o + 4 * NT] = recip_for_pass(gh);
+        pr[o] = t.ak; pr[o + PS] = t.G; pr[o + 2 * PS] = t.stat; pr[o + 3 * PS] = gh; pr[o + 4 * PS] = recip_for_pass(gh);
         if (e == steps - 1) {                       // the final sample (no edge starts there): the backward pass starts on it
             const SampleTerms u = prepass_sample<false>(V, A0, A0, w, max_angular_vel, max_angular_accel, kr[D - 1]);
             pr[5 * RS - 3] = u.ak; pr[5 * RS - 2] = u.G; pr[5 * RS - 1] = u.stat;
@@ -514,6 +537,23 @@ __device__ __forceinline__ double bwd_step(double ak, double gh, double rg, doub
 // reciprocal from the pre-pass, coalesced slot-order streams.
 // ------------------------------------------------------------------------------------------------------------------
 #define CH_INT_MAX 2147483647
+#ifndef VAP_PASS_REGS
+#define VAP_PASS_REGS 72     // one-warp CTAs: 28 per SM, 4144 >= 4096 paths in one wave
+#endif
+#ifndef VAP_PASS_REGS_TMA
+#define VAP_PASS_REGS_TMA 96 // the TMA variant is limited by its shared-memory rings (10 - 12 KB per warp), not by registers
+#endif
+
+// 16-byte read-only load of two consecutive doubles
+__device__ __forceinline__ double2 ldg_d2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void st_d2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+
+// contribution of one step to the travel-time estimate (single precision: it only sizes buffers)
+__device__ __forceinline__ float t_est_term(double va, double vb, float dd_over_dt)
+{
+    const float vm = 0.5f * ((float)va + (float)vb);
+    return __fdividef(dd_over_dt, fmaxf(vm, 0.05f));
+}
 
 // per-path event tables of the forward pass in shared memory
 struct FwdTables {
@@ -521,18 +561,24 @@ struct FwdTables {
     const int* vi; const double* vv; int n_v;        // initial velocity: vv[j] from sample vi[j] on (stops / end included)
 };
 
-// forward chunk: edges lo .. lo+len-1; p points at (row 0, field 0, own column) of the record rows, q at row 0 of the forward
-// velocities.  Edge e = lo + r reads row r and writes the forward velocity of sample e+1 into row r+1 (the bottom of the chunk
-// writes *last: row 0 of the next column, or the tail slot).  NT is a compile-time constant: every access is pointer +
-// immediate.
+// forward chunk: edges lo .. lo+len-1, lo at the first row of a block.  p points at (field 0, own column) of that block of the
+// record rows, q at the same block of the forward velocities (q[r] = velocity at sample lo + r).  A lane only ever writes
+// its OWN column: the velocity of sample lo+len is the start state of the next column's lane, which stores it itself; only
+// the path's last chunk writes it (to the tail slot).  Records come as 16-byte pairs, two steps per pair, the next pair
+// fetched while the current one is being used (two named buffers, no register rotation).  NT is a compile-time constant:
+// every access is pointer + immediate.  old_end: what this lane's previous run produced for sample lo+len (RUN_RERUN).
 #define RUN_SWEEP 0     // first sweep: plain stores
 #define RUN_RERUN 1     // fix-up: bitwise merge detection against the stored velocities
 #define RUN_DRY 2       // warm-up before a speculative chunk: state only, no stores
 template <int NT, int MODE>
-__device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __restrict__ q, double* __restrict__ last,
-                                        int lo, int len, const FwdTables& T, double hw,
+__device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __restrict__ q, double* __restrict__ tail,
+                                        double old_end, int lo, int len, const FwdTables& T, double hw,
                                         double dd, double& v, double& sq, bool prev_same)
 {
+    constexpr int PS = PB * NT, BS = 5 * PS;
+    constexpr bool RERUN = (MODE == RUN_RERUN);
+    constexpr bool DRY = (MODE == RUN_DRY);
+    constexpr bool SWEEP = (MODE == RUN_SWEEP);
     int j = 0;
     while (j + 1 < T.n_b && T.bi[j + 1] <= lo) j++;
     double acc = T.acc[j];
@@ -541,53 +587,193 @@ __device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __
     while (jv + 1 < T.n_v && T.vi[jv + 1] <= lo + 1) jv++;
     double v0n = T.vv[jv];
     int nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX;
-    double aka = __ldg(p), Ga = __ldg(p + NT), sta = __ldg(p + 2 * NT), gha = __ldg(p + 3 * NT), rga = __ldg(p + 4 * NT);
-    double akb, Gb, stb, ghb, rgb;
-    constexpr bool RERUN = (MODE == RUN_RERUN);
-    constexpr bool DRY = (MODE == RUN_DRY);
-    double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = (len > 1) ? q[NT] : *last;
     int e = lo;
     const int hi = lo + len;
 #define FWD_ONE(AK_, G_, ST_, GH_, RG_, OLD_)                                                                        \
         if (e == nb_next) { j++; acc = T.acc[j]; nb_next = (j + 1 < T.n_b) ? T.bi[j + 1] : CH_INT_MAX; }              \
         if (e + 1 == nv_next) { jv++; v0n = T.vv[jv]; nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX; }      \
-        {                                                                                                            \
-            v = fwd_step(AK_, GH_, RG_, ST_, pymin(v0n, G_), v, sq, acc, hw, dd);                                    \
-        }                                                                                                            \
+        v = fwd_step(AK_, GH_, RG_, ST_, pymin(v0n, G_), v, sq, acc, hw, dd);                                        \
         if (RERUN) {                                                                                                 \
             const bool same = same_bits(OLD_, v);                                                                    \
             if (same && prev_same) return true;       /* state equals the old run's: the rest is unchanged */        \
             prev_same = same;                                                                                        \
         }                                                                                                            \
-        if (++e >= hi) { if (!DRY) *last = v; break; }                                                               \
-        p += 5 * NT;                                                                                                 \
-        if (!DRY) { q += NT; *q = v; }
-    while (true) {
-        // ---- buffers a (look-ahead loads never leave the path's rows: they are padded)
-        akb = __ldg(p + 5 * NT); Gb = __ldg(p + 6 * NT); stb = __ldg(p + 7 * NT); ghb = __ldg(p + 8 * NT); rgb = __ldg(p + 9 * NT);
-        if (RERUN) oldb = (e + 2 < hi) ? q[2 * NT] : *last;
-        FWD_ONE(aka, Ga, sta, gha, rga, olda)
-        // ---- buffers b
-        aka = __ldg(p + 5 * NT); Ga = __ldg(p + 6 * NT); sta = __ldg(p + 7 * NT); gha = __ldg(p + 8 * NT); rga = __ldg(p + 9 * NT);
-        if (RERUN) olda = (e + 2 < hi) ? q[2 * NT] : *last;
-        FWD_ONE(akb, Gb, stb, ghb, rgb, oldb)
+        ++e;
+    double2 akA = ldg_d2(p), GA = ldg_d2(p + PS), stA = ldg_d2(p + 2 * PS), ghA = ldg_d2(p + 3 * PS), rgA = ldg_d2(p + 4 * PS);
+    double2 akB, GB, stB, ghB, rgB;
+    double2 oA = make_double2(0.0, 0.0), oB = oA;    // old velocities (RERUN): pair A = samples e, e+1; pair B = e+2, e+3
+    if (RERUN) oA = *reinterpret_cast<const double2*>(q);
+    // whole blocks (look-ahead loads never leave the path's rows: they are padded by one block)
+    for (int blk = len >> 2; blk > 0; --blk) {
+        akB = ldg_d2(p + 2); GB = ldg_d2(p + PS + 2); stB = ldg_d2(p + 2 * PS + 2); ghB = ldg_d2(p + 3 * PS + 2); rgB = ldg_d2(p + 4 * PS + 2);
+        if (RERUN) oB = *reinterpret_cast<const double2*>(q + 2);
+        const double vin = v;
+        FWD_ONE(akA.x, GA.x, stA.x, ghA.x, rgA.x, oA.y)
+        const double v1 = v;
+        if (RERUN) st_d2(q, vin, v1);                 // a re-run may leave at any step: store as soon as a pair is complete
+        FWD_ONE(akA.y, GA.y, stA.y, ghA.y, rgA.y, oB.x)
+        const double v2 = v;
+        p += BS;
+        akA = ldg_d2(p); GA = ldg_d2(p + PS); stA = ldg_d2(p + 2 * PS); ghA = ldg_d2(p + 3 * PS); rgA = ldg_d2(p + 4 * PS);
+        if (RERUN) oA = *reinterpret_cast<const double2*>(q + PS);
+        FWD_ONE(akB.x, GB.x, stB.x, ghB.x, rgB.x, oB.y)
+        if (RERUN) st_d2(q + 2, v2, v);
+        if (SWEEP) { st_d2(q, vin, v1); st_d2(q + 2, v2, v); }   // the whole 32-byte sector at once
+        FWD_ONE(akB.y, GB.y, stB.y, ghB.y, rgB.y, ((e + 1 < hi) ? oA.x : old_end))
+        q += PS;
+    }
+    // ragged end of the path's last chunk: up to three more edges, one at a time (their rows are in the A pairs / row 2)
+    if (e < hi) {
+        if (!DRY) q[0] = v;
+        const int rem = hi - e;
+        {
+            const double old = RERUN ? ((rem > 1) ? oA.y : old_end) : 0.0;
+            FWD_ONE(akA.x, GA.x, stA.x, ghA.x, rgA.x, old)
+            if (!DRY && e < hi) q[1] = v;
+        }
+        if (e < hi) {
+            const double old = RERUN ? ((rem > 2) ? q[2] : old_end) : 0.0;
+            FWD_ONE(akA.y, GA.y, stA.y, ghA.y, rgA.y, old)
+            if (!DRY && e < hi) q[2] = v;
+        }
+        if (e < hi) {
+            const double a2 = __ldg(p + 2), g2 = __ldg(p + PS + 2), s2 = __ldg(p + 2 * PS + 2), h2 = __ldg(p + 3 * PS + 2),
+                         r2 = __ldg(p + 4 * PS + 2);
+            FWD_ONE(a2, g2, s2, h2, r2, old_end)
+        }
     }
 #undef FWD_ONE
+    if (!DRY && tail) *tail = v;
     return false;
 }
 
-// Forward pass.  Chunk c = thread c.  vfT: forward velocities in slot order (vfT[slot(e)] = velocity at sample e).
+// ---- sweeps staged through shared memory by TMA -------------------------------------------------------------------------
+// In the block-of-four layout the share of one WARP (32 columns) in one block row is a contiguous 1 KB per field plane, so
+// the lockstep first sweep does not load records into registers at all: one lane issues one cp.async.bulk per plane and
+// block row (five for the forward pass; six for the backward pass, which also streams the forward velocities) into a two-stage
+// shared-memory ring that completes on an mbarrier, a whole block (four steps) ahead of its use.  A step then takes its five
+// values from shared memory.  Nothing of the stream passes through L1, no look-ahead buffers live in registers, and the HBM
+// reads are 1 KB bursts issued thousands of cycles before they are needed.
+#define TMA_PLANE_DOUBLES (PB * 32)                    // one plane of one stage: 32 columns x 4 rows
+struct WarpRing {
+    double* stage;       // this warp's two stages
+    unsigned bar;        // shared-memory address of its two mbarriers
+    int planes;          // field planes per stage (5 forward, 6 backward)
+    unsigned bytes;      // bytes of one plane copy (32 bytes per column of the warp)
+};
+// lane 0: refill stage `s` with block row `rb`; src[f] = plane f of block row 0 at the warp's first column, strides in doubles
 template <int NT>
-__global__ void __maxnreg__(72) k_fwd_chunked(
+__device__ __forceinline__ void ring_issue(const WarpRing& R, int s, const double* rec_row0, const double* x_row0,
+                                           const double* sb_row0, int rb)
+{
+    constexpr int PS = PB * NT, BS = 5 * PS;
+    const unsigned bar = R.bar + 8 * s;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(R.stage + (size_t)s * R.planes * TMA_PLANE_DOUBLES);
+    fence_proxy_async();                                   // the lanes' reads of this stage precede the TMA writes
+    mbar_expect_tx(bar, R.bytes * R.planes);
+    const double* src = rec_row0 + (size_t)rb * BS;
+#pragma unroll
+    for (int f = 0; f < 5; f++) {
+        const double* g = (f == 2 && sb_row0) ? sb_row0 + (size_t)rb * PS : src + f * PS;
+        bulk_g2s(dst + f * TMA_PLANE_DOUBLES * 8, g, R.bytes, bar);
+    }
+    if (x_row0) bulk_g2s(dst + 5 * TMA_PLANE_DOUBLES * 8, x_row0 + (size_t)rb * PS, R.bytes, bar);
+}
+
+// forward first sweep of one warp: every lane walks its chunk (edges lo .. lo+len-1; len = 0 for an idle lane) in lockstep.
+// rec_w: field 0 of block row 0 at the warp's first column; lc: this lane's column minus the warp's first; q: own column of
+// the forward velocities (block row 0).
+template <int NT>
+__device__ __forceinline__ void fwd_sweep_tma(const WarpRing& R, const double* __restrict__ rec_w, int lc, double* __restrict__ q,
+                                              double* __restrict__ tail, int lo, int len, const FwdTables& T, double hw,
+                                              double dd, double& v, double& sq)
+{
+    constexpr int PS = PB * NT;
+    constexpr int PD = TMA_PLANE_DOUBLES;
+    const int lane = threadIdx.x & 31;
+    const int nbw = __reduce_max_sync(0xffffffffu, (len + PB - 1) >> 2);      // block rows the warp streams
+    if (lane == 0) {
+        if (nbw > 0) ring_issue<NT>(R, 0, rec_w, nullptr, nullptr, 0);
+        if (nbw > 1) ring_issue<NT>(R, 1, rec_w, nullptr, nullptr, 1);
+    }
+    int j = 0;
+    while (j + 1 < T.n_b && T.bi[j + 1] <= lo) j++;
+    double acc = T.acc[j];
+    int nb_next = (j + 1 < T.n_b) ? T.bi[j + 1] : CH_INT_MAX;
+    int jv = 0;                                      // initial velocity of sample e+1
+    while (jv + 1 < T.n_v && T.vi[jv + 1] <= lo + 1) jv++;
+    double v0n = T.vv[jv];
+    int nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX;
+    int e = lo;
+    const int hi = lo + len;
+    const int nfull = len >> 2;
+#define FWD_T(ROW_)                                                                                                  \
+        {                                                                                                            \
+            const double ak_ = S[ROW_], G_ = S[PD + ROW_], st_ = S[2 * PD + ROW_], gh_ = S[3 * PD + ROW_],             \
+                         rg_ = S[4 * PD + ROW_];                                                                     \
+            if (e == nb_next) { j++; acc = T.acc[j]; nb_next = (j + 1 < T.n_b) ? T.bi[j + 1] : CH_INT_MAX; }          \
+            if (e + 1 == nv_next) { jv++; v0n = T.vv[jv]; nv_next = (jv + 1 < T.n_v) ? T.vi[jv + 1] : CH_INT_MAX; }  \
+            v = fwd_step(ak_, gh_, rg_, st_, pymin(v0n, G_), v, sq, acc, hw, dd);                                    \
+            ++e;                                                                                                     \
+        }
+    for (int blk = 0; blk < nbw; ++blk) {
+        const int s = blk & 1;
+        mbar_wait(R.bar + 8 * s, (blk >> 1) & 1);
+        const double* S = R.stage + (size_t)s * 5 * PD + lc * PB;
+        if (blk < nfull) {                           // a whole block of this lane's chunk
+            const double vin = v;
+            FWD_T(0)
+            const double v1 = v;
+            FWD_T(1)
+            const double v2 = v;
+            FWD_T(2)
+            st_d2(q, vin, v1); st_d2(q + 2, v2, v);  // samples e0 .. e0+3: the whole 32-byte sector
+            FWD_T(3)
+            q += PS;
+        } else if (e < hi) {                         // ragged end of the path's last chunk: up to three edges
+            q[0] = v;
+            FWD_T(0)
+            if (e < hi) { q[1] = v; FWD_T(1) }
+            if (e < hi) { q[2] = v; FWD_T(2) }
+        }
+        __syncwarp();
+        if (lane == 0 && blk + 2 < nbw) ring_issue<NT>(R, s, rec_w, nullptr, nullptr, blk + 2);
+    }
+#undef FWD_T
+    if (tail && len > 0) *tail = v;
+}
+
+// The fix-up re-runs and the warm-up run are cold, divergent code: out of line, so that their registers do not count against
+// the lockstep sweep (state goes through a two-element array).
+template <int NT>
+__device__ __noinline__ bool fwd_rerun(const double* p, double* q, double* tail, double old_end, int lo, int len, FwdTables T,
+                                       double hw, double dd, double* st, bool prev_same)
+{
+    double v = st[0], sq = st[1];
+    const bool merged = fwd_run<NT, RUN_RERUN>(p, q, tail, old_end, lo, len, T, hw, dd, v, sq, prev_same);
+    st[0] = v; st[1] = sq;
+    return merged;
+}
+template <int NT>
+__device__ __noinline__ void fwd_dry(const double* p, int lo, int len, FwdTables T, double hw, double dd, double* st)
+{
+    double v = st[0], sq = st[1];
+    fwd_run<NT, RUN_DRY>(p, nullptr, nullptr, 0.0, lo, len, T, hw, dd, v, sq, false);
+    st[0] = v; st[1] = sq;
+}
+
+// Forward pass.  Chunk c = thread c.  vfT: forward velocities in slot order (vfT[slot(e)] = velocity at sample e), the
+// velocity of the last sample in slot RS-1.
+template <int NT, bool TMA>
+__global__ void __maxnreg__(TMA ? VAP_PASS_REGS_TMA : VAP_PASS_REGS) k_fwd_chunked(
     const int* __restrict__ status, const double* __restrict__ cons, double dd, double start_vel, double end_vel,
     long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
     const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
     const int* __restrict__ n_ev, const int* __restrict__ vr_idx, const double* __restrict__ vr_val,
     const int* __restrict__ st_idx, const int* __restrict__ n_vr, double* __restrict__ vfT, int* __restrict__ rounds_out,
-    int warm, int max_rounds)
+    int warm, int max_rounds, int ring_off)
 {
-    extern __shared__ __align__(16) unsigned char s_mem[];
+    extern __shared__ __align__(128) unsigned char s_mem[];
     const int c = threadIdx.x;
     const long long b = blockIdx.x;
     const int VC = 3 * E_cap + 2;                                  // capacity of the initial-velocity table
@@ -641,35 +827,52 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
     const int lo = c * Lc;
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
     const double* P = rec + (size_t)b * RS * 5;
-    double* last = vf + ((lo + len < steps) ? c + 1 : (int)(RS - 1));       // where the velocity of sample lo+len goes
+    double* tail = (active && lo + len == steps) ? vf + (RS - 1) : nullptr;  // only the last chunk stores the final sample
     const double hw = cons[b * 6 + 5] * 0.5;
+    // TMA variant: every warp owns a two-stage ring (5 planes of 1 KB per stage) and two mbarriers behind the tables
+    WarpRing R;
+    if (TMA) {
+        constexpr int WARPS = (NT + 31) / 32;
+        const int w = c >> 5;
+        R.stage = reinterpret_cast<double*>(s_mem + ring_off) + (size_t)w * 2 * 5 * TMA_PLANE_DOUBLES;
+        R.bar = (unsigned)__cvta_generic_to_shared(s_mem + ring_off + (size_t)WARPS * 2 * 5 * TMA_PLANE_DOUBLES * 8 + 16 * w);
+        R.planes = 5;
+        R.bytes = (NT < 32 ? NT : 32) * PB * 8;
+        if ((c & 31) == 0) { mbar_init(R.bar, 1); mbar_init(R.bar + 8, 1); fence_mbar_init(); }
+    }
     __syncthreads();
     FwdTables T;
     T.bi = s_bi; T.acc = s_acc; T.n_b = n_b; T.vi = s_vi; T.vv = s_vv; T.n_v = s_nv;
 
-    // ---- sweep 1: chunk c > 0 starts `wl` steps BEFORE its own range (in the previous column) from the guess "the state-
+    // ---- sweep 1: chunk c > 0 may start `wl` steps BEFORE its own range (in the previous column) from the guess "the state-
     // independent caps bind on the two samples before that point": v[s0] = C[s0-1] = min(v0[s0], G[s0-1]) and
-    // omega_prev = C[s0-2] |kappa[s0-1]|, and only computes (no stores) until it reaches its range: a wrong guess survives for
-    // at most one acceleration ramp, so after the warm-up the state is usually the true one and the fix-up rounds have little
-    // to re-run.  (Exactness never depends on the guess: the rounds below verify bitwise.)
+    // omega_prev = C[s0-2] |kappa[s0-1]|, and only compute (no stores) until it reaches its range.  In this layout a fix-up
+    // re-run costs only the sectors it uses, which is less than the warm-up reads: the default is no warm-up.
+    // (Exactness never depends on the guess: the rounds below verify bitwise.)
     {
         double v = start_vel, sq = 0.0;
         if (active) {
             if (c > 0) {
                 auto v0_at = [&](int x) { int q = 0; while (q + 1 < T.n_v && T.vi[q + 1] <= x) q++; return T.vv[q]; };
-                auto term = [&](int x, int fld) { const int cx = x / Lc, rx = x - cx * Lc; return __ldg(P + ((size_t)rx * 5 + fld) * NT + cx); };
+                auto term = [&](int x, int fld) { const int cx = x / Lc, rx = x - cx * Lc; return __ldg(P + rec_index(rx, fld, cx, NT)); };
                 int wl = warm < Lc ? warm : Lc;                      // the warm-up stays inside the previous column
                 if (wl > lo - 2) wl = lo - 2 > 0 ? lo - 2 : 0;
+                wl &= ~(PB - 1);                                     // ... and starts on a block
                 const int s0 = lo - wl;
                 const double vm1 = (s0 >= 2) ? pymin(v0_at(s0 - 1), term(s0 - 2, 1)) : start_vel;
                 v = pymin(v0_at(s0), term(s0 - 1, 1));
                 const double wp = vm1 * term(s0 - 1, 0);
                 sq = wp * wp;
-                if (wl > 0) fwd_run<NT, RUN_DRY>(P + (size_t)(Lc - wl) * 5 * NT + c - 1, nullptr, nullptr, s0, wl, T, hw, dd, v, sq, false);
+                if (wl > 0) {
+                    double st[2] = {v, sq};
+                    fwd_dry<NT>(P + rec_index(Lc - wl, 0, c - 1, NT), s0, wl, T, hw, dd, st);
+                    v = st[0]; sq = st[1];
+                }
             }
             s_usev[c] = v; s_usew[c] = sq;
-            fwd_run<NT, RUN_SWEEP>(P + c, vf + c, last, lo, len, T, hw, dd, v, sq, false);
+            if (!TMA) fwd_run<NT, RUN_SWEEP>(P + c * PB, vf + c * PB, tail, 0.0, lo, len, T, hw, dd, v, sq, false);
         }
+        if (TMA) fwd_sweep_tma<NT>(R, P + (c & ~31) * PB, c & 31, vf + c * PB, tail, lo, active ? len : 0, T, hw, dd, v, sq);
         s_endv[c] = v; s_endw[c] = sq;
     }
     __syncthreads();
@@ -686,85 +889,210 @@ __global__ void __maxnreg__(72) k_fwd_chunked(
         if (!__syncthreads_or(need)) break;          // also orders this round's reads before its writes
         rounds = round;
         if (need) {
-            double v = in_v, sq = in_w;
-            const bool merged = fwd_run<NT, RUN_RERUN>(P + c, vf + c, last, lo, len, T, hw, dd, v, sq,
-                                                  same_bits(in_v, s_usev[c]));
+            double st[2] = {in_v, in_w};
+            const bool merged = fwd_rerun<NT>(P + c * PB, vf + c * PB, tail, s_endv[c], lo, len, T, hw, dd, st,
+                                              same_bits(in_v, s_usev[c]));
             s_usev[c] = in_v; s_usew[c] = in_w;
-            if (!merged) { s_endv[c] = v; s_endw[c] = sq; }
+            if (!merged) { s_endv[c] = st[0]; s_endw[c] = st[1]; }
         }
         __syncthreads();
     }
     if (c == 0 && rounds_out) rounds_out[2 * b] = rounds;
 }
 
-// backward chunk: edges lo+len-1 down to lo.  p points at (row len-1, field 0, own column) of the record rows, f / o at the
-// same row of the forward / final velocities.  Edge e = lo + r (the reference's step i = e+1 -> e) uses the terms of sample
-// e+1 (fields 0-2 of row r+1; for the chunk's top edge the three `top` values), gh / rg (fields 3-4) and the forward velocity
-// of row r, and writes the final velocity of sample e into row r of the final velocities.
+// backward chunk: edges lo+len-1 down to lo (lo at the first row of a block).  p / f / sb point at (field 0, own column) of the
+// chunk's FIRST block of the record rows / forward velocities / override limits, o at sample lo of the path's final
+// velocities, which this pass writes in SAMPLE order (16-byte pairs: the time stage and the API read them as they are).
+// Edge e = lo + r (the reference's step i = e+1 -> e) uses the terms of sample e+1 (fields 0-2 of row r+1: carried over from
+// the pair above; for the chunk's top edge the three `top` values), gh / rg (fields 3-4) and the forward velocity of row r,
+// and writes the final velocity of sample e.
 // OVR: the path has max_acceleration overrides; the static limit of the backward pass then comes from its own slot-order
 // array `sb` (same slots as the forward velocities) instead of field 2 of the record rows.
 template <int NT, int MODE, bool OVR>
 __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const double* __restrict__ f, double* __restrict__ o,
                                         const double* __restrict__ sb, int lo, int len, double top_ak, double top_G,
                                         double top_st, const int* s_bi, const double* s_acc, int n_b, double acc0, double hw,
-                                        double dd, double& v, double& sq, bool prev_same)
+                                        double dd, double& v, double& sq, bool prev_same, float& est, float dd_over_dt,
+                                        double old_top = 0.0)
 {
+    constexpr int PS = PB * NT, BS = 5 * PS;
+    constexpr bool RERUN = (MODE == RUN_RERUN);
+    constexpr bool DRY = (MODE == RUN_DRY);
+    constexpr bool SWEEP = (MODE == RUN_SWEEP);
     // regime at the chunk start (walking down from D-1): the smallest boundary index > i was the last one applied
     int e = lo + len - 1;                            // current edge; the reference's loop index is i = e + 1
     int j = n_b - 1;
     double acc = acc0;
     while (j >= 0 && s_bi[j] > e + 1) { acc = s_acc[j]; j--; }
     int nb_next = (j >= 0) ? s_bi[j] : -1;
-    double aka = top_ak, Ga = top_G, sta = top_st, akb, Gb, stb;     // terms of sample e+1
-    double gha = __ldg(p + 3 * NT), rga = __ldg(p + 4 * NT), ghb, rgb;
-    constexpr bool RERUN = (MODE == RUN_RERUN);
-    constexpr bool DRY = (MODE == RUN_DRY);
-    double fa = __ldg(f), fb;
-    double olda = 0.0, oldb = 0.0;
-    if (RERUN) olda = *o;
-#define BWD_ONE(AK_, G_, ST_, GH_, RG_, F_, OLD_)                                                                    \
+    // est: travel-time estimate of the chunk's edges, kept up to date by the re-runs (new term minus old term per step; OLDUP_
+    // is the stored velocity of the sample above the step's)
+#define BWD_ONE(AK_, G_, ST_, GH_, RG_, F_, OLD_, OLDUP_)                                                            \
         if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }                             \
-        v = bwd_step(AK_, GH_, RG_, ST_, pymin(F_, G_), v, sq, acc, hw, dd);                                         \
+        {                                                                                                            \
+            const double vup = v;                                                                                    \
+            v = bwd_step(AK_, GH_, RG_, ST_, pymin(F_, G_), v, sq, acc, hw, dd);                                     \
+            if (!DRY) est += t_est_term(vup, v, dd_over_dt);                                                         \
+            if (RERUN) est -= t_est_term(OLDUP_, OLD_, dd_over_dt);                                                  \
+        }                                                                                                            \
         if (RERUN) {                                                                                                 \
             const bool same = same_bits(OLD_, v);                                                                    \
             if (same && prev_same) return true;                                                                      \
             prev_same = same;                                                                                        \
         }                                                                                                            \
-        if (!DRY) *o = v;                                                                                            \
-        if (--e < lo) break;                                                                                         \
-        p -= 5 * NT; f -= NT;                                                                                        \
-        if (OVR) sb -= NT;                                                                                           \
-        if (!DRY) o -= NT;
+        --e;
+    int blk = len >> 2;                              // whole blocks below the ragged top
+    p += (size_t)blk * BS; f += (size_t)blk * PS; sb += (size_t)blk * PS; if (!DRY) o += blk * PB;
+    double tak = top_ak, tG = top_G, tst = top_st;   // terms of sample e+1
+    double oup = old_top;                            // velocity of sample e+1 in this lane's previous run (its start state then)
+    // ragged top of the path's last chunk: up to three edges (rows 4 blk + rem-1 .. 4 blk), one at a time
+    for (int r = (len & 3) - 1; r >= 0; --r) {
+        const double gh = __ldg(p + 3 * PS + r), rg = __ldg(p + 4 * PS + r), fv = __ldg(f + r);
+        const double old = RERUN ? o[r] : 0.0;
+        BWD_ONE(tak, tG, tst, gh, rg, fv, old, oup)
+        if (!DRY) o[r] = v;
+        oup = old;
+        tak = __ldg(p + r); tG = __ldg(p + PS + r); tst = OVR ? __ldg(sb + r) : __ldg(p + 2 * PS + r);
+    }
+    if (blk == 0) return false;
+    // whole blocks, top down: pair B (rows 2, 3) then pair A (rows 0, 1) of each; the next pair is fetched while the current
+    // one is being used
+    p -= BS; f -= PS; sb -= PS; if (!DRY) o -= PB;
+    double2 akB = ldg_d2(p + 2), GB = ldg_d2(p + PS + 2), stB = OVR ? ldg_d2(sb + 2) : ldg_d2(p + 2 * PS + 2),
+            ghB = ldg_d2(p + 3 * PS + 2), rgB = ldg_d2(p + 4 * PS + 2), fB = ldg_d2(f + 2);
+    double2 akA, GA, stA, ghA, rgA, fA;
+    double2 oA = make_double2(0.0, 0.0), oB = oA;
+    if (RERUN) oB = *reinterpret_cast<const double2*>(o + 2);
     while (true) {
-        // ---- buffers a: the next step (edge e-1) needs the terms of sample e (this row) and gh / rg / vf / old of the row
-        // below (at the chunk's first row the look-ahead stays on the row: the values are not used)
-        akb = __ldg(p); Gb = __ldg(p + NT); stb = OVR ? __ldg(sb) : __ldg(p + 2 * NT);
-        if (e > lo) { ghb = __ldg(p - 2 * NT); rgb = __ldg(p - NT); fb = __ldg(f - NT); if (RERUN) oldb = o[-NT]; }
-        else { ghb = 0.0; rgb = 0.0; fb = 0.0; }
-        BWD_ONE(aka, Ga, sta, gha, rga, fa, olda)
-        // ---- buffers b
-        aka = __ldg(p); Ga = __ldg(p + NT); sta = OVR ? __ldg(sb) : __ldg(p + 2 * NT);
-        if (e > lo) { gha = __ldg(p - 2 * NT); rga = __ldg(p - NT); fa = __ldg(f - NT); if (RERUN) olda = o[-NT]; }
-        else { gha = 0.0; rga = 0.0; fa = 0.0; }
-        BWD_ONE(akb, Gb, stb, ghb, rgb, fb, oldb)
+        akA = ldg_d2(p); GA = ldg_d2(p + PS); stA = OVR ? ldg_d2(sb) : ldg_d2(p + 2 * PS); ghA = ldg_d2(p + 3 * PS); rgA = ldg_d2(p + 4 * PS);
+        fA = ldg_d2(f);
+        if (RERUN) oA = *reinterpret_cast<const double2*>(o);
+        BWD_ONE(tak, tG, tst, ghB.y, rgB.y, fB.y, oB.y, oup)
+        const double v3 = v;
+        BWD_ONE(akB.y, GB.y, stB.y, ghB.x, rgB.x, fB.x, oB.x, oB.y)
+        const double v2 = v;
+        if (RERUN) st_d2(o + 2, v2, v3);              // a re-run may leave at any step: store as soon as a pair is complete
+        const double a2 = akB.x, g2 = GB.x, s2 = stB.x;              // terms of row 2, for the edge of row 1
+        const double ob0 = oB.x;
+        const bool more = --blk > 0;
+        if (more) {                                                  // pair B of the block below
+            akB = ldg_d2(p - BS + 2); GB = ldg_d2(p - BS + PS + 2); stB = OVR ? ldg_d2(sb - PS + 2) : ldg_d2(p - BS + 2 * PS + 2);
+            ghB = ldg_d2(p - BS + 3 * PS + 2); rgB = ldg_d2(p - BS + 4 * PS + 2); fB = ldg_d2(f - PS + 2);
+            if (RERUN) oB = *reinterpret_cast<const double2*>(o - PB + 2);
+        }
+        BWD_ONE(a2, g2, s2, ghA.y, rgA.y, fA.y, oA.y, ob0)
+        const double v1 = v;
+        BWD_ONE(akA.y, GA.y, stA.y, ghA.x, rgA.x, fA.x, oA.x, oA.y)
+        if (RERUN) st_d2(o, v, v1);
+        if (SWEEP) { st_d2(o, v, v1); st_d2(o + 2, v2, v3); }        // the whole 32-byte sector at once
+        if (!more) break;
+        oup = oA.x;
+        tak = akA.x; tG = GA.x; tst = stA.x;
+        p -= BS; f -= PS; sb -= PS; if (!DRY) o -= PB;
     }
 #undef BWD_ONE
     return false;
 }
 
-// Backward pass.  Thread k walks column nch-1-k (the k-th chunk counted from the end), so states flow from thread k-1 to
-// thread k as in the forward kernel.  Reads the forward velocities and writes the final ones, both in slot order
-// (velT[RS-1] = end_vel is the last sample); k_untranspose puts them into sample order.  Also accumulates the
-// travel-time estimate used to size the time-domain outputs.
+// backward first sweep of one warp (see fwd_sweep_tma).  The stage holds six planes: |kappa|, G, the static limit (field 2,
+// or the override array), gh, its reciprocal, and the forward velocities.  rec_w / vf_w / sb_w: block row 0 at the warp's
+// LOWEST column; lc: this lane's column minus that one; o: sample lo of the final velocities (sample order).
 template <int NT>
-__global__ void __maxnreg__(72) k_bwd_chunked(
-    const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel,
-    long long RS, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
-    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
-    const int* __restrict__ n_ev, const double* __restrict__ vfT, double* __restrict__ velT, float* __restrict__ t_est,
-    int* __restrict__ rounds_out, int warm, int max_rounds, const double* __restrict__ statB)
+__device__ __forceinline__ void bwd_sweep_tma(const WarpRing& R, const double* __restrict__ rec_w, const double* __restrict__ vf_w,
+                                              const double* __restrict__ sb_w, int lc, double* __restrict__ o, int lo, int len,
+                                              double top_ak, double top_G, double top_st, const int* s_bi, const double* s_acc,
+                                              int n_b, double acc0, double hw, double dd, double& v, double& sq, float& est,
+                                              float dd_over_dt)
 {
-    extern __shared__ __align__(16) unsigned char s_mem[];
+    constexpr int PD = TMA_PLANE_DOUBLES;
+    const int lane = threadIdx.x & 31;
+    const int nbl = (len + PB - 1) >> 2;                                      // block rows of this lane's chunk
+    const int nbw = __reduce_max_sync(0xffffffffu, nbl);                      // block rows the warp streams (top down)
+    if (lane == 0) {
+        if (nbw > 0) ring_issue<NT>(R, 0, rec_w, vf_w, sb_w, nbw - 1);
+        if (nbw > 1) ring_issue<NT>(R, 1, rec_w, vf_w, sb_w, nbw - 2);
+    }
+    int e = lo + len - 1;                            // current edge; the reference's loop index is i = e + 1
+    int j = n_b - 1;
+    double acc = acc0;
+    while (j >= 0 && s_bi[j] > e + 1) { acc = s_acc[j]; j--; }
+    int nb_next = (j >= 0) ? s_bi[j] : -1;
+    double tak = top_ak, tG = top_G, tst = top_st;   // terms of sample e+1
+#define BWD_T(ROW_)                                                                                                  \
+        {                                                                                                            \
+            const double gh_ = S[3 * PD + ROW_], rg_ = S[4 * PD + ROW_], f_ = S[5 * PD + ROW_];                       \
+            if (e + 1 == nb_next) { acc = s_acc[j]; j--; nb_next = (j >= 0) ? s_bi[j] : -1; }                         \
+            const double vup = v;                                                                                    \
+            v = bwd_step(tak, gh_, rg_, tst, pymin(f_, tG), v, sq, acc, hw, dd);                                     \
+            est += t_est_term(vup, v, dd_over_dt);                                                                   \
+            tak = S[ROW_]; tG = S[PD + ROW_]; tst = S[2 * PD + ROW_];                                                \
+            --e;                                                                                                     \
+        }
+    const int nfull = len >> 2, rem = len & 3;
+    o += nfull * PB;                                 // the ragged top block's samples
+    for (int it = 0; it < nbw; ++it) {
+        const int rb = nbw - 1 - it;                 // block row
+        const int s = it & 1;
+        mbar_wait(R.bar + 8 * s, (it >> 1) & 1);
+        const double* S = R.stage + (size_t)s * 6 * PD + lc * PB;
+        if (rb < nfull) {                            // a whole block of this lane's chunk: rows 3 .. 0
+            o -= PB;
+            BWD_T(3)
+            const double v3 = v;
+            BWD_T(2)
+            const double v2 = v;
+            BWD_T(1)
+            const double v1 = v;
+            BWD_T(0)
+            st_d2(o, v, v1); st_d2(o + 2, v2, v3);   // the whole 32-byte sector
+        } else if (rb == nfull && rem > 0) {         // ragged top of the path's last chunk: rows rem-1 .. 0
+            if (rem > 2) { BWD_T(2) o[2] = v; }
+            if (rem > 1) { BWD_T(1) o[1] = v; }
+            BWD_T(0) o[0] = v;
+        }
+        __syncwarp();
+        if (lane == 0 && it + 2 < nbw) ring_issue<NT>(R, s, rec_w, vf_w, sb_w, nbw - 3 - it);
+    }
+#undef BWD_T
+}
+
+struct BwdArgs {
+    const double* p; const double* f; double* o; const double* sb; int lo, len; double top_ak, top_G, top_st;
+    const int* s_bi; const double* s_acc; int n_b; double acc0, hw, dd; float dd_over_dt;
+};
+// cold, divergent code out of line (see fwd_rerun); st = {v, sq}
+template <int NT, bool OVR>
+__device__ __noinline__ bool bwd_rerun(const BwdArgs a, double* st, float* est, bool prev_same, double old_top)
+{
+    double v = st[0], sq = st[1];
+    float e = *est;
+    const bool merged = bwd_run<NT, RUN_RERUN, OVR>(a.p, a.f, a.o, a.sb, a.lo, a.len, a.top_ak, a.top_G, a.top_st, a.s_bi, a.s_acc,
+                                                    a.n_b, a.acc0, a.hw, a.dd, v, sq, prev_same, e, a.dd_over_dt, old_top);
+    st[0] = v; st[1] = sq; *est = e;
+    return merged;
+}
+template <int NT, bool OVR>
+__device__ __noinline__ void bwd_dry(const BwdArgs a, double* st)
+{
+    double v = st[0], sq = st[1];
+    float e = 0.f;
+    bwd_run<NT, RUN_DRY, OVR>(a.p, a.f, nullptr, a.sb, a.lo, a.len, a.top_ak, a.top_G, a.top_st, a.s_bi, a.s_acc, a.n_b, a.acc0,
+                              a.hw, a.dd, v, sq, false, e, a.dd_over_dt);
+    st[0] = v; st[1] = sq;
+}
+
+// Backward pass.  Thread k walks column nch-1-k (the k-th chunk counted from the end), so states flow from thread k-1 to
+// thread k as in the forward kernel.  Reads the forward velocities (slot order) and writes the final ones straight into
+// vel[B][D_cap] in sample order.  Also accumulates the travel-time estimate used to size the time-domain outputs.
+template <int NT, bool TMA>
+__global__ void __maxnreg__(TMA ? VAP_PASS_REGS_TMA : VAP_PASS_REGS) k_bwd_chunked(
+    const int* __restrict__ status, const double* __restrict__ cons, double dd, double dt, double end_vel,
+    long long RS, long long D_cap, const int* __restrict__ n_samples, const double* __restrict__ rec, int E_cap,
+    const double* __restrict__ max_accels, const int* __restrict__ bidx, const int* __restrict__ bval,
+    const int* __restrict__ n_ev, const double* __restrict__ vfT, double* __restrict__ vel, float* __restrict__ t_est,
+    int* __restrict__ rounds_out, int warm, int max_rounds, const double* __restrict__ statB, int ring_off)
+{
+    extern __shared__ __align__(128) unsigned char s_mem[];
     const int k = threadIdx.x;
     const long long b = blockIdx.x;
     double* s_endv = reinterpret_cast<double*>(s_mem);
@@ -777,8 +1105,8 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
     const int steps = D - 1;
-    double* vo = velT + (size_t)b * RS;
-    if (k == 0) { vo[RS - 1] = end_vel; if (rounds_out) rounds_out[2 * b + 1] = 0; }
+    double* vo = vel + (size_t)b * D_cap;
+    if (k == 0) { vo[D - 1] = end_vel; if (rounds_out) rounds_out[2 * b + 1] = 0; }
     if (steps <= 0) return;
     const int n_b = n_ev[2 * b + 1];
     for (int q = k; q < n_b; q += NT) {
@@ -789,7 +1117,7 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     const int Lc = chunk_len(steps, NT);
     const int nch = (steps + Lc - 1) / Lc;
     const bool active = k < nch;
-    const int col = nch - 1 - k;                                   // column (forward chunk index)
+    const int col = active ? nch - 1 - k : 0;                      // column (forward chunk index)
     const int lo = col * Lc;
     const int len = (lo + Lc < steps) ? Lc : steps - lo;
     const double* P = rec + (size_t)b * RS * 5;
@@ -798,66 +1126,77 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     // with max_acceleration overrides the static limit of this pass is in statB (slot order, written by the pre-pass)
     const bool ovr = pass_has_override(max_accels + (size_t)b * E_cap, n_ev[2 * b], cons[b * 6 + 1]) != 0;
     const double* SB = statB + (size_t)b * RS;
+    // TMA variant: every warp owns a two-stage ring (6 planes of 1 KB per stage) and two mbarriers behind the tables
+    WarpRing R;
+    if (TMA) {
+        constexpr int WARPS = (NT + 31) / 32;
+        const int w = k >> 5;
+        R.stage = reinterpret_cast<double*>(s_mem + ring_off) + (size_t)w * 2 * 6 * TMA_PLANE_DOUBLES;
+        R.bar = (unsigned)__cvta_generic_to_shared(s_mem + ring_off + (size_t)WARPS * 2 * 6 * TMA_PLANE_DOUBLES * 8 + 16 * w);
+        R.planes = 6;
+        R.bytes = (NT < 32 ? NT : 32) * PB * 8;
+        if ((k & 31) == 0) { mbar_init(R.bar, 1); mbar_init(R.bar + 8, 1); fence_mbar_init(); }
+    }
     __syncthreads();
 
+    auto rec_of = [&](int x, int fld) {                             // field fld (0-2) of sample x
+        if (fld == 2 && ovr) return __ldg(SB + (x >= steps ? (int)(RS - 1) : edge_slot(x, Lc, NT)));
+        if (x >= steps) return __ldg(P + 5 * RS - 3 + fld);
+        const int cx = x / Lc, rx = x - cx * Lc;
+        return __ldg(P + rec_index(rx, fld, cx, NT));
+    };
+    auto vf_at = [&](int x) { return vf[x >= steps ? (int)(RS - 1) : edge_slot(x, Lc, NT)]; };
     // terms of the sample above the chunk (sample lo+len): row 0 of the next column, or the tail
     double top_ak = 0.0, top_G = 0.0, top_st = 0.0;
-    if (active) {
-        if (lo + len < steps) {
-            top_ak = __ldg(P + col + 1); top_G = __ldg(P + NT + col + 1);
-            top_st = ovr ? __ldg(SB + col + 1) : __ldg(P + 2 * NT + col + 1);
-        } else {
-            top_ak = __ldg(P + 5 * RS - 3); top_G = __ldg(P + 5 * RS - 2);
-            top_st = ovr ? __ldg(SB + RS - 1) : __ldg(P + 5 * RS - 1);
-        }
-    }
-    const size_t r_top = active ? (size_t)(len - 1) : 0;           // row of the chunk's top edge
-    const double* p0 = P + r_top * 5 * NT + (active ? col : 0);
-    const double* f0 = vf + r_top * NT + (active ? col : 0);
-    const double* sb0 = SB + r_top * NT + (active ? col : 0);
-    double* o0 = vo + r_top * NT + (active ? col : 0);
+    if (active) { top_ak = rec_of(lo + len, 0); top_G = rec_of(lo + len, 1); top_st = rec_of(lo + len, 2); }
+    BwdArgs A;
+    A.p = P + col * PB; A.f = vf + col * PB; A.o = vo + lo; A.sb = SB + col * PB; A.lo = lo; A.len = len;
+    A.top_ak = top_ak; A.top_G = top_G; A.top_st = top_st; A.s_bi = s_bi; A.s_acc = s_acc; A.n_b = n_b; A.acc0 = acc0;
+    A.hw = hw; A.dd = dd; A.dd_over_dt = (float)dd / (float)dt;
+    float est = 0.f;                                  // travel-time estimate of this chunk's steps
 
-    // ---- sweep 1: thread k > 0 starts `wl` steps ABOVE its chunk (in the next column) from the guess
-    // v[s0] = min(vel_f[s0], G[s0+1]) (the state-independent part of what step s0+1 produces) and only computes until it
+    // ---- sweep 1: thread k > 0 may start `wl` steps ABOVE its chunk (in the next column) from the guess
+    // v[s0] = min(vel_f[s0], G[s0+1]) (the state-independent part of what step s0+1 produces) and only compute until it
     // reaches its own range (see the forward kernel)
     {
         double v = end_vel, sq = 0.0;
         if (active) {
             if (k > 0) {
                 const int hi = lo + len;                                   // sample at the top of this chunk (< D-1)
-                auto rec_of = [&](int x, int fld) {                         // field fld of sample x
-                    if (fld == 2 && ovr) return __ldg(SB + (x >= steps ? (int)(RS - 1) : edge_slot(x, Lc, NT)));
-                    if (x >= steps) return __ldg(P + 5 * RS - 3 + fld);
-                    const int cx = x / Lc, rx = x - cx * Lc;
-                    return __ldg(P + ((size_t)rx * 5 + fld) * NT + cx);
-                };
                 const int len_up = (hi + Lc < steps) ? Lc : steps - hi;    // edges of the column above
                 int wl = warm < len_up ? warm : len_up;
                 if (hi + wl + 2 > D - 1) wl = (D - 1) - hi - 2 > 0 ? (D - 1) - hi - 2 : 0;
+                wl &= ~(PB - 1);
                 const int s0 = hi + wl;                                    // sample the guess is made at
-                const int s1 = edge_slot(s0, Lc, NT);
-                v = pymin(vf[s1], rec_of(s0 + 1, 1));
+                v = pymin(vf_at(s0), rec_of(s0 + 1, 1));
                 double vp1 = end_vel;
-                if (s0 + 2 <= D - 1) vp1 = pymin(vf[edge_slot(s0 + 1, Lc, NT)], rec_of(s0 + 2, 1));
+                if (s0 + 2 <= D - 1) vp1 = pymin(vf_at(s0 + 1), rec_of(s0 + 2, 1));
                 const double wp = vp1 * rec_of(s0 + 1, 0);
                 sq = wp * wp;
                 if (wl > 0) {
                     // edges s0-1 .. hi of column col+1 (rows wl-1 .. 0); the terms above the first of them are sample s0's
-                    const size_t rw = (size_t)(wl - 1);
-                    const double* pd = P + rw * 5 * NT + col + 1;
-                    const double* fd = vf + rw * NT + col + 1;
-                    const double* sd = SB + rw * NT + col + 1;
-                    if (ovr) bwd_run<NT, RUN_DRY, true>(pd, fd, nullptr, sd, hi, wl, rec_of(s0, 0), rec_of(s0, 1), rec_of(s0, 2),
-                                                        s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
-                    else bwd_run<NT, RUN_DRY, false>(pd, fd, nullptr, sd, hi, wl, rec_of(s0, 0), rec_of(s0, 1), rec_of(s0, 2),
-                                                     s_bi, s_acc, n_b, acc0, hw, dd, v, sq, false);
+                    BwdArgs W = A;
+                    W.p = P + (col + 1) * PB; W.f = vf + (col + 1) * PB; W.o = nullptr; W.sb = SB + (col + 1) * PB;
+                    W.lo = hi; W.len = wl; W.top_ak = rec_of(s0, 0); W.top_G = rec_of(s0, 1); W.top_st = rec_of(s0, 2);
+                    double st[2] = {v, sq};
+                    if (ovr) bwd_dry<NT, true>(W, st); else bwd_dry<NT, false>(W, st);
+                    v = st[0]; sq = st[1];
                 }
             }
             s_usev[k] = v; s_usew[k] = sq;
-            if (ovr) bwd_run<NT, RUN_SWEEP, true>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw, dd,
-                                                  v, sq, false);
-            else bwd_run<NT, RUN_SWEEP, false>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw, dd,
-                                               v, sq, false);
+            if (!TMA) {
+                if (ovr) bwd_run<NT, RUN_SWEEP, true>(A.p, A.f, A.o, A.sb, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw,
+                                                      dd, v, sq, false, est, A.dd_over_dt);
+                else bwd_run<NT, RUN_SWEEP, false>(A.p, A.f, A.o, A.sb, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw,
+                                                   dd, v, sq, false, est, A.dd_over_dt);
+            }
+        }
+        if (TMA) {
+            // the warp's columns: lane 0 has the highest (nch-1-32w); the ring holds the 32 columns that end there
+            const int col_hi = nch - 1 - (k & ~31);
+            const int cs = col_hi > 31 ? col_hi - 31 : 0;
+            bwd_sweep_tma<NT>(R, P + cs * PB, vf + cs * PB, ovr ? SB + cs * PB : nullptr, active ? col - cs : 0, vo + lo, lo,
+                              active ? len : 0, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw, dd, v, sq, est, A.dd_over_dt);
         }
         s_endv[k] = v; s_endw[k] = sq;
     }
@@ -875,34 +1214,20 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
         if (!__syncthreads_or(need)) break;
         rounds = round;
         if (need) {
-            double v = in_v, sq = in_w;
+            double st[2] = {in_v, in_w};
             const bool ps = same_bits(in_v, s_usev[k]);
-            const bool merged = ovr ? bwd_run<NT, RUN_RERUN, true>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc,
-                                                                   n_b, acc0, hw, dd, v, sq, ps)
-                                    : bwd_run<NT, RUN_RERUN, false>(p0, f0, o0, sb0, lo, len, top_ak, top_G, top_st, s_bi, s_acc,
-                                                                    n_b, acc0, hw, dd, v, sq, ps);
+            const bool merged = ovr ? bwd_rerun<NT, true>(A, st, &est, ps, s_usev[k]) : bwd_rerun<NT, false>(A, st, &est, ps, s_usev[k]);
             s_usev[k] = in_v; s_usew[k] = in_w;
-            if (!merged) { s_endv[k] = v; s_endw[k] = sq; }
+            if (!merged) { s_endv[k] = st[0]; s_endw[k] = st[1]; }
         }
         __syncthreads();
     }
     if (k == 0 && rounds_out) rounds_out[2 * b + 1] = rounds;
 
-    // ---- travel-time estimate (single precision is plenty: it only sizes buffers)
+    // ---- travel-time estimate: the sum of the chunks' (single precision is plenty: it only sizes buffers)
     __syncthreads();
-    float est = 0.f;
-    if (active) {
-        const int top = (lo + len < steps) ? col + 1 : (int)(RS - 1);       // slot of the sample above the chunk
-        float vprev = (float)vo[top];
-        for (int sl = (len - 1) * NT + col; sl >= 0; sl -= NT) {
-            const float vcur = (float)vo[sl];
-            const float vm = 0.5f * (vprev + vcur);
-            est += __fdividef((float)dd, fmaxf(vm, 0.05f) * (float)dt);
-            vprev = vcur;
-        }
-    }
     float* s_f = reinterpret_cast<float*>(s_endv);      // end states are no longer needed
-    s_f[k] = est;
+    s_f[k] = active ? est : 0.f;
     __syncthreads();
     if (k == 0 && t_est) {
         float tot = 0.f;
@@ -911,40 +1236,21 @@ __global__ void __maxnreg__(72) k_bwd_chunked(
     }
 }
 
-// slot order -> sample order through a 32 x 32 shared-memory tile (both sides coalesced): vel[e] = vT[slot(e)], and the
-// last sample from slot RS-1.  grid = (row tiles * column tiles, B), 256 threads.
+// slot order -> sample order (only the forward-only mode of vap_fwd_bwd_chunked needs it: the backward pass writes sample
+// order itself): vel[e] = vT[slot(e)], the last sample from slot RS-1.  One thread per sample.
 __global__ void __launch_bounds__(256) k_untranspose(const int* __restrict__ status, const int* __restrict__ n_samples,
                                                      long long D_cap, long long RS, int NT,
                                                      const double* __restrict__ vT, double* __restrict__ vel,
                                                      unsigned tiles_x)
 {
-    __shared__ double tile[32][33];
     const PathTile pt = path_tile(tiles_x);
     const long long b = pt.b;
     if (status[b] != ST_OK) return;
     const int D = n_samples[b];
     const int steps = D - 1;
+    const int e = pt.x * blockDim.x + threadIdx.x;
+    if (e >= D) return;
     const double* src = vT + (size_t)b * RS;
-    double* dst = vel + (size_t)b * D_cap;
-    if (pt.x == 0 && threadIdx.x == 0) dst[D - 1] = src[RS - 1];
-    if (steps <= 0) return;
-    const int Lc = chunk_len(steps, NT);
-    const int ctiles = (NT + 31) >> 5;
-    const int rt = pt.x / ctiles, ct = pt.x - rt * ctiles;
-    const int s0 = rt * 32, c0 = ct * 32;
-    if (s0 >= Lc) return;
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-#pragma unroll
-    for (int r = wrp; r < 32; r += 8) {
-        const int s = s0 + r;
-        tile[r][lane] = (s < Lc && c0 + lane < NT) ? src[(size_t)s * NT + c0 + lane] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = wrp; q < 32; q += 8) {
-        const int c = c0 + q;
-        const int s = s0 + lane;
-        const int e = c * Lc + s;
-        if (s < Lc && c < NT && e < steps) dst[e] = tile[lane][q];
-    }
+    const int Lc = steps > 0 ? chunk_len(steps, NT) : 1;
+    vel[(size_t)b * D_cap + e] = (e < steps) ? src[edge_slot(e, Lc, NT)] : src[RS - 1];
 }

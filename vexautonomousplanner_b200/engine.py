@@ -323,9 +323,9 @@ class Engine:
                 "vap_dist_sample_events")
             self.launches += 3
         chunks = self.chunks if D_cap <= 65536 else 256
-        RS = int(self.lib.vap_pass_row_slots(C.c_int64(D_cap)))     # chunk-interleaved rows of the pass arrays
+        RS = int(self.lib.vap_pass_row_slots(C.c_int64(D_cap), C.c_int(chunks)))     # chunk-interleaved rows of the pass arrays
         rec = self._empty((B, RS, 5)); statB = self._empty((B, RS))
-        vel_f = self._empty((B, RS)); velT = self._empty((B, RS)); vel = outs["vel"] if outs else self._empty((B, D_cap))
+        vel_f = self._empty((B, RS)); vel = outs["vel"] if outs else self._empty((B, D_cap))
         t_est = self._empty((B,), torch.float32)
         rounds = torch.zeros((B, 2), dtype=torch.int32, device=self.device)
         with self._stage("S45_fwd_bwd"):
@@ -333,8 +333,8 @@ class Engine:
                 C.c_int64(B), _p(db.cons), _p(status), C.c_double(self.dd), C.c_double(self.dt), C.c_double(self.start_vel),
                 C.c_double(self.end_vel), C.c_int64(D_cap), _p(n_samples), _p(kap), _p(th), C.c_int(E_cap), _p(ma),
                 _p(bidx), _p(bval), _p(n_ev), _p(vr_idx), _p(vr_val), _p(st_idx), _p(n_vr), _p(rec), _p(statB),
-                _p(vel_f), _p(velT), _p(vel), _p(t_est), _p(rounds), C.c_int(chunks), C.c_int(mode), self._stream()), "vap_fwd_bwd_chunked")
-            self.launches += 4 if mode == 0 else 3
+                _p(vel_f), _p(vel), _p(t_est), _p(rounds), C.c_int(chunks), C.c_int(mode), self._stream()), "vap_fwd_bwd_chunked")
+            self.launches += 3
         extra = dict(t=tq, kap=kap, th=th, max_accels=ma, bidx=bidx, bval=bval, n_ev=n_ev, vel_f=vel_f, rounds=rounds,
                      vr_idx=vr_idx, vr_val=vr_val, st_idx=st_idx, n_vr=n_vr)
         return n_samples, vel, t_est + ins_est, extra
