@@ -310,7 +310,7 @@ def stage_table(torch, eng, db, flush, steps, N):
     Q, P = 1000.0 * B, 1000.0 * N * B            # random paths have one spline each
     # algorithmic bytes per stage: 8 B per fp64 element, each array once per stage that must touch it
     stage_bytes = {"S0_build_path": 8 * (2 * N + 9 * N) * B, "S1_lut": 8 * 2 * Q, "S2_props": 8 * 2 * P,
-                   "S3_dist_sample": 8 * 5 * Dsum, "S45_fwd_bwd": 8 * 4 * Dsum, "S6_resample": 8 * (Dsum + 9 * Tsum)}
+                   "S3_dist_sample": 8 * 5 * Dsum, "S45_fwd_bwd": 8 * 4 * Dsum, "S345_velocity": 8 * 9 * Dsum, "S6_resample": 8 * (Dsum + 9 * Tsum)}
     return stage_ms, stage_bytes, Dsum, Tsum, res
 
 

@@ -177,6 +177,22 @@ int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, do
                         const int32_t* n_vr, double* rec, double* statB, double* vel_f, double* vel, float* t_est,
                         int32_t* rounds, int chunks, int mode, void* stream);
 
+/* S3 + S4 + S5 in ONE call (what Engine.profile uses): vap_dist_sample_events and vap_fwd_bwd_chunked fused.  The distance
+ *     sampling (motion_profile_generator.py:84-176) fills the pre-pass's shared-memory tile directly, so kappa / theta per
+ *     distance sample never go to memory: t / kap / th [B][D_cap] are inspection outputs (pass all three or three NULLs).
+ *     The static acceleration limits of paths with max_acceleration overrides are rewritten after the event resolution
+ *     (k_prepass_ovr).  All other arguments as in the two staged entry points above; same bits.                        */
+int vap_velocity_profile(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
+                         const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags, const int32_t* n_ap,
+                         const double* cons, const int32_t* n_splines, int32_t* status, int64_t n_grid,
+                         const double* dgrid, int samples, int64_t Q_cap, const double* lut_d, const double* lut_t,
+                         const double* total_len, int spn, int64_t P_cap, const double* prop_k, const double* prop_h,
+                         const int32_t* lut_inv, double dd, double dt, double start_vel, double end_vel, int64_t D_cap,
+                         int32_t* n_samples, double* t, double* kap, double* th, int E_cap, double* max_accels,
+                         int32_t* bidx, int32_t* bval, int32_t* n_ev, int32_t* vr_idx, double* vr_val, int32_t* st_idx,
+                         int32_t* n_vr, float* ins_est, int32_t* ev_scratch, double* rec, double* statB, double* vel_f,
+                         double* vel, float* t_est, int32_t* rounds, int chunks, int mode, void* stream);
+
 /* S6  generate_motion_profile time loop + node-0 prologue + turn / wait inserts
  *     (motion_profile_generator.py:414-628, one_dim_mp_generator.py:4-69) and S7 summary rows.
  *     out[8][B][T_cap]: times, positions, linear_vels, accelerations, headings, angular_vels, x, y.

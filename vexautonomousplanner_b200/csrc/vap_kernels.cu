@@ -1264,28 +1264,16 @@ static int launch_passes(bool tma, Args... args)
     return tma ? launch_passes_v<NT, true>(args...) : launch_passes_v<NT, false>(args...);
 }
 
-extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
-                                   double start_vel, double end_vel, int64_t D_cap, const int32_t* n_samples,
-                                   const double* kap, const double* th, int E_cap, const double* max_accels,
-                                   const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
-                                   const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* rec,
-                                   double* statB, double* vel_f, double* vel, float* t_est, int32_t* rounds,
-                                   int chunks, int mode, void* stream)
+// forward and backward passes (+ the forward-only mode's slot order -> sample order) over records that are already in place
+static int run_passes(int64_t B, const double* cons, const int32_t* status, double dd, double dt, double start_vel,
+                      double end_vel, int64_t D_cap, const int32_t* n_samples, int E_cap, const double* max_accels,
+                      const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
+                      const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, const double* rec,
+                      const double* statB, double* vel_f, double* vel, float* t_est, int32_t* rounds, int chunks, int mode,
+                      cudaStream_t stream)
 {
-    if (B <= 0) return 0;
-    if (chunks < 8 || chunks > 256 || (chunks & (chunks - 1)) != 0) return arg_err("vap_fwd_bwd_chunked: chunks must be a power of two in 8 .. 256");
-    if (D_cap > 400000000LL) return arg_err("vap_fwd_bwd_chunked: D_cap too large");
-    if (D_cap & 1) return arg_err("vap_fwd_bwd_chunked: D_cap must be even (the passes move 16-byte pairs)");
     const long long RS = vap_pass_row_slots(D_cap, chunks);
-    const unsigned tx = blocks_for(D_cap + 4 * chunks, 256 * PP_TILES);
-    if ((long long)tx * B > 2147483647LL) return arg_err("vap_fwd_bwd_chunked: more than 2^31 CTAs (tile the batch)");
-    const unsigned grid = tx * (unsigned)B;
-    // the kappa / theta tile: min(chunks, 64) columns x (256 / columns + 1) rows, odd stride; two buffers
-    const size_t sm = 2 * 2 * sizeof(double) * (size_t)prepass_tile_cols(chunks) * prepass_tile_stride(chunks);
-    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec, E_cap, max_accels, bidx,
-                                         bval, n_ev, statB, tx);
-    CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
-    // CTA = one path, one chunk per thread.  One-warp CTAs at 72 registers put 28 independent chains on every SM.
+    // CTA = one path, one chunk per thread.
     const size_t VC = 3 * (size_t)E_cap + 2;
     const size_t ss = ((size_t)chunks * 4 + E_cap + VC) * sizeof(double) + (E_cap + VC) * sizeof(int);
     // warm-up steps a speculative chunk runs before its own range (tuning: VAP_CHUNK_WARM; any value gives the same bits).
@@ -1321,6 +1309,89 @@ extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t*
     if (int rc = passes(true)) return rc;      // writes vel in sample order itself
     CHECK_LAUNCH("vap_fwd_bwd_chunked/bwd");
     return 0;
+}
+
+static int check_pass_args(const char* who, int64_t B, int64_t D_cap, int chunks)
+{
+    (void)B;
+    if (chunks < 8 || chunks > 256 || (chunks & (chunks - 1)) != 0) { snprintf(g_err, sizeof(g_err), "%s: chunks must be a power of two in 8 .. 256", who); return -1; }
+    if (D_cap > 400000000LL) { snprintf(g_err, sizeof(g_err), "%s: D_cap too large", who); return -1; }
+    if (D_cap & 1) { snprintf(g_err, sizeof(g_err), "%s: D_cap must be even (the passes move 16-byte pairs)", who); return -1; }
+    return 0;
+}
+
+extern "C" int vap_fwd_bwd_chunked(int64_t B, const double* cons, const int32_t* status, double dd, double dt,
+                                   double start_vel, double end_vel, int64_t D_cap, const int32_t* n_samples,
+                                   const double* kap, const double* th, int E_cap, const double* max_accels,
+                                   const int32_t* bidx, const int32_t* bval, const int32_t* n_ev, const int32_t* vr_idx,
+                                   const double* vr_val, const int32_t* st_idx, const int32_t* n_vr, double* rec,
+                                   double* statB, double* vel_f, double* vel, float* t_est, int32_t* rounds,
+                                   int chunks, int mode, void* stream)
+{
+    if (B <= 0) return 0;
+    if (check_pass_args("vap_fwd_bwd_chunked", B, D_cap, chunks)) return -1;
+    const long long RS = vap_pass_row_slots(D_cap, chunks);
+    const unsigned tx = blocks_for(D_cap + 4 * chunks, 256 * PP_TILES);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_fwd_bwd_chunked: more than 2^31 CTAs (tile the batch)");
+    const unsigned grid = tx * (unsigned)B;
+    // the kappa / theta tile: min(chunks, 64) columns x (256 / columns + 1) rows, odd stride; two buffers
+    const size_t sm = 2 * 2 * sizeof(double) * (size_t)prepass_tile_cols(chunks) * prepass_tile_stride(chunks);
+    k_prepass<<<grid, 256, sm, STREAM>>>(status, cons, D_cap, n_samples, kap, th, chunks, RS, rec, E_cap, max_accels, bidx,
+                                         bval, n_ev, statB, tx);
+    CHECK_LAUNCH("vap_fwd_bwd_chunked/prepass");
+    return run_passes(B, cons, status, dd, dt, start_vel, end_vel, D_cap, n_samples, E_cap, max_accels, bidx, bval, n_ev, vr_idx,
+                      vr_val, st_idx, n_vr, rec, statB, vel_f, vel, t_est, rounds, chunks, mode, STREAM);
+}
+
+// S3 + S4 + S5 in one call, the fast path: distance sampling fused with the pre-pass (kappa / theta stay on chip), event
+// resolution, the override fix-up of the static limits, forward and backward passes.
+extern "C" int vap_velocity_profile(int64_t B, int N_max, int A_max, const double* node_attr, const int32_t* node_flags,
+                                    const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags,
+                                    const int32_t* n_ap, const double* cons, const int32_t* n_splines, int32_t* status,
+                                    int64_t n_grid, const double* dgrid, int samples, int64_t Q_cap, const double* lut_d,
+                                    const double* lut_t, const double* total_len, int spn, int64_t P_cap,
+                                    const double* prop_k, const double* prop_h, const int32_t* lut_inv, double dd, double dt,
+                                    double start_vel, double end_vel, int64_t D_cap, int32_t* n_samples, double* t,
+                                    double* kap, double* th, int E_cap, double* max_accels, int32_t* bidx, int32_t* bval,
+                                    int32_t* n_ev, int32_t* vr_idx, double* vr_val, int32_t* st_idx, int32_t* n_vr,
+                                    float* ins_est, int32_t* ev_scratch, double* rec, double* statB, double* vel_f,
+                                    double* vel, float* t_est, int32_t* rounds, int chunks, int mode, void* stream)
+{
+    if (B <= 0) return 0;
+    if (E_cap < N_max + A_max + 2) return arg_err("vap_velocity_profile: E_cap < N_max + A_max + 2");
+    if (check_pass_args("vap_velocity_profile", B, D_cap, chunks)) return -1;
+    if ((t != nullptr) != (kap != nullptr) || (t != nullptr) != (th != nullptr))
+        return arg_err("vap_velocity_profile: t, kap and th are inspection outputs: pass all three or none");
+    int Am = A_max > 0 ? A_max : 1;
+    int32_t* ev_wrap = ev_scratch;
+    int32_t* ev_nwrap = ev_wrap + (size_t)B * N_max;
+    int32_t* ev_apc = ev_nwrap + B;
+    int32_t* ev_napc = ev_apc + (size_t)B * Am * EV_AP_CAND;
+    cudaError_t e = cudaMemsetAsync(ev_nwrap, 0, sizeof(int32_t) * (size_t)B, STREAM);
+    if (e != cudaSuccess) return set_err("vap_velocity_profile/memset", e);
+    e = cudaMemsetAsync(ev_napc, 0, sizeof(int32_t) * (size_t)B * Am, STREAM);
+    if (e != cudaSuccess) return set_err("vap_velocity_profile/memset", e);
+    k_count_samples<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, status, status, n_grid, dgrid, total_len, D_cap, n_samples);
+    CHECK_LAUNCH("vap_velocity_profile/count");
+    const long long RS = vap_pass_row_slots(D_cap, chunks);
+    const unsigned tx = blocks_for(D_cap + 4 * chunks, 256 * PP_TILES);
+    if ((long long)tx * B > 2147483647LL) return arg_err("vap_velocity_profile: more than 2^31 CTAs (tile the batch)");
+    const int tc = prepass_tile_cols(chunks);
+    const size_t sm = 2 * 3 * sizeof(double) * (size_t)tc * (((256 / tc) + 2) | 1);
+    k_sample_prepass<<<tx * (unsigned)B, 256, sm, STREAM>>>(N_max, Am, n_nodes, n_splines, status, cons, ap_attr, n_ap, dgrid,
+                                                           samples, Q_cap, lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h,
+                                                           D_cap, n_samples, t, kap, th, ev_wrap, ev_nwrap, ev_apc, ev_napc,
+                                                           lut_inv, chunks, RS, rec, tx);
+    CHECK_LAUNCH("vap_velocity_profile/sample_prepass");
+    k_resolve_events<<<blocks_for(B, 64), 64, 0, STREAM>>>(B, N_max, Am, node_attr, node_flags, n_nodes, ap_attr, ap_flags,
+                                                          n_ap, cons, status, ev_wrap, ev_nwrap, ev_apc, ev_napc, E_cap,
+                                                          max_accels, bidx, bval, n_ev, vr_idx, vr_val, st_idx, n_vr, dt, ins_est);
+    CHECK_LAUNCH("vap_velocity_profile/resolve");
+    k_prepass_ovr<<<(unsigned)B, 256, 0, STREAM>>>(status, cons, n_samples, chunks, RS, rec, E_cap, max_accels, bidx, bval, n_ev,
+                                                  statB);
+    CHECK_LAUNCH("vap_velocity_profile/prepass_ovr");
+    return run_passes(B, cons, status, dd, dt, start_vel, end_vel, D_cap, n_samples, E_cap, max_accels, bidx, bval, n_ev, vr_idx,
+                      vr_val, st_idx, n_vr, rec, statB, vel_f, vel, t_est, rounds, chunks, mode, STREAM);
 }
 
 // ---- v2 time-domain stage ----------------------------------------------------------------------------------------

@@ -421,6 +421,188 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
     }
 }
 
+// ---- S3 + pre-pass fused: distance sampling, event candidates and the pass records in ONE kernel -------------------------
+// k_dist_sample_ev wrote kappa / theta per distance sample (16 bytes) only for k_prepass to read them back through a
+// shared-memory tile; here the tile is FILLED by the sampling itself (distance_to_time + snap gathers, one sample per thread,
+// lanes running along a chunk's consecutive samples) and the records are made from it in slot order, so kappa / theta never
+// go to HBM (t / kappa / theta are written only when the caller asks for them: inspection outputs).  A CTA walks PP_TILES
+// tiles DOWN the rows of its columns; a tile computes rows s0+1 .. s0+TR and takes rows s0-1 (parameter only: the event test
+// needs t of the previous sample) and s0 from the tile before (the first tile computes them itself), so the halo costs
+// 2 TC extra samples per CTA instead of per tile.
+// The records written here use the path's own max_acc: the regimes are not known yet (k_resolve_events runs on the event
+// candidates this kernel emits).  k_prepass_ovr rewrites the static limits of the paths that turn out to have overrides.
+#ifndef VAP_SP_MINB
+#define VAP_SP_MINB 8
+#endif
+__global__ void __launch_bounds__(256, VAP_SP_MINB) k_sample_prepass(
+    int N_max, int A_max, const int* __restrict__ n_nodes, const int* __restrict__ n_splines,
+    const int* __restrict__ status, const double* __restrict__ cons, const double* __restrict__ ap_attr,
+    const int* __restrict__ n_ap, const double* __restrict__ dgrid, int samples, long long Q_cap,
+    const double* __restrict__ lut_d, const double* __restrict__ lut_t, const double* __restrict__ total_len, int spn,
+    long long P_cap, const double* __restrict__ prop_k, const double* __restrict__ prop_h, long long D_cap,
+    const int* __restrict__ n_samples, double* __restrict__ t_out, double* __restrict__ kap_out, double* __restrict__ th_out,
+    int* __restrict__ ev_wrap, int* __restrict__ ev_nwrap, int* __restrict__ ev_apc, int* __restrict__ ev_napc,
+    const int* __restrict__ lut_inv, int NT, long long RS, double* __restrict__ rec, unsigned tiles_x)
+{
+    extern __shared__ double s_tile[];               // two buffers of three planes (t, theta, kappa): TC columns x (TR + 2) rows
+    const PathTile pt = path_tile(tiles_x);
+    const long long b = pt.b;
+    if (status[b] != ST_OK) return;
+    const int D = n_samples[b];
+    const int steps = D - 1;
+    const int sh = 31 - __clz(NT);
+    const int Lc = chunk_len(steps, NT);
+    const int jend = Lc << sh;
+    int j0 = pt.x * (blockDim.x * PP_TILES);
+    if (steps <= 0 || j0 >= jend) return;
+    const int n = n_nodes[b];
+    const double* ld = lut_d + (size_t)b * Q_cap;
+    const double* lt = lut_t + (size_t)b * Q_cap;
+    const int Q = samples * n_splines[b];
+    const double L = total_len[b];
+    const PropGrid pg = prop_grid(spn, n);
+    const int* inv = lut_inv ? lut_inv + (size_t)b * (Q_cap + LUT_INV_HDR + 2) : nullptr;
+    const double* pk = prop_k + (size_t)b * P_cap;
+    const double* ph = prop_h + (size_t)b * P_cap;
+    const double tn = (double)(n - 1);
+    // parameter of sample x (clamped to the last sample, whose parameter is N-1 by definition, :165-176)
+    auto t_of = [&](int x) {
+        if (x >= D - 1) return tn;
+        const double d = dgrid[x];
+        return inv ? distance_to_time_inv(ld, lt, inv, Q, L, n, d) : distance_to_time32(ld, lt, Q, L, n, d);
+    };
+    const int tcsh = sh < 6 ? sh : 6;                // TC = min(NT, 64) columns x TR = 256 / TC rows per tile
+    const int TC = 1 << tcsh;
+    const int trsh = 8 - tcsh;
+    const int TR = 1 << trsh;
+    const int st = (TR + 2) | 1;                     // odd stride; row r of the tile sits at index r + 1 (index 0: row s0-1)
+    __shared__ double s_c[2];                        // per-path constants: one thread divides, not all 256
+    if (threadIdx.x == 0) {
+        const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
+        s_c[0] = 2 * V_ / w_;                        // max_angular_vel   (:81)
+        s_c[1] = 2 * A0_ / w_;                       // max_angular_accel (:82)
+    }
+    const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
+    const int A = n_ap ? n_ap[b] : 0;
+    double* pr = rec + (size_t)b * RS * 5;
+    const int PS = PB * NT;
+    const size_t orow = (size_t)b * D_cap;
+    for (int it = 0; it < PP_TILES && j0 < jend; ++it, j0 += blockDim.x) {
+        double* t_t = s_tile + (it & 1) * (3 * TC * st);
+        double* t_th = t_t + TC * st;
+        double* t_k = t_th + TC * st;
+        const double* o_t = s_tile + ((it & 1) ^ 1) * (3 * TC * st);      // the tile before
+        const int c0 = (j0 >> 2) & (NT - 1);         // first column of the tile (0 unless NT > 64)
+        const int s0 = (j0 >> (sh + 2)) << 2;        // first row of the tile
+        {
+            // rows s0+1 .. s0+TR of every column: one sample per thread, lanes along a column
+            const int cc = threadIdx.x >> trsh, r = threadIdx.x & (TR - 1);
+            int ee = (c0 + cc) * Lc + s0 + 1 + r;
+            ee = ee > D - 1 ? D - 1 : ee;
+            const double t = t_of(ee);
+            double k, h;
+            snap_gather2_32(pk, ph, t, pg, k, h);
+            t_t[cc * st + r + 2] = t; t_th[cc * st + r + 2] = h; t_k[cc * st + r + 2] = k;
+            if (t_out) {                             // inspection outputs (a sample may be computed by two columns: same value)
+                t_out[orow + ee] = t; kap_out[orow + ee] = k; th_out[orow + ee] = h;
+            }
+            if ((int)threadIdx.x < TC) {             // rows s0-1 and s0: from the tile before, or (first tile of the CTA) computed
+                const int c = c0 + threadIdx.x;
+                if (it > 0 && NT <= 64) {            // same columns as the tile before (NT > 64: a CTA's tiles change columns)
+                    t_t[threadIdx.x * st + 0] = o_t[threadIdx.x * st + TR];
+                    t_t[threadIdx.x * st + 1] = o_t[threadIdx.x * st + TR + 1];
+                    t_th[threadIdx.x * st + 1] = o_t[TC * st + threadIdx.x * st + TR + 1];
+                    t_k[threadIdx.x * st + 1] = o_t[2 * TC * st + threadIdx.x * st + TR + 1];
+                } else {
+                    int e0 = c * Lc + s0;
+                    e0 = e0 > D - 1 ? D - 1 : e0;
+                    const double t0 = t_of(e0);
+                    double k0, h0;
+                    snap_gather2_32(pk, ph, t0, pg, k0, h0);
+                    t_t[threadIdx.x * st + 1] = t0; t_th[threadIdx.x * st + 1] = h0; t_k[threadIdx.x * st + 1] = k0;
+                    t_t[threadIdx.x * st + 0] = (e0 > 0) ? t_of(e0 - 1) : 0.0;        // prev_t of sample 0 is 0 (:96)
+                    if (t_out && e0 == 0) { t_out[orow] = t0; kap_out[orow] = k0; th_out[orow] = h0; }
+                }
+            }
+        }
+        __syncthreads();                             // also publishes s_c; the other buffer is free again one barrier later
+        const int j = j0 + threadIdx.x;
+        const int c = (j >> 2) & (NT - 1);
+        const int s = ((j >> (sh + 2)) << 2) + (j & 3);
+        const int e = c * Lc + s;                    // this slot's edge = the sample whose terms this thread evaluates
+        if (s >= Lc || e >= steps) continue;
+        const int tl = (c - c0) * st + (s - s0) + 1;
+        // ---- event candidates of sample e (motion_profile_generator.py:124, :142-146); e <= D-2 here
+        {
+            const double t = t_t[tl], tp = t_t[tl - 1];
+            if (frac1(tp) > frac1(t) && t < tn) {
+                const int slot = atomicAdd(ev_nwrap + b, 1);
+                if (slot < N_max) ev_wrap[(size_t)b * N_max + slot] = e;
+            }
+            for (int q = 0; q < A; q++) {
+                const double x = ap_attr[((size_t)b * A_max + q) * APA + P_T];
+                if (tp < x && t >= x) {
+                    const int slot = atomicAdd(ev_napc + (size_t)b * A_max + q, 1);
+                    if (slot < EV_AP_CAND) ev_apc[((size_t)b * A_max + q) * EV_AP_CAND + slot] = e;
+                }
+            }
+        }
+        // ---- the records of slot j
+        const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
+        const size_t o = (size_t)(j >> (sh + 2)) * (5 * PS) + (size_t)(j & (PS - 1));
+        const SampleTerms tm = prepass_sample<false>(V, A0, A0, w, s_c[0], s_c[1], t_k[tl]);
+        pr[o] = tm.ak; pr[o + PS] = tm.G; pr[o + 2 * PS] = tm.stat; pr[o + 3 * PS] = gh; pr[o + 4 * PS] = recip_for_pass(gh);
+        if (e == steps - 1) {                        // the final sample (no edge starts there): the backward pass starts on it
+            double kl, hl;
+            snap_gather2_32(pk, ph, tn, pg, kl, hl);
+            const SampleTerms u = prepass_sample<false>(V, A0, A0, w, s_c[0], s_c[1], kl);
+            pr[5 * RS - 3] = u.ak; pr[5 * RS - 2] = u.G; pr[5 * RS - 1] = u.stat;
+            if (t_out) { t_out[orow + D - 1] = tn; kap_out[orow + D - 1] = kl; th_out[orow + D - 1] = hl; }
+        }
+    }
+}
+
+// Paths with max_acceleration overrides (node / action point): the static acceleration limits depend on the regime, which
+// k_resolve_events has only now established.  Rewrites field 2 of the records (forward limit of each sample's regime) and
+// fills statB (the backward pass's limit) from field 0 (|kappa|).  One CTA per path: every path without overrides leaves at once.
+__global__ void __launch_bounds__(256) k_prepass_ovr(
+    const int* __restrict__ status, const double* __restrict__ cons, const int* __restrict__ n_samples, int NT, long long RS,
+    double* __restrict__ rec, int E_cap, const double* __restrict__ max_accels, const int* __restrict__ bidx,
+    const int* __restrict__ bval, const int* __restrict__ n_ev, double* __restrict__ statB)
+{
+    const long long b = blockIdx.x;
+    if (status[b] != ST_OK) return;
+    const double A0 = cons[b * 6 + 1];
+    if (!pass_has_override(max_accels + (size_t)b * E_cap, n_ev[2 * b], A0)) return;     // uniform over the CTA
+    const int D = n_samples[b];
+    const int steps = D - 1;
+    if (steps <= 0) return;
+    const int sh = 31 - __clz(NT);
+    const int Lc = chunk_len(steps, NT);
+    const double V = cons[b * 6 + 0], w = cons[b * 6 + 5];
+    const double mav = 2 * V / w, maa = 2 * A0 / w;
+    const int PS = PB * NT;
+    double* pr = rec + (size_t)b * RS * 5;
+    const int nb = n_ev[2 * b + 1];
+    const double dec_b = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + nb - 1]];       // backward max_dec
+    for (int j = threadIdx.x; j < (Lc << sh); j += blockDim.x) {
+        const int c = (j >> 2) & (NT - 1);
+        const int s = ((j >> (sh + 2)) << 2) + (j & 3);
+        const int e = c * Lc + s;
+        if (e >= steps) continue;
+        const size_t o = (size_t)(j >> (sh + 2)) * (5 * PS) + (size_t)(j & (PS - 1));
+        const double acc_f = max_accels[(size_t)b * E_cap + bval[(size_t)b * E_cap + last_le(bidx + (size_t)b * E_cap, nb, e)]];
+        const SampleTerms t = prepass_sample<true>(V, acc_f, dec_b, w, mav, maa, pr[o]);
+        pr[o + 2 * PS] = t.stat;
+        statB[(size_t)b * RS + j] = t.stat_b;
+        if (e == steps - 1) {
+            const SampleTerms u = prepass_sample<true>(V, dec_b, dec_b, w, mav, maa, pr[5 * RS - 3]);
+            pr[5 * RS - 1] = u.stat;
+            statB[(size_t)b * RS + RS - 1] = u.stat_b;
+        }
+    }
+}
+
 // ---- chunk-speculative forward / backward kernels: one CTA per path, one chunk per thread ------------------------
 __device__ __forceinline__ bool same_bits(double a, double b)
 {
