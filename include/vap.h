@@ -232,6 +232,39 @@ int vap_time_profile(int64_t B, int N_max, int A_max, const double* node_attr, c
  *     multiplication and two fused residual corrections (the IEEE quotient, bit for bit); pass NULL to divide directly. */
 int vap_build_lerp_recip(int64_t n, double dd, double* rden, void* stream);
 
+/* ---- The whole hot path behind ONE call ------------------------------------------------------------------------------
+ * vap_profile_batch = build_path (spline_manager.py:42-172) + generate_motion_profile(spline_manager, constraints, dt, dd)
+ * (motion_profile_generator.py:389-628, which starts with rebuild_tables, spline_manager.py:582) for B paths: S0 -> S7 on
+ * `stream`, every intermediate carved out of ONE caller-owned workspace of vap_workspace_bytes(...) bytes (256-byte aligned;
+ * the library allocates nothing).  The caller chooses the capacities: D_cap distance samples (a multiple of 128) and T_cap
+ * time samples per path; sizing is checked on the device, per path: a path that needs more gets status VAP_ERR_CAPACITY
+ * (its true counts are still in n_samples / n_out), the others are unaffected.  need[3] (device i64, may be NULL) receives
+ * the batch maxima {distance samples, estimated time samples incl. inserted rows, a sufficient T_cap from the time loop's own
+ * iteration count (0 while the distance samples did not fit)} over the paths that
+ * are healthy or only lacked capacity: read it back to size a retry.  Paths whose length or travel time is absurd (the
+ * reference's loops would not terminate) get VAP_ERR_DIVERGED.
+ * Inputs: the packed node / action-point tables of vap_build_path / vap_velocity_profile; max_splines >= max_b n_splines[b]
+ * (1 + the number of reverse / turn nodes; N_max - 1 is always enough); dgrid[n_grid >= D_cap + 2] from vap_build_dgrid and
+ * rden[n_rden] from vap_build_lerp_recip (or NULL): path-independent, depend on dd only, build them once.
+ * Outputs: out[8][B][T_cap] (planes out_plane_stride elements apart, 0 = B*T_cap): times, positions, linear_vels,
+ * accelerations, headings, angular_vels, x, y; n_out[B]; nodes_map[B][N_max+1]; actions_map[B][max(A_max,1)]; n_maps[B][2];
+ * status[B]; summary[B][5]; vel[B][D_cap] (forward_backward_pass); n_samples[B].                                          */
+int64_t vap_workspace_bytes(int64_t B, int N_max, int A_max, int max_splines, int lut_samples, int samples_per_node,
+                            int64_t D_cap, int64_t T_cap, int chunks);
+int vap_profile_batch(int64_t B, int N_max, int A_max, int max_splines, const double* node_attr,
+                      const int32_t* node_flags, const int32_t* n_nodes, const double* ap_attr, const int32_t* ap_flags,
+                      const int32_t* n_ap, const double* cons, double dt, double dd, double start_vel, double end_vel,
+                      int lut_samples, int samples_per_node, int64_t D_cap, int64_t T_cap, int chunks, const double* dgrid,
+                      int64_t n_grid, const double* rden, int64_t n_rden, void* workspace, int64_t workspace_bytes,
+                      double* out, int64_t out_plane_stride, int32_t* n_out, int32_t* nodes_map, int32_t* actions_map,
+                      int32_t* n_maps, int32_t* status, double* summary, double* vel, int32_t* n_samples, int64_t* need,
+                      void* stream);
+/* S7 on its own: summary[b] = {n_out, total_length (0 if total_len is NULL), times[-1], max |linear_vels|, status} from the
+ * output streams (the rows the ranks of a sharded job gather).  vap_resample / vap_time_profile / vap_profile_batch already
+ * write these rows; this entry serves callers that produced `out` some other way (a tile loop, a re-used buffer).        */
+int vap_summary(int64_t B, int64_t T_cap, int64_t out_plane_stride, const double* out, const int32_t* n_out,
+                const int32_t* status, const double* total_len, double* summary, void* stream);
+
 /* S1' QuinticHermiteSpline.get_arc_length (Gauss-Legendre, quintic_hermite_spline.py:592-644) and
  *     get_parameter_by_arc_length (:661-717) for n queries on spline `spl[q]` of path `path[q]`.
  *     gl_pts / gl_wts[npts] = np.polynomial.legendre.leggauss(npts) from the host (device copies).

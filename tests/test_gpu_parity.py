@@ -676,3 +676,119 @@ def test_bad_lengths_do_not_break_the_batch():
             assert int(res.n_out[b]) == int(ref.n_out[b])
             assert torch.equal(res.out[:, b, : int(res.n_out[b])], ref.out[:, b, : int(ref.n_out[b])])
         assert res.vel.shape[1] < 40000                     # the outliers did not size the distance-domain rows
+
+
+@pytest.mark.gpu
+def test_profile_batch_single_c_entry_raw_ctypes(ora):
+    """The drop-in boundary as a C caller sees it (include/vap.h): the whole hot path through the ONE symbol
+    vap_profile_batch, on buffers from cudaMalloc, with no Engine, no torch tensors and no Python orchestration.  Checked
+    against the oracle on every path of a mixed batch, against Engine.profile bit for bit, and for the device-side
+    capacity protocol (VAP_ERR_CAPACITY + need[] -> retry)."""
+    import ctypes as C
+    from vexautonomousplanner_b200 import _lib, synth
+    from vexautonomousplanner_b200.engine import Engine
+    torch.zeros(1, device="cuda")                             # the CUDA runtime is loaded (and its context created) by torch
+    L = _lib.lib()
+    rt = C.CDLL([ln.split()[-1] for ln in open("/proc/self/maps") if "libcudart" in ln][0])
+    rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rt.cudaFree.argtypes = [C.c_void_p]
+    H2D, D2H = 1, 2
+    bufs = []
+
+    def dev(nbytes):
+        p = C.c_void_p()
+        assert rt.cudaMalloc(C.byref(p), max(int(nbytes), 256)) == 0
+        bufs.append(p)
+        return p
+
+    def up(a):
+        a = np.ascontiguousarray(a)
+        p = dev(a.nbytes)
+        assert rt.cudaMemcpy(p, a.ctypes.data_as(C.c_void_p), a.nbytes, H2D) == 0
+        return p
+
+    def down(p, shape, dtype):
+        a = np.empty(shape, dtype=dtype)
+        assert rt.cudaMemcpy(a.ctypes.data_as(C.c_void_p), p, a.nbytes, D2H) == 0
+        return a
+
+    packed = synth.mixed_paths(48, 8, seed=11)
+    B, N, A = packed.B, packed.N_max, packed.A_max
+    S = packed.max_splines()
+    dt, dd, samples, spn, chunks = 0.01, 0.005, 1000, 1000, 32
+    d_in = [up(x) for x in (packed.node_attr, packed.node_flags, packed.n_nodes, packed.ap_attr, packed.ap_flags, packed.n_ap,
+                            packed.cons)]
+
+    def run(D_cap, T_cap):
+        n_grid = D_cap + 2
+        dgrid, rden = dev(8 * n_grid), dev(8 * n_grid)
+        assert L.vap_build_dgrid(C.c_int64(n_grid), C.c_double(dd), dgrid, None) == 0
+        assert L.vap_build_lerp_recip(C.c_int64(n_grid), C.c_double(dd), rden, None) == 0
+        nbytes = L.vap_workspace_bytes(C.c_int64(B), N, A, S, samples, spn, C.c_int64(D_cap), C.c_int64(T_cap), chunks)
+        assert nbytes > 0
+        ws = dev(nbytes)
+        o = dict(out=dev(8 * 8 * B * T_cap), n_out=dev(4 * B), nodes_map=dev(4 * B * (N + 1)), actions_map=dev(4 * B * max(A, 1)),
+                 n_maps=dev(8 * B), status=dev(4 * B), summary=dev(40 * B), vel=dev(8 * B * D_cap), n_samples=dev(4 * B),
+                 need=dev(24))
+        rc = L.vap_profile_batch(C.c_int64(B), N, A, S, *d_in, C.c_double(dt), C.c_double(dd), C.c_double(0.01), C.c_double(0.01),
+                                 samples, spn, C.c_int64(D_cap), C.c_int64(T_cap), chunks, dgrid, C.c_int64(n_grid), rden,
+                                 C.c_int64(n_grid), ws, C.c_int64(nbytes), o["out"], C.c_int64(0), o["n_out"], o["nodes_map"],
+                                 o["actions_map"], o["n_maps"], o["status"], o["summary"], o["vel"], o["n_samples"], o["need"], None)
+        assert rc == 0, L.vap_last_error()
+        assert rt.cudaDeviceSynchronize() == 0
+        return dict(out=down(o["out"], (8, B, T_cap), np.float64), n_out=down(o["n_out"], (B,), np.int32),
+                    nodes_map=down(o["nodes_map"], (B, N + 1), np.int32), actions_map=down(o["actions_map"], (B, max(A, 1)), np.int32),
+                    n_maps=down(o["n_maps"], (B, 2), np.int32), status=down(o["status"], (B,), np.int32),
+                    summary=down(o["summary"], (B, 5), np.float64), vel=down(o["vel"], (B, D_cap), np.float64),
+                    n_samples=down(o["n_samples"], (B,), np.int32), need=down(o["need"], (3,), np.int64))
+
+    try:
+        # 1. undersized on purpose: every path reports VAP_ERR_CAPACITY or fits; need[] says what the batch wants
+        small = run(1024, 256)
+        assert (small["status"] == -4).any()
+        d_need, t_est, _ = (int(v) for v in small["need"])
+        assert d_need > 1024
+        # 2. the retry a C caller would make
+        D_cap = (d_need + 8 + 127) // 128 * 128
+        got = run(D_cap, int(t_est * 1.10) + 64)
+        if (got["status"] == -4).any():                       # the time estimate is only an estimate: one more exact retry
+            got = run(D_cap, int(max(got["need"][1], got["need"][2])) + 64)
+        assert (got["status"] == 0).all(), (got["status"], got["need"], got["n_samples"], got["n_out"], D_cap)
+        # 3. every path against the oracle (engine arithmetic: mode 1), integers exact
+        for b in range(B):
+            na_ = int(packed.n_ap[b])
+            ref = ora.full(packed.node_attr[b], packed.node_flags[b], packed.ap_attr[b, :na_] if na_ else None,
+                           packed.ap_flags[b, :na_] if na_ else None, packed.cons[b])
+            T = int(got["n_out"][b])
+            assert T == ref["T"] and int(got["n_samples"][b]) == ref["D"]
+            nm, am = (int(v) for v in got["n_maps"][b])
+            assert got["nodes_map"][b, :nm].tolist() == ref["nodes_map"].tolist()
+            assert got["actions_map"][b, :am].tolist() == ref["actions_map"].tolist()
+            np.testing.assert_allclose(got["vel"][b, :ref["D"]], ref["vel"], rtol=1e-6, atol=1e-12)
+            tols = dict(times=(1e-6, 1e-12), linear_vels=(1e-6, 1e-9), angular_vels=(1e-6, 1e-9), headings=(1e-9, 1e-10),
+                        x=(1e-9, 1e-10), y=(1e-9, 1e-10))
+            for i, nm_ in enumerate(("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")):
+                if nm_ in tols:
+                    np.testing.assert_allclose(got["out"][i, b, :T], ref[nm_], rtol=tols[nm_][0], atol=tols[nm_][1],
+                                               err_msg=f"path {b} {nm_}")
+        # 4. bit for bit what the staged Python orchestration (Engine.profile) returns
+        eng = Engine("cuda:0")
+        res = eng.profile(eng.upload(packed))
+        torch.cuda.synchronize()
+        assert np.array_equal(res.n_out.cpu().numpy(), got["n_out"])
+        for b in range(B):
+            T = int(got["n_out"][b])
+            assert np.array_equal(res.out[:, b, :T].cpu().numpy(), got["out"][:, b, :T])
+            assert np.array_equal(res.vel[b, :int(got["n_samples"][b])].cpu().numpy(), got["vel"][b, :int(got["n_samples"][b])])
+        np.testing.assert_array_equal(res.summary.cpu().numpy(), got["summary"])
+        # 5. the Engine's thin wrapper over the same symbol
+        rb = eng.profile_batch(eng.upload(packed))
+        torch.cuda.synchronize()
+        assert np.array_equal(rb.n_out.cpu().numpy(), got["n_out"]) and bool((rb.status == 0).all())
+        for b in range(0, B, 7):
+            T = int(got["n_out"][b])
+            assert np.array_equal(rb.out[:, b, :T].cpu().numpy(), got["out"][:, b, :T])
+    finally:
+        for p in bufs:
+            rt.cudaFree(p)

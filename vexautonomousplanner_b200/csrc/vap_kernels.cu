@@ -466,6 +466,11 @@ __global__ void k_count_samples(long long B, const int* __restrict__ status_in, 
         if (dgrid[mid] < L) lo = mid + 1; else hi = mid;
     }
     long long D = lo + 1;
+    if (lo >= n_grid) {               // the grid itself is too short to count on: an upper estimate from the length (sizing only)
+        const double est = ceil(L / (dgrid[1] - dgrid[0])) + 2.0;
+        D = est < 2147483647.0 ? (long long)est : 2147483647LL;
+        if (D <= D_cap) D = D_cap + 1;
+    }
     if (lo >= n_grid || D > D_cap) { status[b] = ST_CAPACITY; n_samples[b] = (int)(D > 2147483647LL ? 2147483647LL : D); return; }
     n_samples[b] = (int)D;
 }
@@ -1649,5 +1654,220 @@ extern "C" int vap_compact_rows(int64_t R, const char* slots, const int32_t* len
     if (R <= 0) return 0;
     k_compact_rows<<<blocks_for(R * 32, 256), 256, 0, STREAM>>>(R, slots, lens, reinterpret_cast<const long long*>(offsets), text);
     CHECK_LAUNCH("vap_compact_rows");
+    return 0;
+}
+
+// =====================================================================================================
+// The whole hot path behind ONE call: generate_motion_profile(spline_manager, constraints)
+// (motion_profile_generator.py:389-628, incl. build_path and rebuild_tables) for a batch, out of one caller workspace.
+// =====================================================================================================
+#define VAP_DIST_LIMIT 5.0e7     // more distance samples than this per path (an infinite length too): ST_DIVERGED
+#define VAP_TIME_LIMIT 1.0e7     // more time samples than this per path: treated as a non-terminating profile (ST_DIVERGED)
+
+// paths whose sampling loop `while d < total_length` would never end / never fit are flagged before anything is sized on them
+__global__ void k_flag_lengths(long long B, const int* __restrict__ gstatus, const double* __restrict__ total_len, double dd,
+                               int* __restrict__ status)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int s = gstatus[b];
+    if (s == ST_OK && total_len[b] / dd > VAP_DIST_LIMIT) s = ST_DIVERGED;      // false for NaN (the reference's loops do not run)
+    status[b] = s;
+}
+// after the velocity stage: flag absurd travel times, publish what the batch needs (need[0] = max distance samples,
+// need[1] = max estimated time samples incl. inserted rows; both over healthy paths) so that a caller can size a retry
+__global__ void k_flag_times(long long B, int* __restrict__ status, const int* __restrict__ n_samples,
+                             const float* __restrict__ t_est, const float* __restrict__ ins_est,
+                             unsigned long long* __restrict__ need)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int s = status[b];
+    if (s != ST_OK && s != ST_CAPACITY) return;
+    atomicMax(need, (unsigned long long)(n_samples[b] > 0 ? n_samples[b] : 0));
+    if (s != ST_OK) return;
+    const float est = t_est[b] + ins_est[b];
+    if (!(est < (float)VAP_TIME_LIMIT)) { status[b] = ST_DIVERGED; return; }
+    atomicMax(need + 1, (unsigned long long)est);
+}
+// row counts once the time stage has run: the main-loop iterations (exact even when the rows did not fit) plus the bound of
+// the rows that waits and turn profiles insert
+__global__ void k_need_rows(long long B, const int* __restrict__ status, const int* __restrict__ n_main,
+                            const float* __restrict__ ins_est, unsigned long long* __restrict__ need)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int s = status[b];
+    if (s == ST_OK || s == ST_CAPACITY)
+        atomicMax(need + 2, (unsigned long long)(n_main[b] > 0 ? n_main[b] : 0) + (unsigned long long)ceilf(ins_est[b]) + 8ull);
+}
+
+struct WsCarver {
+    char* base; size_t off;
+    template <typename T> T* take(size_t n)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+struct BatchScratch {
+    double *seg, *param_end, *seglen, *scratch9, *lut_d, *lut_t, *total_len, *prop_k, *prop_h, *ma, *vr_val, *rec, *statB, *vel_f,
+           *stage;
+    int32_t *first_node, *n_splines, *gstatus, *lut_inv, *bidx, *bval, *n_ev, *vr_idx, *st_idx, *n_vr, *scr, *rounds, *seg_tab,
+            *scr2, *n_main;
+    float *ins_est, *t_est;
+    unsigned long long* need;
+    int64_t Q_cap, P_cap, RS; int E_cap;
+};
+static size_t carve_batch(char* base, int64_t B, int N_max, int A_max, int max_splines, int samples, int spn, int64_t D_cap,
+                          int64_t T_cap, int chunks, BatchScratch& s)
+{
+    WsCarver w{base, 0};
+    const int S = max_splines > 0 ? max_splines : 1;
+    s.Q_cap = (int64_t)samples * S; s.P_cap = (int64_t)spn * N_max; s.E_cap = N_max + A_max + 2;
+    s.RS = vap_pass_row_slots(D_cap, chunks);
+    const size_t nscr = (size_t)vap_event_scratch_ints(B, N_max, A_max);
+    s.seg = w.take<double>((size_t)B * (N_max > 1 ? N_max - 1 : 1) * 12);
+    s.first_node = w.take<int32_t>((size_t)B * (N_max + 1));
+    s.param_end = w.take<double>((size_t)B * N_max);
+    s.seglen = w.take<double>((size_t)B * N_max);
+    s.n_splines = w.take<int32_t>(B);
+    s.gstatus = w.take<int32_t>(B);
+    s.scratch9 = w.take<double>((size_t)B * N_max * 9);
+    s.lut_d = w.take<double>((size_t)B * s.Q_cap);
+    s.lut_t = w.take<double>((size_t)B * s.Q_cap);
+    s.total_len = w.take<double>(B);
+    s.lut_inv = w.take<int32_t>((size_t)B * vap_lut_index_row_ints(s.Q_cap));
+    s.prop_k = w.take<double>((size_t)B * s.P_cap);
+    s.prop_h = w.take<double>((size_t)B * s.P_cap);
+    s.ma = w.take<double>((size_t)B * s.E_cap);
+    s.bidx = w.take<int32_t>((size_t)B * s.E_cap);
+    s.bval = w.take<int32_t>((size_t)B * s.E_cap);
+    s.n_ev = w.take<int32_t>((size_t)B * 2);
+    s.vr_idx = w.take<int32_t>((size_t)B * s.E_cap);
+    s.vr_val = w.take<double>((size_t)B * s.E_cap);
+    s.st_idx = w.take<int32_t>((size_t)B * s.E_cap);
+    s.n_vr = w.take<int32_t>((size_t)B * 2);
+    s.ins_est = w.take<float>(B);
+    s.t_est = w.take<float>(B);
+    s.scr = w.take<int32_t>(nscr);
+    s.rounds = w.take<int32_t>((size_t)B * 2);
+    s.rec = w.take<double>((size_t)B * s.RS * 5);
+    s.statB = w.take<double>((size_t)B * s.RS);
+    s.vel_f = w.take<double>((size_t)B * s.RS);
+    s.stage = w.take<double>((size_t)8 * B * (T_cap + 1));
+    s.seg_tab = w.take<int32_t>((size_t)3 * B * s.E_cap + B);
+    s.scr2 = w.take<int32_t>(nscr);
+    s.n_main = w.take<int32_t>(B);
+    s.need = w.take<unsigned long long>(4);
+    return (w.off + 255) & ~(size_t)255;
+}
+
+static int check_batch_args(const char* who, int64_t B, int N_max, int A_max, int max_splines, int samples, int spn,
+                            int64_t D_cap, int64_t T_cap, int chunks)
+{
+    if (B < 0 || N_max < 2 || A_max < 0 || max_splines < 1 || max_splines > N_max || samples < 2 || spn < 2 || T_cap < 1) {
+        snprintf(g_err, sizeof(g_err), "%s: bad sizes", who); return -1;
+    }
+    if (D_cap < 128 || D_cap % 128 != 0) { snprintf(g_err, sizeof(g_err), "%s: D_cap must be a positive multiple of 128", who); return -1; }
+    return check_pass_args(who, B, D_cap, chunks);
+}
+
+extern "C" int64_t vap_workspace_bytes(int64_t B, int N_max, int A_max, int max_splines, int lut_samples, int samples_per_node,
+                                       int64_t D_cap, int64_t T_cap, int chunks)
+{
+    if (check_batch_args("vap_workspace_bytes", B, N_max, A_max, max_splines, lut_samples, samples_per_node, D_cap, T_cap, chunks))
+        return -1;
+    BatchScratch s;
+    return (int64_t)carve_batch(nullptr, B, N_max, A_max, max_splines, lut_samples, samples_per_node, D_cap, T_cap, chunks, s);
+}
+
+extern "C" int vap_profile_batch(int64_t B, int N_max, int A_max, int max_splines, const double* node_attr,
+                                 const int32_t* node_flags, const int32_t* n_nodes, const double* ap_attr,
+                                 const int32_t* ap_flags, const int32_t* n_ap, const double* cons, double dt, double dd,
+                                 double start_vel, double end_vel, int lut_samples, int samples_per_node, int64_t D_cap,
+                                 int64_t T_cap, int chunks, const double* dgrid, int64_t n_grid, const double* rden,
+                                 int64_t n_rden, void* workspace, int64_t workspace_bytes, double* out,
+                                 int64_t out_plane_stride, int32_t* n_out, int32_t* nodes_map, int32_t* actions_map,
+                                 int32_t* n_maps, int32_t* status, double* summary, double* vel, int32_t* n_samples,
+                                 int64_t* need, void* stream)
+{
+    if (B == 0) return 0;
+    if (check_batch_args("vap_profile_batch", B, N_max, A_max, max_splines, lut_samples, samples_per_node, D_cap, T_cap, chunks))
+        return -1;
+    if (!dgrid || n_grid < D_cap + 2) return arg_err("vap_profile_batch: dgrid (vap_build_dgrid) must hold at least D_cap + 2 entries");
+    if (!workspace) return arg_err("vap_profile_batch: workspace is NULL");
+    BatchScratch s;
+    const size_t bytes = carve_batch(static_cast<char*>(workspace), B, N_max, A_max, max_splines, lut_samples, samples_per_node,
+                                     D_cap, T_cap, chunks, s);
+    if ((int64_t)bytes > workspace_bytes) return arg_err("vap_profile_batch: workspace smaller than vap_workspace_bytes(...)");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return arg_err("vap_profile_batch: workspace must be 256-byte aligned");
+    cudaError_t e = cudaMemsetAsync(s.need, 0, 4 * sizeof(unsigned long long), STREAM);
+    if (e != cudaSuccess) return set_err("vap_profile_batch/memset", e);
+    int rc;
+    // S0 build_path, S1 distance table (+ inverse index), S2 curvature / heading tables  (rebuild_tables, spline_manager.py:582)
+    if ((rc = vap_build_path(B, N_max, node_attr, node_flags, n_nodes, s.seg, s.first_node, s.param_end, s.seglen, s.n_splines,
+                             s.gstatus, s.scratch9, nullptr, nullptr, stream))) return rc;
+    if ((rc = vap_build_lut(B, N_max, s.seg, s.first_node, s.param_end, s.n_splines, s.gstatus, lut_samples, s.Q_cap, s.lut_d,
+                            s.lut_t, s.total_len, stream))) return rc;
+    if ((rc = vap_build_lut_index(B, s.n_splines, s.gstatus, lut_samples, s.Q_cap, s.lut_d, s.total_len, s.lut_inv, stream))) return rc;
+    if ((rc = vap_build_props(B, N_max, n_nodes, s.seg, s.first_node, s.param_end, s.n_splines, s.gstatus, samples_per_node,
+                              s.P_cap, s.prop_k, s.prop_h, stream))) return rc;
+    k_flag_lengths<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, s.gstatus, s.total_len, dd, status);
+    CHECK_LAUNCH("vap_profile_batch/flag_lengths");
+    // S3 + S4 + S5
+    if ((rc = vap_velocity_profile(B, N_max, A_max, node_attr, node_flags, n_nodes, ap_attr, ap_flags, n_ap, cons, s.n_splines,
+                                   status, n_grid, dgrid, lut_samples, s.Q_cap, s.lut_d, s.lut_t, s.total_len, samples_per_node,
+                                   s.P_cap, s.prop_k, s.prop_h, s.lut_inv, dd, dt, start_vel, end_vel, D_cap, n_samples, nullptr,
+                                   nullptr, nullptr, s.E_cap, s.ma, s.bidx, s.bval, s.n_ev, s.vr_idx, s.vr_val, s.st_idx, s.n_vr,
+                                   s.ins_est, s.scr, s.rec, s.statB, s.vel_f, vel, s.t_est, s.rounds, chunks, 0, stream))) return rc;
+    k_flag_times<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, status, n_samples, s.t_est, s.ins_est, s.need);
+    CHECK_LAUNCH("vap_profile_batch/flag_times");
+    // S6 + S7
+    if ((rc = vap_time_profile(B, N_max, A_max, node_attr, node_flags, n_nodes, ap_attr, ap_flags, n_ap, cons, status, dt, dd,
+                               s.seg, s.first_node, s.param_end, s.n_splines, lut_samples, s.Q_cap, s.lut_d, s.lut_t, s.total_len,
+                               samples_per_node, s.P_cap, s.prop_k, s.prop_h, D_cap, n_samples, vel, T_cap, out, nodes_map,
+                               actions_map, n_maps, n_out, summary, s.n_main, s.stage, s.E_cap, s.seg_tab, s.scr2,
+                               out_plane_stride, s.lut_inv, rden, rden ? n_rden : 0, stream))) return rc;
+    k_need_rows<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, status, s.n_main, s.ins_est, s.need);
+    CHECK_LAUNCH("vap_profile_batch/need_rows");
+    if (need) {
+        e = cudaMemcpyAsync(need, s.need, 3 * sizeof(int64_t), cudaMemcpyDeviceToDevice, STREAM);
+        if (e != cudaSuccess) return set_err("vap_profile_batch/need", e);
+    }
+    return 0;
+}
+
+// S7 on its own: summary[b] = {n_out, total_length, times[-1], max |linear_vels|, status} from the output streams
+// (what the ranks of a sharded job gather; vap_resample / vap_time_profile / vap_profile_batch already write it).
+__global__ void __launch_bounds__(128) k_summary(long long T_cap, long long plane, const double* __restrict__ out,
+                                                 const int* __restrict__ n_out, const int* __restrict__ status,
+                                                 const double* __restrict__ total_len, double* __restrict__ summary)
+{
+    const long long b = blockIdx.x;
+    __shared__ double s_m[128];
+    const int st = status[b];
+    const long long T = (st == ST_OK) ? n_out[b] : 0;
+    const double* v = out + 2 * plane + (size_t)b * T_cap;
+    double m = 0.0;
+    for (long long i = threadIdx.x; i < T; i += blockDim.x) m = fmax(m, fabs(v[i]));
+    s_m[threadIdx.x] = m;
+    __syncthreads();
+    for (int k = 64; k > 0; k >>= 1) { if ((int)threadIdx.x < k) s_m[threadIdx.x] = fmax(s_m[threadIdx.x], s_m[threadIdx.x + k]); __syncthreads(); }
+    if (threadIdx.x == 0) {
+        double* r = summary + (size_t)b * 5;
+        r[0] = (double)n_out[b]; r[1] = total_len ? total_len[b] : 0.0;
+        r[2] = T > 0 ? out[(size_t)b * T_cap + T - 1] : 0.0; r[3] = s_m[0]; r[4] = (double)st;
+    }
+}
+extern "C" int vap_summary(int64_t B, int64_t T_cap, int64_t out_plane_stride, const double* out, const int32_t* n_out,
+                           const int32_t* status, const double* total_len, double* summary, void* stream)
+{
+    if (B <= 0) return 0;
+    const long long plane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
+    k_summary<<<(unsigned)B, 128, 0, STREAM>>>(T_cap, plane, out, n_out, status, total_len, summary);
+    CHECK_LAUNCH("vap_summary");
     return 0;
 }

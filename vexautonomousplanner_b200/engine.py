@@ -641,6 +641,59 @@ class Engine:
         (run(new_db)); a batch that still does not fit is detected on the device and redone exactly, outside the graph."""
         return GraphedProfile(self, db, tiles, to_host=to_host, margin=margin)
 
+    # ------------------------------------------------------------------ whole path, one C call
+    def plan_capacities(self, db: DeviceBatch, margin: float = 1.0):
+        """(D_cap, T_cap) for this batch shape: the cached plan, or one exact profile() that measures them."""
+        key = (db.B, db.N_max, db.A_max, db.max_splines)
+        if key not in self._plan:
+            self.profile(db, reuse_plan=False)
+        D_cap, T_cap = self._plan[key]
+        if margin > 1.0:
+            D_cap, T_cap = (int(D_cap * margin) + 127) // 128 * 128, int(T_cap * margin) + 64
+        return D_cap, T_cap
+
+    def profile_batch(self, db: DeviceBatch, D_cap: Optional[int] = None, T_cap: Optional[int] = None,
+                      _retry: int = 0) -> ProfileResult:
+        """The whole hot path through the single C entry point vap_profile_batch (include/vap.h): S0 -> S7 out of ONE
+        workspace, capacities checked on the device.  Without capacities the cached plan (or one exact profile()) sizes
+        the call; a path that outgrows them comes back as ST_CAPACITY and the call is redone with the sizes the device
+        reported in `need` (bounded retries)."""
+        B = db.B
+        if D_cap is None or T_cap is None:
+            D_cap, T_cap = self.plan_capacities(db)
+        D_cap = (int(D_cap) + 127) // 128 * 128
+        chunks = self.chunks if D_cap <= 65536 else 256
+        grid, rden = self.dgrid(D_cap + 2), self.lerp_recip(D_cap + 2)
+        nbytes = int(self.lib.vap_workspace_bytes(C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max), C.c_int(max(db.max_splines, 1)),
+                                                  C.c_int(self.samples), C.c_int(self.spn), C.c_int64(D_cap), C.c_int64(T_cap),
+                                                  C.c_int(chunks)))
+        if nbytes < 0:
+            raise _lib.VapError("vap_workspace_bytes: " + self.lib.vap_last_error().decode())
+        ws = torch.empty((nbytes + 255,), dtype=torch.uint8, device=self.device)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        out = self._empty((8, B, T_cap))
+        nodes_map = self._empty((B, db.N_max + 1), torch.int32)
+        actions_map = self._empty((B, max(db.A_max, 1)), torch.int32)
+        n_maps = self._empty((B, 2), torch.int32); n_out = self._empty((B,), torch.int32)
+        status = self._empty((B,), torch.int32); summary = self._empty((B, 5))
+        vel = self._empty((B, D_cap)); n_samples = self._empty((B,), torch.int32)
+        need = torch.zeros((3,), dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.vap_profile_batch(
+            C.c_int64(B), C.c_int(db.N_max), C.c_int(db.A_max), C.c_int(max(db.max_splines, 1)), _p(db.node_attr),
+            _p(db.node_flags), _p(db.n_nodes), _p(db.ap_attr), _p(db.ap_flags), _p(db.n_ap), _p(db.cons), C.c_double(self.dt),
+            C.c_double(self.dd), C.c_double(self.start_vel), C.c_double(self.end_vel), C.c_int(self.samples), C.c_int(self.spn),
+            C.c_int64(D_cap), C.c_int64(T_cap), C.c_int(chunks), _p(grid), C.c_int64(grid.numel()),
+            _p(rden if self.accelerators else None), C.c_int64(rden.numel()), C.c_void_p(ws_ptr), C.c_int64(nbytes), _p(out),
+            C.c_int64(0), _p(n_out), _p(nodes_map), _p(actions_map), _p(n_maps), _p(status), _p(summary), _p(vel), _p(n_samples),
+            _p(need), self._stream()), "vap_profile_batch")
+        self.launches += 19
+        res = ProfileResult(B, T_cap, out, n_out, nodes_map, actions_map, n_maps, status, summary, vel, n_samples)
+        res.extra = dict(need=need, workspace=ws)
+        if _retry < MAX_RETRIES and bool((status == ST_CAPACITY).any().item()):
+            d_need, t_est, t_exact = (int(v) for v in need.tolist())
+            return self.profile_batch(db, max(D_cap, d_need + 8), max(T_cap, int(max(t_est, t_exact) * 1.10) + 64), _retry + 1)
+        return res
+
     # ------------------------------------------------------------------ whole path
     def _plan_distance(self, t: Tables, status: torch.Tensor) -> int:
         """D_cap from the longest healthy path.  Paths whose length is infinite or absurd (the reference's sampling loop
