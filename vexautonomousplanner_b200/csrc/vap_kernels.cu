@@ -1379,7 +1379,7 @@ extern "C" int vap_velocity_profile(int64_t B, int N_max, int A_max, const doubl
     k_count_samples<<<blocks_for(B, 128), 128, 0, STREAM>>>(B, status, status, n_grid, dgrid, total_len, D_cap, n_samples);
     CHECK_LAUNCH("vap_velocity_profile/count");
     const long long RS = vap_pass_row_slots(D_cap, chunks);
-    const unsigned tx = blocks_for(D_cap + 4 * chunks, 256 * PP_TILES);
+    const unsigned tx = blocks_for(D_cap + 4 * chunks, 256 * SP_TILES);
     if ((long long)tx * B > 2147483647LL) return arg_err("vap_velocity_profile: more than 2^31 CTAs (tile the batch)");
     const int tc = prepass_tile_cols(chunks);
     const size_t sm = 2 * 3 * sizeof(double) * (size_t)tc * (((256 / tc) + 2) | 1);

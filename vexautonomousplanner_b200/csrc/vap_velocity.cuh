@@ -434,6 +434,9 @@ __global__ void __launch_bounds__(256, 8) k_prepass(
 #ifndef VAP_SP_MINB
 #define VAP_SP_MINB 8
 #endif
+#ifndef SP_TILES
+#define SP_TILES 8          // 256-slot tiles per CTA of the fused sampling + pre-pass kernel
+#endif
 __global__ void __launch_bounds__(256, VAP_SP_MINB) k_sample_prepass(
     int N_max, int A_max, const int* __restrict__ n_nodes, const int* __restrict__ n_splines,
     const int* __restrict__ status, const double* __restrict__ cons, const double* __restrict__ ap_attr,
@@ -451,16 +454,27 @@ __global__ void __launch_bounds__(256, VAP_SP_MINB) k_sample_prepass(
     const int D = n_samples[b];
     const int steps = D - 1;
     const int sh = 31 - __clz(NT);
-    const int Lc = chunk_len(steps, NT);
+    const int Lc = (((steps + NT - 1) >> sh) + PB - 1) & ~(PB - 1);      // chunk_len(steps, NT); NT is a power of two
     const int jend = Lc << sh;
-    int j0 = pt.x * (blockDim.x * PP_TILES);
+    int j0 = pt.x * (blockDim.x * SP_TILES);
     if (steps <= 0 || j0 >= jend) return;
     const int n = n_nodes[b];
     const double* ld = lut_d + (size_t)b * Q_cap;
     const double* lt = lut_t + (size_t)b * Q_cap;
     const int Q = samples * n_splines[b];
     const double L = total_len[b];
-    const PropGrid pg = prop_grid(spn, n);
+    // per-path constants that cost divisions: made by ONE thread, published with the first tile's barrier
+    __shared__ double s_c[4];
+    if (threadIdx.x == 0) {
+        const PropGrid g0 = prop_grid(spn, n);
+        const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
+        s_c[0] = 2 * V_ / w_;                        // max_angular_vel   (:81)
+        s_c[1] = 2 * A0_ / w_;                       // max_angular_accel (:82)
+        s_c[2] = g0.step; s_c[3] = g0.inv_step;
+    }
+    __syncthreads();
+    PropGrid pg;
+    pg.P = spn * n; pg.n = n; pg.step = s_c[2]; pg.inv_step = s_c[3];
     const int* inv = lut_inv ? lut_inv + (size_t)b * (Q_cap + LUT_INV_HDR + 2) : nullptr;
     const double* pk = prop_k + (size_t)b * P_cap;
     const double* ph = prop_h + (size_t)b * P_cap;
@@ -476,18 +490,12 @@ __global__ void __launch_bounds__(256, VAP_SP_MINB) k_sample_prepass(
     const int trsh = 8 - tcsh;
     const int TR = 1 << trsh;
     const int st = (TR + 2) | 1;                     // odd stride; row r of the tile sits at index r + 1 (index 0: row s0-1)
-    __shared__ double s_c[2];                        // per-path constants: one thread divides, not all 256
-    if (threadIdx.x == 0) {
-        const double V_ = cons[b * 6 + 0], A0_ = cons[b * 6 + 1], w_ = cons[b * 6 + 5];
-        s_c[0] = 2 * V_ / w_;                        // max_angular_vel   (:81)
-        s_c[1] = 2 * A0_ / w_;                       // max_angular_accel (:82)
-    }
     const double V = cons[b * 6 + 0], A0 = cons[b * 6 + 1], w = cons[b * 6 + 5];
     const int A = n_ap ? n_ap[b] : 0;
     double* pr = rec + (size_t)b * RS * 5;
     const int PS = PB * NT;
     const size_t orow = (size_t)b * D_cap;
-    for (int it = 0; it < PP_TILES && j0 < jend; ++it, j0 += blockDim.x) {
+    for (int it = 0; it < SP_TILES && j0 < jend; ++it, j0 += blockDim.x) {
         double* t_t = s_tile + (it & 1) * (3 * TC * st);
         double* t_th = t_t + TC * st;
         double* t_k = t_th + TC * st;
@@ -525,7 +533,7 @@ __global__ void __launch_bounds__(256, VAP_SP_MINB) k_sample_prepass(
                 }
             }
         }
-        __syncthreads();                             // also publishes s_c; the other buffer is free again one barrier later
+        __syncthreads();                             // the other buffer is free again one barrier later
         const int j = j0 + threadIdx.x;
         const int c = (j >> 2) & (NT - 1);
         const int s = ((j >> (sh + 2)) << 2) + (j & 3);
