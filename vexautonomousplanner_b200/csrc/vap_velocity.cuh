@@ -738,6 +738,11 @@ __device__ __forceinline__ double bwd_step(double ak, double gh, double rg, doub
 __device__ __forceinline__ double2 ldg_d2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st_d2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
 
+// a lone lane of a fix-up re-run asks the L2 for the sectors it will need a few blocks on (its own loads only look two steps
+// ahead, which does not cover an HBM round trip; the lockstep sweeps have the TMA ring for that)
+#define RERUN_PF 4
+__device__ __forceinline__ void l2_prefetch(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
+
 // contribution of one step to the travel-time estimate (single precision: it only sizes buffers)
 __device__ __forceinline__ float t_est_term(double va, double vb, float dd_over_dt)
 {
@@ -794,7 +799,21 @@ __device__ __forceinline__ bool fwd_run(const double* __restrict__ p, double* __
     double2 oA = make_double2(0.0, 0.0), oB = oA;    // old velocities (RERUN): pair A = samples e, e+1; pair B = e+2, e+3
     if (RERUN) oA = *reinterpret_cast<const double2*>(q);
     // whole blocks (look-ahead loads never leave the path's rows: they are padded by one block)
+    if (RERUN) {
+#pragma unroll
+        for (int k = 1; k < RERUN_PF; k++)
+            if (k < (len >> 2)) {
+#pragma unroll
+                for (int f = 0; f < 5; f++) l2_prefetch(p + (size_t)k * BS + f * PS);
+                l2_prefetch(q + (size_t)k * PS);
+            }
+    }
     for (int blk = len >> 2; blk > 0; --blk) {
+        if (RERUN && blk > RERUN_PF) {
+#pragma unroll
+            for (int f = 0; f < 5; f++) l2_prefetch(p + (size_t)RERUN_PF * BS + f * PS);
+            l2_prefetch(q + (size_t)RERUN_PF * PS);
+        }
         akB = ldg_d2(p + 2); GB = ldg_d2(p + PS + 2); stB = ldg_d2(p + 2 * PS + 2); ghB = ldg_d2(p + 3 * PS + 2); rgB = ldg_d2(p + 4 * PS + 2);
         if (RERUN) oB = *reinterpret_cast<const double2*>(q + 2);
         const double vin = v;
@@ -1148,12 +1167,30 @@ __device__ __forceinline__ bool bwd_run(const double* __restrict__ p, const doub
     // whole blocks, top down: pair B (rows 2, 3) then pair A (rows 0, 1) of each; the next pair is fetched while the current
     // one is being used
     p -= BS; f -= PS; sb -= PS; if (!DRY) o -= PB;
+    if (RERUN) {
+#pragma unroll
+        for (int k = 1; k < RERUN_PF; k++)
+            if (k < blk) {
+#pragma unroll
+                for (int fl = 0; fl < 5; fl++) if (!(OVR && fl == 2)) l2_prefetch(p - (size_t)k * BS + fl * PS);
+                l2_prefetch(f - (size_t)k * PS);
+                l2_prefetch(o - k * PB);
+                if (OVR) l2_prefetch(sb - (size_t)k * PS);
+            }
+    }
     double2 akB = ldg_d2(p + 2), GB = ldg_d2(p + PS + 2), stB = OVR ? ldg_d2(sb + 2) : ldg_d2(p + 2 * PS + 2),
             ghB = ldg_d2(p + 3 * PS + 2), rgB = ldg_d2(p + 4 * PS + 2), fB = ldg_d2(f + 2);
     double2 akA, GA, stA, ghA, rgA, fA;
     double2 oA = make_double2(0.0, 0.0), oB = oA;
     if (RERUN) oB = *reinterpret_cast<const double2*>(o + 2);
     while (true) {
+        if (RERUN && blk > RERUN_PF) {
+#pragma unroll
+            for (int fl = 0; fl < 5; fl++) if (!(OVR && fl == 2)) l2_prefetch(p - (size_t)RERUN_PF * BS + fl * PS);
+            l2_prefetch(f - (size_t)RERUN_PF * PS);
+            l2_prefetch(o - RERUN_PF * PB);
+            if (OVR) l2_prefetch(sb - (size_t)RERUN_PF * PS);
+        }
         akA = ldg_d2(p); GA = ldg_d2(p + PS); stA = OVR ? ldg_d2(sb) : ldg_d2(p + 2 * PS); ghA = ldg_d2(p + 3 * PS); rgA = ldg_d2(p + 4 * PS);
         fA = ldg_d2(f);
         if (RERUN) oA = *reinterpret_cast<const double2*>(o);
