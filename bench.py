@@ -336,6 +336,18 @@ def run_cfg2(args):
     eng = Engine(dev, chunks=args.chunks)
     db = eng.upload(packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    if args.profile_step:
+        # what profiles/tools/capture.sh runs under ncu: the same step, eager and unpipelined (every kernel one launch)
+        for _ in range(max(args.warmup, 1)):
+            eng.profile(db, reuse_plan=True)
+        torch.cuda.synchronize()
+        l0 = eng.launches
+        for _ in range(args.steps):
+            flush.zero_()
+            eng.profile(db, reuse_plan=True)
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_step": True, "steps": args.steps, "launches_per_step": (eng.launches - l0) // args.steps}))
+        return
     depth = max(1, args.pipeline)
     pipe = PipelinedProfiler(eng, db, depth=depth)
     gatherer = SummaryGatherer([B] * world, dev)
@@ -685,6 +697,8 @@ def main():
     ap.add_argument("--tile", type=int, default=8192, help="cfg3: paths per tile")
     ap.add_argument("--margin", type=float, default=1.3, help="cfg3: capacity margin over the first tile's plan")
     ap.add_argument("--e2e-tiles", type=int, default=1, help="tiles of the end-to-end (host in / host out) run")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="cfg2: run only warm-up + K eager, unpipelined steps (the command profiles/tools/capture.sh puts under ncu)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 3 if args.config == "cfg3" else 10

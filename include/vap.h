@@ -321,6 +321,11 @@ int vap_row_text_stride(void);
 int vap_format_rows(int64_t R, const double* rows, const uint8_t* kinds, char* slots, int32_t* lens, void* stream);
 int vap_compact_rows(int64_t R, const char* slots, const int32_t* lens, const int64_t* offsets, char* text, void* stream);
 
+/* Bounds diagnostics of a -DVAP_BOUNDS_CHECK build (profiles/tools/bounds_check.py; compute-sanitizer is closed on the GPU
+ * pool this was developed on): out_host[32] (HOST memory) = violations per check site (0..15) and checks executed per site
+ * (16..31); returns <0 in a release build, where the checks are compiled away.                                          */
+int vap_diag_read(uint64_t* out_host, int reset);
+
 /* Measurement hook: `ctas` CTAs of 256 threads run `iters` rounds of 8 independent fp64 FMA chains each
  * (flops = ctas * 256 * iters * 16); bench.py times it to report the MEASURED fp64 peak that fp64-pipe
  * utilisations are quoted against.  out: one device double (never written).        */

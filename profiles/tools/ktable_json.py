@@ -1,13 +1,13 @@
 """ncu launch list (CSV of profiles/tools/ncu_table.sh) -> per-kernel / per-stage JSON table that bench.py reads for the
-measured DRAM traffic of the dominant stage.  usage: ktable_json.py <launches.csv> <out.json> [peak GB/s]"""
+measured DRAM traffic of the dominant stage.  usage: ktable_json.py <launches.csv> <out.json> [peak GB/s] [commit]"""
 import collections
 import csv
 import json
 import sys
 
 STAGE = {"k_build_path": "S0_build_path", "k_build_lut": "S1_lut", "k_build_lut_index": "S1_lut", "k_build_props": "S2_props",
-         "k_count_samples": "S3_dist_sample", "k_dist_sample_ev": "S3_dist_sample", "k_resolve_events": "S3_dist_sample",
-         "k_prepass": "S45_fwd_bwd", "k_fwd_chunked": "S45_fwd_bwd", "k_bwd_chunked": "S45_fwd_bwd", "k_untranspose": "S45_fwd_bwd",
+         "k_count_samples": "S345_velocity", "k_sample_prepass": "S345_velocity", "k_resolve_events": "S345_velocity",
+         "k_prepass_ovr": "S345_velocity", "k_fwd_chunked": "S345_velocity", "k_bwd_chunked": "S345_velocity",
          "k_time_state": "S6_resample", "k_time_sample": "S6_resample", "k_time_events": "S6_resample",
          "k_time_finalize": "S6_resample"}
 M = {"ms": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__bytes_write.sum", "inst": "smsp__inst_executed.sum",
@@ -18,6 +18,7 @@ M = {"ms": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__
 def main():
     src, dst = sys.argv[1], sys.argv[2]
     peak = float(sys.argv[3]) if len(sys.argv) > 3 else 6544.7
+    commit = sys.argv[4] if len(sys.argv) > 4 else None
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
     hdr = rows[0]
     ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
@@ -51,9 +52,10 @@ def main():
     for s in stages.values():
         s["ms"] = round(s["ms"], 4)
         s["dram_bytes_per_step"] = round(s["dram_bytes_per_step"], -5)
-    out = {"command": "bash profiles/tools/ncu_table.sh (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
+    out = {"command": "bash profiles/tools/capture.sh (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
                       "smsp__inst_executed.sum,smsp__issue_active...,sm__pipe_fp64_cycles_active...,sm__warps_active... "
-                      "--clock-control none python bench.py --steps 2 --warmup 3 --no-cpu --graph 0 --tiles 1)",
+                      "--clock-control none python bench.py --profile-step --steps 2 --warmup 2)",
+           "commit": commit,
            "workload": "4096 random 8-node paths, 1 B200",
            "note": "per-launch averages over the sampled steps; ncu serialises kernels and runs them cold, compare SHARES with "
                    "bench.py's CUDA-event stage times",

@@ -792,3 +792,54 @@ def test_profile_batch_single_c_entry_raw_ctypes(ora):
     finally:
         for p in bufs:
             rt.cudaFree(p)
+
+
+@pytest.mark.gpu
+def test_cfg3_full_tile_against_oracle(ora):
+    """BASELINE configs[2] at full tile size: ONE 16 384-path tile of the 2**20-path job (seed 1, 16 nodes) in one call;
+    a strided sample of its paths against oracle.full_batch (integers exact, summaries within the north-star tolerances),
+    plus size-independent properties over all of it (status, monotone times, bounded velocities, determinism)."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    B = 16384
+    packed = synth.random_paths(B, 16, seed=1)
+    eng = Engine("cuda:0")
+    db = eng.upload(packed)
+    res = eng.profile(db)
+    torch.cuda.synchronize()
+    assert bool((res.status == 0).all().item())
+    summ = res.summary.cpu().numpy()
+    sel = np.arange(0, B, 257)
+    ref = ora.full_batch(packed.node_attr[sel], packed.node_flags[sel], packed.cons[sel])
+    assert (ref[:, 4] == 0).all()
+    assert np.array_equal(summ[sel, 0], ref[:, 0])                          # T: bit-exact sample indexing
+    np.testing.assert_allclose(summ[sel, 1], ref[:, 1], rtol=1e-12)         # total length
+    np.testing.assert_allclose(summ[sel, 2], ref[:, 2], rtol=1e-6)          # t_end
+    np.testing.assert_allclose(summ[sel, 3], ref[:, 3], rtol=1e-6)          # max |v|
+    for b in (0, 4097, B - 1):                                              # three whole trajectories
+        r1 = ora.full(packed.node_attr[b], packed.node_flags[b], None, None, packed.cons[b])
+        got = res.path(b)
+        assert len(got["times"]) == r1["T"] and int(res.n_samples[b]) == r1["D"]
+        assert got["nodes_map"].tolist() == r1["nodes_map"].tolist()
+        np.testing.assert_allclose(got["x"], r1["x"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got["y"], r1["y"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got["linear_vels"], r1["linear_vels"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got["times"], r1["times"], rtol=1e-6, atol=1e-12)
+    # properties over the whole tile
+    T = res.n_out.long()
+    idx = torch.arange(res.T_cap, device=T.device)[None, :]
+    valid = idx < T[:, None]
+    times = res.stream("times")
+    dtm = times[:, 1:] - times[:, :-1]
+    assert bool((dtm[valid[:, 1:]] > 0).all().item())
+    v = res.stream("linear_vels")
+    assert bool((v[valid].abs() <= 4.0 * (1 + 1e-12)).all().item())
+    assert torch.equal(res.summary[:, 0].long(), T)
+    # determinism: the same tile through the single C entry point gives the same bits
+    rb = eng.profile_batch(db)
+    torch.cuda.synchronize()
+    assert torch.equal(rb.n_out, res.n_out)
+    m = min(rb.T_cap, res.T_cap)
+    vb = torch.arange(m, device=T.device)[None, :] < T[:, None]
+    for i in range(8):
+        assert torch.equal(rb.out[i, :, :m][vb], res.out[i, :, :m][vb])

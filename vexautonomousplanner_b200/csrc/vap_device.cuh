@@ -68,6 +68,18 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // generic-proxy reads of a shared-memory slot must precede the async-proxy (TMA) writes that refill it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- bounds diagnostics (-DVAP_BOUNDS_CHECK; compute-sanitizer is closed on the GPU pool this was developed on) ------------
+// Every hand-computed index of the TMA rings, the chunk-interleaved pass arrays and the sampling tiles is tested against the
+// extent of its array before the access; a violation is counted per site (vap_diag_read) instead of faulting.  The release
+// build compiles the checks away.
+#ifdef VAP_BOUNDS_CHECK
+#define VAP_DIAG_SITES 32
+__device__ unsigned long long g_vap_diag[VAP_DIAG_SITES];
+#define VAP_CHECK(site, cond) do { if (!(cond)) atomicAdd(&g_vap_diag[site], 1ull); else atomicAdd(&g_vap_diag[16 + ((site) & 15)], 1ull); } while (0)
+#else
+#define VAP_CHECK(site, cond) do { } while (0)
+#endif
+
 // Kernels whose grid is (tiles of one path) x (paths) are launched on a 1-D grid of tiles_x * B CTAs (grid.y stops at
 // 65535 paths); a CTA finds its path and its tile with one division.  Tiles of a path stay adjacent in launch order.
 struct PathTile { long long b; unsigned x; };

@@ -1871,3 +1871,22 @@ extern "C" int vap_summary(int64_t B, int64_t T_cap, int64_t out_plane_stride, c
     CHECK_LAUNCH("vap_summary");
     return 0;
 }
+
+// bounds diagnostics (see vap_device.cuh): out[32] = violations per site (0..15) and checks executed per site (16..31);
+// returns -1 in a build without -DVAP_BOUNDS_CHECK.  reset != 0 clears the counters afterwards.
+extern "C" int vap_diag_read(uint64_t* out_host, int reset)
+{
+#ifdef VAP_BOUNDS_CHECK
+    cudaError_t e = cudaMemcpyFromSymbol(out_host, g_vap_diag, sizeof(unsigned long long) * VAP_DIAG_SITES);
+    if (e != cudaSuccess) return set_err("vap_diag_read", e);
+    if (reset) {
+        unsigned long long z[VAP_DIAG_SITES] = {0};
+        e = cudaMemcpyToSymbol(g_vap_diag, z, sizeof(z));
+        if (e != cudaSuccess) return set_err("vap_diag_read/reset", e);
+    }
+    return 0;
+#else
+    (void)out_host; (void)reset;
+    return arg_err("vap_diag_read: this build has no bounds diagnostics (compile with -DVAP_BOUNDS_CHECK)");
+#endif
+}

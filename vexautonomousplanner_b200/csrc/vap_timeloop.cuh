@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
             const unsigned bytes = TS_BLK * sizeof(double);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier reads of the slot precede the TMA writes
             mbar_expect_tx(mb + 8 * sl, with_r ? 2 * bytes : bytes);
+            VAP_CHECK(10, (size_t)(blk + 1) * TS_BLK <= (size_t)D_cap && sl * bytes + bytes <= TS_RING * sizeof(double) &&
+                              (!with_r || (blk + 1) * (long long)TS_BLK <= n_rden));
             bulk_g2s(ring_s + sl * bytes, vv + (size_t)blk * TS_BLK, bytes, mb + 8 * sl);
             if (with_r) bulk_g2s(ring_s + TS_RDEN * sizeof(double) + sl * bytes, rden + (size_t)blk * TS_BLK, bytes, mb + 8 * sl);
             pend |= 1u << sl;

@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(256, VAP_SP_MINB) k_sample_prepass(
             const double t = t_of(ee);
             double k, h;
             snap_gather2_32(pk, ph, t, pg, k, h);
+            VAP_CHECK(8, cc < TC && r + 2 < st && ee >= 0 && ee <= D - 1 && D <= D_cap);
             t_t[cc * st + r + 2] = t; t_th[cc * st + r + 2] = h; t_k[cc * st + r + 2] = k;
             if (t_out) {                             // inspection outputs (a sample may be computed by two columns: same value)
                 t_out[orow + ee] = t; kap_out[orow + ee] = k; th_out[orow + ee] = h;
@@ -558,6 +559,7 @@ __global__ void __launch_bounds__(256, VAP_SP_MINB) k_sample_prepass(
         // ---- the records of slot j
         const double gh = 2 * fabs(t_th[tl + 1] - t_th[tl]);
         const size_t o = (size_t)(j >> (sh + 2)) * (5 * PS) + (size_t)(j & (PS - 1));
+        VAP_CHECK(9, tl >= 1 && tl + 1 < TC * st && o + 4 * PS < (size_t)(5 * RS - 3) && c - c0 >= 0 && c - c0 < TC && s - s0 >= 0 && s - s0 < TR);
         const SampleTerms tm = prepass_sample<false>(V, A0, A0, w, s_c[0], s_c[1], t_k[tl]);
         pr[o] = tm.ak; pr[o + PS] = tm.G; pr[o + 2 * PS] = tm.stat; pr[o + 3 * PS] = gh; pr[o + 4 * PS] = recip_for_pass(gh);
         if (e == steps - 1) {                        // the final sample (no edge starts there): the backward pass starts on it
@@ -869,6 +871,10 @@ struct WarpRing {
     unsigned bar;        // shared-memory address of its two mbarriers
     int planes;          // field planes per stage (5 forward, 6 backward)
     unsigned bytes;      // bytes of one plane copy (32 bytes per column of the warp)
+#ifdef VAP_BOUNDS_CHECK
+    const double *rec_lo, *rec_hi, *x_lo, *x_hi;     // the path's record rows / slot-order rows (forward velocities, override limits)
+    unsigned smem_lo, smem_hi, bar_hi;               // the CTA's rings; its mbarriers sit behind them
+#endif
 };
 // lane 0: refill stage `s` with block row `rb`; src[f] = plane f of block row 0 at the warp's first column, strides in doubles
 template <int NT>
@@ -881,12 +887,31 @@ __device__ __forceinline__ void ring_issue(const WarpRing& R, int s, const doubl
     fence_proxy_async();                                   // the lanes' reads of this stage precede the TMA writes
     mbar_expect_tx(bar, R.bytes * R.planes);
     const double* src = rec_row0 + (size_t)rb * BS;
+    if (NT == 32 && !sb_row0) {
+        // 32 chunks: the five planes of a block row are contiguous in memory and in the stage: ONE 5 KB copy
+#ifdef VAP_BOUNDS_CHECK
+        VAP_CHECK(1, rb >= 0 && src >= R.rec_lo && src + 5 * R.bytes / 8 <= R.rec_hi && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        VAP_CHECK(2, dst >= R.smem_lo && dst + 5 * R.bytes <= R.smem_hi && bar >= R.smem_hi && bar + 8 <= R.bar_hi);
+#endif
+        bulk_g2s(dst, src, 5 * R.bytes, bar);
+    } else
 #pragma unroll
     for (int f = 0; f < 5; f++) {
         const double* g = (f == 2 && sb_row0) ? sb_row0 + (size_t)rb * PS : src + f * PS;
+#ifdef VAP_BOUNDS_CHECK
+        if (f == 2 && sb_row0) VAP_CHECK(0, rb >= 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0);
+        else VAP_CHECK(1, rb >= 0 && g >= R.rec_lo && g + R.bytes / 8 <= R.rec_hi && (reinterpret_cast<uintptr_t>(g) & 15) == 0);
+        VAP_CHECK(2, dst + f * TMA_PLANE_DOUBLES * 8 >= R.smem_lo && dst + f * TMA_PLANE_DOUBLES * 8 + R.bytes <= R.smem_hi && bar >= R.smem_hi && bar + 8 <= R.bar_hi);
+#endif
         bulk_g2s(dst + f * TMA_PLANE_DOUBLES * 8, g, R.bytes, bar);
     }
-    if (x_row0) bulk_g2s(dst + 5 * TMA_PLANE_DOUBLES * 8, x_row0 + (size_t)rb * PS, R.bytes, bar);
+    if (x_row0) {
+#ifdef VAP_BOUNDS_CHECK
+        VAP_CHECK(3, x_row0 + (size_t)rb * PS >= R.x_lo && x_row0 + (size_t)rb * PS + R.bytes / 8 <= R.x_hi);
+        VAP_CHECK(2, dst + 5 * TMA_PLANE_DOUBLES * 8 + R.bytes <= R.smem_hi);
+#endif
+        bulk_g2s(dst + 5 * TMA_PLANE_DOUBLES * 8, x_row0 + (size_t)rb * PS, R.bytes, bar);
+    }
 }
 
 // forward first sweep of one warp: every lane walks its chunk (edges lo .. lo+len-1; len = 0 for an idle lane) in lockstep.
@@ -929,6 +954,7 @@ __device__ __forceinline__ void fwd_sweep_tma(const WarpRing& R, const double* _
         const int s = blk & 1;
         mbar_wait(R.bar + 8 * s, (blk >> 1) & 1);
         const double* S = R.stage + (size_t)s * 5 * PD + lc * PB;
+        VAP_CHECK(6, lc >= 0 && lc < 32 && (unsigned)__cvta_generic_to_shared(S + 4 * PD + 3) + 8 <= R.smem_hi);
         if (blk < nfull) {                           // a whole block of this lane's chunk
             const double vin = v;
             FWD_T(0)
@@ -1047,6 +1073,12 @@ __global__ void __maxnreg__(TMA ? VAP_PASS_REGS_TMA : VAP_PASS_REGS) k_fwd_chunk
         R.bar = (unsigned)__cvta_generic_to_shared(s_mem + ring_off + (size_t)WARPS * 2 * 5 * TMA_PLANE_DOUBLES * 8 + 16 * w);
         R.planes = 5;
         R.bytes = (NT < 32 ? NT : 32) * PB * 8;
+#ifdef VAP_BOUNDS_CHECK
+        R.rec_lo = P; R.rec_hi = P + 5 * RS; R.x_lo = R.x_hi = nullptr;
+        R.smem_lo = (unsigned)__cvta_generic_to_shared(s_mem + ring_off);
+        R.smem_hi = R.smem_lo + WARPS * 2 * 5 * TMA_PLANE_DOUBLES * 8;
+        R.bar_hi = R.smem_hi + 16 * WARPS;
+#endif
         if ((c & 31) == 0) { mbar_init(R.bar, 1); mbar_init(R.bar + 8, 1); fence_mbar_init(); }
     }
     __syncthreads();
@@ -1079,6 +1111,9 @@ __global__ void __maxnreg__(TMA ? VAP_PASS_REGS_TMA : VAP_PASS_REGS) k_fwd_chunk
                 }
             }
             s_usev[c] = v; s_usew[c] = sq;
+            // extent of what this lane's runs touch (look-ahead block included): record rows and forward-velocity row
+            VAP_CHECK(4, c * PB + PB <= PB * NT && (size_t)(((len + 3) >> 2) + 1) * 5 * PB * NT <= (size_t)(5 * RS - 3) &&
+                             (size_t)(((len + 3) >> 2) + 1) * PB * NT <= (size_t)(RS - 1) && lo + len <= steps);
             if (!TMA) fwd_run<NT, RUN_SWEEP>(P + c * PB, vf + c * PB, tail, 0.0, lo, len, T, hw, dd, v, sq, false);
         }
         if (TMA) fwd_sweep_tma<NT>(R, P + (c & ~31) * PB, c & 31, vf + c * PB, tail, lo, active ? len : 0, T, hw, dd, v, sq);
@@ -1262,6 +1297,7 @@ __device__ __forceinline__ void bwd_sweep_tma(const WarpRing& R, const double* _
         const int s = it & 1;
         mbar_wait(R.bar + 8 * s, (it >> 1) & 1);
         const double* S = R.stage + (size_t)s * 6 * PD + lc * PB;
+        VAP_CHECK(7, lc >= 0 && lc < 32 && (unsigned)__cvta_generic_to_shared(S + 5 * PD + 3) + 8 <= R.smem_hi);
         if (rb < nfull) {                            // a whole block of this lane's chunk: rows 3 .. 0
             o -= PB;
             BWD_T(3)
@@ -1362,6 +1398,12 @@ __global__ void __maxnreg__(TMA ? VAP_PASS_REGS_TMA : VAP_PASS_REGS) k_bwd_chunk
         R.bar = (unsigned)__cvta_generic_to_shared(s_mem + ring_off + (size_t)WARPS * 2 * 6 * TMA_PLANE_DOUBLES * 8 + 16 * w);
         R.planes = 6;
         R.bytes = (NT < 32 ? NT : 32) * PB * 8;
+#ifdef VAP_BOUNDS_CHECK
+        R.rec_lo = P; R.rec_hi = P + 5 * RS; R.x_lo = vf; R.x_hi = vf + RS;
+        R.smem_lo = (unsigned)__cvta_generic_to_shared(s_mem + ring_off);
+        R.smem_hi = R.smem_lo + WARPS * 2 * 6 * TMA_PLANE_DOUBLES * 8;
+        R.bar_hi = R.smem_hi + 16 * WARPS;
+#endif
         if ((k & 31) == 0) { mbar_init(R.bar, 1); mbar_init(R.bar + 8, 1); fence_mbar_init(); }
     }
     __syncthreads();
@@ -1411,6 +1453,9 @@ __global__ void __maxnreg__(TMA ? VAP_PASS_REGS_TMA : VAP_PASS_REGS) k_bwd_chunk
                 }
             }
             s_usev[k] = v; s_usew[k] = sq;
+            VAP_CHECK(5, col >= 0 && col * PB + PB <= PB * NT && (size_t)(((len + 3) >> 2) + 1) * 5 * PB * NT <= (size_t)(5 * RS - 3) &&
+                             (size_t)(((len + 3) >> 2) + 1) * PB * NT <= (size_t)(RS - 1) && A.o + len <= vo + D - 1 &&
+                             lo + len <= steps && D <= D_cap);
             if (!TMA) {
                 if (ovr) bwd_run<NT, RUN_SWEEP, true>(A.p, A.f, A.o, A.sb, lo, len, top_ak, top_G, top_st, s_bi, s_acc, n_b, acc0, hw,
                                                       dd, v, sq, false, est, A.dd_over_dt);
