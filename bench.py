@@ -415,7 +415,7 @@ def run_cfg2(args):
                   "GBps": round(stage_bytes[k] / 1e9 / (v * 1e-3), 1)} for k, v in stage_ms.items()}
     dom = max(stage_ms, key=stage_ms.get)
     achieved = stage_bytes[dom] / 1e9 / (stage_ms[dom] * 1e-3)
-    total_bytes = sum(stage_bytes.values())
+    total_bytes = sum(stage_bytes[k] for k in stage_ms)          # only the stages that ran (fused or staged velocity stage)
     prof, prof_name = load_kernel_table(B, N)
     traffic, ncu_kernels, prof_commit = None, None, None
     if prof is not None:
