@@ -394,6 +394,9 @@ __global__ void __launch_bounds__(256) k_build_lut_index(const int* __restrict__
 // =====================================================================================================
 // S2  precompute_path_properties: one thread per (path, table entry)
 // =====================================================================================================
+#ifndef PROPS_PER_THREAD
+#define PROPS_PER_THREAD 8     // table entries per thread: the per-path preamble (geometry pointers, the grid step's division) is paid once
+#endif
 __global__ void __launch_bounds__(256) k_build_props(int N_max, const int* __restrict__ n_nodes,
                                                      const double* __restrict__ seg,
                                                      const int* __restrict__ first_node,
@@ -404,19 +407,24 @@ __global__ void __launch_bounds__(256) k_build_props(int N_max, const int* __res
                                                      unsigned tiles_x)
 {
     const PathTile pt = path_tile(tiles_x);
-    long long b = pt.b;
-    long long j = (long long)pt.x * blockDim.x + threadIdx.x;
-    int n = n_nodes[b];
-    long long P = (long long)spn * n;
-    if (status[b] != ST_OK || j >= P || P > P_cap) return;
-    PathGeo g = path_geo(b, N_max, seg, first_node, param_end, n_splines);
-    double step = (double)(n - 1) / (double)(P - 1);
-    double t = prop_param(j, P, n, step);
-    double dx, dy, ddx, ddy, k, h;
-    eval_path_d12(g, t, dx, dy, ddx, ddy);
-    curv_heading(dx, dy, ddx, ddy, k, h);
-    prop_k[(size_t)b * P_cap + j] = k;
-    prop_h[(size_t)b * P_cap + j] = h;
+    const long long b = pt.b;
+    const int n = n_nodes[b];
+    const int P = spn * n;
+    int j = (int)pt.x * (blockDim.x * PROPS_PER_THREAD) + threadIdx.x;
+    if (status[b] != ST_OK || j >= P || (long long)P > P_cap) return;
+    const PathGeo g = path_geo(b, N_max, seg, first_node, param_end, n_splines);
+    const double step = (double)(n - 1) / (double)(P - 1);
+    double* pk = prop_k + (size_t)b * P_cap;
+    double* ph = prop_h + (size_t)b * P_cap;
+#pragma unroll 1
+    for (int it = 0; it < PROPS_PER_THREAD && j < P; ++it, j += blockDim.x) {
+        const double t = prop_param(j, P, n, step);
+        double dx, dy, ddx, ddy, k, h;
+        eval_path_d12(g, t, dx, dy, ddx, ddy);
+        curv_heading(dx, dy, ddx, ddy, k, h);
+        pk[j] = k;
+        ph[j] = h;
+    }
 }
 
 // table queries for the scalar API
@@ -1052,7 +1060,7 @@ extern "C" int vap_build_props(int64_t B, int N_max, const int32_t* n_nodes, con
                                void* stream)
 {
     if (B <= 0) return 0;
-    const unsigned tx = blocks_for(P_cap, 256);
+    const unsigned tx = blocks_for(P_cap, 256 * PROPS_PER_THREAD);
     if ((long long)tx * B > 2147483647LL) return arg_err("vap_build_props: more than 2^31 CTAs (tile the batch)");
     const unsigned grid = tx * (unsigned)B;
     k_build_props<<<grid, 256, 0, STREAM>>>(N_max, n_nodes, seg, first_node, param_end, n_splines, status, spn, P_cap,

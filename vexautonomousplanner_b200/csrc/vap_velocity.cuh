@@ -114,10 +114,21 @@ __global__ void k_resolve_events(long long B, int N_max, int A_max, const double
     int* wr = ev_wrap + (size_t)b * N_max;
     int nw = ev_nwrap[b];
     if (nw > N_max) { status[b] = ST_EVENTS; return; }
-    for (int i = 1; i < nw; i++) {           // sort wrap samples ascending
-        int x = wr[i], j = i - 1;
-        while (j >= 0 && wr[j] > x) { wr[j + 1] = wr[j]; j--; }
-        wr[j + 1] = x;
+    // sort the wrap samples ascending: they arrive in the order of the atomics, i.e. by tile of the chunk-interleaved
+    // sampling kernel (far from sorted), so a shell sort (Ciura gaps) instead of a plain insertion sort: a path with 800 nodes
+    // took 6.9 ms here with the latter
+    {
+        const int gaps[9] = {1750, 701, 301, 132, 57, 23, 10, 4, 1};
+        for (int gi = 0; gi < 9; gi++) {
+            const int gap = gaps[gi];
+            if (gap >= nw) continue;
+            for (int i = gap; i < nw; i++) {
+                const int x = wr[i];
+                int j = i - gap;
+                while (j >= 0 && wr[j] > x) { wr[j + gap] = wr[j]; j -= gap; }
+                wr[j + gap] = x;
+            }
+        }
     }
     int n_acc = 0, n_b = 0, nvr = 0, nst = 0;
     double max_velocity = (na[A_MAXVEL] > 0) ? na[A_MAXVEL] : V;
