@@ -336,6 +336,17 @@ def run_cfg2(args):
     eng = Engine(dev, chunks=args.chunks)
     db = eng.upload(packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    # what a caller pays ONCE per batch shape and every timed step below does not: the first call sizes D_cap / T_cap from
+    # the data (two read-backs), builds the path-independent tables and grows the allocator's pools
+    torch.cuda.synchronize()
+    t_first = time.perf_counter()
+    eng.profile(db, reuse_plan=True)
+    torch.cuda.synchronize()
+    first_call_ms = (time.perf_counter() - t_first) * 1e3
+    t_second = time.perf_counter()
+    eng.profile(db, reuse_plan=True)
+    torch.cuda.synchronize()
+    second_call_ms = (time.perf_counter() - t_second) * 1e3
     if args.profile_step:
         # what profiles/tools/capture.sh runs under ncu: the same step, eager and unpipelined (every kernel one launch)
         for _ in range(max(args.warmup, 1)):
@@ -488,6 +499,7 @@ def run_cfg2(args):
                        "l2": "flushed before every timed step (256 MB write on the step's stream); a step also streams "
                              "about 5 GB of intermediates through the 126 MB L2",
                        "pipeline_depth": depth, "cuda_graph": True, "ms_per_step_serial": serial_ms,
+                       "first_call_ms": round(first_call_ms, 2), "second_call_eager_ms": round(second_call_ms, 2),
                        "pipelining": "consecutive steps are independent batches: two CUDA graphs replayed on two streams; "
                                      "timed region = K steps enqueued back to back, CUDA events on the launching stream "
                                      "around the whole region, max over ranks",

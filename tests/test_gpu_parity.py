@@ -870,3 +870,38 @@ def test_repeated_runs_are_bitwise_identical():
             assert torch.equal(got.out[i, :, :m][valid[:, :m]], ref.out[i, :, :m][valid[:, :m]]), (k, i)
         dm = min(got.vel.shape[1], ref.vel.shape[1])
         assert torch.equal(got.vel[:, :dm][dvalid[:, :dm]], ref.vel[:, :dm][dvalid[:, :dm]]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [8, 32, 64])
+def test_fused_velocity_stage_equals_staged_entry_points(chunks):
+    """vap_velocity_profile (sampling fused with the pre-pass, k_prepass_ovr after the event resolution) against the two
+    staged entry points it replaces (vap_dist_sample_events + vap_fwd_bwd_chunked, kappa / theta through memory): every
+    output of the velocity stage and the final trajectories bit for bit, on a mixed batch with overrides."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    packed = synth.mixed_paths(320, 8, seed=9)
+    a = Engine("cuda:0", chunks=chunks, fused_velocity=True)
+    b = Engine("cuda:0", chunks=chunks, fused_velocity=False)
+    ra = a.profile(a.upload(packed), keep=True)
+    rb = b.profile(b.upload(packed), keep=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ra.status, rb.status) and bool((ra.status == 0).all())
+    assert torch.equal(ra.n_samples, rb.n_samples) and torch.equal(ra.n_out, rb.n_out)
+    D = ra.n_samples.long()
+    dv = torch.arange(ra.vel.shape[1], device=D.device)[None, :] < D[:, None]
+    for key in ("t", "kap", "th"):
+        assert torch.equal(ra.extra[key][dv], rb.extra[key][dv]), key
+    assert torch.equal(ra.vel[dv], rb.vel[dv])
+    for key in ("n_ev", "n_vr"):
+        assert torch.equal(ra.extra[key], rb.extra[key]), key
+    ne = ra.extra["n_ev"].long()
+    em = torch.arange(ra.extra["max_accels"].shape[1], device=D.device)[None, :]
+    assert torch.equal(ra.extra["max_accels"][em < ne[:, 0:1]], rb.extra["max_accels"][em < ne[:, 0:1]])
+    assert torch.equal(ra.extra["bidx"][em < ne[:, 1:2]], rb.extra["bidx"][em < ne[:, 1:2]])
+    assert torch.equal(ra.extra["bval"][em < ne[:, 1:2]], rb.extra["bval"][em < ne[:, 1:2]])
+    T = ra.n_out.long()
+    tv = torch.arange(min(ra.T_cap, rb.T_cap), device=D.device)[None, :] < T[:, None]
+    m = tv.shape[1]
+    for i in range(8):
+        assert torch.equal(ra.out[i, :, :m][tv], rb.out[i, :, :m][tv]), i

@@ -127,7 +127,8 @@ class Engine:
 
     def __init__(self, device="cuda:0", dt: float = 0.01, dd: float = 0.005, lut_samples: int = 1000,
                  samples_per_node: int = 1000, start_vel: float = 0.01, end_vel: float = 0.01,
-                 velocity_impl: str = "chunked", chunks: int = 32, time_impl: str = "split", accelerators: bool = True):
+                 velocity_impl: str = "chunked", chunks: int = 32, time_impl: str = "split", accelerators: bool = True,
+                 fused_velocity: bool = True):
         if not torch.cuda.is_available():
             raise _lib.VapError("no CUDA device: vexautonomousplanner_b200 has no CPU fallback")
         self.lib = _lib.lib()
@@ -144,6 +145,9 @@ class Engine:
         # accelerators=False passes NULL for the inverse LUT index and the lerp reciprocals (binary search / plain division
         # instead: same bits, slower); tests use it to pin the equivalence
         self.accelerators = bool(accelerators)
+        # fused_velocity=False runs S3 and S4+S5 through the two staged entry points (vap_dist_sample_events +
+        # vap_fwd_bwd_chunked: kappa / theta go through memory) instead of vap_velocity_profile: same bits, tests pin it
+        self.fused_velocity = bool(fused_velocity)
         self._dgrid: Optional[torch.Tensor] = None
         self._rden: Optional[torch.Tensor] = None
         self._retired: list = []                # outgrown path-independent tables, kept alive for captured graphs
@@ -296,11 +300,12 @@ class Engine:
         return vel, ma, bidx, bval, n_ev, t_est
 
     def velocity_chunked(self, db: DeviceBatch, g: Geometry, t: Tables, status: torch.Tensor, D_cap: int, mode: int = 0,
-                         outs: Optional[dict] = None, want_t: bool = True, fused: bool = True):
+                         outs: Optional[dict] = None, want_t: bool = True, fused: Optional[bool] = None):
         """S3 + events + S4 + S5, fast path: sampling fused with the hoisted pre-pass (vap_velocity_profile), sample-parallel
         events, chunk-speculative passes.  want_t: also write t / kappa / theta per distance sample (inspection outputs).
         fused=False runs the two staged entry points instead (vap_dist_sample_events + vap_fwd_bwd_chunked: same bits)."""
         B = db.B
+        fused = self.fused_velocity if fused is None else fused
         E_cap = db.N_max + db.A_max + 2
         grid = self.dgrid(D_cap + 2)
         n_samples = outs["n_samples"] if outs else self._empty((B,), torch.int32)
