@@ -99,6 +99,291 @@ __device__ __forceinline__ bool recip_safe_num(double a)
     return (aa < 1e280) && ((aa > 1e-280) || (a == 0.0));
 }
 
+// shared-memory load at a 32-bit shared address + constant byte offset.  `volatile` keeps the load where it is written: the
+// time loop issues its five loads BEFORE the warp vote so that the vote resolves in the shadow of their latency.
+template <int OFF>
+__device__ __forceinline__ double lds_f64(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// recip_safe_num on the exponent field (integer pipe): |a| in [2^-930, 2^930) -- inside (1e-280, 1e280) -- or a == 0
+__device__ __forceinline__ bool recip_safe_exp(double a)
+{
+    const unsigned hi = (unsigned)__double2hiint(a) & 0x7fffffffu;
+    return ((hi - (93u << 20)) < ((1953u - 93u) << 20)) | (a == 0.0);
+}
+
+// a / b given r = RN(1/b), SPECULATIVELY: the quotient after ONE residual correction (faithful, and almost always already
+// the correctly rounded one) goes on; the second correction runs beside the dependent chain and `same` tells whether it
+// changed anything.  same == true: the value returned IS div_recip's (the IEEE quotient); false: the caller redoes the step.
+__device__ __forceinline__ double div_recip_spec(double a, double b, double r, bool& same)
+{
+    const double q0 = a * r;
+    const double q1 = fma(fma(-b, q0, a), r, q0);
+    const double q2 = fma(fma(-b, q1, a), r, q1);
+    same = (q1 == q2);
+    return q1;
+}
+
+// A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row (and the lerp
+// reciprocals) are staged through a per-thread shared-memory ring by TMA bulk copies one 128-sample block ahead, so the loop
+// never waits on HBM.
+//
+// The kernel runs ONE warp per scheduler with a few paths per warp, so its time is the dependent-instruction latency of a
+// step times the step count of the longest path (measured on B200: 8.2 cycles per dependent DADD/DMUL/DFMA, 18 per
+// double<->int conversion, 29 per shared-memory load, ~100 for an inlined division whose reciprocal refinement sits on the
+// chain; a taken branch costs ~30 cycles of a lone warp, and instructions issue in order, so independent work placed
+// after a stalled instruction does not start early).  Structure (round 2):
+//   * FAST RUN: an inner loop whose body is one straight-line block with ONE not-taken exit test and the loop-back
+//     branch.  It computes a whole step speculatively in registers, tests every condition under which those values are the
+//     reference's (`ok`), and only then commits.  Everything rare -- the path's first / last intervals, a position that
+//     left the staged block, odd operands -- leaves the loop BEFORE anything is committed and is handled outside.
+//   * a ring slot holds a 128-sample block PLUS the two samples behind it (the copy is 130 doubles), so the three samples
+//     and two reciprocals of a step sit at fixed offsets from one address whatever the position inside the block.
+//   * floor(pos / dd) comes from one round-toward-zero addition of 2^52 (8 cycles; the integer is the low word of the sum
+//     and the double is the sum minus 2^52), not from F2I + FRND (18 each).
+//   * the clips are evaluated as parallel candidates: both comparisons of a clip pair are issued together and the selects
+//     pick among values that are already there (v + (-max_dec) dt and v + max_acc dt do not wait for the division).
+//   * block change: when the position enters the next block, the block behind it is refilled with the block after next
+//     (issued a whole block -- about twenty steps -- before its first use) and the fast run resumes.
+//   * GENERIC STEP (the `!ok` leftovers, a handful per path): the reference's step with ordinary divisions and global loads.
+// Both produce the reference's bits: the fast run's quotients are IEEE quotients (div_recip), its index is verified against
+// xs[i] = fl(i dd) exactly as np.searchsorted defines it, and the candidate selects reproduce np.clip's order.
+#ifndef VAP_TS_SPEC
+#define VAP_TS_SPEC 2
+#endif
+#define TS_SLOT 132                 // doubles per ring slot: a 128-sample block + the 2 samples behind it (+2: 16-byte multiples)
+#define TS_STRIDE2 (4 * TS_SLOT)    // per-thread slice: two velocity slots, then two reciprocal slots
+__global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
+                                                   const int* __restrict__ status, double dt, double dd,
+                                                   const double* __restrict__ total_len, long long D_cap,
+                                                   const int* __restrict__ n_samples, const double* __restrict__ vel,
+                                                   long long M_cap, double* __restrict__ stage, int* __restrict__ n_main,
+                                                   const double* __restrict__ rden, long long n_rden)
+{
+    extern __shared__ __align__(16) double s_ring[];
+    // this thread's two mbarriers (one per ring slot) live behind the rings
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(s_ring + (size_t)blockDim.x * TS_STRIDE2 + 2 * threadIdx.x);
+    mbar_init(mb, 1);
+    mbar_init(mb + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // the lanes of a warp leave the fast run TOGETHER (a vote), so every lane stays in the loop until the warp is done:
+    // a lane without a path (or with a failed one) takes part in the votes as "finished"
+    const unsigned mask = __activemask();              // every thread of the CTA (one warp at most) is here: nothing diverged yet
+    const bool in_range = b < B;
+    const bool part = in_range && status[b] == ST_OK;
+    if (in_range && !part) n_main[b] = 0;
+    if (!in_range) b = 0;                              // harmless addresses for the lanes without a path (never dereferenced)
+    const double L = part ? total_len[b] : 0.0;
+    const double max_acc = part ? cons[b * 6 + 1] : 1.0, max_dec = part ? cons[b * 6 + 2] : 1.0;
+    const int D = part ? n_samples[b] : 4;
+    const double* vv = vel + (size_t)b * D_cap;
+    const double inv_dd = 1.0 / dd, inv_dt = 1.0 / dt;
+    const size_t plane = (size_t)B * (M_cap + 1);
+    double* P = stage + TS_POS * plane + (size_t)b * (M_cap + 1);
+    const double* ring = s_ring + (size_t)threadIdx.x * TS_STRIDE2;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    if (rden == nullptr) n_rden = 0;                   // no table: the fast run is disabled
+    const int nblk = (int)((D_cap + TS_BLK - 1) / TS_BLK);
+    unsigned phase = 0, pend = 0;                      // per slot: parity to wait for / a copy is in flight
+    auto wait_slot = [&](int sl) {
+        if ((pend >> sl) & 1u) {
+            mbar_wait(mb + 8 * sl, (phase >> sl) & 1u);
+            phase ^= 1u << sl;
+            pend &= ~(1u << sl);
+        }
+    };
+    auto stage_block = [&](int blk) {          // rows are padded to a multiple of TS_BLK samples by the host
+        const int sl = blk & 1;
+        wait_slot(sl);                          // never two copies in flight on one barrier
+        if (blk < nblk) {
+            // the block and the two samples behind it (they belong to the next block of the same row; the row's last
+            // block has nothing behind it and the fast run never reads there: i1 + 2 <= D - 2)
+            const unsigned nv = (blk + 1 < nblk) ? TS_BLK + 2 : TS_BLK;
+            const long long rem = n_rden - (long long)blk * TS_BLK;        // reciprocals left from this block on
+            const unsigned nr_ = rem >= TS_BLK + 2 ? TS_BLK + 2 : (rem >= TS_BLK ? TS_BLK : 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier reads of the slot precede the TMA writes
+            mbar_expect_tx(mb + 8 * sl, (nv + nr_) * (unsigned)sizeof(double));
+            VAP_CHECK(10, (size_t)blk * TS_BLK + nv <= (size_t)D_cap && nv <= TS_SLOT && nr_ <= TS_SLOT &&
+                              (long long)blk * TS_BLK + nr_ <= n_rden);
+            bulk_g2s(ring_s + sl * (unsigned)(TS_SLOT * sizeof(double)), vv + (size_t)blk * TS_BLK, nv * (unsigned)sizeof(double), mb + 8 * sl);
+            if (nr_) bulk_g2s(ring_s + (2 + sl) * (unsigned)(TS_SLOT * sizeof(double)), rden + (size_t)blk * TS_BLK,
+                              nr_ * (unsigned)sizeof(double), mb + 8 * sl);
+            pend |= 1u << sl;
+        }
+    };
+    int blk_lo = 0;                             // block blk_lo is resident and complete; block blk_lo+1 is in flight or resident
+    if (part) {
+        stage_block(0);
+        stage_block(1);
+        wait_slot(0);
+    }
+    double pos = 0.0, v = part ? vv[0] : 0.0;
+    const double vlast = part ? vv[D - 1] : 0.0;
+    int k = 0;                                          // 32-bit: the row limit is far below 2^31
+    const double hdt = 0.1 * dt;
+    // fast-run index range: i1 <= D-4 (both lerps strictly inside the row) and i1 + 1 inside the staged reciprocals
+    const long long nr = (n_rden / TS_BLK) * TS_BLK;    // the reciprocals are staged in whole blocks
+    const long long il = ((long long)D - 3 < nr - 2) ? (long long)D - 3 : nr - 2;
+    const double dlim = (double)(il > 0 ? il : 0);     // fast run: 0 <= pos / dd < dlim  (dlim < 2^31)
+    const double ndec = -max_dec;
+    const double lo_dt = ndec * dt, hi_dt = max_acc * dt;
+    long long k_lim64 = 16 * M_cap + 1000000;           // far beyond any terminating profile of this capacity class
+    if (k_lim64 > VAP_ROW_LIMIT) k_lim64 = VAP_ROW_LIMIT;
+    const int k_limit = (int)k_lim64;
+    const int m_cap = (int)(M_cap < 2147483647LL ? M_cap : 2147483647LL);
+    // the fast run stores without a clamp, and its clip candidates assume -max_dec < max_acc (np.clip(x, lo, hi) of an
+    // x <= lo is lo only then); otherwise every step is a generic step
+    const int k_fast = (ndec < max_acc) ? (k_limit < m_cap ? k_limit : m_cap) : 0;
+    const double two52 = 4503599627370496.0;
+    bool fin = !part;                                   // this lane's path is finished (or it has none)
+    bool okp = true;                                    // the lane's last fast step was committed
+    bool req = false;                                   // this lane asked for the exit from the fast run
+    while (__any_sync(mask, !fin)) {                    // the fast run is left by a request only: never enter it without a live lane
+        // ---------------- fast run over block blk_lo ----------------
+        {
+            const int lo = blk_lo * TS_BLK;
+            // shared address of the block: [rb + 8 (i - lo)] = vel[i], [rb + 8 (2 TS_SLOT + i - lo)] = rden[i]
+            const unsigned rb = ring_s + (unsigned)(blk_lo & 1) * (unsigned)(TS_SLOT * sizeof(double));
+            double* sp = P + k;                                   // stage row of step k (the other planes follow at `plane`)
+            for (;;) {
+                const double e = pos * inv_dd;
+                const double em = __dadd_rz(e, two52);            // 2^52 + floor(e) for 0 <= e < 2^31
+                const int i1 = __double2loint(em);
+                const double ef = em - two52;                     // == trunc(e) there
+                const unsigned off = (unsigned)(i1 - lo);
+                const unsigned q = rb + 8u * (off < (unsigned)(TS_BLK - 1) ? off : (unsigned)(TS_BLK - 1));   // memory-safe whatever pos is
+                const double y0 = lds_f64<0>(q), y1 = lds_f64<8>(q), y2 = lds_f64<16>(q);
+                const double r1 = lds_f64<2 * TS_SLOT * 8>(q), r2 = lds_f64<2 * TS_SLOT * 8 + 8>(q);
+                // ONE warp-uniform exit, decided while the loads are in flight: some lane left its block, or its last step
+                // was refused.  Everybody leaves together, so no lane waits at a reconvergence point for the others' events.
+                req = ((off >= (unsigned)TS_BLK) | !okp) & !fin;
+                if (__any_sync(mask, req)) break;
+                const double x2 = pos + dd;
+                const double x0 = ef * dd, x1 = (ef + 1.0) * dd, xx2 = (ef + 2.0) * dd;      // (double)(i1 + j) == ef + j exactly
+                const double n1 = (pos - x0) * (y1 - y0), n2 = (x2 - x1) * (y2 - y1);
+#if VAP_TS_SPEC >= 1
+                bool s1, s2, s3;
+                const double tv1 = y0 + div_recip_spec(n1, x1 - x0, r1, s1);
+                const double tv2 = y1 + div_recip_spec(n2, xx2 - x1, r2, s2);
+#else
+                const bool s1 = true, s2 = true;
+                const double tv1 = y0 + div_recip(n1, x1 - x0, r1);
+                const double tv2 = y1 + div_recip(n2, xx2 - x1, r2);
+#endif
+                const double tvm = (tv1 + tv2) / 2;
+#if VAP_TS_SPEC >= 2
+                const bool s0 = !(0.001 > tvm);                   // max(tvm, 0.001) == tvm, or the step is redone generically
+                const double tv = tvm;
+#else
+                const bool s0 = true;
+                const double tv = (0.001 > tvm) ? 0.001 : tvm;    // max(tvm, 0.001)
+#endif
+                const double da = tv - v;
+#if VAP_TS_SPEC >= 1
+                const double ar = div_recip_spec(da, dt, inv_dt, s3);
+#else
+                const bool s3 = true;
+                const double ar = div_recip(da, dt, inv_dt);      // da == +0 gives +0 (da is never -0: tv >= 0.001)
+#endif
+                // np.clip(ar, -max_dec, max_acc) and accel dt: both comparisons at once, then selects among ready values
+                const bool c1 = ar > ndec, pb = ar < max_acc;
+                const double prod = ar * dt;
+                const double accel = c1 ? (pb ? ar : max_acc) : ndec;
+                const double inc = c1 ? (pb ? prod : hi_dt) : lo_dt;
+                const double vn = v + inc;
+                // np.clip(vn, 0, tv)
+#if VAP_TS_SPEC >= 3
+                const bool s4 = vn > 0.0;                         // vn <= 0 (a stop) and v <= 0.1 (start / end of a path): generic
+                const double v_new = (vn < tv) ? vn : tv;
+                const double half = 0.5 * accel * dt * dt;
+                const bool s5 = !(v_new <= 0.1);
+                const double dpos = v_new * dt + half;
+#else
+                const bool s4 = true, s5 = true;
+                const double zsel = (0.0 < tv) ? 0.0 : tv;
+                const bool c3 = vn > 0.0, p4 = vn < tv;
+                const double v_new = c3 ? (p4 ? vn : tv) : zsel;
+                const double half = 0.5 * accel * dt * dt;
+                const double dpos = ((v_new <= 0.1) ? hdt : v_new * dt) + half;
+#endif
+                const double pos_new = pos + dpos;
+                const bool ok = (pos < L) & (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
+                                (r1 * r2 > 0.0) & recip_safe_exp(n1) & recip_safe_exp(n2) & recip_safe_exp(da) & (k < k_fast) &
+                                s0 & s1 & s2 & s3 & s4 & s5;
+                if (ok) { sp[0] = pos; sp[TS_VEL * plane] = v_new; sp[TS_ACC * plane] = accel; sp[TS_TV * plane] = tv; }
+                sp += ok; k += ok;
+                v = ok ? v_new : v;
+                pos = ok ? pos_new : pos;
+                okp = ok;
+            }
+        }
+        // ---------------- service: only the lanes that asked ----------------
+        if (req) {
+            if (!(pos < L)) fin = true;
+            else if (k >= k_limit) { k = -1; fin = true; }                 // diverging loop: report instead of hanging
+            else {
+                // block change: the position entered a later block
+                const double e = pos * inv_dd;
+                const int ic = (e > 0.0) ? ((e < 2147483000.0) ? __double2int_rz(e) : 2147483000) : 0;
+                bool moved = false;
+                while (blk_lo + 1 < nblk && ic >= (blk_lo + 1) * TS_BLK) { blk_lo++; stage_block(blk_lo + 1); moved = true; }
+                if (moved) wait_slot(blk_lo & 1);
+                else {
+                    // generic step (first / last intervals of a path, odd operands, positions outside the staged block):
+                    // always correct, so every service makes progress (a block change or a step).
+                    // rows have M_cap + 1 slots: steps beyond the capacity (the path is then re-run with a larger one) all
+                    // land in the last slot, so the stores need no predicate
+                    const int ks = k < m_cap ? k : m_cap;
+                    P[ks] = pos;
+                    const double x2 = pos + dd;
+                    double tv1, tv2;
+                    const int j1 = uniform_index32(pos, dd, inv_dd, D);
+                    const int j2 = uniform_index32(x2, dd, inv_dd, D);
+                    if (j1 < 0) tv1 = vv[0];
+                    else if (j1 >= D - 1) tv1 = vlast;
+                    else {
+                        double a0 = (double)j1 * dd, a1 = (double)(j1 + 1) * dd, b0 = vv[j1], b1 = vv[j1 + 1];
+                        tv1 = b0 + div_pos((pos - a0) * (b1 - b0), a1 - a0);
+                    }
+                    if (j2 < 0) tv2 = vv[0];
+                    else if (j2 >= D - 1) tv2 = vlast;
+                    else {
+                        double a0 = (double)j2 * dd, a1 = (double)(j2 + 1) * dd, b0 = vv[j2], b1 = vv[j2 + 1];
+                        tv2 = b0 + div_pos((x2 - a0) * (b1 - b0), a1 - a0);
+                    }
+                    const double tvm = (tv1 + tv2) / 2;
+                    const double tv = (0.001 > tvm) ? 0.001 : tvm;                 // max(tvm, 0.001)
+                    const double da = tv - v;
+                    double accel = div_pos(da, dt);
+                    accel = (accel > ndec) ? accel : ndec;                         // np.clip(accel, -max_dec, max_acc)
+                    accel = (accel < max_acc) ? accel : max_acc;
+                    double vn = v + accel * dt;
+                    vn = (vn > 0.0) ? vn : 0.0;                                    // np.clip(v, 0, tv)
+                    v = (vn < tv) ? vn : tv;
+                    const double half = 0.5 * accel * dt * dt;
+                    const double dpos = ((v <= 0.1) ? hdt : v * dt) + half;
+                    pos += dpos;
+                    P[ks + TS_VEL * plane] = v; P[ks + TS_ACC * plane] = accel; P[ks + TS_TV * plane] = tv;
+                    k++;
+                }
+            }
+        }
+        okp = true;
+    }
+    if (!part) return;
+    wait_slot(0);                                // no TMA write may be in flight when the CTA's shared memory is released
+    wait_slot(1);
+    if (k >= 0 && k <= m_cap) P[k] = pos;
+    n_main[b] = k;                                      // -1: diverged
+}
+
+#ifdef VAP_TS_V1
 // A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row (and the lerp
 // reciprocals) are staged through a per-thread shared-memory ring by TMA bulk copies two 128-sample blocks ahead, so the loop
 // never waits on HBM.
@@ -111,7 +396,7 @@ __device__ __forceinline__ bool recip_safe_num(double a)
 // (no int->double round trip), both lerp divisions and the division by dt use tabulated / hoisted reciprocals (five
 // dependent operations each, no slow-path branch inside the chain), every validity condition of the fast path is
 // evaluated off the chain and tested ONCE; a step that fails the test is redone on the generic path.
-__global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
+__global__ void __launch_bounds__(32) k_time_state_v1(long long B, const double* __restrict__ cons,
                                                    const int* __restrict__ status, double dt, double dd,
                                                    const double* __restrict__ total_len, long long D_cap,
                                                    const int* __restrict__ n_samples, const double* __restrict__ vel,
@@ -255,6 +540,8 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     if (k >= 0 && k <= m_cap) P[k] = pos;
     n_main[b] = k;                                      // -1: diverged
 }
+
+#endif
 
 // exactness check of div_const against the IEEE division (test hook)
 __global__ void k_test_div_const(long long n, unsigned long long seed, double b, unsigned long long* __restrict__ bad)
