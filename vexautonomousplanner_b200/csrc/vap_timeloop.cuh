@@ -152,9 +152,6 @@ __device__ __forceinline__ double div_recip_spec(double a, double b, double r, b
 //   * GENERIC STEP (the `!ok` leftovers, a handful per path): the reference's step with ordinary divisions and global loads.
 // Both produce the reference's bits: the fast run's quotients are IEEE quotients (div_recip), its index is verified against
 // xs[i] = fl(i dd) exactly as np.searchsorted defines it, and the candidate selects reproduce np.clip's order.
-#ifndef VAP_TS_SPEC
-#define VAP_TS_SPEC 2
-#endif
 #define TS_SLOT 132                 // doubles per ring slot: a 128-sample block + the 2 samples behind it (+2: 16-byte multiples)
 #define TS_STRIDE2 (4 * TS_SLOT)    // per-thread slice: two velocity slots, then two reciprocal slots
 __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
@@ -172,13 +169,13 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // the lanes of a warp leave the fast run TOGETHER (a vote), so every lane stays in the loop until the warp is done:
-    // a lane without a path (or with a failed one) takes part in the votes as "finished"
-    const unsigned mask = __activemask();              // every thread of the CTA (one warp at most) is here: nothing diverged yet
-    const bool in_range = b < B;
-    const bool part = in_range && status[b] == ST_OK;
-    if (in_range && !part) n_main[b] = 0;
-    if (!in_range) b = 0;                              // harmless addresses for the lanes without a path (never dereferenced)
+    // the lanes of a warp leave the fast run TOGETHER (a vote), so every lane with a path stays in the loop until the warp
+    // is done; a failed path takes part in the votes as "finished" (its own stage row takes the stores nobody reads)
+    if (b >= B) return;
+    const long long left = B - (long long)blockIdx.x * blockDim.x;                    // lanes of this CTA that have a path
+    const unsigned mask = left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u);
+    const bool part = status[b] == ST_OK;
+    if (!part) n_main[b] = 0;
     const double L = part ? total_len[b] : 0.0;
     const double max_acc = part ? cons[b * 6 + 1] : 1.0, max_dec = part ? cons[b * 6 + 2] : 1.0;
     const int D = part ? n_samples[b] : 4;
@@ -241,7 +238,8 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     // x <= lo is lo only then); otherwise every step is a generic step
     const int k_fast = (ndec < max_acc) ? (k_limit < m_cap ? k_limit : m_cap) : 0;
     const double two52 = 4503599627370496.0;
-    bool fin = !part;                                   // this lane's path is finished (or it has none)
+    bool fin = !part;                                   // this lane's path is finished (or failed before this stage)
+    double pos_fin = 0.0;                               // its final position (a finished lane keeps stepping on scratch values)
     bool okp = true;                                    // the lane's last fast step was committed
     bool req = false;                                   // this lane asked for the exit from the fast run
     while (__any_sync(mask, !fin)) {                    // the fast run is left by a request only: never enter it without a live lane
@@ -250,47 +248,35 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
             const int lo = blk_lo * TS_BLK;
             // shared address of the block: [rb + 8 (i - lo)] = vel[i], [rb + 8 (2 TS_SLOT + i - lo)] = rden[i]
             const unsigned rb = ring_s + (unsigned)(blk_lo & 1) * (unsigned)(TS_SLOT * sizeof(double));
-            double* sp = P + k;                                   // stage row of step k (the other planes follow at `plane`)
+            double* sp = P + (k < 0 ? 0 : (k < m_cap ? k : m_cap));   // stage row of step k (the other planes follow at `plane`)
+            const double pos_hi = (double)(lo + TS_BLK) * dd;     // xs[lo + TS_BLK]: from here on the position is in the next block
+            double pos_s = pos, v_s = v;                          // the state before the last commit
             for (;;) {
                 const double e = pos * inv_dd;
                 const double em = __dadd_rz(e, two52);            // 2^52 + floor(e) for 0 <= e < 2^31
+                // ONE warp-uniform exit per step: some lane's position left its block, or its last step was refused.  The
+                // test is on the position itself (resolved long before the integer index), and the vote completes while
+                // the address is computed and the five loads are issued: the branch behind them does not wait.
+                req = ((pos >= pos_hi) | !okp) & !fin;
+                const bool leave = __any_sync(mask, req);
                 const int i1 = __double2loint(em);
                 const double ef = em - two52;                     // == trunc(e) there
                 const unsigned off = (unsigned)(i1 - lo);
                 const unsigned q = rb + 8u * (off < (unsigned)(TS_BLK - 1) ? off : (unsigned)(TS_BLK - 1));   // memory-safe whatever pos is
                 const double y0 = lds_f64<0>(q), y1 = lds_f64<8>(q), y2 = lds_f64<16>(q);
                 const double r1 = lds_f64<2 * TS_SLOT * 8>(q), r2 = lds_f64<2 * TS_SLOT * 8 + 8>(q);
-                // ONE warp-uniform exit, decided while the loads are in flight: some lane left its block, or its last step
-                // was refused.  Everybody leaves together, so no lane waits at a reconvergence point for the others' events.
-                req = ((off >= (unsigned)TS_BLK) | !okp) & !fin;
-                if (__any_sync(mask, req)) break;
+                if (leave) break;
                 const double x2 = pos + dd;
                 const double x0 = ef * dd, x1 = (ef + 1.0) * dd, xx2 = (ef + 2.0) * dd;      // (double)(i1 + j) == ef + j exactly
                 const double n1 = (pos - x0) * (y1 - y0), n2 = (x2 - x1) * (y2 - y1);
-#if VAP_TS_SPEC >= 1
                 bool s1, s2, s3;
                 const double tv1 = y0 + div_recip_spec(n1, x1 - x0, r1, s1);
                 const double tv2 = y1 + div_recip_spec(n2, xx2 - x1, r2, s2);
-#else
-                const bool s1 = true, s2 = true;
-                const double tv1 = y0 + div_recip(n1, x1 - x0, r1);
-                const double tv2 = y1 + div_recip(n2, xx2 - x1, r2);
-#endif
                 const double tvm = (tv1 + tv2) / 2;
-#if VAP_TS_SPEC >= 2
                 const bool s0 = !(0.001 > tvm);                   // max(tvm, 0.001) == tvm, or the step is redone generically
                 const double tv = tvm;
-#else
-                const bool s0 = true;
-                const double tv = (0.001 > tvm) ? 0.001 : tvm;    // max(tvm, 0.001)
-#endif
                 const double da = tv - v;
-#if VAP_TS_SPEC >= 1
-                const double ar = div_recip_spec(da, dt, inv_dt, s3);
-#else
-                const bool s3 = true;
-                const double ar = div_recip(da, dt, inv_dt);      // da == +0 gives +0 (da is never -0: tv >= 0.001)
-#endif
+                const double ar = div_recip_spec(da, dt, inv_dt, s3);      // da == +0 gives +0 (da is never -0: tv >= 0.001)
                 // np.clip(ar, -max_dec, max_acc) and accel dt: both comparisons at once, then selects among ready values
                 const bool c1 = ar > ndec, pb = ar < max_acc;
                 const double prod = ar * dt;
@@ -298,34 +284,29 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const double inc = c1 ? (pb ? prod : hi_dt) : lo_dt;
                 const double vn = v + inc;
                 // np.clip(vn, 0, tv)
-#if VAP_TS_SPEC >= 3
-                const bool s4 = vn > 0.0;                         // vn <= 0 (a stop) and v <= 0.1 (start / end of a path): generic
-                const double v_new = (vn < tv) ? vn : tv;
-                const double half = 0.5 * accel * dt * dt;
-                const bool s5 = !(v_new <= 0.1);
-                const double dpos = v_new * dt + half;
-#else
-                const bool s4 = true, s5 = true;
                 const double zsel = (0.0 < tv) ? 0.0 : tv;
                 const bool c3 = vn > 0.0, p4 = vn < tv;
                 const double v_new = c3 ? (p4 ? vn : tv) : zsel;
                 const double half = 0.5 * accel * dt * dt;
                 const double dpos = ((v_new <= 0.1) ? hdt : v_new * dt) + half;
-#endif
                 const double pos_new = pos + dpos;
                 const bool ok = (pos < L) & (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
-                                (r1 * r2 > 0.0) & recip_safe_exp(n1) & recip_safe_exp(n2) & recip_safe_exp(da) & (k < k_fast) &
-                                s0 & s1 & s2 & s3 & s4 & s5;
-                if (ok) { sp[0] = pos; sp[TS_VEL * plane] = v_new; sp[TS_ACC * plane] = accel; sp[TS_TV * plane] = tv; }
+                                (off < (unsigned)TS_BLK) & (r1 * r2 > 0.0) & recip_safe_exp(n1) & recip_safe_exp(n2) &
+                                recip_safe_exp(da) & (k < k_fast) & s0 & s1 & s2 & s3;
+                // The commit is unconditional -- no select on the dependent chain, no branch: a refused step (and every step
+                // of a finished lane) writes values nobody reads into the row's slot k, which the generic step or the final
+                // store rewrites, and the lane leaves at the next vote, where the state of before the commit comes back.
+                sp[0] = pos; sp[TS_VEL * plane] = v_new; sp[TS_ACC * plane] = accel; sp[TS_TV * plane] = tv;
+                pos_s = pos; v_s = v;
+                pos = pos_new; v = v_new;
                 sp += ok; k += ok;
-                v = ok ? v_new : v;
-                pos = ok ? pos_new : pos;
                 okp = ok;
             }
+            if (!okp) { pos = pos_s; v = v_s; }                   // undo the refused step
         }
         // ---------------- service: only the lanes that asked ----------------
         if (req) {
-            if (!(pos < L)) fin = true;
+            if (!(pos < L)) { fin = true; pos_fin = pos; }
             else if (k >= k_limit) { k = -1; fin = true; }                 // diverging loop: report instead of hanging
             else {
                 // block change: the position entered a later block
@@ -377,6 +358,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
         okp = true;
     }
     if (!part) return;
+    pos = pos_fin;
     wait_slot(0);                                // no TMA write may be in flight when the CTA's shared memory is released
     wait_slot(1);
     if (k >= 0 && k <= m_cap) P[k] = pos;
