@@ -24,7 +24,8 @@ SITES = {0: "ring: override-limit source alignment", 1: "ring: record source ins
          4: "forward pass: extent of a chunk's loads / stores", 5: "backward pass: extent of a chunk's loads / stores",
          6: "forward sweep: shared-memory read inside the stage", 7: "backward sweep: shared-memory read inside the stage",
          8: "sampling tile: store index, sample index", 9: "sampling: tile read index, record offset",
-         10: "time loop: TMA block inside the velocity row / ring slot"}
+         10: "time loop: TMA block inside the velocity row / ring slot",
+         11: "time loop: the step's five shared-memory reads inside the thread's ring slice"}
 
 
 def main():
@@ -51,7 +52,7 @@ def main():
         viol, checks = v[:16], v[16:]
         bad += int(viol.sum())
         print(f"{name:55s} status ok={ok}  violations={int(viol.sum())}  checks executed={int(checks.sum())}")
-        for s in range(11):
+        for s in range(12):
             if checks[s] or viol[s]:
                 print(f"    site {s:2d} {SITES[s]:62s} checked {int(checks[s]):12d}  violations {int(viol[s])}")
     print("TOTAL violations:", bad)

@@ -1443,26 +1443,19 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     // Serial per-path chains are latency-bound (about 4.6 cycles per dependent instruction, measured): spread the paths
     // over the warp schedulers (148 SMs x 4) with few paths per warp, so that one path's data-dependent branches stall
     // few other paths and the schedulers still have another warp to issue from.  VAP_STATE_LANES overrides (tuning).
+    // More than ten paths per warp loses more to the paths' unequal lengths and block changes than a second or third warp
+    // per scheduler costs (measured, 16 384 x 8 nodes: 28 lanes 6.2 ms, 10 lanes 3.8 ms for the whole time stage).
     int lanes = (int)((B + 591) / 592);
+    if (lanes > 10) lanes = 10;
     if (const char* ev = getenv("VAP_STATE_LANES")) lanes = atoi(ev);
     lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
     const size_t ring_bytes = (size_t)lanes * (TS_STRIDE2 * sizeof(double) + 16);    // rings + two mbarriers per path
-#ifdef VAP_TS_V1
-    if (getenv("VAP_TS_V1")) {                 // A/B build only: the round-1 kernel
-        const size_t rb1 = (size_t)lanes * (TS_STRIDE * sizeof(double) + 16);
-        cudaFuncSetAttribute(k_time_state_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * (TS_STRIDE * sizeof(double) + 16)));
-        k_time_state_v1<<<blocks_for(B, lanes), lanes, rb1, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
-                                                                      vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);
-    } else
-#endif
-    {
     if (ring_bytes > 48 * 1024) {      // per device and cheap: no process-global "already set" flag (the library keeps no state)
         cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * (TS_STRIDE2 * sizeof(double) + 16)));
         if (ea != cudaSuccess) return set_err("vap_time_profile/attr", ea);
     }
     k_time_state<<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
                                                                      vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);
-    }
     CHECK_LAUNCH("vap_time_profile/state");
     const unsigned tx = blocks_for(M_cap, 256);
     if ((long long)tx * B > 2147483647LL) return arg_err("vap_time_profile: more than 2^31 CTAs (tile the batch)");

@@ -55,9 +55,6 @@ __device__ __forceinline__ double div_const(double a, double b, double r)
 }
 
 #define TS_BLK 128                 // samples per staged block of the velocity row
-#define TS_RING (2 * TS_BLK)       // two blocks resident per thread
-#define TS_STRIDE (2 * TS_RING + 4) // per-thread stride in doubles: velocity ring + reciprocal ring (16-byte aligned, spreads banks)
-#define TS_RDEN (TS_RING + 2)      // offset of the reciprocal ring inside a thread's slice
 
 // index of np.searchsorted(xs, x, side='right') - 1 on xs[i] = fl(i*dd), 32-bit arithmetic
 __device__ __forceinline__ int uniform_index32(double x, double dd, double inv_dd, int D)
@@ -135,23 +132,36 @@ __device__ __forceinline__ double div_recip_spec(double a, double b, double r, b
 // The kernel runs ONE warp per scheduler with a few paths per warp, so its time is the dependent-instruction latency of a
 // step times the step count of the longest path (measured on B200: 8.2 cycles per dependent DADD/DMUL/DFMA, 18 per
 // double<->int conversion, 29 per shared-memory load, ~100 for an inlined division whose reciprocal refinement sits on the
-// chain; a taken branch costs ~30 cycles of a lone warp, and instructions issue in order, so independent work placed
-// after a stalled instruction does not start early).  Structure (round 2):
-//   * FAST RUN: an inner loop whose body is one straight-line block with ONE not-taken exit test and the loop-back
-//     branch.  It computes a whole step speculatively in registers, tests every condition under which those values are the
-//     reference's (`ok`), and only then commits.  Everything rare -- the path's first / last intervals, a position that
-//     left the staged block, odd operands -- leaves the loop BEFORE anything is committed and is handled outside.
+// chain; a taken branch costs 15-30 cycles of a lone warp, and instructions issue in order, so independent work placed
+// after a stalled instruction does not start early).  Structure (round 2; 443 cycles per step on a lone path, was 729):
+//   * FAST RUN: an inner loop whose body is one straight-line block -- no branch but the loop-back.  A step is computed
+//     and COMMITTED unconditionally (no select on the dependent chain); `ok` collects, off the chain, every condition
+//     under which the committed values are the reference's.  A lane whose step was not ok asks for the exit at the next
+//     vote; outside the loop the state of before that step comes back (a shadow copy) and the step is redone generically.
+//   * ONE warp-uniform exit per step (__any_sync): some lane's position left its staged block, or its last step was refused.
+//     Everybody leaves together and the lanes that asked are served, so no lane ever waits at a reconvergence point for the
+//     other lanes' events (a per-lane `break` made the first lane out wait for ALL the others: +40 % time).  The vote is
+//     taken on the position itself (pos >= xs[lo + 128], resolved long before the integer index) and completes while the
+//     address is computed and the five loads are issued, so the branch behind them does not wait.
 //   * a ring slot holds a 128-sample block PLUS the two samples behind it (the copy is 130 doubles), so the three samples
 //     and two reciprocals of a step sit at fixed offsets from one address whatever the position inside the block.
-//   * floor(pos / dd) comes from one round-toward-zero addition of 2^52 (8 cycles; the integer is the low word of the sum
-//     and the double is the sum minus 2^52), not from F2I + FRND (18 each).
-//   * the clips are evaluated as parallel candidates: both comparisons of a clip pair are issued together and the selects
-//     pick among values that are already there (v + (-max_dec) dt and v + max_acc dt do not wait for the division).
-//   * block change: when the position enters the next block, the block behind it is refilled with the block after next
-//     (issued a whole block -- about twenty steps -- before its first use) and the fast run resumes.
-//   * GENERIC STEP (the `!ok` leftovers, a handful per path): the reference's step with ordinary divisions and global loads.
-// Both produce the reference's bits: the fast run's quotients are IEEE quotients (div_recip), its index is verified against
+//   * floor(pos / dd) comes from one round-toward-zero addition of 2^52 (the integer is the low word of the sum and the
+//     double is the sum minus 2^52), not from F2I + FRND.
+//   * the three quotients go on after ONE residual correction; the second correction runs beside the chain and the step is
+//     only ok if it changed nothing (div_recip_spec), i.e. if the value used IS the IEEE quotient.
+//   * max(tvm, 0.001) is taken as tvm (ok only if that is what max returns); the clips pick among candidates that are
+//     already there: both comparisons of a pair are issued together, -max_dec dt and max_acc dt do not wait for the division.
+//   * block change (service code, outside the loop): when the position enters the next block, the block behind it is
+//     refilled with the block after next -- issued a whole block (about twenty steps) before its first use.
+//   * GENERIC STEP (service code: first / last intervals of a path, odd operands; a handful per path): the reference's
+//     step with ordinary divisions and global loads.  It is always correct, so every service makes progress.
+// Both produce the reference's bits: the fast run's quotients are verified IEEE quotients, its index is verified against
 // xs[i] = fl(i dd) exactly as np.searchsorted defines it, and the candidate selects reproduce np.clip's order.
+// Tried and measured on cfg4 (one path, 263 228 steps; time stage 96.4 ms with the round-1 kernel): per-lane break 69 ms
+// (but +8 % on batches, see above); vote + predicated commit 74; + speculative quotients 68.6; + tvm speculation 66.4;
+// + unconditional commit and the vote on the position 59.3; |da| range test on the fp pipe instead of the exponent field
+// 57.9 (kept); also speculating v > 0.1 and vn > 0: 87 (too many generic steps on a path with 800 nodes); integer tests
+// of the reciprocals' high words instead of r1 r2 > 0: 71; #pragma unroll 2: 62.
 #define TS_SLOT 132                 // doubles per ring slot: a 128-sample block + the 2 samples behind it (+2: 16-byte multiples)
 #define TS_STRIDE2 (4 * TS_SLOT)    // per-thread slice: two velocity slots, then two reciprocal slots
 __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
@@ -263,6 +273,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const double ef = em - two52;                     // == trunc(e) there
                 const unsigned off = (unsigned)(i1 - lo);
                 const unsigned q = rb + 8u * (off < (unsigned)(TS_BLK - 1) ? off : (unsigned)(TS_BLK - 1));   // memory-safe whatever pos is
+                VAP_CHECK(11, q >= ring_s && q + (2 * TS_SLOT + 2) * 8 <= ring_s + TS_STRIDE2 * 8 && (q & 7u) == 0);
                 const double y0 = lds_f64<0>(q), y1 = lds_f64<8>(q), y2 = lds_f64<16>(q);
                 const double r1 = lds_f64<2 * TS_SLOT * 8>(q), r2 = lds_f64<2 * TS_SLOT * 8 + 8>(q);
                 if (leave) break;
@@ -276,7 +287,9 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const bool s0 = !(0.001 > tvm);                   // max(tvm, 0.001) == tvm, or the step is redone generically
                 const double tv = tvm;
                 const double da = tv - v;
-                const double ar = div_recip_spec(da, dt, inv_dt, s3);      // da == +0 gives +0 (da is never -0: tv >= 0.001)
+                // da == +0 gives +0 (da is never -0: tv >= 0.001).  |da| needs no lower bound: v >= 0 and tv >= 0.001 (s0), so
+                // the difference is 0, or exact and >= ulp(0.0005) (Sterbenz), or >= tv / 2; `ok` tests the upper bound / NaN.
+                const double ar = div_recip_spec(da, dt, inv_dt, s3);
                 // np.clip(ar, -max_dec, max_acc) and accel dt: both comparisons at once, then selects among ready values
                 const bool c1 = ar > ndec, pb = ar < max_acc;
                 const double prod = ar * dt;
@@ -291,8 +304,8 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const double dpos = ((v_new <= 0.1) ? hdt : v_new * dt) + half;
                 const double pos_new = pos + dpos;
                 const bool ok = (pos < L) & (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
-                                (off < (unsigned)TS_BLK) & (r1 * r2 > 0.0) & recip_safe_exp(n1) & recip_safe_exp(n2) &
-                                recip_safe_exp(da) & (k < k_fast) & s0 & s1 & s2 & s3;
+                                (off < (unsigned)TS_BLK) & (r1 * r2 > 0.0) & recip_safe_exp(n1) &
+                                recip_safe_exp(n2) & (fabs(da) < 0x1p930) & (k < k_fast) & s0 & s1 & s2 & s3;
                 // The commit is unconditional -- no select on the dependent chain, no branch: a refused step (and every step
                 // of a finished lane) writes values nobody reads into the row's slot k, which the generic step or the final
                 // store rewrites, and the lane leaves at the next vote, where the state of before the commit comes back.
@@ -364,166 +377,6 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     if (k >= 0 && k <= m_cap) P[k] = pos;
     n_main[b] = k;                                      // -1: diverged
 }
-
-#ifdef VAP_TS_V1
-// A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row (and the lerp
-// reciprocals) are staged through a per-thread shared-memory ring by TMA bulk copies two 128-sample blocks ahead, so the loop
-// never waits on HBM.
-//
-// The kernel runs ONE warp per scheduler with a few paths per warp, so its time is the dependent-instruction latency of a
-// step times the step count of the longest path (measured on B200: 8.2 cycles per dependent DADD/DMUL/DFMA, 18 per
-// double<->int conversion, 29 per shared-memory load, ~100 for an inlined division whose reciprocal refinement sits on the
-// chain, and instructions issue in order, so independent work placed after a stalled instruction does not start early).
-// The common step is therefore written as one straight-line block: the interval index comes from trunc() in the fp domain
-// (no int->double round trip), both lerp divisions and the division by dt use tabulated / hoisted reciprocals (five
-// dependent operations each, no slow-path branch inside the chain), every validity condition of the fast path is
-// evaluated off the chain and tested ONCE; a step that fails the test is redone on the generic path.
-__global__ void __launch_bounds__(32) k_time_state_v1(long long B, const double* __restrict__ cons,
-                                                   const int* __restrict__ status, double dt, double dd,
-                                                   const double* __restrict__ total_len, long long D_cap,
-                                                   const int* __restrict__ n_samples, const double* __restrict__ vel,
-                                                   long long M_cap, double* __restrict__ stage, int* __restrict__ n_main,
-                                                   const double* __restrict__ rden, long long n_rden)
-{
-    extern __shared__ __align__(16) double s_ring[];
-    // this thread's two mbarriers (one per ring slot) live behind the rings
-    const unsigned mb = (unsigned)__cvta_generic_to_shared(s_ring + (size_t)blockDim.x * TS_STRIDE + 2 * threadIdx.x);
-    mbar_init(mb, 1);
-    mbar_init(mb + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    if (status[b] != ST_OK) { n_main[b] = 0; return; }
-    const double L = total_len[b];
-    const double max_acc = cons[b * 6 + 1], max_dec = cons[b * 6 + 2];
-    const int D = n_samples[b];
-    const double* vv = vel + (size_t)b * D_cap;
-    const double inv_dd = 1.0 / dd, inv_dt = 1.0 / dt;
-    const size_t plane = (size_t)B * (M_cap + 1);
-    double* P = stage + TS_POS * plane + (size_t)b * (M_cap + 1);
-    double* Vo = stage + TS_VEL * plane + (size_t)b * (M_cap + 1);
-    double* Ao = stage + TS_ACC * plane + (size_t)b * (M_cap + 1);
-    double* To = stage + TS_TV * plane + (size_t)b * (M_cap + 1);
-    double* ring = s_ring + (size_t)threadIdx.x * TS_STRIDE;
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-    if (rden == nullptr) n_rden = 0;                   // no table: the fast path is disabled
-    const int nblk = (int)((D_cap + TS_BLK - 1) / TS_BLK);
-    unsigned phase = 0, pend = 0;                      // per slot: parity to wait for / a copy is in flight
-    auto wait_slot = [&](int sl) {
-        if ((pend >> sl) & 1u) {
-            mbar_wait(mb + 8 * sl, (phase >> sl) & 1u);
-            phase ^= 1u << sl;
-            pend &= ~(1u << sl);
-        }
-    };
-    auto stage_block = [&](int blk) {          // rows are padded to a multiple of TS_BLK samples by the host
-        const int sl = blk & 1;
-        wait_slot(sl);                          // never two copies in flight on one barrier
-        if (blk < nblk) {
-            const bool with_r = (long long)(blk + 1) * TS_BLK <= n_rden;      // the same block of the lerp reciprocals
-            const unsigned bytes = TS_BLK * sizeof(double);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier reads of the slot precede the TMA writes
-            mbar_expect_tx(mb + 8 * sl, with_r ? 2 * bytes : bytes);
-            VAP_CHECK(10, (size_t)(blk + 1) * TS_BLK <= (size_t)D_cap && sl * bytes + bytes <= TS_RING * sizeof(double) &&
-                              (!with_r || (blk + 1) * (long long)TS_BLK <= n_rden));
-            bulk_g2s(ring_s + sl * bytes, vv + (size_t)blk * TS_BLK, bytes, mb + 8 * sl);
-            if (with_r) bulk_g2s(ring_s + TS_RDEN * sizeof(double) + sl * bytes, rden + (size_t)blk * TS_BLK, bytes, mb + 8 * sl);
-            pend |= 1u << sl;
-        }
-    };
-    int blk_lo = 0;                             // blocks blk_lo and blk_lo+1 are resident (or in flight: `pend`)
-    stage_block(0);
-    stage_block(1);
-    wait_slot(0);
-    wait_slot(1);
-    double pos = 0.0, v = vv[0];
-    const double vlast = vv[D - 1];
-    int k = 0;                                          // 32-bit: the row limit is far below 2^31
-    const double hdt = 0.1 * dt;
-    // fast-path index range: i1 <= D-4 (both lerps strictly inside the row) and i1 + 1 inside the reciprocal table
-    const long long nr = (n_rden / TS_BLK) * TS_BLK;    // the reciprocals are staged in whole blocks
-    const long long il = ((long long)D - 3 < nr - 2) ? (long long)D - 3 : nr - 2;
-    const int ilim = il > 0 ? (int)il : 0;             // index clamp (memory safety only)
-    const double dlim = (double)ilim;                  // fast path: 0 <= pos / dd < ilim
-    const double ndec = -max_dec;
-    long long k_lim64 = 16 * M_cap + 1000000;           // far beyond any terminating profile of this capacity class
-    if (k_lim64 > VAP_ROW_LIMIT) k_lim64 = VAP_ROW_LIMIT;
-    const int k_limit = (int)k_lim64;
-    const int m_cap = (int)(M_cap < 2147483647LL ? M_cap : 2147483647LL);
-    while (pos < L) {
-        if (k >= k_limit) { k = -1; break; }                           // diverging loop: report instead of hanging
-        // rows have M_cap + 1 slots: steps beyond the capacity (the path is then re-run with a larger one) all land in the
-        // last slot, so the stores need no predicate
-        const int ks = k < m_cap ? k : m_cap;
-        P[ks] = pos;
-        double tv1, tv2;
-        const double x2 = pos + dd;
-        // Fast path: the interval index is guessed as trunc(pos / dd) and VERIFIED against xs[i] = fl(i*dd) (that is the
-        // definition of np.searchsorted(side='right') - 1), and lerp(pos + dd) is verified to fall in the next interval;
-        // anything else (first / last samples, a guess off by one, a position that moved backwards) takes the generic path.
-        const double e = pos * inv_dd;
-        const double ef = trunc(e);
-        int i1 = __double2int_rz(e);                                   // = (int)ef whenever the fast path applies
-        i1 = i1 < 0 ? 0 : (i1 > ilim ? ilim : i1);                      // memory-safe whatever pos is
-        const double x0 = ef * dd, x1 = (ef + 1.0) * dd, xx2 = (ef + 2.0) * dd;      // (double)(i1 + k) == ef + k exactly
-        // Invariant: block blk_lo is complete; block blk_lo+1 is complete unless its slot is still pending.
-        if (i1 + 2 >= (blk_lo + 1) * TS_BLK) {
-            if (i1 >= (blk_lo + 1) * TS_BLK) {
-                while (i1 >= (blk_lo + 1) * TS_BLK) { blk_lo++; stage_block(blk_lo + 1); }
-                wait_slot(blk_lo & 1);                   // the block the position is in now
-            }
-            if (i1 + 2 >= (blk_lo + 1) * TS_BLK) wait_slot((blk_lo + 1) & 1);
-        }
-        // everything below is computed unconditionally (the loads are safe for any index); `fast` collects, off the
-        // dependent chain, every condition under which the values are the reference's
-        const double y0 = ring[i1 & (TS_RING - 1)], y1 = ring[(i1 + 1) & (TS_RING - 1)], y2 = ring[(i1 + 2) & (TS_RING - 1)];
-        const double r1 = ring[TS_RDEN + (i1 & (TS_RING - 1))], r2 = ring[TS_RDEN + ((i1 + 1) & (TS_RING - 1))];
-        const double n1 = (pos - x0) * (y1 - y0), n2 = (x2 - x1) * (y2 - y1);
-        tv1 = y0 + div_recip(n1, x1 - x0, r1);
-        tv2 = y1 + div_recip(n2, xx2 - x1, r2);
-        const bool fast = (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
-                          (i1 >= blk_lo * TS_BLK) & (r1 * r2 > 0.0) & recip_safe_num(n1) & recip_safe_num(n2);
-        if (!fast) {
-            const int j1 = uniform_index32(pos, dd, inv_dd, D);
-            const int j2 = uniform_index32(x2, dd, inv_dd, D);
-            if (j1 < 0) tv1 = vv[0];
-            else if (j1 >= D - 1) tv1 = vlast;
-            else {
-                double a0 = (double)j1 * dd, a1 = (double)(j1 + 1) * dd, b0 = vv[j1], b1 = vv[j1 + 1];
-                tv1 = b0 + div_pos((pos - a0) * (b1 - b0), a1 - a0);
-            }
-            if (j2 < 0) tv2 = vv[0];
-            else if (j2 >= D - 1) tv2 = vlast;
-            else {
-                double a0 = (double)j2 * dd, a1 = (double)(j2 + 1) * dd, b0 = vv[j2], b1 = vv[j2 + 1];
-                tv2 = b0 + div_pos((x2 - a0) * (b1 - b0), a1 - a0);
-            }
-        }
-        const double tvm = (tv1 + tv2) / 2;
-        const double tv = (0.001 > tvm) ? 0.001 : tvm;                 // max(tvm, 0.001)
-        const double da = tv - v;
-        double accel = div_recip(da, dt, inv_dt);
-        if (!recip_safe_num(da)) accel = div_pos(da, dt);              // tiny / huge / non-finite numerators (never on sane input)
-        accel = (da == 0.0) ? da : accel;
-        accel = (accel > ndec) ? accel : ndec;                         // np.clip(accel, -max_dec, max_acc)
-        accel = (accel < max_acc) ? accel : max_acc;
-        double vn = v + accel * dt;
-        vn = (vn > 0.0) ? vn : 0.0;                                    // np.clip(v, 0, tv)
-        v = (vn < tv) ? vn : tv;
-        const double half = 0.5 * accel * dt * dt;
-        const double dpos = ((v <= 0.1) ? hdt : v * dt) + half;
-        pos += dpos;
-        Vo[ks] = v; Ao[ks] = accel; To[ks] = tv;
-        k++;
-    }
-    wait_slot(0);                                // no TMA write may be in flight when the CTA's shared memory is released
-    wait_slot(1);
-    if (k >= 0 && k <= m_cap) P[k] = pos;
-    n_main[b] = k;                                      // -1: diverged
-}
-
-#endif
 
 // exactness check of div_const against the IEEE division (test hook)
 __global__ void k_test_div_const(long long n, unsigned long long seed, double b, unsigned long long* __restrict__ bad)
