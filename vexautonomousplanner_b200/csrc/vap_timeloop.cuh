@@ -54,7 +54,9 @@ __device__ __forceinline__ double div_const(double a, double b, double r)
     return q;
 }
 
+#ifndef TS_BLK
 #define TS_BLK 128                 // samples per staged block of the velocity row
+#endif
 
 // index of np.searchsorted(xs, x, side='right') - 1 on xs[i] = fl(i*dd), 32-bit arithmetic
 __device__ __forceinline__ int uniform_index32(double x, double dd, double inv_dd, int D)
@@ -162,7 +164,7 @@ __device__ __forceinline__ double div_recip_spec(double a, double b, double r, b
 // + unconditional commit and the vote on the position 59.3; |da| range test on the fp pipe instead of the exponent field
 // 57.9 (kept); also speculating v > 0.1 and vn > 0: 87 (too many generic steps on a path with 800 nodes); integer tests
 // of the reciprocals' high words instead of r1 r2 > 0: 71; #pragma unroll 2: 62.
-#define TS_SLOT 132                 // doubles per ring slot: a 128-sample block + the 2 samples behind it (+2: 16-byte multiples)
+#define TS_SLOT (TS_BLK + 4)         // doubles per ring slot: a 128-sample block + the 2 samples behind it (+2: 16-byte multiples)
 #define TS_STRIDE2 (4 * TS_SLOT)    // per-thread slice: two velocity slots, then two reciprocal slots
 __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
                                                    const int* __restrict__ status, double dt, double dd,
