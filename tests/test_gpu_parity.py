@@ -277,6 +277,49 @@ def test_chunked_equals_serial_bitwise():
             assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64))
 
 
+def test_time_loop_lane_counts_and_failed_paths_bitwise(monkeypatch):
+    """The time loop's warps leave their fast run on a vote, and the paths of a warp are served in turns: the result must not
+    depend on how many paths share a warp (1 ... 32, ragged last warp), on failed paths sitting in a live warp (they only
+    vote), or on a capacity so small that most steps land in the overflow slot -- all bit for bit against the
+    reference-shaped serial kernel (k_resample)."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    from vexautonomousplanner_b200.packing import rotation_table
+    packed = synth.mixed_paths(77, 8, seed=21)
+    packed.node_flags[5, packed.n_nodes[5] - 1] |= 1          # reverse at the last node: status -2 inside a live warp
+    packed.n_nodes[33] = 1                                    # fewer than two points: status -1
+    packed.node_attr[:, :, 10], packed.node_attr[:, :, 11] = rotation_table(packed.node_attr[:, :, 2],
+                                                                             (packed.node_flags & 1) != 0)
+    ser = Engine("cuda:0", velocity_impl="serial", time_impl="serial")
+    db = ser.upload(packed)
+    ref = ser.profile(db)
+    torch.cuda.synchronize()
+    assert int(ref.status[5]) == -2 and int(ref.status[33]) == -1 and int((ref.status == 0).sum()) == 75
+    n = ref.n_out.long()
+    for lanes in ("1", "3", "7", "10", "32"):
+        monkeypatch.setenv("VAP_STATE_LANES", lanes)
+        got = Engine("cuda:0").profile(db)
+        torch.cuda.synchronize()
+        assert torch.equal(ref.status, got.status), lanes
+        assert torch.equal(ref.n_out, got.n_out), lanes
+        Tm = min(ref.T_cap, got.T_cap)
+        mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+        for i in range(8):
+            assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64)), (lanes, i)
+        assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64)), lanes
+    monkeypatch.delenv("VAP_STATE_LANES")
+    # an undersized row capacity: the paths come back as ST_CAPACITY with their true needs, and the redo is exact
+    eng = Engine("cuda:0")
+    D_cap, _ = eng.plan_capacities(db)
+    small = eng.profile_batch(db, D_cap, 256)
+    torch.cuda.synchronize()
+    assert torch.equal(ref.n_out, small.n_out)
+    Tm = min(ref.T_cap, small.T_cap)
+    mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+    for i in range(8):
+        assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), small.out[i][:, :Tm][mt].view(torch.int64)), i
+
+
 def test_short_paths_and_chunk_edges():
     """Paths far shorter than the chunk count (one step per chunk, idle chunks), lengths around multiples of the chunk
     count, a stop node (exact reset of the forward pass) and every warm-up length: fast == serial bit for bit."""
