@@ -184,8 +184,9 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     // the lanes of a warp leave the fast run TOGETHER (a vote), so every lane with a path stays in the loop until the warp
     // is done; a failed path takes part in the votes as "finished" (its own stage row takes the stores nobody reads)
     if (b >= B) return;
-    const long long left = B - (long long)blockIdx.x * blockDim.x;                    // lanes of this CTA that have a path
-    const unsigned mask = left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u);
+    const long long left = B - (long long)blockIdx.x * blockDim.x;                    // paths from this CTA's first one on
+    const int nl = left < (long long)blockDim.x ? (int)left : (int)blockDim.x;       // lanes of this CTA that have a path
+    const unsigned mask = nl >= 32 ? 0xffffffffu : ((1u << nl) - 1u);
     const bool part = status[b] == ST_OK;
     if (!part) n_main[b] = 0;
     const double L = part ? total_len[b] : 0.0;
