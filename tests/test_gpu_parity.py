@@ -320,6 +320,36 @@ def test_time_loop_lane_counts_and_failed_paths_bitwise(monkeypatch):
         assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), small.out[i][:, :Tm][mt].view(torch.int64)), i
 
 
+@pytest.mark.parametrize("dt,dd", [(0.01, 0.005), (0.025, 0.01), (0.004, 0.02)])
+def test_time_loop_fuzz_constraints_bitwise(dt, dd):
+    """The fast time loop against the reference-shaped serial kernel on constraints far from the factory values -- crawling
+    and very fast robots, max_dec large enough for the position to move BACKWARDS in a step (delta_pos < 0 when
+    max_dec > 0.2 / dt), steps that jump over many distance samples or stay inside one -- bit for bit, status included."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    rng = np.random.default_rng(int(dt * 1e4) + 7)
+    packed = synth.mixed_paths(640, 8, seed=31)
+    B = packed.cons.shape[0]
+    packed.cons[:, 0] = rng.uniform(0.3, 14.0, B)            # max_vel
+    packed.cons[:, 1] = 10.0 ** rng.uniform(-0.7, 1.6, B)    # max_acc 0.2 ... 40
+    packed.cons[:, 2] = 10.0 ** rng.uniform(-0.7, 2.2, B)    # max_dec 0.2 ... 160
+    packed.cons[:, 5] = rng.uniform(0.4, 2.5, B)             # track width
+    ser = Engine("cuda:0", dt=dt, dd=dd, time_impl="serial")
+    fast = Engine("cuda:0", dt=dt, dd=dd)
+    ref = ser.profile(ser.upload(packed))
+    got = fast.profile(fast.upload(packed))
+    torch.cuda.synchronize()
+    assert torch.equal(ref.status, got.status)
+    assert int((ref.status == 0).sum()) > B // 2
+    assert torch.equal(ref.n_out, got.n_out)
+    n = ref.n_out.long()
+    Tm = min(ref.T_cap, got.T_cap)
+    mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+    for i in range(8):
+        assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64)), i
+    assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64))
+
+
 def test_short_paths_and_chunk_edges():
     """Paths far shorter than the chunk count (one step per chunk, idle chunks), lengths around multiples of the chunk
     count, a stop node (exact reset of the forward pass) and every warm-up length: fast == serial bit for bit."""
