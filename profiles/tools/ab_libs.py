@@ -6,7 +6,6 @@ import sys, time, torch
 sys.path.insert(0, '.')
 from vexautonomousplanner_b200 import synth
 from vexautonomousplanner_b200.engine import Engine
-import numpy as np
 def run(tag, packed, reps=5):
     eng = Engine("cuda:0")
     db = eng.upload(packed)
@@ -20,8 +19,7 @@ def run(tag, packed, reps=5):
     st = {}
     for name, s, e in eng.stage_events:
         st[name] = st.get(name, 0.0) + s.elapsed_time(e) / reps
-    chk = float(res.summary[:, :].double().sum()) if hasattr(res, "summary") and res.summary is not None else 0.0
-    print(f"{tag}: S6 {st.get('S6_resample', 0):.3f} ms  total {sum(st.values()):.3f} ms  n_out_sum={int(res.n_out.sum())}", flush=True)
+    print(f"{tag}: " + "  ".join(f"{k.split('_')[0]} {v:.3f}" for k, v in st.items()) + f"  total {sum(st.values()):.3f} ms  n_out_sum={int(res.n_out.sum())}", flush=True)
 for name, packed in (("cfg2 4096x8", synth.random_paths(4096, 8, seed=1)), ("8192x16", synth.random_paths(8192, 16, seed=1)),
                      ("mixed 4096x8", synth.mixed_paths(4096, 8, seed=3)), ("cfg4 1x801", synth.long_path(801, seed=2))):
     run(name, packed)
