@@ -296,8 +296,9 @@ def test_time_loop_lane_counts_and_failed_paths_bitwise(monkeypatch):
     torch.cuda.synchronize()
     assert int(ref.status[5]) == -2 and int(ref.status[33]) == -1 and int((ref.status == 0).sum()) == 75
     n = ref.n_out.long()
-    for lanes in ("1", "3", "7", "10", "32"):
+    for lanes, blk in (("1", "128"), ("3", "64"), ("7", "128"), ("7", "64"), ("10", "64"), ("32", "128"), ("32", "64")):
         monkeypatch.setenv("VAP_STATE_LANES", lanes)
+        monkeypatch.setenv("VAP_STATE_BLK", blk)          # samples per staged ring block (64 is what large batches use)
         got = Engine("cuda:0").profile(db)
         torch.cuda.synchronize()
         assert torch.equal(ref.status, got.status), lanes
@@ -308,6 +309,7 @@ def test_time_loop_lane_counts_and_failed_paths_bitwise(monkeypatch):
             assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64)), (lanes, i)
         assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64)), lanes
     monkeypatch.delenv("VAP_STATE_LANES")
+    monkeypatch.delenv("VAP_STATE_BLK")
     # an undersized row capacity: the paths come back as ST_CAPACITY with their true needs, and the redo is exact
     eng = Engine("cuda:0")
     D_cap, _ = eng.plan_capacities(db)

@@ -1439,7 +1439,7 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     if (e != cudaSuccess) return set_err("vap_time_profile/memset", e);
     e = cudaMemsetAsync(ev_napc, 0, sizeof(int32_t) * (size_t)B * Am, STREAM);
     if (e != cudaSuccess) return set_err("vap_time_profile/memset", e);
-    if (D_cap % TS_BLK != 0) return arg_err("vap_time_profile: D_cap must be a multiple of 128 (rows are staged in 128-sample blocks)");
+    if (D_cap % 128 != 0) return arg_err("vap_time_profile: D_cap must be a multiple of 128 (rows are staged in 128-sample blocks)");
     // Serial per-path chains are latency-bound (about 4.6 cycles per dependent instruction, measured): spread the paths
     // over the warp schedulers (148 SMs x 4) with few paths per warp, so that one path's data-dependent branches stall
     // few other paths and the schedulers still have another warp to issue from.  VAP_STATE_LANES overrides (tuning).
@@ -1449,13 +1449,22 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     if (lanes > 10) lanes = 10;
     if (const char* ev = getenv("VAP_STATE_LANES")) lanes = atoi(ev);
     lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
-    const size_t ring_bytes = (size_t)lanes * (TS_STRIDE2 * sizeof(double) + 16);    // rings + two mbarriers per path
+    // ring blocks of 128 samples while every path's ring fits on the chip at once (148 SMs x 32 paths), 64 beyond
+    bool big = B > 148 * 32;
+    if (const char* ev = getenv("VAP_STATE_BLK")) big = atoi(ev) == 64;               // tests / tuning
+    const size_t ring_bytes = (size_t)lanes * ((big ? ts_stride(64) : ts_stride(128)) * sizeof(double) + 16);   // rings + two mbarriers per path
     if (ring_bytes > 48 * 1024) {      // per device and cheap: no process-global "already set" flag (the library keeps no state)
-        cudaError_t ea = cudaFuncSetAttribute(k_time_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * (TS_STRIDE2 * sizeof(double) + 16)));
+        const int mx = (int)(32 * (ts_stride(128) * sizeof(double) + 16));
+        cudaError_t ea = big ? cudaFuncSetAttribute(k_time_state<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)
+                             : cudaFuncSetAttribute(k_time_state<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ea != cudaSuccess) return set_err("vap_time_profile/attr", ea);
     }
-    k_time_state<<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
-                                                                     vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);
+    if (big)
+        k_time_state<64><<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
+                                                                             vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);
+    else
+        k_time_state<128><<<blocks_for(B, lanes), lanes, ring_bytes, STREAM>>>(B, cons, status, dt, dd, total_len, D_cap, n_samples,
+                                                                              vel, M_cap, stage, n_main, rden, rden ? n_rden : 0);
     CHECK_LAUNCH("vap_time_profile/state");
     const unsigned tx = blocks_for(M_cap, 256);
     if ((long long)tx * B > 2147483647LL) return arg_err("vap_time_profile: more than 2^31 CTAs (tile the batch)");

@@ -54,9 +54,6 @@ __device__ __forceinline__ double div_const(double a, double b, double r)
     return q;
 }
 
-#ifndef TS_BLK
-#define TS_BLK 128                 // samples per staged block of the velocity row
-#endif
 
 // index of np.searchsorted(xs, x, side='right') - 1 on xs[i] = fl(i*dd), 32-bit arithmetic
 __device__ __forceinline__ int uniform_index32(double x, double dd, double inv_dd, int D)
@@ -128,7 +125,7 @@ __device__ __forceinline__ double div_recip_spec(double a, double b, double r, b
 }
 
 // A: the state recurrence (motion_profile_generator.py:523,567-583).  One thread per path; the velocity row (and the lerp
-// reciprocals) are staged through a per-thread shared-memory ring by TMA bulk copies one 128-sample block ahead, so the loop
+// reciprocals) are staged through a per-thread shared-memory ring by TMA bulk copies one block (BLK = 128 or 64 samples) ahead, so the loop
 // never waits on HBM.
 //
 // The kernel runs ONE warp per scheduler with a few paths per warp, so its time is the dependent-instruction latency of a
@@ -145,7 +142,7 @@ __device__ __forceinline__ double div_recip_spec(double a, double b, double r, b
 //     other lanes' events (a per-lane `break` made the first lane out wait for ALL the others: +40 % time).  The vote is
 //     taken on the position itself (pos >= xs[lo + 128], resolved long before the integer index) and completes while the
 //     address is computed and the five loads are issued, so the branch behind them does not wait.
-//   * a ring slot holds a 128-sample block PLUS the two samples behind it (the copy is 130 doubles), so the three samples
+//   * a ring slot holds a BLK-sample block PLUS the two samples behind it (the copy is BLK + 2 doubles), so the three samples
 //     and two reciprocals of a step sit at fixed offsets from one address whatever the position inside the block.
 //   * floor(pos / dd) comes from one round-toward-zero addition of 2^52 (the integer is the low word of the sum and the
 //     double is the sum minus 2^52), not from F2I + FRND.
@@ -164,8 +161,13 @@ __device__ __forceinline__ double div_recip_spec(double a, double b, double r, b
 // + unconditional commit and the vote on the position 59.3; |da| range test on the fp pipe instead of the exponent field
 // 57.9 (kept); also speculating v > 0.1 and vn > 0: 87 (too many generic steps on a path with 800 nodes); integer tests
 // of the reciprocals' high words instead of r1 r2 > 0: 71; #pragma unroll 2: 62.
-#define TS_SLOT (TS_BLK + 4)         // doubles per ring slot: a 128-sample block + the 2 samples behind it (+2: 16-byte multiples)
-#define TS_STRIDE2 (4 * TS_SLOT)    // per-thread slice: two velocity slots, then two reciprocal slots
+// BLK samples per staged block: 128 for batches whose rings all fit on the chip at once (fewest block changes), 64 for larger
+// ones (half the shared memory per path: the other batch's kernels in flight keep theirs; the 2^20-path job runs 4.6 %
+// faster).  Per thread: two velocity slots, then two reciprocal slots of BLK + 4 doubles (the block, the 2 samples behind it,
+// 2 of padding: 16-byte multiples).
+__host__ __device__ constexpr int ts_slot(int BLK) { return BLK + 4; }
+__host__ __device__ constexpr int ts_stride(int BLK) { return 4 * ts_slot(BLK); }
+template <int BLK>
 __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __restrict__ cons,
                                                    const int* __restrict__ status, double dt, double dd,
                                                    const double* __restrict__ total_len, long long D_cap,
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
 {
     extern __shared__ __align__(16) double s_ring[];
     // this thread's two mbarriers (one per ring slot) live behind the rings
-    const unsigned mb = (unsigned)__cvta_generic_to_shared(s_ring + (size_t)blockDim.x * TS_STRIDE2 + 2 * threadIdx.x);
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(s_ring + (size_t)blockDim.x * ts_stride(BLK) + 2 * threadIdx.x);
     mbar_init(mb, 1);
     mbar_init(mb + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -196,10 +198,10 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     const double inv_dd = 1.0 / dd, inv_dt = 1.0 / dt;
     const size_t plane = (size_t)B * (M_cap + 1);
     double* P = stage + TS_POS * plane + (size_t)b * (M_cap + 1);
-    const double* ring = s_ring + (size_t)threadIdx.x * TS_STRIDE2;
+    const double* ring = s_ring + (size_t)threadIdx.x * ts_stride(BLK);
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     if (rden == nullptr) n_rden = 0;                   // no table: the fast run is disabled
-    const int nblk = (int)((D_cap + TS_BLK - 1) / TS_BLK);
+    const int nblk = (int)((D_cap + BLK - 1) / BLK);
     unsigned phase = 0, pend = 0;                      // per slot: parity to wait for / a copy is in flight
     auto wait_slot = [&](int sl) {
         if ((pend >> sl) & 1u) {
@@ -208,21 +210,21 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
             pend &= ~(1u << sl);
         }
     };
-    auto stage_block = [&](int blk) {          // rows are padded to a multiple of TS_BLK samples by the host
+    auto stage_block = [&](int blk) {          // rows are padded to a multiple of BLK samples by the host
         const int sl = blk & 1;
         wait_slot(sl);                          // never two copies in flight on one barrier
         if (blk < nblk) {
             // the block and the two samples behind it (they belong to the next block of the same row; the row's last
             // block has nothing behind it and the fast run never reads there: i1 + 2 <= D - 2)
-            const unsigned nv = (blk + 1 < nblk) ? TS_BLK + 2 : TS_BLK;
-            const long long rem = n_rden - (long long)blk * TS_BLK;        // reciprocals left from this block on
-            const unsigned nr_ = rem >= TS_BLK + 2 ? TS_BLK + 2 : (rem >= TS_BLK ? TS_BLK : 0);
+            const unsigned nv = (blk + 1 < nblk) ? BLK + 2 : BLK;
+            const long long rem = n_rden - (long long)blk * BLK;        // reciprocals left from this block on
+            const unsigned nr_ = rem >= BLK + 2 ? BLK + 2 : (rem >= BLK ? BLK : 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier reads of the slot precede the TMA writes
             mbar_expect_tx(mb + 8 * sl, (nv + nr_) * (unsigned)sizeof(double));
-            VAP_CHECK(10, (size_t)blk * TS_BLK + nv <= (size_t)D_cap && nv <= TS_SLOT && nr_ <= TS_SLOT &&
-                              (long long)blk * TS_BLK + nr_ <= n_rden);
-            bulk_g2s(ring_s + sl * (unsigned)(TS_SLOT * sizeof(double)), vv + (size_t)blk * TS_BLK, nv * (unsigned)sizeof(double), mb + 8 * sl);
-            if (nr_) bulk_g2s(ring_s + (2 + sl) * (unsigned)(TS_SLOT * sizeof(double)), rden + (size_t)blk * TS_BLK,
+            VAP_CHECK(10, (size_t)blk * BLK + nv <= (size_t)D_cap && nv <= ts_slot(BLK) && nr_ <= ts_slot(BLK) &&
+                              (long long)blk * BLK + nr_ <= n_rden);
+            bulk_g2s(ring_s + sl * (unsigned)(ts_slot(BLK) * sizeof(double)), vv + (size_t)blk * BLK, nv * (unsigned)sizeof(double), mb + 8 * sl);
+            if (nr_) bulk_g2s(ring_s + (2 + sl) * (unsigned)(ts_slot(BLK) * sizeof(double)), rden + (size_t)blk * BLK,
                               nr_ * (unsigned)sizeof(double), mb + 8 * sl);
             pend |= 1u << sl;
         }
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     int k = 0;                                          // 32-bit: the row limit is far below 2^31
     const double hdt = 0.1 * dt;
     // fast-run index range: i1 <= D-4 (both lerps strictly inside the row) and i1 + 1 inside the staged reciprocals
-    const long long nr = (n_rden / TS_BLK) * TS_BLK;    // the reciprocals are staged in whole blocks
+    const long long nr = (n_rden / BLK) * BLK;    // the reciprocals are staged in whole blocks
     const long long il = ((long long)D - 3 < nr - 2) ? (long long)D - 3 : nr - 2;
     const double dlim = (double)(il > 0 ? il : 0);     // fast run: 0 <= pos / dd < dlim  (dlim < 2^31)
     const double ndec = -max_dec;
@@ -258,11 +260,11 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
     while (__any_sync(mask, !fin)) {                    // the fast run is left by a request only: never enter it without a live lane
         // ---------------- fast run over block blk_lo ----------------
         {
-            const int lo = blk_lo * TS_BLK;
-            // shared address of the block: [rb + 8 (i - lo)] = vel[i], [rb + 8 (2 TS_SLOT + i - lo)] = rden[i]
-            const unsigned rb = ring_s + (unsigned)(blk_lo & 1) * (unsigned)(TS_SLOT * sizeof(double));
+            const int lo = blk_lo * BLK;
+            // shared address of the block: [rb + 8 (i - lo)] = vel[i], [rb + 8 (2 ts_slot(BLK) + i - lo)] = rden[i]
+            const unsigned rb = ring_s + (unsigned)(blk_lo & 1) * (unsigned)(ts_slot(BLK) * sizeof(double));
             double* sp = P + (k < 0 ? 0 : (k < m_cap ? k : m_cap));   // stage row of step k (the other planes follow at `plane`)
-            const double pos_hi = (double)(lo + TS_BLK) * dd;     // xs[lo + TS_BLK]: from here on the position is in the next block
+            const double pos_hi = (double)(lo + BLK) * dd;     // xs[lo + BLK]: from here on the position is in the next block
             double pos_s = pos, v_s = v;                          // the state before the last commit
             for (;;) {
                 const double e = pos * inv_dd;
@@ -275,10 +277,10 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const int i1 = __double2loint(em);
                 const double ef = em - two52;                     // == trunc(e) there
                 const unsigned off = (unsigned)(i1 - lo);
-                const unsigned q = rb + 8u * (off < (unsigned)(TS_BLK - 1) ? off : (unsigned)(TS_BLK - 1));   // memory-safe whatever pos is
-                VAP_CHECK(11, q >= ring_s && q + (2 * TS_SLOT + 2) * 8 <= ring_s + TS_STRIDE2 * 8 && (q & 7u) == 0);
+                const unsigned q = rb + 8u * (off < (unsigned)(BLK - 1) ? off : (unsigned)(BLK - 1));   // memory-safe whatever pos is
+                VAP_CHECK(11, q >= ring_s && q + (2 * ts_slot(BLK) + 2) * 8 <= ring_s + ts_stride(BLK) * 8 && (q & 7u) == 0);
                 const double y0 = lds_f64<0>(q), y1 = lds_f64<8>(q), y2 = lds_f64<16>(q);
-                const double r1 = lds_f64<2 * TS_SLOT * 8>(q), r2 = lds_f64<2 * TS_SLOT * 8 + 8>(q);
+                const double r1 = lds_f64<2 * ts_slot(BLK) * 8>(q), r2 = lds_f64<2 * ts_slot(BLK) * 8 + 8>(q);
                 if (leave) break;
                 const double x2 = pos + dd;
                 const double x0 = ef * dd, x1 = (ef + 1.0) * dd, xx2 = (ef + 2.0) * dd;      // (double)(i1 + j) == ef + j exactly
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const double dpos = ((v_new <= 0.1) ? hdt : v_new * dt) + half;
                 const double pos_new = pos + dpos;
                 const bool ok = (pos < L) & (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
-                                (off < (unsigned)TS_BLK) & (r1 * r2 > 0.0) & recip_safe_exp(n1) &
+                                (off < (unsigned)BLK) & (r1 * r2 > 0.0) & recip_safe_exp(n1) &
                                 recip_safe_exp(n2) & (fabs(da) < 0x1p930) & (k < k_fast) & s0 & s1 & s2 & s3;
                 // The commit is unconditional -- no select on the dependent chain, no branch: a refused step (and every step
                 // of a finished lane) writes values nobody reads into the row's slot k, which the generic step or the final
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const double e = pos * inv_dd;
                 const int ic = (e > 0.0) ? ((e < 2147483000.0) ? __double2int_rz(e) : 2147483000) : 0;
                 bool moved = false;
-                while (blk_lo + 1 < nblk && ic >= (blk_lo + 1) * TS_BLK) { blk_lo++; stage_block(blk_lo + 1); moved = true; }
+                while (blk_lo + 1 < nblk && ic >= (blk_lo + 1) * BLK) { blk_lo++; stage_block(blk_lo + 1); moved = true; }
                 if (moved) wait_slot(blk_lo & 1);
                 else {
                     // generic step (first / last intervals of a path, odd operands, positions outside the staged block):
