@@ -19,7 +19,9 @@
  *        -5 the reference's time loop would not terminate for this input (e.g. max_dec >= 20 ft/s^2 makes a step
  *           move backwards) or would emit more than 5e7 rows: the engine stops instead of hanging the GPU
  *        -6 more node crossings / action-point candidates than the per-path event tables hold (N_max wraps,
- *           4 candidate samples per action point): a permanent condition, unlike -4 it does not go away on a retry
+ *           4 candidate samples per action point): a permanent condition, unlike -4 it does not go away on a retry.
+ *           The time stage never returns it: a path whose position oscillates across an action point or a node
+ *           (steps that move backwards, max_dec > 0.2 / dt) is redone there by the reference-shaped serial kernel.
  *   - the library keeps no global mutable state and allocates nothing.
  *
  * Packed layouts

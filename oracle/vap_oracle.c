@@ -722,6 +722,7 @@ long ora_profile(int n, const double* na, const int* nf, int A, const double* ap
         if (frac1(t) < frac1(prev_t) && t < end_param) {
             nodes_map[nm++] = o.T;
             node_idx += 1;
+            if (node_idx >= n) { rc = ORA_ERR_INDEX; break; }   /* spline_manager.nodes[node_idx] :530 -> IndexError */
             const double* a = na + (size_t)node_idx * NA;
             if (a[A_TURN] != 0) {   /* handle_turn :487-507 */
                 double angle = a[A_TURN] * (PI / 180.0);    /* np.radians */

@@ -121,3 +121,72 @@ def test_engine_against_reference_many_regimes():
         streams = [p[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
         _check(f, i, int(res.n_samples[i]), len(p["times"]), float(res.summary[i, 1]), p["nodes_map"], p["actions_map"],
                streams, p["vel"])
+
+
+OSC = os.path.join(GOLDEN_DIR, "oscillation_reference.npz")
+_TOL = {0: (1e-6, 1e-12), 1: (1e-9, 1e-10), 2: (1e-6, 1e-9), 3: (1e-6, 1e-6), 4: (1e-9, 1e-10), 5: (1e-6, 1e-9),
+        6: (1e-9, 1e-10), 7: (1e-9, 1e-10)}
+
+
+def _check_osc(f, i, status, T, nodes_map, streams):
+    """One case of oscillation_reference.npz (tests/golden/make_golden_oscillation.py: the unmodified reference on paths
+    whose position moves backwards near a stop, max_dec > 0.2 / dt): either the reference raised IndexError (-2: more
+    node transitions than nodes) or it returned, and then T and nodes_map -- extra transitions included -- are exact."""
+    assert status == int(f["status"][i]), (i, status, int(f["status"][i]))
+    if status != 0:
+        return
+    assert T == int(f["T"][i]), (i, T, int(f["T"][i]))
+    assert list(nodes_map) == f["nodes_map"][i][: int(f["n_nm"][i])].tolist(), i
+    idx = np.arange(0, T, int(f["stride"]))[:120]
+    want = f["samples"][i][:, : len(idx)]
+    got = np.stack([s[idx] for s in streams])
+    assert np.any(np.diff(streams[1]) < 0), "the case is supposed to have steps that move backwards"
+    for s in range(8):
+        np.testing.assert_allclose(got[s], want[s], rtol=_TOL[s][0], atol=_TOL[s][1], err_msg=f"case {i} stream {s}")
+
+
+def test_oracle_against_reference_oscillation(oracle_mod):
+    o = oracle_mod
+    o.set_sq_mode(0)
+    f = dict(np.load(OSC))
+    assert sorted(set(f["status"].tolist())) == [-2, 0]
+    for i in range(len(f["n"])):
+        n = int(f["n"][i])
+        try:
+            r = o.full(f["node_attr"][i][:n], f["node_flags"][i][:n], None, None, f["cons"][i], dt=float(f["dt"][i]),
+                       dd=float(f["dd"][i]))
+        except o.OracleError as e:
+            _check_osc(f, i, e.code, 0, [], None)
+            continue
+        streams = [r[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
+        _check_osc(f, i, 0, r["T"], r["nodes_map"], streams)
+        np.testing.assert_allclose(r["summary"][2], f["t_end"][i], rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_engine_against_reference_oscillation():
+    """The same cases through the engine, fast and reference-shaped kernels: IndexError cases come back as status -2, the
+    others with the reference's T and nodes_map (the extra node transitions of an oscillating position included)."""
+    import torch
+    from vexautonomousplanner_b200.engine import Engine
+    from vexautonomousplanner_b200.packing import PackedPaths
+    f = dict(np.load(OSC))
+    B = len(f["n"])
+    for dt, dd in sorted(set(zip(f["dt"].tolist(), f["dd"].tolist()))):
+        sel = [i for i in range(B) if f["dt"][i] == dt and f["dd"][i] == dd]
+        nb = len(sel)
+        packed = PackedPaths(np.ascontiguousarray(f["node_attr"][sel]), np.ascontiguousarray(f["node_flags"][sel]).astype(np.int32),
+                             f["n"][sel].astype(np.int32), np.zeros((nb, 1, 4)), np.zeros((nb, 1), dtype=np.int32),
+                             np.zeros(nb, dtype=np.int32), np.ascontiguousarray(f["cons"][sel]))
+        for impl in (dict(), dict(velocity_impl="serial", time_impl="serial")):
+            eng = Engine("cuda:0", dt=dt, dd=dd, **impl)
+            res = eng.profile(eng.upload(packed))
+            torch.cuda.synchronize()
+            for j, i in enumerate(sel):
+                st = int(res.status[j])
+                if st != 0:
+                    _check_osc(f, i, st, 0, [], None)
+                    continue
+                p = res.path(j)
+                streams = [p[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
+                _check_osc(f, i, 0, len(p["times"]), p["nodes_map"], streams)

@@ -322,6 +322,43 @@ def test_time_loop_lane_counts_and_failed_paths_bitwise(monkeypatch):
         assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), small.out[i][:, :Tm][mt].view(torch.int64)), i
 
 
+def test_oscillating_positions_are_redone_serially():
+    """30-node mixed paths, dt = 0.02, dd = 0.0025 and max_dec up to 160: near stops the position moves back and forth across
+    action points and node boundaries more often than the parallel event detection has candidate slots for (27 of these
+    2048 paths).  The time stage redoes exactly those paths with the reference-shaped serial kernel: same status (OK), same
+    bits as the all-serial run, nothing left as VAP_ERR_EVENTS."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    rng = np.random.default_rng(1001)
+    rng.choice([3, 5, 8, 12, 20, 30]); rng.choice([97, 640, 2048, 5000])     # the draws of the stress run that found the case
+    packed = synth.mixed_paths(2048, 30, seed=201)
+    B = packed.cons.shape[0]
+    packed.cons[:, 0] = rng.uniform(0.3, 14.0, B)
+    packed.cons[:, 1] = 10.0 ** rng.uniform(-0.7, 1.6, B)
+    packed.cons[:, 2] = 10.0 ** rng.uniform(-0.7, 2.2, B)
+    packed.cons[:, 5] = rng.uniform(0.4, 2.5, B)
+    ser = Engine("cuda:0", dt=0.02, dd=0.0025, time_impl="serial")
+    fast = Engine("cuda:0", dt=0.02, dd=0.0025)
+    ref = ser.profile(ser.upload(packed))
+    db = fast.upload(packed)
+    for got in (fast.profile(db), fast.profile_batch(db)):          # staged entry points and the single C call
+        torch.cuda.synchronize()
+        assert int((got.status == -6).sum()) == 0
+        assert torch.equal(ref.status, got.status)
+        assert torch.equal(ref.n_out, got.n_out)
+        n = ref.n_out.long()
+        Tm = min(ref.T_cap, got.T_cap)
+        mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]
+        for i in range(8):
+            assert torch.equal(ref.out[i][:, :Tm][mt].view(torch.int64), got.out[i][:, :Tm][mt].view(torch.int64)), i
+        assert torch.equal(ref.n_maps, got.n_maps)
+        nmm = torch.arange(ref.nodes_map.shape[1], device=n.device)[None, :] < ref.n_maps[:, 0:1]
+        assert torch.equal(ref.nodes_map[nmm], got.nodes_map[nmm])
+        am = torch.arange(ref.actions_map.shape[1], device=n.device)[None, :] < ref.n_maps[:, 1:2]
+        assert torch.equal(ref.actions_map[am], got.actions_map[am])
+        assert torch.equal(ref.summary.view(torch.int64), got.summary.view(torch.int64))
+
+
 @pytest.mark.parametrize("dt,dd", [(0.01, 0.005), (0.025, 0.01), (0.004, 0.02)])
 def test_time_loop_fuzz_constraints_bitwise(dt, dd):
     """The fast time loop against the reference-shaped serial kernel on constraints far from the factory values -- crawling
@@ -343,7 +380,8 @@ def test_time_loop_fuzz_constraints_bitwise(dt, dd):
     torch.cuda.synchronize()
     assert torch.equal(ref.status, got.status)
     assert int((ref.status == 0).sum()) > B // 2
-    assert torch.equal(ref.n_out, got.n_out)
+    bad = (ref.n_out != got.n_out).nonzero().flatten().tolist()
+    assert not bad, [(b, int(ref.n_out[b]), int(got.n_out[b]), int(fast._n_main[b])) for b in bad[:6]]
     n = ref.n_out.long()
     Tm = min(ref.T_cap, got.T_cap)
     mt = torch.arange(Tm, device=n.device)[None, :] < n[:, None]

@@ -710,17 +710,22 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
                                                  const double* __restrict__ vel, long long T_cap,
                                                  double* __restrict__ out, int* __restrict__ nodes_map,
                                                  int* __restrict__ actions_map, int* __restrict__ n_maps,
-                                                 int* __restrict__ n_out, double* __restrict__ summary)
+                                                 int* __restrict__ n_out, double* __restrict__ summary,
+                                                 long long oplane, int only_status)
 {
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int st = status[b];
+    // only_status != 0: the pass that redoes, reference-shaped, the paths the split time stage gave up on (status ==
+    // only_status, i.e. ST_EVENTS: a position that oscillates across an action point or a node more often than the
+    // candidate tables hold); every other path leaves untouched
+    if (only_status != 0) { if (st != only_status) return; st = ST_OK; }
     const double L = total_len[b];
     int* nmap = nodes_map + (size_t)b * (N_max + 1);
     int* amap = actions_map + (size_t)b * (A_max > 0 ? A_max : 1);
     int nm = 0, am = 0;
     OutRows o;
-    size_t plane = (size_t)B * T_cap;
+    size_t plane = oplane > 0 ? (size_t)oplane : (size_t)B * T_cap;
     o.tm = out + (size_t)b * T_cap; o.pos = o.tm + plane; o.lin = o.pos + plane; o.acc = o.lin + plane;
     o.head = o.acc + plane; o.ang = o.head + plane; o.x = o.ang + plane; o.y = o.x + plane;
     o.cap = T_cap; o.T = 0;
@@ -773,6 +778,9 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
             if (frac1(t) < frac1(prev_t) && t < end_param) {
                 nmap[nm++] = (int)o.T;
                 node_idx += 1;
+                // spline_manager.nodes[node_idx] (:530) raises IndexError once a position that oscillates across node
+                // boundaries (steps that move backwards) has produced more crossings than there are nodes
+                if (node_idx >= n) { st = ST_INDEX; break; }
                 const double* a = na + (size_t)node_idx * NA;
                 if (a[A_TURN] != 0) {                 // handle_turn (:487-507)
                     if (!have_rows) { st = ST_INDEX; break; }
@@ -853,6 +861,7 @@ __global__ void __launch_bounds__(64) k_resample(long long B, int N_max, int A_m
     }
     long long T = (st == ST_OK || st == ST_CAPACITY) ? o.T : 0;
     if (T > 0 && T <= T_cap) last_time = o.tm[T - 1];
+    if (!(st == ST_OK || st == ST_CAPACITY)) { last_time = 0.0; max_abs_v = 0.0; }     // a failed path has no t_end / max |v|
     n_out[b] = (int)T;
     n_maps[2 * b] = nm; n_maps[2 * b + 1] = am;
     status[b] = st;
@@ -1146,7 +1155,7 @@ extern "C" int vap_resample(int64_t B, int N_max, int A_max, const double* node_
                                                     n_ap, cons, status, dt, dd, seg, first_node, param_end, n_splines,
                                                     samples, Q_cap, lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h,
                                                     D_cap, n_samples, vel, T_cap, out, nodes_map, actions_map, n_maps,
-                                                    n_out, summary);
+                                                    n_out, summary, 0, 0);
     CHECK_LAUNCH("vap_resample");
     return 0;
 }
@@ -1421,7 +1430,6 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
                                 int64_t out_plane_stride, const int32_t* lut_inv, const double* rden, int64_t n_rden,
                                 void* stream)
 {
-    (void)ap_flags;
     const long long oplane = out_plane_stride > 0 ? out_plane_stride : B * T_cap;
     if (B <= 0) return 0;
     if (E_cap < N_max + A_max + 2) return arg_err("vap_time_profile: E_cap < N_max + A_max + 2");
@@ -1482,6 +1490,16 @@ extern "C" int vap_time_profile(int64_t B, int N_max, int A_max, const double* n
     k_time_finalize<<<grid, 256, 0, STREAM>>>(B, status, M_cap, n_main, stage, E_cap, seg_k, seg_off, seg_rev, n_seg,
                                               T_cap, oplane, out, summary, tx);
     CHECK_LAUNCH("vap_time_profile/finalize");
+    // A path whose position moves BACKWARDS in some steps (max_dec > 0.2 / dt) can cross the same action point or node
+    // boundary again and again; the parallel event detection above then runs out of candidate slots and flags the path
+    // ST_EVENTS.  Such paths are redone by the reference-shaped serial kernel, one thread per path, straight into the same
+    // outputs (every other thread of this launch returns after one load: a few microseconds per call).
+    k_resample<<<blocks_for(B, 32), 32, 0, STREAM>>>(B, N_max, A_max, node_attr, node_flags, n_nodes, ap_attr, ap_flags, n_ap,
+                                                    cons, status, dt, dd, seg, first_node, param_end, n_splines, samples,
+                                                    Q_cap, lut_d, lut_t, total_len, spn, P_cap, prop_k, prop_h, D_cap,
+                                                    n_samples, vel, T_cap, out, nodes_map, actions_map, n_maps, n_out,
+                                                    summary, oplane, ST_EVENTS);
+    CHECK_LAUNCH("vap_time_profile/serial redo");
     return 0;
 }
 

@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(32) k_time_state(long long B, const double* __
                 const double half = 0.5 * accel * dt * dt;
                 const double dpos = ((v_new <= 0.1) ? hdt : v_new * dt) + half;
                 const double pos_new = pos + dpos;
-                const bool ok = (pos < L) & (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
+                // !fin: a finished lane keeps stepping on scratch values while the rest of its warp works; with steps that move
+                // backwards those values can wander back below L into a perfectly valid-looking state, and the lane must
+                // not take the path up again (it did, before this test was here: n_main came out 7495 instead of 2051)
+                const bool ok = !fin & (pos < L) & (e >= 0.0) & (e < dlim) & (x0 <= pos) & (pos < x1) & (x1 <= x2) & (x2 < xx2) &
                                 (off < (unsigned)BLK) & (r1 * r2 > 0.0) & recip_safe_exp(n1) &
                                 recip_safe_exp(n2) & (fabs(da) < 0x1p930) & (k < k_fast) & s0 & s1 & s2 & s3;
                 // The commit is unconditional -- no select on the dependent chain, no branch: a refused step (and every step
@@ -593,6 +596,7 @@ __global__ void __launch_bounds__(32) k_time_events(
                     wptr++;
                     nmap[nm++] = (int)T;
                     node_idx += 1;
+                    if (node_idx >= n) { st = ST_INDEX; break; }  // spline_manager.nodes[node_idx] (:530): IndexError
                     const double* a = na + (size_t)node_idx * NA;
                     if (a[A_TURN] != 0) {                        // handle_turn (:487-507)
                         double angle = a[A_TURN] * (VAP_PI / 180.0);
@@ -655,6 +659,7 @@ __global__ void __launch_bounds__(32) k_time_events(
     n_out[b] = (int)T;
     n_maps[2 * b] = nm; n_maps[2 * b + 1] = am;
     status[b] = st;
+    if (!(st == ST_OK || st == ST_CAPACITY)) last_time = 0.0;             // a failed path has no t_end (as in k_resample)
     sr[0] = (double)T; sr[1] = L; sr[2] = last_time; sr[3] = 0.0; sr[4] = (double)st;
 }
 

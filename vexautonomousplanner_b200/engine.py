@@ -9,6 +9,7 @@ sampling -> S3 events + S4 forward + S5 backward -> S6 time-domain resampling (+
 from __future__ import annotations
 
 import ctypes as C
+import os
 from contextlib import contextmanager
 from dataclasses import dataclass, field
 from typing import Dict, Optional
@@ -23,6 +24,7 @@ OUT_NAMES = ("times", "positions", "linear_vels", "accelerations", "headings", "
 ST_OK, ST_FALSE, ST_INDEX, ST_VALUE, ST_CAPACITY, ST_DIVERGED, ST_EVENTS = 0, -1, -2, -3, -4, -5, -6
 ROW_LIMIT = 1.0e7      # more time samples than this per path: treated as a non-terminating profile (status -5)
 DIST_LIMIT = 5.0e7     # more distance samples than this per path (L / dd; an infinite length too): status -5
+_POISON = bool(int(os.environ.get("VAP_POISON", "0")))
 MAX_RETRIES = 2        # exact re-runs after a capacity overflow; a status that survives them is returned as it is
 
 
@@ -174,7 +176,10 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _empty(self, shape, dtype=torch.float64):
-        return torch.empty(shape, dtype=dtype, device=self.device)
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        if _POISON:                  # debugging aid (VAP_POISON=1): scratch starts as NaN / a large odd integer, never as zeros
+            t.fill_(float("nan") if dtype.is_floating_point else (1 if dtype == torch.uint8 else 0x5a5a5a5))
+        return t
 
     def upload(self, p: PackedPaths) -> DeviceBatch:
         return DeviceBatch.from_packed(p, self.device)
@@ -435,7 +440,7 @@ class Engine:
             _p(n_out), _p(summary), _p(n_main), _p(stage), C.c_int(E_cap), _p(seg_tab), _p(scr), C.c_int64(plane_stride),
             _p(t.lut_inv if self.accelerators else None), _p(rden if self.accelerators else None), C.c_int64(rden.numel()),
             self._stream()), "vap_time_profile")
-        self.launches += 4
+        self.launches += 5
         self._n_main = n_main
         return out, nodes_map, actions_map, n_maps, n_out, summary
 
@@ -691,7 +696,7 @@ class Engine:
             _p(rden if self.accelerators else None), C.c_int64(rden.numel()), C.c_void_p(ws_ptr), C.c_int64(nbytes), _p(out),
             C.c_int64(0), _p(n_out), _p(nodes_map), _p(actions_map), _p(n_maps), _p(status), _p(summary), _p(vel), _p(n_samples),
             _p(need), self._stream()), "vap_profile_batch")
-        self.launches += 19
+        self.launches += 20
         res = ProfileResult(B, T_cap, out, n_out, nodes_map, actions_map, n_maps, status, summary, vel, n_samples)
         res.extra = dict(need=need, workspace=ws)
         if _retry < MAX_RETRIES and bool((status == ST_CAPACITY).any().item()):
