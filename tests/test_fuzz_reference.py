@@ -128,15 +128,17 @@ _TOL = {0: (1e-6, 1e-12), 1: (1e-9, 1e-10), 2: (1e-6, 1e-9), 3: (1e-6, 1e-6), 4:
         6: (1e-9, 1e-10), 7: (1e-9, 1e-10)}
 
 
-def _check_osc(f, i, status, T, nodes_map, streams):
+def _check_osc(f, i, status, T, nodes_map, actions_map, streams):
     """One case of oscillation_reference.npz (tests/golden/make_golden_oscillation.py: the unmodified reference on paths
-    whose position moves backwards near a stop, max_dec > 0.2 / dt): either the reference raised IndexError (-2: more
-    node transitions than nodes) or it returned, and then T and nodes_map -- extra transitions included -- are exact."""
+    whose position moves backwards near a stop, max_dec > 0.2 / dt; half of them with turns, waits and action points):
+    either the reference raised IndexError (-2: more node transitions than nodes) or it returned, and then T, nodes_map --
+    extra transitions included -- and actions_map are exact."""
     assert status == int(f["status"][i]), (i, status, int(f["status"][i]))
     if status != 0:
         return
     assert T == int(f["T"][i]), (i, T, int(f["T"][i]))
     assert list(nodes_map) == f["nodes_map"][i][: int(f["n_nm"][i])].tolist(), i
+    assert list(actions_map) == f["actions_map"][i][: int(f["n_am"][i])].tolist(), i
     idx = np.arange(0, T, int(f["stride"]))[:120]
     want = f["samples"][i][:, : len(idx)]
     got = np.stack([s[idx] for s in streams])
@@ -149,24 +151,25 @@ def test_oracle_against_reference_oscillation(oracle_mod):
     o = oracle_mod
     o.set_sq_mode(0)
     f = dict(np.load(OSC))
-    assert sorted(set(f["status"].tolist())) == [-2, 0]
+    assert sorted(set(f["status"].tolist())) == [-2, 0] and len(f["n"]) == 16
     for i in range(len(f["n"])):
-        n = int(f["n"][i])
+        n, A = int(f["n"][i]), int(f["n_ap"][i])
         try:
-            r = o.full(f["node_attr"][i][:n], f["node_flags"][i][:n], None, None, f["cons"][i], dt=float(f["dt"][i]),
-                       dd=float(f["dd"][i]))
+            r = o.full(f["node_attr"][i][:n], f["node_flags"][i][:n], f["ap_attr"][i][:A] if A else None,
+                       f["ap_flags"][i][:A] if A else None, f["cons"][i], dt=float(f["dt"][i]), dd=float(f["dd"][i]))
         except o.OracleError as e:
-            _check_osc(f, i, e.code, 0, [], None)
+            _check_osc(f, i, e.code, 0, [], [], None)
             continue
         streams = [r[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
-        _check_osc(f, i, 0, r["T"], r["nodes_map"], streams)
+        _check_osc(f, i, 0, r["T"], r["nodes_map"], r["actions_map"], streams)
         np.testing.assert_allclose(r["summary"][2], f["t_end"][i], rtol=1e-6)
 
 
 @pytest.mark.gpu
 def test_engine_against_reference_oscillation():
     """The same cases through the engine, fast and reference-shaped kernels: IndexError cases come back as status -2, the
-    others with the reference's T and nodes_map (the extra node transitions of an oscillating position included)."""
+    others with the reference's T, nodes_map (the extra node transitions of an oscillating position included) and
+    actions_map."""
     import torch
     from vexautonomousplanner_b200.engine import Engine
     from vexautonomousplanner_b200.packing import PackedPaths
@@ -174,10 +177,10 @@ def test_engine_against_reference_oscillation():
     B = len(f["n"])
     for dt, dd in sorted(set(zip(f["dt"].tolist(), f["dd"].tolist()))):
         sel = [i for i in range(B) if f["dt"][i] == dt and f["dd"][i] == dd]
-        nb = len(sel)
         packed = PackedPaths(np.ascontiguousarray(f["node_attr"][sel]), np.ascontiguousarray(f["node_flags"][sel]).astype(np.int32),
-                             f["n"][sel].astype(np.int32), np.zeros((nb, 1, 4)), np.zeros((nb, 1), dtype=np.int32),
-                             np.zeros(nb, dtype=np.int32), np.ascontiguousarray(f["cons"][sel]))
+                             f["n"][sel].astype(np.int32), np.ascontiguousarray(f["ap_attr"][sel]),
+                             np.ascontiguousarray(f["ap_flags"][sel]).astype(np.int32), f["n_ap"][sel].astype(np.int32),
+                             np.ascontiguousarray(f["cons"][sel]))
         for impl in (dict(), dict(velocity_impl="serial", time_impl="serial")):
             eng = Engine("cuda:0", dt=dt, dd=dd, **impl)
             res = eng.profile(eng.upload(packed))
@@ -185,8 +188,8 @@ def test_engine_against_reference_oscillation():
             for j, i in enumerate(sel):
                 st = int(res.status[j])
                 if st != 0:
-                    _check_osc(f, i, st, 0, [], None)
+                    _check_osc(f, i, st, 0, [], [], None)
                     continue
                 p = res.path(j)
                 streams = [p[k] for k in ("times", "positions", "linear_vels", "accelerations", "headings", "angular_vels", "x", "y")]
-                _check_osc(f, i, 0, len(p["times"]), p["nodes_map"], streams)
+                _check_osc(f, i, 0, len(p["times"]), p["nodes_map"], p["actions_map"], streams)
