@@ -670,6 +670,37 @@ def test_fuzz_summaries_against_oracle(eng, ora, kind, nn):
     np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=1e-6)         # max |v|
 
 
+@pytest.mark.parametrize("dt,dd", [(0.01, 0.005), (0.02, 0.0025)])
+def test_fuzz_extreme_constraints_against_oracle(ora, dt, dd):
+    """Mixed paths with constraints far from the factory values (crawling and very fast robots, max_acc 0.2 ... 40, wide and
+    narrow track widths; max_dec below 0.2 / dt so that no step moves backwards -- the oscillating regime is chaotic in the
+    last bits of the tables and has its own bitwise and reference-pinned tests) and a second dt / dd pair, against the
+    oracle: status and time-sample count exact for every path, summary values within the north-star tolerances."""
+    from vexautonomousplanner_b200 import synth
+    from vexautonomousplanner_b200.engine import Engine
+    rng = np.random.default_rng(int(dd * 1e5) + 3)
+    packed = synth.mixed_paths(600, 8, seed=91)
+    B = packed.cons.shape[0]
+    packed.cons[:, 0] = rng.uniform(0.3, 14.0, B)
+    packed.cons[:, 1] = 10.0 ** rng.uniform(-0.7, 1.6, B)
+    packed.cons[:, 2] = 10.0 ** rng.uniform(-0.7, np.log10(0.18 / dt), B)
+    packed.cons[:, 5] = rng.uniform(0.4, 2.5, B)
+    eng = Engine("cuda:0", dt=dt, dd=dd)
+    res = eng.profile(eng.upload(packed))
+    torch.cuda.synchronize()
+    got = res.summary.cpu().numpy()
+    want = ora.full_batch(packed.node_attr, packed.node_flags, packed.cons, n_ap=packed.n_ap, ap_attr=packed.ap_attr,
+                          ap_flags=packed.ap_flags, dt=dt, dd=dd, cap_d=400000, cap_t=400000)
+    assert (got[:, 4] == want[:, 4]).all(), np.nonzero(got[:, 4] != want[:, 4])[0][:10].tolist()
+    ok = want[:, 4] == 0
+    assert ok.sum() > B // 2
+    bad = np.nonzero((got[:, 0] != want[:, 0]) & ok)[0]
+    assert bad.size == 0, f"time-sample counts differ for paths {bad[:10].tolist()}"
+    np.testing.assert_allclose(got[ok, 1], want[ok, 1], rtol=1e-12)        # total length
+    np.testing.assert_allclose(got[ok, 2], want[ok, 2], rtol=1e-6)         # t_end
+    np.testing.assert_allclose(got[ok, 3], want[ok, 3], rtol=1e-6)         # max |v|
+
+
 def test_degenerate_inputs_never_hang(eng):
     """Inputs for which the reference would loop forever or blow up come back with a status instead of hanging the GPU:
     a deceleration limit so large that a step moves backwards, an absurd wait, an absurdly slow turn profile."""
