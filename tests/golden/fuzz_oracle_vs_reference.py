@@ -4,7 +4,8 @@ only; see make_golden.py for the headless recipe): random paths with turns, reve
 points, constraints far from the factory values (max_vel 0.3 ... 14, max_acc 0.2 ... 40, max_dec up to 10^argv[3]), three dt
 and three dd values.  Compares status (incl. the reference's IndexError / ValueError), T, nodes_map, actions_map exactly and
 the streams within the north-star tolerances.  usage: fuzz_oracle_vs_reference.py [seed] [cases] [log10 of the largest
-max_dec].  Last runs: seeds 11 and 12, 24 + 40 cases, max_dec up to 18 and 160: 0 mismatches."""
+max_dec].  Last runs: seeds 11, 12 and 21, 24 + 40 + 60 cases, max_dec up to 18 / 160 / 160: 0 mismatches (two long, slowly
+accelerating paths of seed 21 deviate by 2.3e-10 ft in position and x after 4000 rows: the <= 4 ulp of the tables, amplified)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -72,7 +73,11 @@ for case in range(NC):
             coords = np.array(coords, dtype=float).reshape(-1, 2)
             for nm_, a_, tol in (("times", times, 1e-6), ("positions", positions, 1e-9), ("linear_vels", lin, 1e-6), ("headings", head, 1e-9)):
                 if not np.allclose(np.array(a_, dtype=float), r[nm_], rtol=tol, atol=1e-9): msg = f"stream {nm_} differs"; break
-            if not msg and not np.allclose(coords[:, 0], r["x"], rtol=1e-9, atol=1e-10): msg = "x differs"
+            if not msg and not np.allclose(coords[:, 0], r["x"], rtol=1e-9, atol=1e-9):   # north star: 1e-9 on positions
+                dx = np.abs(coords[:, 0] - r["x"]); k = int(np.argmax(dx))
+                dp = np.abs(np.array(positions, dtype=float) - r["positions"])
+                msg = (f"x differs: max |dx| {dx.max():.3e} at row {k} of {T} (x = {coords[k, 0]!r} vs {r['x'][k]!r}), "
+                       f"max |dpos| {dp.max():.3e}, |dpos| there {dp[k]:.3e}")
     bad += bool(msg)
     print(f"case {case}: n={n} A={A} dt={dt} dd={dd} cons={[round(x,2) for x in cons[:3]]} ref={st_r} {'OK' if not msg else 'MISMATCH ' + msg}", flush=True)
 print("MISMATCHES", bad, "in", NC, "cases,", round(time.time() - t0), "s")
