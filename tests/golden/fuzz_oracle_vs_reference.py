@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Direct fuzz of the C oracle against the UNMODIFIED reference (needs /root/reference, so it runs in the build container
-only; see make_golden.py for the headless recipe): random paths with turns, reverse, stops, waits, overrides and action
-points, constraints far from the factory values (max_vel 0.3 ... 14, max_acc 0.2 ... 40, max_dec up to 10^argv[3]), three dt
+only; see make_golden.py for the headless recipe): random paths with turns, reverse, stops, waits, overrides, user tangents and (sorted or
+unsorted) action points, constraints far from the factory values (max_vel 0.3 ... 14, max_acc 0.2 ... 40, max_dec up to 10^argv[3]), three dt
 and three dd values.  Compares status (incl. the reference's IndexError / ValueError), T, nodes_map, actions_map exactly and
 the streams within the north-star tolerances.  usage: fuzz_oracle_vs_reference.py [seed] [cases] [log10 of the largest
-max_dec].  Last runs: seeds 11, 12, 21 and 31, 24 + 40 + 60 + 80 cases, max_dec up to 18 / 160 / 160 / 20: 0 mismatches (two long, slowly
+max_dec].  Last runs: seeds 11, 12, 21, 31 and 41 (the last with user tangents and unsorted action points), 24 + 40 + 60 + 80 + 80
+cases, max_dec up to 18 / 160 / 160 / 20 / 20: 0 mismatches (two long, slowly
 accelerating paths of seed 21 deviate by 2.3e-10 ft in position and x after 4000 rows: the <= 4 ulp of the tables, amplified)."""
 import os, sys, time
 import numpy as np
@@ -30,10 +31,15 @@ for case in range(NC):
         if i <= n - 2 and rng.random() < 0.2: kw["wait_time"] = float(rng.choice([0.1, 0.25, 0.005]))
         if rng.random() < 0.15: kw["max_velocity"] = float(rng.uniform(0.5, 6))
         if rng.random() < 0.15: kw["max_acceleration"] = float(rng.uniform(0.5, 20))
+        if rng.random() < 0.12:                      # user tangent with its own magnitudes
+            a_ = rng.uniform(0, 2 * np.pi)
+            kw["tangent"] = np.array([np.cos(a_), np.sin(a_)])
+            kw["incoming_magnitude"] = float(rng.uniform(0.5, 3.0)); kw["outgoing_magnitude"] = float(rng.uniform(0.5, 3.0))
         nodes.append(mg.Node(**kw))
     if nodes[0].turn != 0 and rng.random() < 0.7: nodes[0].turn = 0
     A = int(rng.integers(0, MAXA + 1))
-    ts = np.sort(rng.uniform(0.2, n - 1.2, A))
+    ts = rng.uniform(0.2, n - 1.2, A)
+    if case % 3 != 2: ts = np.sort(ts)              # every third case keeps its action points UNSORTED
     aps = [mg.ActionPoint(float(t), stop=bool(rng.random() < 0.3), wait_time=float(rng.choice([0, 0.1])),
                           max_velocity=float(rng.choice([0, 2.0])), max_acceleration=float(rng.choice([0, 4.0]))) for t in ts]
     cons = [float(rng.uniform(0.3, 14.0)), float(10 ** rng.uniform(-0.7, 1.6)), float(10 ** rng.uniform(-0.7, float(sys.argv[3]) if len(sys.argv) > 3 else 1.25)), 0.8, 16.0,
@@ -43,6 +49,8 @@ for case in range(NC):
     for i, nd in enumerate(nodes):
         na[i, 0:2] = pts[i]; na[i, 2], na[i, 3], na[i, 4], na[i, 5] = nd.turn, nd.wait_time, nd.max_velocity, nd.max_acceleration
         nf[i] |= (1 if nd.is_reverse_node else 0) | (2 if nd.stop else 0)
+        if nd.tangent is not None:
+            na[i, 6:8] = nd.tangent; na[i, 8] = nd.incoming_magnitude; na[i, 9] = nd.outgoing_magnitude; nf[i] |= 4
         na[i, 10], na[i, 11] = 1.0, 0.0
         if nd.turn != 0:
             ang = np.radians(nd.turn) + (np.pi if nd.is_reverse_node else 0); na[i, 10], na[i, 11] = np.cos(ang), np.sin(ang)
