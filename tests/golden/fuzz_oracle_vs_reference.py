@@ -4,7 +4,7 @@ only; see make_golden.py for the headless recipe): random paths with turns, reve
 unsorted) action points, constraints far from the factory values (max_vel 0.3 ... 14, max_acc 0.2 ... 40, max_dec up to 10^argv[3]), three dt
 and three dd values.  Compares status (incl. the reference's IndexError / ValueError), T, nodes_map, actions_map exactly and
 the streams within the north-star tolerances.  usage: fuzz_oracle_vs_reference.py [seed] [cases] [log10 of the largest
-max_dec].  Last runs: seeds 11, 12, 21, 31 and 41 (the last with user tangents and unsorted action points), 24 + 40 + 60 + 80 + 80
+max_dec].  Last runs: seeds 11, 12, 21, 31 and 41 (the last with user tangents and unsorted action points), 24 + 40 + 60 + 80 + 80 (+ 60 more with seed 51)
 cases, max_dec up to 18 / 160 / 160 / 20 / 20: 0 mismatches (two long, slowly
 accelerating paths of seed 21 deviate by 2.3e-10 ft in position and x after 4000 rows: the <= 4 ulp of the tables, amplified)."""
 import os, sys, time
